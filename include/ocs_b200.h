@@ -1,0 +1,212 @@
+/* ocs_b200.h -- C ABI of the B200-native RK4 trajectory sweeps
+ *
+ * Drop-in boundary for ONE hot path of DrDanRyan/Optimal-Control-Solvers: the
+ * fixed-step RK4 forward state sweep and the backward discrete-adjoint (costate)
+ * sweep behind single_shooting / an RK4-grid fb_sweep, batched over independent
+ * trajectories.  The reference is pure MATLAB and has no FFI; every entry point
+ * below names the MATLAB method it replaces (paths relative to the reference
+ * tree).  A MEX gateway (optimal-control-solvers_b200/matlab/ocs_b200_mex.c) and a Python ctypes
+ * binding (optimal-control-solvers_b200/_lib.py) bind exactly these symbols.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from ocs_b200_last_error(handle) (or with handle == NULL for
+ *     create-time failures).  Nothing throws or longjmps across this boundary.
+ *   - all host arrays are FP64, MATLAB (column-major) layout, read-only inputs
+ *     are never retained past the call.
+ *   - n = number of true states, m = n+1 (augmented with the running objective,
+ *     last row), nc = controls, N = RK4 steps, G = 2N+1 grid points (nodes and
+ *     interval midpoints), K = control basis size, Bt = trajectories in a batch.
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device
+ *     and fails with OCS_B200_ERR_CUDA when there is none.
+ */
+#ifndef OCS_B200_H
+#define OCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define OCS_B200_API __declspec(dllexport)
+#else
+#define OCS_B200_API __attribute__((visibility("default")))
+#endif
+
+#define OCS_B200_ABI_VERSION 1
+
+/* status codes */
+enum {
+    OCS_B200_OK = 0,
+    OCS_B200_ERR_ARG = 1,      /* bad argument / size / call order (MATLAB would raise a size error) */
+    OCS_B200_ERR_CUDA = 2,     /* CUDA runtime/driver error, sticky for the handle */
+    OCS_B200_ERR_COMPILE = 3,  /* NVRTC compilation of a generated problem failed (log in last_error) */
+    OCS_B200_ERR_STATE = 4,    /* compute_adjoints before compute_states, etc. */
+    OCS_B200_ERR_NOMEM = 5
+};
+
+/* built-in problems (device functions compiled into the library) */
+enum {
+    OCS_B200_PROBLEM_TEST = 0  /* tests/TestOCProblem.m:13-38, params = {c, m, r} */
+};
+
+/* arithmetic mode */
+enum {
+    OCS_B200_MATH_FAST = 0,    /* FMA contraction on (default nvcc -fmad=true) */
+    OCS_B200_MATH_STRICT = 1   /* every operation rounded separately, like MATLAB's element-wise ops */
+};
+
+/* reductions over the batch (ocs_b200_reduce_J) */
+enum { OCS_B200_REDUCE_SUM = 0, OCS_B200_REDUCE_MIN = 1, OCS_B200_REDUCE_MAX = 2 };
+
+typedef struct ocs_b200_handle ocs_b200_handle;
+
+/* ------------------------------------------------------------------ lifetime */
+
+/* Replaces the constructors RK4Integrator(tspan) (Integrator/RK4Integrator.m:16-25) and
+ * RK4InfiniteIntegrator(tspan, tspanExtra, uStar) (Integrator/RK4InfiniteIntegrator.m:12-17).
+ *   tspan        [N+1]   node times of the main horizon
+ *   tspan_extra  [N2+1]  node times of the tail horizon, or NULL / N2 == 0 for a finite horizon
+ *   uStar        [nc]    constant tail control (read at problem-binding time; may be NULL when N2 == 0)
+ *   device       CUDA device ordinal
+ *   math_mode    OCS_B200_MATH_FAST or OCS_B200_MATH_STRICT
+ * h = diff(tspan) and the augmented grid t (nodes + midpoints) are formed with the same
+ * single IEEE operations as RK4Integrator.m:17-24 and can be read back with ocs_b200_get_grid. */
+OCS_B200_API int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extra,
+                                 int device, int math_mode, ocs_b200_handle **out);
+
+/* delete(obj): frees the device-resident trajectory store (the xK cache of RK4Integrator.m:8-10). */
+OCS_B200_API int ocs_b200_destroy(ocs_b200_handle *h);
+
+/* Message of the last failure on this handle (h == NULL: last create-time failure). Never NULL. */
+OCS_B200_API const char *ocs_b200_last_error(const ocs_b200_handle *h);
+
+OCS_B200_API int ocs_b200_abi_version(void);
+
+/* Property t / h of RK4Integrator (Integrator/RK4Integrator.m:4-5).  segment 0 = main, 1 = tail.
+ * t [2N+1], h [N]; either may be NULL. */
+OCS_B200_API int ocs_b200_get_grid(const ocs_b200_handle *h, int segment, double *t, double *hstep);
+
+/* ------------------------------------------------------------------ problem (OCProblem/OCProblem.m:3-21) */
+
+/* Bind a built-in OCProblem (F, dFdx_times_vec, dFdu_times_vec compiled into the library). */
+OCS_B200_API int ocs_b200_set_problem_builtin(ocs_b200_handle *h, int problem_id);
+
+/* Bind a generated OCProblem: CUDA source of the device functions emitted by the
+ * make_from_symbolic CUDA backend (replaces matlabFunction in functions/make_from_symbolic.m:27-31),
+ * compiled here with NVRTC for sm_100a together with the sweep kernels.
+ *   kernel_include_dir: directory holding rk4_kernels.cuh (NULL = the library's own csrc directory). */
+OCS_B200_API int ocs_b200_set_problem_source(ocs_b200_handle *h, const char *cuda_source,
+                                             int n, int nc, int np, const char *kernel_include_dir);
+
+/* Problem parameters (TestOCProblem.m:16-18 c,m,r; make_from_symbolic.m:3-4 params struct).
+ *   params [np x nbatch] column-major; nbatch == 1: shared by the batch, else one column per trajectory. */
+OCS_B200_API int ocs_b200_set_params(ocs_b200_handle *h, const double *params, int np, long nbatch);
+
+/* uStar of RK4InfiniteIntegrator.m:15 (constant tail control, [nc]). */
+OCS_B200_API int ocs_b200_set_tail_control(ocs_b200_handle *h, const double *uStar, int nc);
+
+/* ------------------------------------------------------------------ control (Control/Control.m:4-14) */
+
+/* Attach the basis matrix B of a Control object (PWConstantControl.m:30-38, PWLinearControl.m:31-50,
+ * ChebyshevControl.m:21-31): B is K x G column-major, built by the host on integrator.t.
+ * Columns with <= 2 adjacent non-zeros are stored as an (index, w0, w1) table -- the index is the
+ * reference's control-grid index, taken from B itself, hence bit-exact; denser B is kept dense.
+ * With a basis attached, compute_u (u = reshape(v,nc,[])*B) and compute_dJdv (dJdv = dJdu*B') are
+ * fused into the sweeps.  K == 0 detaches. */
+OCS_B200_API int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B);
+
+/* Reads back the compressed basis: k_index[G] (0-based first non-zero row) and nnz[G]; NULL to skip.
+ * For a dense basis k_index is all 0 and nnz all K. */
+OCS_B200_API int ocs_b200_get_control_index(const ocs_b200_handle *h, int32_t *k_index, int32_t *nnz);
+
+/* Control coefficients v (argument of compute_u, PWLinearControl.m:59-62): [(nc*K) x nbatch],
+ * element (k*nc + c) = control c, basis k (0-based).  nbatch == 1: shared; else one column per trajectory. */
+OCS_B200_API int ocs_b200_set_control_v(ocs_b200_handle *h, const double *v, long nbatch);
+
+/* Control values on the grid (argument u of compute_states, RK4Integrator.m:28): [nc x G x nbatch]. */
+OCS_B200_API int ocs_b200_set_control_u(ocs_b200_handle *h, const double *u, long nbatch);
+
+/* u = control.compute_u(v) for the current v: [nc x G x nb] for trajectories [b0, b0+nb)
+ * (nb is clamped to 1 for a shared control). */
+OCS_B200_API int ocs_b200_get_control_u(ocs_b200_handle *h, long b0, long nb, double *u);
+
+/* ------------------------------------------------------------------ sweeps */
+
+/* [x, J] = integrator.compute_states(prob, x0, u)  (RK4Integrator.m:28-56; with a tail:
+ * RK4InfiniteIntegrator.m:20-24) for Bt trajectories at once.
+ *   x0     [n x Bt]
+ *   J      [Bt]       objective (J1 + J2 with a tail)                         (may be NULL)
+ *   xT     [n x Bt]   state at the end of the main horizon                    (may be NULL)
+ *   status [Bt]       0 = finite, 1 = J or x(T) not finite                    (may be NULL)
+ * Node states stay on the device for compute_adjoints / fetch_states. */
+OCS_B200_API int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, long Bt,
+                                         double *J, double *xT, int32_t *status);
+
+/* [lam, dJdu] = integrator.compute_adjoints(prob, u [, lamT])  (RK4Integrator.m:59-121,
+ * RK4InfiniteIntegrator.m:27-30) fused with dJdv = control.compute_dJdv(dJdu) when a basis is attached.
+ * Uses the trajectories of the last compute_states on this handle (RK4Integrator.m:8-10).
+ *   lamT  [m x nbatch] terminal costate of the main horizon, nbatch in {1, Bt}; NULL = e_m
+ *         (ignored when the handle has a tail: the tail sweep supplies it, RK4InfiniteIntegrator.m:28-29)
+ *   dJdv  [(nc*K) x Bt]   (NULL to skip; requires a basis)
+ *   lam0  [m x Bt]        lam(:,1), the free-initial-state gradient of single_shooting.m:147-148 (NULL to skip) */
+OCS_B200_API int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_nbatch,
+                                           double *dJdv, double *lam0);
+
+/* Full grids for trajectories [b0, b0+nb), exactly the arrays the MATLAB methods return:
+ *   x    [m x (N+1) x nb]   (RK4Integrator.m:54)     lam  [m x (N+1) x nb]  (RK4Integrator.m:68-89)
+ *   dJdu [nc x G x nb]      (RK4Integrator.m:97-121)
+ * segment 0 = main horizon, 1 = tail.  Any pointer may be NULL. */
+OCS_B200_API int ocs_b200_fetch_states(ocs_b200_handle *h, int segment, long b0, long nb, double *x);
+OCS_B200_API int ocs_b200_fetch_adjoints(ocs_b200_handle *h, int segment, long b0, long nb,
+                                         double *lam, double *dJdu);
+
+/* One fb_sweep iteration loop on the RK4 grid (functions/fb_sweep.m:79-115 composed with the RK4
+ * sweeps): u lives on the G grid points per trajectory; per sweep  x = forward(u), lam = adjoint(u),
+ * uNew = ControlChar(t, x, lam) clamped to bounds (make_from_symbolic.m:102-112), convergence
+ * max_j |uNew-u| / (uRelTol |u| + uAbsTol) <= 1 (fb_sweep.m:107-110) per trajectory.
+ *   x0 [n x Bt]; u0 [nc x G x nbatch] initial control (nbatch in {1, Bt});
+ *   bounds [nc x 2] ControlBounds; relax = 1 is the reference's pure replacement (fb_sweep.m:96).
+ *   J [Bt], sweeps [Bt] (sweeps used), converged [Bt] (0/1), max_change [Bt]: any may be NULL.
+ * The converged control stays on the device (ocs_b200_get_control_u), states/adjoints via fetch_*. */
+OCS_B200_API int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt,
+                                   const double *u0, long u0_nbatch, const double *bounds,
+                                   double uRelTol, double uAbsTol, int nSWEEPS, double relax,
+                                   double *J, int32_t *sweeps, int32_t *converged, double *max_change);
+
+/* Batch reduction of the last J (warp-shuffle tree): value and arg index (index may be NULL). */
+OCS_B200_API int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, long *index);
+
+/* ------------------------------------------------------------------ device-resident variants
+ * Same sweeps with caller-owned DEVICE buffers in structure-of-arrays layout [row][Bt]
+ * (batch fastest) -- for pipelines that keep the batch in HBM and for multi-GPU gathers.
+ * stream: a cudaStream_t (NULL = the handle's own stream). */
+OCS_B200_API int ocs_b200_set_stream(ocs_b200_handle *h, void *cuda_stream);
+OCS_B200_API int ocs_b200_set_control_v_dev(ocs_b200_handle *h, const double *v_soa, long nbatch);
+OCS_B200_API int ocs_b200_compute_states_dev(ocs_b200_handle *h, const double *x0_soa, long Bt,
+                                             double *J, double *xT_soa, int32_t *status);
+OCS_B200_API int ocs_b200_compute_adjoints_dev(ocs_b200_handle *h, const double *lamT_soa, long lamT_nbatch,
+                                               double *dJdv_soa, double *lam0_soa);
+OCS_B200_API int ocs_b200_synchronize(ocs_b200_handle *h);
+
+/* Device time (ms, CUDA events on the launch stream) and launch count of the sweep kernels since
+ * the last call with reset != 0. */
+OCS_B200_API int ocs_b200_kernel_stats(ocs_b200_handle *h, int reset, double *ms_forward, double *ms_reverse,
+                                       long *launches);
+/* enable/disable the CUDA-event bracketing used by ocs_b200_kernel_stats (off by default) */
+OCS_B200_API int ocs_b200_set_profiling(ocs_b200_handle *h, int on);
+
+/* ------------------------------------------------------------------ measurement helpers (not on the path) */
+
+/* FP64 FMA peak of the device (dependent DFMA chains, all SMs): TFLOP/s. */
+OCS_B200_API int ocs_b200_measure_fp64_peak(int device, double *tflops);
+/* HBM streaming bandwidth with the sweeps' access pattern (FP64 coalesced write + read): GB/s each. */
+OCS_B200_API int ocs_b200_measure_hbm(int device, size_t bytes, double *write_gbs, double *read_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCS_B200_H */

@@ -1,0 +1,10 @@
+"""B200-native RK4 trajectory sweeps behind the OCProblem / Control / Integrator plugin
+API of DrDanRyan/Optimal-Control-Solvers.  Everything that computes goes through
+libocs_b200.so (hand-written sm_100a CUDA, C ABI in include/ocs_b200.h)."""
+from . import _lib
+from ._lib import OcsError
+from .host import (ChebyshevControl, Control, CudaRK4InfiniteIntegrator, CudaRK4Integrator, OCProblem,
+                   PWConstantControl, PWLinearControl, TestOCProblem, matlab_linspace)
+
+__all__ = ["OcsError", "CudaRK4Integrator", "CudaRK4InfiniteIntegrator", "Control", "PWConstantControl",
+           "PWLinearControl", "ChebyshevControl", "OCProblem", "TestOCProblem", "matlab_linspace"]

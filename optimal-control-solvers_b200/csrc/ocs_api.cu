@@ -1,0 +1,1343 @@
+// ocs_api.cu -- host side of the C ABI declared in include/ocs_b200.h.
+//
+// Owns the device-resident trajectory store (the xK cache of
+// Integrator/RK4Integrator.m:8-10, node states only), packs the batch-invariant
+// grid / control tables into per-grid-point records, picks the sweep kernel variant
+// and launches it.  No arithmetic of the path runs on the host except forming the
+// grid (diff / midpoints, RK4Integrator.m:17-24), h/2, h/3, h/6 and -- for a control
+// shared by the whole batch -- the product u = v*B for the G grid points.
+// There is no CPU fallback: without a CUDA device every compute call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ocs_b200.h"
+#include "kernel_table.h"
+
+#define OCS_NS ocs_host
+#include "rk4_kernels.cuh"
+using ocs_host::SweepArgs;
+
+extern "C" void ocs_builtin_table_test_fast(ocs_kernel_table *t);
+extern "C" void ocs_builtin_table_test_strict(ocs_kernel_table *t);
+// nvrtc_problem.cu
+int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int strict, const char *include_dir,
+                        ocs_kernel_table *table, void **library, std::string *log);
+void ocs_unload_problem(void *library);
+
+namespace {
+
+std::string g_create_error = "";
+std::mutex g_mutex;
+
+struct Segment {
+    int N = 0;
+    std::vector<double> tspan, t, h;
+    double *d_gprec = nullptr, *d_steprec = nullptr;
+    double *d_xs = nullptr;   // node states [n][N+1][Bt]
+    size_t xs_cap = 0;        // doubles
+    int R = 0;
+    bool records_dirty = true;
+};
+
+enum { CTRL_NONE = 0, CTRL_V_SHARED, CTRL_V_BATCH, CTRL_U_SHARED, CTRL_U_BATCH };
+enum { BASIS_NONE = 0, BASIS_SPARSE = 1, BASIS_DENSE = 2 };
+
+struct DevBuf {
+    double *p = nullptr;
+    size_t cap = 0;   // doubles
+};
+
+}  // namespace
+
+struct ocs_b200_handle {
+    int device = 0;
+    int math_mode = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int sticky = 0;
+
+    Segment seg[2];
+    bool has_tail = false;
+
+    // problem
+    bool have_problem = false;
+    ocs_kernel_table kt{};
+    void *gen_library = nullptr;
+    std::string gen_source, gen_include;
+    int gen_n = 0, gen_nc = 0, gen_np = 0;
+    bool is_generated = false;
+
+    // params
+    std::vector<double> params_shared;
+    long params_nbatch = 0;
+    DevBuf d_params;
+    std::vector<double> uStar;
+
+    // control
+    int basis_kind = BASIS_NONE;
+    int K = 0;
+    std::vector<int32_t> bk, bnnz;
+    std::vector<double> bw0, bw1, bdense;
+    int ctrl_mode = CTRL_NONE;
+    std::vector<double> ctrl_shared;   // v (nc*K) or u (nc*G)
+    long ctrl_nbatch = 0;
+    DevBuf d_v, d_ug;
+    const double *v_ext = nullptr;     // caller-owned device v (set_control_v_dev)
+    bool user_lamT = false;            // last compute_adjoints carried an explicit lamT (kept in d_lamT_user)
+    long user_lamT_ld = 0;
+
+    // batch state
+    long Bt = 0;
+    bool have_states = false;
+    DevBuf d_x0, d_J, d_xT, d_lamT_tail, d_lamT_user, d_dJdv, d_lam0, d_stage, d_stage2, d_maxchg;
+    int *d_status = nullptr;
+    size_t status_cap = 0;
+    int *d_frozen = nullptr, *d_sweeps = nullptr;
+    size_t frozen_cap = 0;
+    double *d_bounds = nullptr;
+    double *d_red = nullptr;   // reduction scratch
+
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double ms_fwd = 0, ms_rev = 0;
+    long launches = 0;
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        if (code == OCS_B200_ERR_CUDA) sticky = code;
+        return code;
+    }
+};
+
+namespace {
+
+typedef ocs_b200_handle H;
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return h->fail(OCS_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                           __FILE__, __LINE__);                                                         \
+    } while (0)
+#define TRY(expr)                  \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != 0) return rc_;  \
+    } while (0)
+
+int ensure(H *h, DevBuf &b, size_t n)
+{
+    if (b.cap >= n && b.p) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, std::max<size_t>(n, 1) * sizeof(double));
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        cudaGetLastError();
+        return h->fail(OCS_B200_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(double),
+                       cudaGetErrorString(e));
+    }
+    b.cap = n;
+    return 0;
+}
+
+int ensure_raw(H *h, double **p, size_t *cap, size_t n)
+{
+    DevBuf b;
+    b.p = *p;
+    b.cap = *cap;
+    int rc = ensure(h, b, n);
+    *p = b.p;
+    *cap = b.cap;
+    return rc;
+}
+
+// ---------------------------------------------------------------- layout kernels
+// dst[perm(r)][ldd] (SoA, batch fastest)  <-  src[b][rows] (MATLAB column-major rows x nb)
+// perm(r) = (r % nc) * (rows / nc) + r / nc   when nc > 1 regroups [c + nc*j] -> [c*G + j]
+__global__ void to_soa_kernel(const double *__restrict__ src, double *__restrict__ dst, long rows, long nb, long ldd,
+                              int nc)
+{
+    __shared__ double tile[32][33];
+    const long b0 = (long)blockIdx.x * 32, r0 = (long)blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const long b = b0 + k, r = r0 + threadIdx.x;
+        if (b < nb && r < rows) tile[k][threadIdx.x] = src[(size_t)b * rows + r];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const long r = r0 + k, b = b0 + threadIdx.x;
+        if (b < nb && r < rows) {
+            const long rp = nc > 1 ? (r % nc) * (rows / nc) + r / nc : r;
+            dst[(size_t)rp * ldd + b] = tile[threadIdx.x][k];
+        }
+    }
+}
+// inverse: dst[b][rows] <- src[perm(r)][lds]
+__global__ void from_soa_kernel(const double *__restrict__ src, double *__restrict__ dst, long rows, long nb, long lds,
+                                int nc)
+{
+    __shared__ double tile[32][33];
+    const long b0 = (long)blockIdx.x * 32, r0 = (long)blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const long r = r0 + k, b = b0 + threadIdx.x;
+        if (b < nb && r < rows) {
+            const long rp = nc > 1 ? (r % nc) * (rows / nc) + r / nc : r;
+            tile[k][threadIdx.x] = src[(size_t)rp * lds + b];
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const long b = b0 + k, r = r0 + threadIdx.x;
+        if (b < nb && r < rows) dst[(size_t)b * rows + r] = tile[threadIdx.x][k];
+    }
+}
+
+int to_soa(H *h, const double *d_src, double *d_dst, long rows, long nb, long ldd, int nc = 1)
+{
+    if (rows == 0 || nb == 0) return 0;
+    dim3 grid((unsigned)((nb + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    to_soa_kernel<<<grid, block, 0, h->stream>>>(d_src, d_dst, rows, nb, ldd, nc);
+    CK(cudaGetLastError());
+    return 0;
+}
+int from_soa(H *h, const double *d_src, double *d_dst, long rows, long nb, long lds, int nc = 1)
+{
+    if (rows == 0 || nb == 0) return 0;
+    dim3 grid((unsigned)((nb + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    from_soa_kernel<<<grid, block, 0, h->stream>>>(d_src, d_dst, rows, nb, lds, nc);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// host [rows x nb] (column-major) -> device SoA [rows][nb]
+int upload_soa(H *h, const double *host, DevBuf &dst, long rows, long nb, int nc = 1)
+{
+    TRY(ensure(h, dst, (size_t)rows * nb));
+    if (rows == 1) {
+        CK(cudaMemcpyAsync(dst.p, host, sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    TRY(ensure(h, h->d_stage, (size_t)rows * nb));
+    CK(cudaMemcpyAsync(h->d_stage.p, host, sizeof(double) * rows * nb, cudaMemcpyHostToDevice, h->stream));
+    return to_soa(h, h->d_stage.p, dst.p, rows, nb, nb, nc);
+}
+// device SoA [rows][ld] (first nb columns from b0) -> host [rows x nb]
+int download_soa(H *h, const double *d_src, long ld, long b0, double *host, long rows, long nb, int nc = 1)
+{
+    if (rows == 1) {
+        CK(cudaMemcpyAsync(host, d_src + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    }
+    TRY(ensure(h, h->d_stage, (size_t)rows * nb));
+    TRY(from_soa(h, d_src + b0, h->d_stage.p, rows, nb, ld, nc));
+    CK(cudaMemcpyAsync(host, h->d_stage.p, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------- batch reductions (warp shuffles)
+struct RedPair {
+    double v;
+    long i;
+};
+template <int OP>
+__device__ __forceinline__ RedPair red_combine(RedPair a, RedPair b)
+{
+    if (OP == OCS_B200_REDUCE_SUM) return RedPair{a.v + b.v, 0};
+    bool take_b;
+    if (OP == OCS_B200_REDUCE_MIN)
+        take_b = (b.v < a.v) || (b.v == a.v && b.i < a.i);
+    else
+        take_b = (b.v > a.v) || (b.v == a.v && b.i < a.i);
+    return take_b ? b : a;
+}
+template <int OP>
+__device__ __forceinline__ RedPair warp_reduce(RedPair x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        RedPair y;
+        y.v = __shfl_down_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_down_sync(0xffffffffu, x.i, o);
+        x = red_combine<OP>(x, y);
+    }
+    return x;
+}
+// one block per partial; final pass with one block.  Deterministic (fixed tree).
+template <int OP>
+__global__ void reduce_kernel(const double *__restrict__ J, const long *__restrict__ idx_in, long nvals, double *out_v,
+                              long *out_i)
+{
+    __shared__ RedPair ws[32];
+    const double ident = OP == OCS_B200_REDUCE_SUM ? 0.0 : (OP == OCS_B200_REDUCE_MIN ? INFINITY : -INFINITY);
+    RedPair acc{ident, 0x7fffffffffffffffL};
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nvals; k += (long)gridDim.x * blockDim.x) {
+        RedPair x{J[k], idx_in ? idx_in[k] : k};
+        acc = red_combine<OP>(acc, x);
+    }
+    acc = warp_reduce<OP>(acc);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) ws[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        RedPair x = lane < nw ? ws[lane] : RedPair{ident, 0x7fffffffffffffffL};
+        x = warp_reduce<OP>(x);
+        if (lane == 0) {
+            out_v[blockIdx.x] = x.v;
+            out_i[blockIdx.x] = x.i;
+        }
+    }
+}
+
+// fb_sweep bookkeeping: freeze trajectories whose normalised control change is <= 1
+__global__ void fb_update_kernel(const double *__restrict__ maxchg, int *frozen, int *sweeps, int sweep, long nb,
+                                 int *n_open)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int open = 0;
+    if (b < nb && !frozen[b]) {
+        sweeps[b] = sweep;
+        if (maxchg[b] <= 1.0)
+            frozen[b] = 1;   // fb_sweep.m:110-111
+        else
+            open = 1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, open);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_open, __popc(bal));
+}
+
+__global__ void broadcast_rows_kernel(const double *__restrict__ col, double *dst, long rows, long nb)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    for (long r = 0; r < rows; ++r) dst[(size_t)r * nb + b] = col[r];
+}
+
+// ---------------------------------------------------------------- records
+inline int even(int x) { return (x + 1) & ~1; }
+
+int basis_width(const H *h, int si)
+{
+    if (si != 0) return 0;
+    if (h->basis_kind == BASIS_SPARSE) return 3;
+    if (h->basis_kind == BASIS_DENSE) return h->K;
+    return 0;
+}
+
+// u(:,j) = reshape(v,nc,[]) * B(:,j) for a shared v -- same operation order as ControlEval::eval
+void shared_u_from_v(const H *h, int j, double *u)
+{
+    const int nc = h->kt.nc;
+    if (h->basis_kind == BASIS_SPARSE) {
+        const int k = h->bk[j];
+        for (int c = 0; c < nc; ++c) {
+            double s = h->ctrl_shared[(size_t)k * nc + c] * h->bw0[j];
+            if (h->bw1[j] != 0.0) s = s + h->ctrl_shared[(size_t)(k + 1) * nc + c] * h->bw1[j];
+            u[c] = s;
+        }
+    } else {
+        const int K = h->K;
+        for (int c = 0; c < nc; ++c) {
+            double s = h->ctrl_shared[c] * h->bdense[(size_t)K * j];
+            for (int k = 1; k < K; ++k) s = s + h->ctrl_shared[(size_t)k * nc + c] * h->bdense[k + (size_t)K * j];
+            u[c] = s;
+        }
+    }
+}
+
+int build_records(H *h, int si)
+{
+    Segment &s = h->seg[si];
+    if (!s.records_dirty) return 0;
+    const int N = s.N, G = 2 * N + 1, nc = h->kt.nc, ntt = h->kt.ntt;
+    const int off_u = 1 + ntt, off_b = off_u + nc, bw = basis_width(h, si);
+    const int R = even(off_b + bw);
+    std::vector<double> rec((size_t)G * R, 0.0);
+    std::vector<double> u(nc);
+    for (int j = 0; j < G; ++j) {
+        double *r = &rec[(size_t)j * R];
+        r[0] = s.t[j];
+        if (si == 1) {
+            for (int c = 0; c < nc; ++c) r[off_u + c] = h->uStar[c];   // RK4InfiniteIntegrator.m:15
+        } else if (h->ctrl_mode == CTRL_V_SHARED) {
+            shared_u_from_v(h, j, u.data());
+            for (int c = 0; c < nc; ++c) r[off_u + c] = u[c];
+        } else if (h->ctrl_mode == CTRL_U_SHARED) {
+            for (int c = 0; c < nc; ++c) r[off_u + c] = h->ctrl_shared[c + (size_t)nc * j];
+        }
+        if (bw == 3) {
+            r[off_b] = (double)h->bk[j];
+            r[off_b + 1] = h->bw0[j];
+            r[off_b + 2] = h->bw1[j];
+        } else if (bw > 0) {
+            for (int k = 0; k < h->K; ++k) r[off_b + k] = h->bdense[k + (size_t)h->K * j];
+        }
+    }
+    std::vector<double> st((size_t)N * 4);
+    for (int i = 0; i < N; ++i) {
+        st[4 * i] = s.h[i];
+        st[4 * i + 1] = s.h[i] / 2;   // obj.h(i)/2   RK4Integrator.m:40
+        st[4 * i + 2] = s.h[i] / 3;   // obj.h(i)/3   :77
+        st[4 * i + 3] = s.h[i] / 6;   // obj.h(i)/6   :51
+    }
+    if (s.d_gprec) CK(cudaFree(s.d_gprec));
+    if (s.d_steprec) CK(cudaFree(s.d_steprec));
+    s.d_gprec = s.d_steprec = nullptr;
+    CK(cudaMalloc(&s.d_gprec, rec.size() * sizeof(double)));
+    CK(cudaMalloc(&s.d_steprec, st.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(s.d_gprec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(s.d_steprec, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // rec/st are stack-owned host vectors
+    s.R = R;
+    if (ntt > 0 && h->params_nbatch == 1) {
+        void *args[] = {(void *)&s.d_gprec, (void *)&G, (void *)&s.R, (void *)&h->d_params.p};
+        CK(cudaLaunchKernel(h->kt.tt, dim3((G + 127) / 128), dim3(128), args, 0, h->stream));
+    }
+    s.records_dirty = false;
+    return 0;
+}
+
+void mark_dirty(H *h)
+{
+    h->seg[0].records_dirty = h->seg[1].records_dirty = true;
+}
+
+int check_ready(H *h)
+{
+    if (h->sticky) return h->sticky;
+    if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "no problem bound (ocs_b200_set_problem_*)");
+    if (h->params_nbatch == 0 && h->kt.np > 0) return h->fail(OCS_B200_ERR_STATE, "no parameters set (ocs_b200_set_params)");
+    if (h->has_tail && (int)h->uStar.size() != h->kt.nc)
+        return h->fail(OCS_B200_ERR_STATE, "tail horizon without uStar (ocs_b200_set_tail_control)");
+    return 0;
+}
+
+// fills the batch-invariant part of a SweepArgs
+void base_args(H *h, int si, SweepArgs &a)
+{
+    Segment &s = h->seg[si];
+    memset(&a, 0, sizeof a);
+    a.N = s.N;
+    a.R = s.R;
+    a.off_u = 1 + h->kt.ntt;
+    a.off_b = a.off_u + h->kt.nc;
+    a.K = h->K;
+    // tile: keep the staged records under ~24 KB so that many blocks stay resident
+    int S = 32;
+    while (S > 4 && ((size_t)(2 * S + 1) * s.R + 4 * S) * sizeof(double) > 24 * 1024) S >>= 1;
+    a.S = S;
+    a.gprec = s.d_gprec;
+    a.steprec = s.d_steprec;
+    a.p = h->d_params.p;
+    a.ldp = h->params_nbatch > 1 ? h->params_nbatch : 0;
+}
+
+size_t smem_bytes(const SweepArgs &a) { return ((size_t)(2 * a.S + 1) * a.R + 4 * a.S) * sizeof(double); }
+
+int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward)
+{
+    if (!kernel) return h->fail(OCS_B200_ERR_ARG, "this control/basis/parameter combination has no kernel variant");
+    if (a.nb <= 0) return 0;
+    const int threads = h->kt.threads;
+    const unsigned blocks = (unsigned)((a.nb + threads - 1) / threads);
+    void *args[] = {(void *)&a};
+    if (h->profiling) CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(cudaLaunchKernel(kernel, dim3(blocks), dim3(threads), args, smem_bytes(a), h->stream));
+    if (h->profiling) {
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        CK(cudaEventSynchronize(h->ev[1]));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        (is_forward ? h->ms_fwd : h->ms_rev) += ms;
+    }
+    h->launches++;
+    return 0;
+}
+
+int pb_index(const H *h) { return h->params_nbatch > 1 ? 1 : 0; }
+
+int main_umode(const H *h)
+{
+    switch (h->ctrl_mode) {
+        case CTRL_V_BATCH: return 1;
+        case CTRL_U_BATCH: return 2;
+        default: return 0;
+    }
+}
+
+// forward sweep(s) over trajectories [b0, b0+nb) of the resident batch; xgrid optional (fetch)
+int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool write_outputs)
+{
+    const int n = h->kt.n;
+    const long Bt = h->Bt;
+    for (int si = 0; si < (h->has_tail ? 2 : 1); ++si) {
+        if (only_segment >= 0 && si != only_segment) continue;
+        TRY(build_records(h, si));
+        Segment &s = h->seg[si];
+        SweepArgs a;
+        base_args(h, si, a);
+        a.nb = nb;
+        a.ldb = Bt;
+        if (a.ldp) a.p = h->d_params.p + b0;
+        a.x0 = (si == 0 ? h->d_x0.p : h->d_xT.p) + b0;
+        a.xs = s.d_xs + b0;
+        a.xgrid = d_xgrid;
+        if (write_outputs) {
+            a.J = h->d_J.p + b0;
+            a.J_accumulate = si == 1;
+            a.status = h->d_status + b0;
+            if (si == 0) a.xT = h->d_xT.p + b0;
+        }
+        int um = si == 0 ? main_umode(h) : 0, bm = 0;
+        if (um == 1) {
+            bm = h->basis_kind;
+            a.v = (h->v_ext ? h->v_ext : h->d_v.p) + b0;
+        } else if (um == 2) {
+            a.ug = h->d_ug.p + b0;
+        }
+        TRY(launch(h, h->kt.fwd[um][bm][pb_index(h)], a, true));
+    }
+    return 0;
+}
+
+// reverse sweep(s): tail first (RK4InfiniteIntegrator.m:28), then the main horizon (:29)
+int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, long ldl, double *d_dJdv,
+                double *d_lam0, double *d_lamgrid, double *d_dJdugrid)
+{
+    const long Bt = h->Bt;
+    const int m = h->kt.n + 1;
+    for (int si = (h->has_tail ? 1 : 0); si >= 0; --si) {
+        if (only_segment >= 0 && si != only_segment) {
+            // fetching the main grid still needs the tail's lam(:,1); it is cached in d_lamT_tail
+            continue;
+        }
+        TRY(build_records(h, si));
+        Segment &s = h->seg[si];
+        SweepArgs a;
+        base_args(h, si, a);
+        a.nb = nb;
+        a.ldb = Bt;
+        if (a.ldp) a.p = h->d_params.p + b0;
+        a.xs = s.d_xs + b0;
+        int um = 0, bm = 0;
+        if (si == 1) {
+            TRY(ensure(h, h->d_lamT_tail, (size_t)m * Bt));
+            a.lam0 = h->d_lamT_tail.p + b0;
+            if (only_segment == 1) {
+                a.lamgrid = d_lamgrid;
+                a.dJdugrid = d_dJdugrid;
+            }
+        } else {
+            if (h->has_tail) {
+                a.lamT = h->d_lamT_tail.p + b0;
+                a.ldl = Bt;
+            } else if (d_lamT) {
+                a.lamT = d_lamT + (ldl ? b0 : 0);
+                a.ldl = ldl;
+            }
+            a.dJdv = d_dJdv;
+            a.lam0 = d_lam0;
+            a.lamgrid = d_lamgrid;
+            a.dJdugrid = d_dJdugrid;
+            um = main_umode(h);
+            if (um == 1) {
+                bm = h->basis_kind;
+                a.v = (h->v_ext ? h->v_ext : h->d_v.p) + b0;
+            } else if (um == 2) {
+                a.ug = h->d_ug.p + b0;
+                if (d_dJdv) return h->fail(OCS_B200_ERR_ARG, "dJdv needs coefficients v, not a per-trajectory u grid");
+            } else if (d_dJdv) {
+                bm = h->basis_kind;
+            }
+            if (d_dJdv && h->basis_kind == BASIS_NONE)
+                return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
+        }
+        TRY(launch(h, h->kt.rev[um][bm][pb_index(h)], a, false));
+    }
+    return 0;
+}
+
+int alloc_batch(H *h, long Bt)
+{
+    const int n = h->kt.n, m = n + 1;
+    TRY(ensure(h, h->d_x0, (size_t)n * Bt));
+    TRY(ensure(h, h->d_J, (size_t)Bt));
+    TRY(ensure(h, h->d_xT, (size_t)n * Bt));
+    if (h->status_cap < (size_t)Bt) {
+        if (h->d_status) CK(cudaFree(h->d_status));
+        h->d_status = nullptr;
+        CK(cudaMalloc(&h->d_status, sizeof(int) * Bt));
+        h->status_cap = Bt;
+    }
+    for (int si = 0; si < (h->has_tail ? 2 : 1); ++si) {
+        Segment &s = h->seg[si];
+        TRY(ensure_raw(h, &s.d_xs, &s.xs_cap, (size_t)n * (s.N + 1) * Bt));
+    }
+    (void)m;
+    return 0;
+}
+
+int validate_control(H *h, long Bt)
+{
+    const int nc = h->kt.nc;
+    switch (h->ctrl_mode) {
+        case CTRL_NONE: return h->fail(OCS_B200_ERR_STATE, "no control set (ocs_b200_set_control_v / _u)");
+        case CTRL_V_SHARED:
+        case CTRL_V_BATCH:
+            if (h->basis_kind == BASIS_NONE)
+                return h->fail(OCS_B200_ERR_STATE, "control coefficients v need a basis (ocs_b200_set_control_basis)");
+            if (h->ctrl_mode == CTRL_V_BATCH && h->ctrl_nbatch != Bt)
+                return h->fail(OCS_B200_ERR_ARG, "v has %ld columns but the batch has %ld trajectories", h->ctrl_nbatch, Bt);
+            if (h->ctrl_mode == CTRL_V_SHARED && (long)h->ctrl_shared.size() != (long)nc * h->K)
+                return h->fail(OCS_B200_ERR_ARG, "v must have nc*K = %d entries", nc * h->K);
+            if (h->basis_kind == BASIS_DENSE && h->kt.kd == 0 && h->K > OCS_KDENSE_MAX && h->ctrl_mode == CTRL_V_BATCH)
+                return h->fail(OCS_B200_ERR_ARG, "dense basis with K = %d > %d needs a generated problem", h->K, OCS_KDENSE_MAX);
+            return 0;
+        case CTRL_U_BATCH:
+            if (h->ctrl_nbatch != Bt)
+                return h->fail(OCS_B200_ERR_ARG, "u has %ld pages but the batch has %ld trajectories", h->ctrl_nbatch, Bt);
+            return 0;
+        default: return 0;
+    }
+}
+
+int states_common(H *h, long Bt)
+{
+    TRY(validate_control(h, Bt));
+    if (h->params_nbatch > 1 && h->params_nbatch != Bt)
+        return h->fail(OCS_B200_ERR_ARG, "params have %ld columns but the batch has %ld trajectories", h->params_nbatch, Bt);
+    h->Bt = Bt;
+    TRY(run_forward(h, 0, Bt, -1, nullptr, true));
+    h->have_states = true;
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+
+extern "C" {
+
+int ocs_b200_abi_version(void) { return OCS_B200_ABI_VERSION; }
+
+const char *ocs_b200_last_error(const ocs_b200_handle *h)
+{
+    if (!h) return g_create_error.c_str();
+    return h->err.c_str();
+}
+
+static int check_tspan(const double *ts, int N)
+{
+    for (int i = 0; i <= N; ++i)
+        if (!std::isfinite(ts[i])) return 1;
+    return 0;
+}
+
+int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extra, int device, int math_mode,
+                    ocs_b200_handle **out)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!out) {
+        g_create_error = "out is NULL";
+        return OCS_B200_ERR_ARG;
+    }
+    *out = nullptr;
+    if (N < 1 || !tspan || (N2 > 0 && !tspan_extra) || N2 < 0 || check_tspan(tspan, N) ||
+        (N2 > 0 && check_tspan(tspan_extra, N2))) {
+        g_create_error = "tspan must hold at least two finite times (and tspan_extra when N2 > 0)";
+        return OCS_B200_ERR_ARG;
+    }
+    if (math_mode != OCS_B200_MATH_FAST && math_mode != OCS_B200_MATH_STRICT) {
+        g_create_error = "unknown math_mode";
+        return OCS_B200_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no CUDA device available (there is no CPU fallback): ") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return OCS_B200_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device ordinal out of range";
+        return OCS_B200_ERR_ARG;
+    }
+    ocs_b200_handle *h = new (std::nothrow) ocs_b200_handle();
+    if (!h) {
+        g_create_error = "out of host memory";
+        return OCS_B200_ERR_NOMEM;
+    }
+    h->device = device;
+    h->math_mode = math_mode;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->ev[k]);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        delete h;
+        return OCS_B200_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    for (int si = 0; si < 2; ++si) {
+        const int Ns = si == 0 ? N : N2;
+        const double *ts = si == 0 ? tspan : tspan_extra;
+        if (Ns == 0) continue;
+        Segment &s = h->seg[si];
+        s.N = Ns;
+        s.tspan.assign(ts, ts + Ns + 1);
+        s.h.resize(Ns);
+        s.t.resize(2 * Ns + 1);
+        for (int i = 0; i < Ns; ++i) s.h[i] = ts[i + 1] - ts[i];                      // diff(tspan)          :17
+        for (int i = 0; i <= Ns; ++i) s.t[2 * i] = ts[i];                             // t(1:2:end) = tspan    :22
+        for (int i = 0; i < Ns; ++i) s.t[2 * i + 1] = (ts[i] + ts[i + 1]) / 2;        // midpoints             :23
+    }
+    h->has_tail = N2 > 0;
+    *out = h;
+    return 0;
+}
+
+int ocs_b200_destroy(ocs_b200_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int si = 0; si < 2; ++si) {
+        cudaFree(h->seg[si].d_gprec);
+        cudaFree(h->seg[si].d_steprec);
+        cudaFree(h->seg[si].d_xs);
+    }
+    DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
+                      &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg};
+    for (DevBuf *b : bufs) cudaFree(b->p);
+    cudaFree(h->d_status);
+    cudaFree(h->d_frozen);
+    cudaFree(h->d_sweeps);
+    cudaFree(h->d_bounds);
+    cudaFree(h->d_red);
+    for (int k = 0; k < 4; ++k)
+        if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    if (h->gen_library) ocs_unload_problem(h->gen_library);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaGetLastError();
+    delete h;
+    return 0;
+}
+
+int ocs_b200_get_grid(const ocs_b200_handle *h, int segment, double *t, double *hstep)
+{
+    if (!h || segment < 0 || segment > 1 || h->seg[segment].N == 0) return OCS_B200_ERR_ARG;
+    const Segment &s = h->seg[segment];
+    if (t) memcpy(t, s.t.data(), sizeof(double) * s.t.size());
+    if (hstep) memcpy(hstep, s.h.data(), sizeof(double) * s.h.size());
+    return 0;
+}
+
+int ocs_b200_set_problem_builtin(ocs_b200_handle *h, int problem_id)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (problem_id != OCS_B200_PROBLEM_TEST) return h->fail(OCS_B200_ERR_ARG, "unknown built-in problem %d", problem_id);
+    if (h->math_mode == OCS_B200_MATH_STRICT)
+        ocs_builtin_table_test_strict(&h->kt);
+    else
+        ocs_builtin_table_test_fast(&h->kt);
+    h->have_problem = true;
+    h->is_generated = false;
+    h->have_states = false;
+    mark_dirty(h);
+    return 0;
+}
+
+int ocs_b200_set_problem_source(ocs_b200_handle *h, const char *cuda_source, int n, int nc, int np,
+                                const char *kernel_include_dir)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (!cuda_source || n < 1 || nc < 1 || np < 0) return h->fail(OCS_B200_ERR_ARG, "bad generated-problem description");
+    try {
+        CK(cudaSetDevice(h->device));
+        h->gen_source = cuda_source;
+        h->gen_include = kernel_include_dir ? kernel_include_dir : "";
+        h->gen_n = n;
+        h->gen_nc = nc;
+        h->gen_np = np;
+        const int kd = (h->basis_kind == BASIS_DENSE) ? h->K : 0;
+        std::string log;
+        ocs_kernel_table kt{};
+        void *lib = nullptr;
+        int rc = ocs_compile_problem(cuda_source, n, nc, np, kd, h->math_mode == OCS_B200_MATH_STRICT,
+                                     h->gen_include.empty() ? nullptr : h->gen_include.c_str(), &kt, &lib, &log);
+        if (rc != 0) return h->fail(rc, "generated problem did not compile:\n%s", log.c_str());
+        if (h->gen_library) ocs_unload_problem(h->gen_library);
+        h->gen_library = lib;
+        h->kt = kt;
+        h->have_problem = true;
+        h->is_generated = true;
+        h->have_states = false;
+        mark_dirty(h);
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_set_params(ocs_b200_handle *h, const double *params, int np, long nbatch)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting parameters");
+    if (np != h->kt.np || nbatch < 1 || (!params && np > 0))
+        return h->fail(OCS_B200_ERR_ARG, "the problem takes %d parameters (got %d, nbatch %ld)", h->kt.np, np, nbatch);
+    try {
+        CK(cudaSetDevice(h->device));
+        if (nbatch == 1) {
+            h->params_shared.assign(params, params + np);
+            TRY(ensure(h, h->d_params, np));
+            CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        } else {
+            TRY(upload_soa(h, params, h->d_params, np, nbatch));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        h->params_nbatch = nbatch;
+        mark_dirty(h);
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_set_tail_control(ocs_b200_handle *h, const double *uStar, int nc)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting uStar");
+    if (!uStar || nc != h->kt.nc) return h->fail(OCS_B200_ERR_ARG, "uStar must have nc = %d entries", h->kt.nc);
+    h->uStar.assign(uStar, uStar + nc);
+    h->seg[1].records_dirty = true;
+    return 0;
+}
+
+int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    try {
+        if (K == 0) {
+            h->basis_kind = BASIS_NONE;
+            h->K = 0;
+            mark_dirty(h);
+            return 0;
+        }
+        if (K < 0 || !B) return h->fail(OCS_B200_ERR_ARG, "bad basis");
+        const int G = 2 * h->seg[0].N + 1;
+        std::vector<int32_t> bk(G), nnz(G);
+        std::vector<double> w0(G), w1(G);
+        bool sparse = true;
+        for (int j = 0; j < G; ++j) {
+            const double *col = B + (size_t)K * j;
+            int first = -1, last = -1, cnt = 0;
+            for (int k = 0; k < K; ++k) {
+                if (!std::isfinite(col[k])) return h->fail(OCS_B200_ERR_ARG, "basis matrix holds a non-finite entry");
+                if (col[k] != 0.0) {
+                    if (first < 0) first = k;
+                    last = k;
+                    ++cnt;
+                }
+            }
+            nnz[j] = cnt;
+            if (cnt == 0) {   // an all-zero column: u_j = 0
+                bk[j] = 0;
+                w0[j] = 0.0;
+                w1[j] = 0.0;
+            } else if (cnt <= 2 && last - first <= 1) {
+                bk[j] = first;
+                w0[j] = col[first];
+                w1[j] = last > first ? col[last] : 0.0;
+            } else {
+                sparse = false;
+            }
+        }
+        h->K = K;
+        h->bnnz = nnz;
+        if (sparse) {
+            h->basis_kind = BASIS_SPARSE;
+            h->bk = bk;
+            h->bw0 = w0;
+            h->bw1 = w1;
+            h->bdense.clear();
+        } else {
+            h->basis_kind = BASIS_DENSE;
+            h->bdense.assign(B, B + (size_t)K * G);
+            h->bk.assign(G, 0);
+            for (int j = 0; j < G; ++j) h->bnnz[j] = K;
+        }
+        // a generated problem is specialised on the dense basis size
+        if (h->is_generated && h->basis_kind == BASIS_DENSE && h->kt.kd != K) {
+            std::string src = h->gen_source, inc = h->gen_include;
+            TRY(ocs_b200_set_problem_source(h, src.c_str(), h->gen_n, h->gen_nc, h->gen_np, inc.empty() ? nullptr : inc.c_str()));
+        }
+        h->ctrl_mode = CTRL_NONE;   // coefficients belong to the previous basis
+        mark_dirty(h);
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_get_control_index(const ocs_b200_handle *h, int32_t *k_index, int32_t *nnz)
+{
+    if (!h || h->basis_kind == BASIS_NONE) return OCS_B200_ERR_STATE;
+    const int G = 2 * h->seg[0].N + 1;
+    if (k_index) memcpy(k_index, h->bk.data(), sizeof(int32_t) * G);
+    if (nnz) memcpy(nnz, h->bnnz.data(), sizeof(int32_t) * G);
+    return 0;
+}
+
+int ocs_b200_set_control_v(ocs_b200_handle *h, const double *v, long nbatch)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting the control");
+    if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "attach a control basis before setting v");
+    if (!v || nbatch < 1) return h->fail(OCS_B200_ERR_ARG, "bad v");
+    try {
+        CK(cudaSetDevice(h->device));
+        const long rows = (long)h->kt.nc * h->K;
+        h->v_ext = nullptr;
+        if (nbatch == 1) {
+            h->ctrl_shared.assign(v, v + rows);
+            h->ctrl_mode = CTRL_V_SHARED;
+        } else {
+            TRY(upload_soa(h, v, h->d_v, rows, nbatch));
+            CK(cudaStreamSynchronize(h->stream));
+            h->ctrl_mode = CTRL_V_BATCH;
+        }
+        h->ctrl_nbatch = nbatch;
+        h->seg[0].records_dirty = true;
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_set_control_v_dev(ocs_b200_handle *h, const double *v_soa, long nbatch)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "attach a control basis before setting v");
+    if (!v_soa || nbatch < 2) return h->fail(OCS_B200_ERR_ARG, "device v needs one column per trajectory");
+    h->v_ext = v_soa;
+    h->ctrl_mode = CTRL_V_BATCH;
+    h->ctrl_nbatch = nbatch;
+    h->seg[0].records_dirty = true;
+    return 0;
+}
+
+int ocs_b200_set_control_u(ocs_b200_handle *h, const double *u, long nbatch)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting the control");
+    if (!u || nbatch < 1) return h->fail(OCS_B200_ERR_ARG, "bad u");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int nc = h->kt.nc, G = 2 * h->seg[0].N + 1;
+        h->v_ext = nullptr;
+        if (nbatch == 1) {
+            h->ctrl_shared.assign(u, u + (size_t)nc * G);
+            h->ctrl_mode = CTRL_U_SHARED;
+        } else {
+            TRY(upload_soa(h, u, h->d_ug, (long)nc * G, nbatch, nc));
+            CK(cudaStreamSynchronize(h->stream));
+            h->ctrl_mode = CTRL_U_BATCH;
+        }
+        h->ctrl_nbatch = nbatch;
+        h->seg[0].records_dirty = true;
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_get_control_u(ocs_b200_handle *h, long b0, long nb, double *u)
+{
+    if (!h || !u) return OCS_B200_ERR_ARG;
+    if (!h->have_problem || h->ctrl_mode == CTRL_NONE) return h->fail(OCS_B200_ERR_STATE, "no control set");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int nc = h->kt.nc, G = 2 * h->seg[0].N + 1;
+        if (h->ctrl_mode == CTRL_U_SHARED) {
+            memcpy(u, h->ctrl_shared.data(), sizeof(double) * nc * G);
+            return 0;
+        }
+        if (h->ctrl_mode == CTRL_V_SHARED) {
+            for (int j = 0; j < G; ++j) shared_u_from_v(h, j, u + (size_t)nc * j);
+            return 0;
+        }
+        if (h->ctrl_mode == CTRL_U_BATCH) {
+            if (b0 < 0 || nb < 1 || b0 + nb > h->ctrl_nbatch) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
+            TRY(download_soa(h, h->d_ug.p, h->ctrl_nbatch, b0, u, (long)nc * G, nb, nc));
+            CK(cudaStreamSynchronize(h->stream));
+            return 0;
+        }
+        // per-trajectory coefficients: evaluate v*B on the host for the requested columns
+        if (b0 < 0 || nb < 1 || b0 + nb > h->ctrl_nbatch) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
+        const long rows = (long)nc * h->K;
+        std::vector<double> vcols((size_t)rows * nb);
+        TRY(download_soa(h, h->v_ext ? h->v_ext : h->d_v.p, h->ctrl_nbatch, b0, vcols.data(), rows, nb));
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<double> keep = h->ctrl_shared;
+        for (long b = 0; b < nb; ++b) {
+            h->ctrl_shared.assign(vcols.begin() + b * rows, vcols.begin() + (b + 1) * rows);
+            for (int j = 0; j < G; ++j) shared_u_from_v(h, j, u + (size_t)nc * (j + (size_t)G * b));
+        }
+        h->ctrl_shared = keep;
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_set_stream(ocs_b200_handle *h, void *cuda_stream)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return 0;
+}
+
+int ocs_b200_synchronize(ocs_b200_handle *h)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int ocs_b200_compute_states_dev(ocs_b200_handle *h, const double *x0_soa, long Bt, double *J, double *xT_soa,
+                                int32_t *status)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!x0_soa || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n;
+        TRY(alloc_batch(h, Bt));
+        CK(cudaMemcpyAsync(h->d_x0.p, x0_soa, sizeof(double) * n * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        TRY(states_common(h, Bt));
+        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        if (xT_soa) CK(cudaMemcpyAsync(xT_soa, h->d_xT.p, sizeof(double) * n * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, long Bt, double *J, double *xT, int32_t *status)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!x0 || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n;
+        TRY(alloc_batch(h, Bt));
+        TRY(upload_soa(h, x0, h->d_x0, n, Bt));
+        TRY(states_common(h, Bt));
+        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (xT) TRY(download_soa(h, h->d_xT.p, Bt, 0, xT, n, Bt));
+        if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+static int adjoints_common(ocs_b200_handle *h, const double *d_lamT, long ldl, double *d_dJdv, double *d_lam0)
+{
+    const int nc = h->kt.nc;
+    if (d_dJdv) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * nc * h->K * h->Bt, h->stream));
+    return run_reverse(h, 0, h->Bt, -1, d_lamT, ldl, d_dJdv, d_lam0, nullptr, nullptr);
+}
+
+int ocs_b200_compute_adjoints_dev(ocs_b200_handle *h, const double *lamT_soa, long lamT_nbatch, double *dJdv_soa,
+                                  double *lam0_soa)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "compute_adjoints needs a preceding compute_states on this handle");
+    if (lamT_soa && lamT_nbatch != 1 && lamT_nbatch != h->Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
+    try {
+        CK(cudaSetDevice(h->device));
+        h->user_lamT = false;
+        return adjoints_common(h, lamT_soa, lamT_soa && lamT_nbatch > 1 ? h->Bt : 0, dJdv_soa, lam0_soa);
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_nbatch, double *dJdv, double *lam0)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "compute_adjoints needs a preceding compute_states on this handle");
+    if (lamT && lamT_nbatch != 1 && lamT_nbatch != h->Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+        const long Bt = h->Bt;
+        const double *d_lamT = nullptr;
+        h->user_lamT = lamT != nullptr;
+        h->user_lamT_ld = lamT && lamT_nbatch > 1 ? Bt : 0;
+        if (lamT) {
+            TRY(upload_soa(h, lamT, h->d_lamT_user, m, lamT_nbatch));
+            d_lamT = h->d_lamT_user.p;
+        }
+        double *d_dJdv = nullptr, *d_lam0 = nullptr;
+        if (dJdv) {
+            TRY(ensure(h, h->d_dJdv, (size_t)nc * h->K * Bt));
+            d_dJdv = h->d_dJdv.p;
+        }
+        TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
+        d_lam0 = h->d_lam0.p;
+        TRY(adjoints_common(h, d_lamT, lamT && lamT_nbatch > 1 ? Bt : 0, d_dJdv, d_lam0));
+        if (dJdv) TRY(download_soa(h, d_dJdv, Bt, 0, dJdv, (long)nc * h->K, Bt));
+        if (lam0) {
+            // d_stage may be in use by the dJdv transpose above: stream order keeps it safe
+            TRY(download_soa(h, d_lam0, Bt, 0, lam0, m, Bt));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_fetch_states(ocs_b200_handle *h, int segment, long b0, long nb, double *x)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "fetch_states needs a preceding compute_states");
+    if (segment < 0 || segment > 1 || (segment == 1 && !h->has_tail)) return h->fail(OCS_B200_ERR_ARG, "no such segment");
+    if (b0 < 0 || nb < 1 || b0 + nb > h->Bt) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
+    if (!x) return 0;
+    try {
+        CK(cudaSetDevice(h->device));
+        const int m = h->kt.n + 1;
+        const size_t cnt = (size_t)m * (h->seg[segment].N + 1) * nb;
+        TRY(ensure(h, h->d_stage2, cnt));
+        // re-run the (deterministic) forward sweep of the requested trajectories with the full grid
+        // written out, J row included; the resident store is rewritten with identical values
+        TRY(run_forward(h, b0, nb, segment, h->d_stage2.p, false));
+        CK(cudaMemcpyAsync(x, h->d_stage2.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_fetch_adjoints(ocs_b200_handle *h, int segment, long b0, long nb, double *lam, double *dJdu)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "fetch_adjoints needs a preceding compute_states");
+    if (segment < 0 || segment > 1 || (segment == 1 && !h->has_tail)) return h->fail(OCS_B200_ERR_ARG, "no such segment");
+    if (b0 < 0 || nb < 1 || b0 + nb > h->Bt) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int m = h->kt.n + 1, nc = h->kt.nc;
+        const int N = h->seg[segment].N, G = 2 * N + 1;
+        const size_t nl = (size_t)m * (N + 1) * nb, nu = (size_t)nc * G * nb;
+        TRY(ensure(h, h->d_stage2, nl + nu));
+        double *d_lam = h->d_stage2.p, *d_du = h->d_stage2.p + nl;
+        if (segment == 0 && h->has_tail) {
+            // lamT of the main horizon = lam2(:,1) of the tail (RK4InfiniteIntegrator.m:28-29)
+            TRY(run_reverse(h, b0, nb, 1, nullptr, 0, nullptr, nullptr, nullptr, nullptr));
+        }
+        // the terminal costate of the last compute_adjoints (host API) is reused
+        const double *d_lamT = (segment == 0 && !h->has_tail && h->user_lamT) ? h->d_lamT_user.p : nullptr;
+        TRY(run_reverse(h, b0, nb, segment, d_lamT, h->user_lamT_ld, nullptr, nullptr, lam ? d_lam : nullptr,
+                        dJdu ? d_du : nullptr));
+        if (lam) CK(cudaMemcpyAsync(lam, d_lam, sizeof(double) * nl, cudaMemcpyDeviceToHost, h->stream));
+        if (dJdu) CK(cudaMemcpyAsync(dJdu, d_du, sizeof(double) * nu, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const double *u0, long u0_nbatch,
+                      const double *bounds, double uRelTol, double uAbsTol, int nSWEEPS, double relax, double *J,
+                      int32_t *sweeps, int32_t *converged, double *max_change)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!x0 || !u0 || !bounds || Bt < 1 || nSWEEPS < 1 || (u0_nbatch != 1 && u0_nbatch != Bt))
+        return h->fail(OCS_B200_ERR_ARG, "bad fb_sweep arguments");
+    if (h->has_tail) return h->fail(OCS_B200_ERR_ARG, "fb_sweep runs on a finite horizon");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n, nc = h->kt.nc, G = 2 * h->seg[0].N + 1;
+        if (h->params_nbatch > 1 && h->params_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "params batch mismatch");
+        h->Bt = Bt;
+        TRY(alloc_batch(h, Bt));
+        TRY(upload_soa(h, x0, h->d_x0, n, Bt));
+        // control on the grid, one copy per trajectory
+        if (u0_nbatch == Bt) {
+            TRY(upload_soa(h, u0, h->d_ug, (long)nc * G, Bt, nc));
+        } else {
+            TRY(ensure(h, h->d_ug, (size_t)nc * G * Bt));
+            TRY(ensure(h, h->d_stage, (size_t)nc * G));
+            std::vector<double> perm((size_t)nc * G);
+            for (int j = 0; j < G; ++j)
+                for (int c = 0; c < nc; ++c) perm[(size_t)c * G + j] = u0[c + (size_t)nc * j];
+            CK(cudaMemcpyAsync(h->d_stage.p, perm.data(), sizeof(double) * nc * G, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            broadcast_rows_kernel<<<(unsigned)((Bt + 255) / 256), 256, 0, h->stream>>>(h->d_stage.p, h->d_ug.p, (long)nc * G, Bt);
+            CK(cudaGetLastError());
+        }
+        h->v_ext = nullptr;
+        h->ctrl_mode = CTRL_U_BATCH;
+        h->ctrl_nbatch = Bt;
+        h->seg[0].records_dirty = true;
+        if (h->frozen_cap < (size_t)Bt) {
+            cudaFree(h->d_frozen);
+            cudaFree(h->d_sweeps);
+            h->d_frozen = h->d_sweeps = nullptr;
+            CK(cudaMalloc(&h->d_frozen, sizeof(int) * (Bt + 1)));
+            CK(cudaMalloc(&h->d_sweeps, sizeof(int) * Bt));
+            h->frozen_cap = Bt;
+        }
+        int *d_nopen = h->d_frozen + Bt;
+        CK(cudaMemsetAsync(h->d_frozen, 0, sizeof(int) * (Bt + 1), h->stream));
+        CK(cudaMemsetAsync(h->d_sweeps, 0, sizeof(int) * Bt, h->stream));
+        TRY(ensure(h, h->d_maxchg, Bt));
+        if (!h->d_bounds) CK(cudaMalloc(&h->d_bounds, sizeof(double) * 2 * 64));
+        if (nc > 64) return h->fail(OCS_B200_ERR_ARG, "too many controls");
+        {
+            // ControlBounds is nc x 2 column-major; the kernels read [c][lo,hi]
+            std::vector<double> bb(2 * nc);
+            for (int c = 0; c < nc; ++c) {
+                bb[2 * c] = bounds[c];
+                bb[2 * c + 1] = bounds[c + nc];
+            }
+            CK(cudaMemcpyAsync(h->d_bounds, bb.data(), sizeof(double) * 2 * nc, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        TRY(build_records(h, 0));
+        for (int sweep = 1; sweep <= nSWEEPS; ++sweep) {
+            SweepArgs a;
+            base_args(h, 0, a);
+            a.nb = Bt;
+            a.ldb = Bt;
+            a.x0 = h->d_x0.p;
+            a.xs = h->seg[0].d_xs;
+            a.ug = h->d_ug.p;
+            a.J = h->d_J.p;
+            a.xT = h->d_xT.p;
+            a.status = h->d_status;
+            a.frozen = h->d_frozen;
+            TRY(launch(h, h->kt.fwd[2][0][pb_index(h)], a, true));
+            SweepArgs r;
+            base_args(h, 0, r);
+            r.nb = Bt;
+            r.ldb = Bt;
+            r.xs = h->seg[0].d_xs;
+            r.ug = h->d_ug.p;
+            r.bounds = h->d_bounds;
+            r.uRelTol = uRelTol;
+            r.uAbsTol = uAbsTol;
+            r.relax = relax;
+            r.max_change = h->d_maxchg.p;
+            r.frozen = h->d_frozen;
+            TRY(launch(h, h->kt.fbrev[pb_index(h)], r, false));
+            CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
+            fb_update_kernel<<<(unsigned)((Bt + 255) / 256), 256, 0, h->stream>>>(h->d_maxchg.p, h->d_frozen, h->d_sweeps,
+                                                                                sweep, Bt, d_nopen);
+            CK(cudaGetLastError());
+            int nopen = 0;
+            CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (nopen == 0) break;
+        }
+        h->have_states = true;
+        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (sweeps) CK(cudaMemcpyAsync(sweeps, h->d_sweeps, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (converged) CK(cudaMemcpyAsync(converged, h->d_frozen, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (max_change) CK(cudaMemcpyAsync(max_change, h->d_maxchg.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, long *index)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "reduce_J needs a preceding compute_states");
+    if (!value || op < 0 || op > 2) return h->fail(OCS_B200_ERR_ARG, "bad reduction");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int nblk = 296, thr = 256;
+        if (!h->d_red) CK(cudaMalloc(&h->d_red, (sizeof(double) + sizeof(long)) * (nblk + 1)));
+        double *pv = h->d_red;
+        long *pi = reinterpret_cast<long *>(h->d_red + nblk + 1);
+#define RUN(OP)                                                                                            \
+    reduce_kernel<OP><<<nblk, thr, 0, h->stream>>>(h->d_J.p, nullptr, h->Bt, pv, pi);                        \
+    reduce_kernel<OP><<<1, thr, 0, h->stream>>>(pv, pi, nblk, pv + nblk, pi + nblk);
+        if (op == OCS_B200_REDUCE_SUM) { RUN(OCS_B200_REDUCE_SUM) }
+        else if (op == OCS_B200_REDUCE_MIN) { RUN(OCS_B200_REDUCE_MIN) }
+        else { RUN(OCS_B200_REDUCE_MAX) }
+#undef RUN
+        CK(cudaGetLastError());
+        long idx = 0;
+        CK(cudaMemcpyAsync(value, pv + nblk, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&idx, pi + nblk, sizeof(long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (index) *index = op == OCS_B200_REDUCE_SUM ? -1 : idx;
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_set_profiling(ocs_b200_handle *h, int on)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    h->profiling = on != 0;
+    return 0;
+}
+
+int ocs_b200_kernel_stats(ocs_b200_handle *h, int reset, double *ms_forward, double *ms_reverse, long *launches)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (ms_forward) *ms_forward = h->ms_fwd;
+    if (ms_reverse) *ms_reverse = h->ms_rev;
+    if (launches) *launches = h->launches;
+    if (reset) {
+        h->ms_fwd = h->ms_rev = 0;
+        h->launches = 0;
+    }
+    return 0;
+}
+
+}  // extern "C"

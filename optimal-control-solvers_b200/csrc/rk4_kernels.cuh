@@ -1,0 +1,639 @@
+// rk4_kernels.cuh -- sm_100a sweep kernels of the B200-native RK4 trajectory path.
+//
+// One trajectory per thread.  The small augmented state [x; J], the costate and
+// the RK4 stage values live in registers; node states needed by the reverse sweep
+// are stored in HBM in structure-of-arrays layout [component][step][batch] so that
+// a warp's 32 trajectories write/read 256 contiguous bytes.  Everything that is the
+// same for every trajectory of the batch (times, step sizes, time-only
+// sub-expressions, shared control values, control basis entries) is packed into
+// per-grid-point records and staged through shared memory tile by tile.
+//
+// Arithmetic follows, operation by operation,
+//   Integrator/RK4Integrator.m:28-56   compute_states
+//   Integrator/RK4Integrator.m:59-94   compute_adjoints
+//   Integrator/RK4Integrator.m:97-121  compute_dJdu
+//   Control/*Control.m                 compute_u (v*B) and compute_dJdv (dJdu*B')
+// of the reference (paths relative to the reference tree).
+//
+// The file is compiled three ways: by nvcc with FMA contraction (namespace
+// ocs_fast), by nvcc with -fmad=false (namespace ocs_strict) and by NVRTC at run
+// time for generated problems (namespace ocs_gen).  It therefore only uses what
+// NVRTC provides without host headers.
+#pragma once
+
+#ifndef OCS_NS
+#error "define OCS_NS before including rk4_kernels.cuh"
+#endif
+
+#ifndef OCS_THREADS
+#define OCS_THREADS 128
+#endif
+#ifndef OCS_KDENSE_MAX
+#define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
+#endif
+
+namespace OCS_NS {
+
+// How the control reaches a trajectory.
+enum { UMODE_UNIFORM = 0,   // u_j shared by the batch, read from the grid-point record
+       UMODE_COEF = 1,      // per-trajectory coefficients v, evaluated through the basis
+       UMODE_GRID = 2 };    // per-trajectory values on the G grid points
+// How dJdu is folded into dJdv (and how UMODE_COEF evaluates u).
+enum { BMODE_NONE = 0, BMODE_SPARSE = 1, BMODE_DENSE = 2 };
+
+// Argument block of one sweep over one RK4 segment (main horizon or tail).
+// SoA device arrays have leading dimension ldb (the batch stride); the kernel
+// handles trajectories [0, nb) of them, so a sub-range is a pointer offset.
+struct SweepArgs {
+    int N;                  // RK4 steps
+    int S;                  // steps per shared-memory tile
+    int R;                  // doubles per grid-point record
+    int off_u;              // record offset of the shared control values (UMODE_UNIFORM)
+    int off_b;              // record offset of the basis part: (k, w0, w1) or B(0..K-1, j)
+    int K;                  // basis size
+    long nb;                // trajectories handled
+    long ldb;               // batch stride of SoA arrays
+    long ldp;               // batch stride of per-trajectory params
+    const double *gprec;    // [2N+1][R]  t_j, time-table values, control part
+    const double *steprec;  // [N][4]     h, h/2, h/3, h/6
+    const double *x0;       // [n][ldb]
+    const double *p;        // [np] or [np][ldp]
+    const double *v;        // UMODE_COEF: [(k*nc+c)][ldb]
+    double *ug;             // UMODE_GRID: [nc][2N+1][ldb]   (fb_sweep updates it in place)
+    double *xs;             // node-state store [n][N+1][ldb]
+    // forward outputs
+    double *J;              // [nb]
+    int J_accumulate;       // J = J_in + J_segment (RK4InfiniteIntegrator.m:23)
+    double *xT;             // [n][ldb]
+    int *status;            // [nb]
+    double *xgrid;          // MATLAB layout m x (N+1) x nb, or null
+    // reverse inputs / outputs
+    const double *lamT;     // [m][ldl] or null (= e_m, RK4Integrator.m:63-66)
+    long ldl;               // batch stride of lamT; 0 = shared column
+    double *dJdv;           // [(k*nc+c)][ldb], zero-initialised, or null
+    double *lam0;           // [m][ldb] or null
+    double *lamgrid;        // MATLAB layout m x (N+1) x nb, or null
+    double *dJdugrid;       // MATLAB layout nc x (2N+1) x nb, or null
+    // fb_sweep (reverse kernel with control update; see fb_reverse_body)
+    const double *bounds;   // [nc][2]
+    double uRelTol, uAbsTol, relax;
+    double *max_change;     // [nb]
+    const int *frozen;      // [nb] trajectories already converged (skipped), or null
+};
+
+__device__ __forceinline__ size_t soa(long row, long ld, long b) { return (size_t)row * (size_t)ld + (size_t)b; }
+
+// ------------------------------------------------------------------ control evaluation
+// Evaluates u(:,j) for one trajectory while the sweep walks the grid monotonically
+// (up in the forward sweep, down in the reverse sweep).
+template <int nc, int UMODE, int BMODE, int KD>
+struct ControlEval {
+    static constexpr int KA = (KD > 0 ? KD : OCS_KDENSE_MAX);
+    int kcur;
+    double vlo[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
+    double vhi[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
+    double vd[(UMODE == UMODE_COEF && BMODE == BMODE_DENSE) ? KA * nc : 1];
+
+    __device__ __forceinline__ void init(const SweepArgs &a, long bb)
+    {
+        kcur = -0x40000000;
+        if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
+            const int K = KD > 0 ? KD : a.K;
+#pragma unroll
+            for (int k = 0; k < KA; ++k)
+                if (k < K) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) vd[k * nc + c] = a.v[soa(k * nc + c, a.ldb, bb)];
+                }
+        }
+    }
+
+    // u(:,j) = reshape(v,nc,[]) * B(:,j)   (PWLinearControl.m:59-62 and twins)
+    __device__ __forceinline__ void eval(const SweepArgs &a, const double *rec, int j, long bb, double *u)
+    {
+        if constexpr (UMODE == UMODE_UNIFORM) {
+#pragma unroll
+            for (int c = 0; c < nc; ++c) u[c] = rec[a.off_u + c];
+        } else if constexpr (UMODE == UMODE_GRID) {
+            const int G = 2 * a.N + 1;
+#pragma unroll
+            for (int c = 0; c < nc; ++c) u[c] = a.ug[soa((long)c * G + j, a.ldb, bb)];
+        } else if constexpr (BMODE == BMODE_SPARSE) {
+            const int k = (int)rec[a.off_b];
+            const double w0 = rec[a.off_b + 1], w1 = rec[a.off_b + 2];
+            if (k != kcur) {   // uniform across the block: every trajectory shares the grid
+                const bool up = (k == kcur + 1), down = (k == kcur - 1);
+                if (up) {          // forward sweep: the window slides up by one knot
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) vlo[c] = vhi[c];
+                } else if (down) { // reverse sweep: slides down
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) vhi[c] = vlo[c];
+                }
+                if (!up) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) vlo[c] = a.v[soa((long)k * nc + c, a.ldb, bb)];
+                }
+                if (!down) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c)
+                        vhi[c] = (k + 1 < a.K) ? a.v[soa((long)(k + 1) * nc + c, a.ldb, bb)] : 0.0;
+                }
+                kcur = k;
+            }
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+                double s = vlo[c] * w0;            // w0 == 1, w1 == 0: exact copy of v (PWConstantControl)
+                if (w1 != 0.0) s = s + vhi[c] * w1;
+                u[c] = s;
+            }
+        } else {
+            const int K = KD > 0 ? KD : a.K;
+#pragma unroll
+            for (int c = 0; c < nc; ++c) u[c] = vd[c] * rec[a.off_b];
+#pragma unroll
+            for (int k = 1; k < KA; ++k)
+                if (k < K) {
+                    const double bk = rec[a.off_b + k];
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) u[c] = u[c] + vd[k * nc + c] * bk;
+                }
+        }
+    }
+};
+
+// dJdv = dJdu * B'  (PWLinearControl.m:53-56 and twins) accumulated while the reverse
+// sweep walks the grid downwards; dJdu itself is never materialised.
+template <int nc, int BMODE, int KD>
+struct GradAcc {
+    static constexpr int KA = (KD > 0 ? KD : OCS_KDENSE_MAX);
+    int kcur;
+    double lo[BMODE == BMODE_SPARSE ? nc : 1];
+    double hi[BMODE == BMODE_SPARSE ? nc : 1];
+    double ad[BMODE == BMODE_DENSE ? KA * nc : 1];
+
+    __device__ __forceinline__ void init(const SweepArgs &a)
+    {
+        kcur = -0x40000000;
+        if constexpr (BMODE == BMODE_SPARSE) {
+#pragma unroll
+            for (int c = 0; c < nc; ++c) lo[c] = hi[c] = 0.0;
+        }
+        if constexpr (BMODE == BMODE_DENSE) {
+#pragma unroll
+            for (int k = 0; k < KA * nc; ++k) ad[k] = 0.0;
+        }
+        (void)a;
+    }
+
+    __device__ __forceinline__ void flush(const SweepArgs &a, int k, const double *val, long b, bool active)
+    {
+        if (k < 0 || k >= a.K || !active) return;
+#pragma unroll
+        for (int c = 0; c < nc; ++c) {
+            const size_t idx = soa((long)k * nc + c, a.ldb, b);
+            a.dJdv[idx] = a.dJdv[idx] + val[c];   // buffer is zero-initialised; one owner thread per column
+        }
+    }
+
+    __device__ __forceinline__ void add(const SweepArgs &a, const double *rec, const double *d, long b, bool active)
+    {
+        if constexpr (BMODE == BMODE_SPARSE) {
+            const int k = (int)rec[a.off_b];
+            const double w0 = rec[a.off_b + 1], w1 = rec[a.off_b + 2];
+            if (k != kcur) {
+                if (k == kcur - 1) {           // window slides down by one knot
+                    flush(a, kcur + 1, hi, b, active);
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) { hi[c] = lo[c]; lo[c] = 0.0; }
+                } else {
+                    flush(a, kcur + 1, hi, b, active);
+                    flush(a, kcur, lo, b, active);
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) lo[c] = hi[c] = 0.0;
+                }
+                kcur = k;
+            }
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+                lo[c] = lo[c] + d[c] * w0;
+                if (w1 != 0.0) hi[c] = hi[c] + d[c] * w1;
+            }
+        } else if constexpr (BMODE == BMODE_DENSE) {
+            const int K = KD > 0 ? KD : a.K;
+#pragma unroll
+            for (int k = 0; k < KA; ++k)
+                if (k < K) {
+                    const double bk = rec[a.off_b + k];
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) ad[k * nc + c] = ad[k * nc + c] + d[c] * bk;
+                }
+        }
+    }
+
+    __device__ __forceinline__ void finish(const SweepArgs &a, long b, bool active)
+    {
+        if constexpr (BMODE == BMODE_SPARSE) {
+            flush(a, kcur + 1, hi, b, active);
+            flush(a, kcur, lo, b, active);
+        } else if constexpr (BMODE == BMODE_DENSE) {
+            const int K = KD > 0 ? KD : a.K;
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < KA; ++k)
+                    if (k < K) {
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) a.dJdv[soa((long)k * nc + c, a.ldb, b)] = ad[k * nc + c];
+                    }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------ tile staging
+// Copies the grid-point records [2*i0, 2*(i0+ns)] and step records [i0, i0+ns) of one
+// tile into shared memory.  All threads of the block take part.
+__device__ __forceinline__ void stage_tile(const SweepArgs &a, int i0, int ns, double *gp, double *st)
+{
+    __syncthreads();   // the previous tile has been consumed by every warp
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(a.gprec + (size_t)2 * i0 * a.R);
+        double2 *dst = reinterpret_cast<double2 *>(gp);
+        const int cnt = ((2 * ns + 1) * a.R) >> 1;   // R is even, records are 16-byte aligned
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = src[k];
+    }
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(a.steprec + (size_t)4 * i0);
+        double2 *dst = reinterpret_cast<double2 *>(st);
+        const int cnt = ns * 2;
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ forward sweep
+// RK4Integrator.m:28-56 for one trajectory per thread.
+template <class P, int UMODE, int BMODE, bool PB, int KD>
+__device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
+{
+    constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
+    constexpr bool TT = (!PB) && (P::ntt > 0);
+    const int N = a.N, S = a.S, R = a.R;
+    double *gp = sm;
+    double *st = sm + (size_t)(2 * S + 1) * R;
+
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = b < a.nb;
+    const long bb = active ? b : a.nb - 1;   // idle lanes shadow the last trajectory and never store
+    if (a.frozen && a.frozen[bb]) active = false;   // fb_sweep: converged trajectories are left as they are
+
+    double p[np > 0 ? np : 1];
+#pragma unroll
+    for (int k = 0; k < np; ++k) p[k] = PB ? a.p[soa(k, a.ldp, bb)] : a.p[k];
+
+    double y[m];
+#pragma unroll
+    for (int c = 0; c < n; ++c) y[c] = a.x0[soa(c, a.ldb, bb)];
+    y[n] = 0.0;                                                   // xK(:,1,1) = [x0; 0]   :33
+
+    ControlEval<nc, UMODE, BMODE, KD> ctl;
+    ctl.init(a, bb);
+    double uL[nc], uM[nc], uR[nc];
+
+    for (int i0 = 0; i0 < N; i0 += S) {
+        const int ns = (N - i0 < S) ? (N - i0) : S;
+        stage_tile(a, i0, ns, gp, st);
+        if (i0 == 0) ctl.eval(a, gp, 0, bb, uL);
+        for (int s = 0; s < ns; ++s) {
+            const int i = i0 + s;
+            const double *rL = gp + (size_t)(2 * s) * R, *rM = rL + R, *rR = rM + R;
+            const double h = st[4 * s], h2 = st[4 * s + 1], h6 = st[4 * s + 3];
+            if (active) {
+                if (a.xs) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) a.xs[soa((long)c * (N + 1) + i, a.ldb, b)] = y[c];
+                }
+                if (a.xgrid) {
+#pragma unroll
+                    for (int c = 0; c < m; ++c) a.xgrid[c + (size_t)m * (i + (size_t)(N + 1) * b)] = y[c];
+                }
+            }
+            ctl.eval(a, rM, 2 * i + 1, bb, uM);
+            ctl.eval(a, rR, 2 * i + 2, bb, uR);
+
+            double F[m], acc[m], ys[n];
+            P::template F<TT>(rL + 1, rL[0], y, uL, p, F);                       // F1   :39
+#pragma unroll
+            for (int c = 0; c < m; ++c) acc[c] = F[c];
+#pragma unroll
+            for (int c = 0; c < n; ++c) ys[c] = y[c] + h2 * F[c];                 // xK2  :40
+            P::template F<TT>(rM + 1, rM[0], ys, uM, p, F);                      // F2   :42
+#pragma unroll
+            for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
+#pragma unroll
+            for (int c = 0; c < n; ++c) ys[c] = y[c] + h2 * F[c];                 // xK3  :43
+            P::template F<TT>(rM + 1, rM[0], ys, uM, p, F);                      // F3   :45
+#pragma unroll
+            for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
+#pragma unroll
+            for (int c = 0; c < n; ++c) ys[c] = y[c] + h * F[c];                  // xK4  :46
+            P::template F<TT>(rR + 1, rR[0], ys, uR, p, F);                      // F4   :48
+#pragma unroll
+            for (int c = 0; c < m; ++c) y[c] = y[c] + h6 * (acc[c] + F[c]);       // :50-51
+#pragma unroll
+            for (int c = 0; c < nc; ++c) uL[c] = uR[c];
+        }
+    }
+
+    if (active) {
+        if (a.xs) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) a.xs[soa((long)c * (N + 1) + N, a.ldb, b)] = y[c];
+        }
+        if (a.xgrid) {
+#pragma unroll
+            for (int c = 0; c < m; ++c) a.xgrid[c + (size_t)m * (N + (size_t)(N + 1) * b)] = y[c];
+        }
+        if (a.xT) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) a.xT[soa(c, a.ldb, b)] = y[c];
+        }
+        double Jv = y[n];                                           // J = x(end,end)   :55
+        if (a.J) {
+            if (a.J_accumulate) Jv = a.J[b] + Jv;                   // J = J1 + J2  (RK4InfiniteIntegrator.m:23)
+            a.J[b] = Jv;
+        }
+        if (a.status) {
+            bool ok = isfinite(Jv);
+#pragma unroll
+            for (int c = 0; c < n; ++c) ok = ok && isfinite(y[c]);
+            a.status[b] = (a.J_accumulate ? a.status[b] : 0) | (ok ? 0 : 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ reverse sweep
+// RK4Integrator.m:59-121 for one trajectory per thread.  Stage states 2..4 are
+// recomputed from the stored node state with the same device functions as the forward
+// sweep (16 B/step of HBM traffic instead of 64).  FB = fb_sweep variant: no dJdu; the
+// control on the grid is replaced by ControlChar(t, x, lam) and the normalised change
+// is reduced per trajectory (functions/fb_sweep.m:96,107-110).
+template <class P, int UMODE, int BMODE, bool PB, int KD, bool FB>
+__device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
+{
+    constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
+    constexpr bool TT = (!PB) && (P::ntt > 0);
+    const int N = a.N, S = a.S, R = a.R, G = 2 * N + 1;
+    double *gp = sm;
+    double *st = sm + (size_t)(2 * S + 1) * R;
+
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = b < a.nb;
+    const long bb = active ? b : a.nb - 1;
+    if (a.frozen && a.frozen[bb]) active = false;       // fb_sweep: converged trajectories keep their control
+
+    double p[np > 0 ? np : 1];
+#pragma unroll
+    for (int k = 0; k < np; ++k) p[k] = PB ? a.p[soa(k, a.ldp, bb)] : a.p[k];
+
+    double lam[m];
+#pragma unroll
+    for (int c = 0; c < m; ++c)
+        lam[c] = a.lamT ? a.lamT[soa(c, a.ldl, a.ldl ? bb : 0)] : (c == n ? 1.0 : 0.0);   // :63-66
+    if (a.lamgrid && active) {
+#pragma unroll
+        for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (N + (size_t)(N + 1) * b)] = lam[c];
+    }
+
+    ControlEval<nc, UMODE, BMODE, KD> ctl;
+    ctl.init(a, bb);
+    GradAcc<nc, BMODE, KD> gacc;
+    gacc.init(a);
+
+    double uL[nc], uM[nc], uR[nc], dcar[nc];
+    double y1[n], ynext[n];
+    double xR[n];            // FB: node state and costate to the right (for midpoint averages)
+    double maxchg = 0.0;
+#pragma unroll
+    for (int c = 0; c < nc; ++c) dcar[c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < n; ++c) ynext[c] = a.xs[soa((long)c * (N + 1) + (N - 1), a.ldb, bb)];
+    if constexpr (FB) {
+#pragma unroll
+        for (int c = 0; c < n; ++c) xR[c] = a.xs[soa((long)c * (N + 1) + N, a.ldb, bb)];
+    }
+
+    const int i0_last = ((N - 1) / S) * S;
+    for (int i0 = i0_last; i0 >= 0; i0 -= S) {
+        const int ns = (N - i0 < S) ? (N - i0) : S;
+        stage_tile(a, i0, ns, gp, st);
+        if (i0 == i0_last) ctl.eval(a, gp + (size_t)(2 * ns) * R, 2 * N, bb, uR);
+        for (int s = ns - 1; s >= 0; --s) {
+            const int i = i0 + s;
+            const double *rL = gp + (size_t)(2 * s) * R, *rM = rL + R, *rR = rM + R;
+            const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
+#pragma unroll
+            for (int c = 0; c < n; ++c) y1[c] = ynext[c];
+            if (i > 0) {   // prefetch the next node state: its HBM latency overlaps this step's arithmetic
+#pragma unroll
+                for (int c = 0; c < n; ++c) ynext[c] = a.xs[soa((long)c * (N + 1) + (i - 1), a.ldb, bb)];
+            }
+            ctl.eval(a, rM, 2 * i + 1, bb, uM);
+            ctl.eval(a, rL, 2 * i, bb, uL);
+
+            // stage states of the forward step (RK4Integrator.m:39-46), recomputed
+            double F[m], y2[n], y3[n], y4[n];
+            P::template F<TT>(rL + 1, rL[0], y1, uL, p, F);
+#pragma unroll
+            for (int c = 0; c < n; ++c) y2[c] = y1[c] + h2 * F[c];
+            P::template F<TT>(rM + 1, rM[0], y2, uM, p, F);
+#pragma unroll
+            for (int c = 0; c < n; ++c) y3[c] = y1[c] + h2 * F[c];
+            P::template F<TT>(rM + 1, rM[0], y3, uM, p, F);
+#pragma unroll
+            for (int c = 0; c < n; ++c) y4[c] = y1[c] + h * F[c];
+
+            double k4[m], k3[m], k2[m], k1[m], g3[n], g2[n], g1[n], g0[n];
+#pragma unroll
+            for (int c = 0; c < m; ++c) k4[c] = h6 * lam[c];                              // :73
+            P::template X<TT>(rR + 1, rR[0], y4, uR, p, k4, g3);                         // :74-75
+#pragma unroll
+            for (int c = 0; c < n; ++c) k3[c] = h3 * lam[c] + h * g3[c];                  // :77
+            k3[n] = h3 * lam[n];
+            P::template X<TT>(rM + 1, rM[0], y3, uM, p, k3, g2);                         // :78-79
+#pragma unroll
+            for (int c = 0; c < n; ++c) k2[c] = h3 * lam[c] + h2 * g2[c];                 // :81
+            k2[n] = h3 * lam[n];
+            P::template X<TT>(rM + 1, rM[0], y2, uM, p, k2, g1);                         // :82-83
+#pragma unroll
+            for (int c = 0; c < n; ++c) k1[c] = h6 * lam[c] + h2 * g1[c];                 // :85
+            k1[n] = h6 * lam[n];
+            P::template X<TT>(rL + 1, rL[0], y1, uL, p, k1, g0);                         // :86-88
+
+            if constexpr (!FB) {
+                if (BMODE != BMODE_NONE || a.dJdugrid) {
+                    // dJdu at the right node: stage 1 of step i+1 (carried) + stage 4 of step i   :112-120
+                    double d[nc], e[nc];
+                    P::template U<TT>(rR + 1, rR[0], y4, uR, p, k4, d);
+                    if (i < N - 1) {
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) d[c] = dcar[c] + d[c];
+                    }
+                    gacc.add(a, rR, d, b, active);
+                    if (a.dJdugrid && active) {
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 2) + (size_t)G * b)] = d[c];
+                    }
+                    // midpoint: stages 2 and 3   :105-109
+                    P::template U<TT>(rM + 1, rM[0], y2, uM, p, k2, d);
+                    P::template U<TT>(rM + 1, rM[0], y3, uM, p, k3, e);
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) d[c] = d[c] + e[c];
+                    gacc.add(a, rM, d, b, active);
+                    if (a.dJdugrid && active) {
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 1) + (size_t)G * b)] = d[c];
+                    }
+                    // left node: stage 1 of this step, completed by the next iteration (or the left end :101-102)
+                    P::template U<TT>(rL + 1, rL[0], y1, uL, p, k1, dcar);
+                }
+            }
+
+            double lamR[n];
+#pragma unroll
+            for (int c = 0; c < n; ++c) {
+                lamR[c] = lam[c];
+                lam[c] = lam[c] + g1[c] + g2[c] + g3[c] + g0[c];                           // :86
+            }
+            if (a.lamgrid && active) {
+#pragma unroll
+                for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (i + (size_t)(N + 1) * b)] = lam[c];
+            }
+
+            if constexpr (FB) {
+                // uNew at the right node and at the midpoint of step i (midpoint x, lam = mean of the
+                // neighbouring nodes, the same formula the grid uses for t, RK4Integrator.m:23)
+                double un[nc], xm[n], lm[n];
+                P::template ControlChar<TT>(rR + 1, rR[0], xR, lamR, p, a.bounds, un);
+#pragma unroll
+                for (int c = 0; c < nc; ++c) {
+                    const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);   // fb_sweep.m:107-108
+                    maxchg = fmax(maxchg, w);
+                    const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
+                    if (active) a.ug[soa((long)c * G + (2 * i + 2), a.ldb, b)] = uw;
+                }
+#pragma unroll
+                for (int c = 0; c < n; ++c) { xm[c] = (y1[c] + xR[c]) / 2; lm[c] = (lam[c] + lamR[c]) / 2; }
+                P::template ControlChar<TT>(rM + 1, rM[0], xm, lm, p, a.bounds, un);
+#pragma unroll
+                for (int c = 0; c < nc; ++c) {
+                    const double w = fabs(un[c] - uM[c]) / (a.uRelTol * fabs(uM[c]) + a.uAbsTol);
+                    maxchg = fmax(maxchg, w);
+                    const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uM[c] + a.relax * un[c];
+                    if (active) a.ug[soa((long)c * G + (2 * i + 1), a.ldb, b)] = uw;
+                }
+#pragma unroll
+                for (int c = 0; c < n; ++c) xR[c] = y1[c];
+            }
+#pragma unroll
+            for (int c = 0; c < nc; ++c) uR[c] = uL[c];
+        }
+    }
+
+    if constexpr (!FB) {
+        if (BMODE != BMODE_NONE || a.dJdugrid) {
+            gacc.add(a, gp, dcar, b, active);                                              // left end :101-102
+            if (a.dJdugrid && active) {
+#pragma unroll
+                for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((size_t)G * b)] = dcar[c];
+            }
+            gacc.finish(a, b, active);
+        }
+    } else {
+        double un[nc];
+        double lam0[n];
+#pragma unroll
+        for (int c = 0; c < n; ++c) lam0[c] = lam[c];
+        P::template ControlChar<TT>(gp + 1, gp[0], xR, lam0, p, a.bounds, un);
+#pragma unroll
+        for (int c = 0; c < nc; ++c) {
+            const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);
+            maxchg = fmax(maxchg, w);
+            const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
+            if (active) a.ug[soa((long)c * G, a.ldb, b)] = uw;
+        }
+        if (active && a.max_change) a.max_change[b] = maxchg;
+    }
+    if (a.lam0 && active) {
+#pragma unroll
+        for (int c = 0; c < m; ++c) a.lam0[soa(c, a.ldb, b)] = lam[c];
+    }
+}
+
+// ------------------------------------------------------------------ small helper kernels
+
+// Fills the time-table slots of the grid-point records: every sub-expression of the
+// right-hand sides that depends only on t and batch-uniform parameters is evaluated once
+// per grid point here (with the same device code the in-thread variant would run).
+template <class P>
+__device__ __forceinline__ void time_table_body(double *gprec, int G, int R, const double *p)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= G) return;
+    double pr[P::np > 0 ? P::np : 1];
+#pragma unroll
+    for (int k = 0; k < P::np; ++k) pr[k] = p[k];
+    double tt[P::ntt > 0 ? P::ntt : 1];
+    P::time_table(gprec[(size_t)j * R], pr, tt);
+#pragma unroll
+    for (int k = 0; k < P::ntt; ++k) gprec[(size_t)j * R + 1 + k] = tt[k];
+}
+
+}  // namespace OCS_NS
+
+// Kernel entry points.  OCS_DEFINE_KERNELS(P, tag) emits the extern "C" __global__
+// wrappers of every sweep variant for problem P; the host looks them up by name.
+#define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD)                                                        \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
+        ocs_fwd_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
+    {                                                                                                  \
+        extern __shared__ double2 ocs_smem2[];                                                         \
+        OCS_NS::forward_body<P, UM, BM, (PB != 0), KD>(a, reinterpret_cast<double *>(ocs_smem2));      \
+    }
+#define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD)                                                        \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
+        ocs_rev_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
+    {                                                                                                  \
+        extern __shared__ double2 ocs_smem2[];                                                         \
+        OCS_NS::reverse_body<P, UM, BM, (PB != 0), KD, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
+    }
+#define OCS_FB_KERNEL(P, tag, PB)                                                                     \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
+        ocs_fbrev_##tag##_p##PB(const OCS_NS::SweepArgs a)                                             \
+    {                                                                                                  \
+        extern __shared__ double2 ocs_smem2[];                                                         \
+        OCS_NS::reverse_body<P, 2, 0, (PB != 0), 0, true>(a, reinterpret_cast<double *>(ocs_smem2));   \
+    }
+#define OCS_TT_KERNEL(P, tag)                                                                         \
+    extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int R, const double *p)              \
+    {                                                                                                  \
+        OCS_NS::time_table_body<P>(gprec, G, R, p);                                                    \
+    }
+
+#define OCS_DEFINE_KERNELS_PB(P, tag, PB, KD)   \
+    OCS_FWD_KERNEL(P, tag, 0, 0, PB, KD)        \
+    OCS_FWD_KERNEL(P, tag, 1, 1, PB, KD)        \
+    OCS_FWD_KERNEL(P, tag, 1, 2, PB, KD)        \
+    OCS_FWD_KERNEL(P, tag, 2, 0, PB, KD)        \
+    OCS_REV_KERNEL(P, tag, 0, 0, PB, KD)        \
+    OCS_REV_KERNEL(P, tag, 0, 1, PB, KD)        \
+    OCS_REV_KERNEL(P, tag, 0, 2, PB, KD)        \
+    OCS_REV_KERNEL(P, tag, 1, 1, PB, KD)        \
+    OCS_REV_KERNEL(P, tag, 1, 2, PB, KD)        \
+    OCS_REV_KERNEL(P, tag, 2, 0, PB, KD)        \
+    OCS_FB_KERNEL(P, tag, PB)
+
+#define OCS_DEFINE_KERNELS(P, tag, KD)   \
+    OCS_DEFINE_KERNELS_PB(P, tag, 0, KD) \
+    OCS_DEFINE_KERNELS_PB(P, tag, 1, KD) \
+    OCS_TT_KERNEL(P, tag)

@@ -1,0 +1,3 @@
+from .controls import ChebyshevControl, Control, PWConstantControl, PWLinearControl, matlab_linspace
+from .integrators import CudaRK4InfiniteIntegrator, CudaRK4Integrator
+from .problems import OCProblem, TestOCProblem
