@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 trajectory-steps/s of the batched RK4 forward + discrete-adjoint sweep.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one single_shooting objective+gradient evaluation (functions/single_shooting.m:137-150:
+compute_u -> compute_states -> compute_adjoints -> compute_dJdv) over the whole batch of
+BASELINE.json configs[1]: 2^20 random initial conditions x 1000 RK4 steps of the bundled test
+problem with a shared PWLinearControl (K = 101).  One trajectory-step = one RK4 step of one
+trajectory, forward AND adjoint.  N > 1: every rank owns its own 2^20
+trajectories (weak scaling) and J, x(T) are all-gathered over NCCL inside the timed region.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
+host-buffer C ABI with the copies inside the timed region; `roofline` is for the dominant
+kernel; `cpu_baseline` is the CPU oracle (a C restatement of the MATLAB reference -- neither
+MATLAB nor Octave exists in this image) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload: BASELINE.json configs[1] (SURVEY.md section 8d "cfg2")
+BT = 1 << 20
+N_STEPS = 1000
+T_END = 10.0
+K_PWL = 101
+PARAMS = dict(c=1.5, m=3.0, r=0.05)          # tests/backprop_test.m:9-11
+WORKLOAD = ("cfg2: batched single_shooting evaluation of tests/TestOCProblem.m, 2^20 random x0 x 1000 RK4 steps, "
+            "shared PWLinearControl K=101, forward + discrete adjoint (J, dJdv)")
+
+# ---- algorithmic work per trajectory-step (add/mul/div/exp = 1, FMA = 2)
+# TestOCProblem: C_F = 10, C_X = 8, C_U = 7, m = 2, nc = 1.  The control is shared by the batch, so
+# its evaluation is per grid point, not per trajectory: c_u = 0.  c_v = 4 (PWLinear dJdv scatter).
+FLOP_FWD = 4 * 10 + 13 * 2                    # 66
+FLOP_REV = 4 * 8 + 14 * 2 + 4 * 7 + 2 * 1 + 2 * 4   # 98
+BYTES_FWD = 8                                 # node state written once (n = 1)
+BYTES_REV = 8                                 # ... and read once
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+            return
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_oracle_run(ntraj, nthreads=0, mode=1):
+    """Times the C restatement oracle on `ntraj` trajectories of the bench workload.
+    Returns (trajectory-steps/s, threads used)."""
+    from oracle import oracle_c, rk4_oracle
+    oracle_c.build()
+    tspan = rk4_oracle.matlab_linspace(0.0, T_END, N_STEPS + 1)
+    ctl = rk4_oracle.PWLinearControl(rk4_oracle.RK4Integrator(tspan).t, K_PWL, 1)
+    v = np.random.default_rng(1).random(K_PWL)
+    x0 = np.random.default_rng(2).uniform(0.5, 2.5, (1, ntraj))
+    t0 = time.perf_counter()
+    oracle_c.evaluate(list(PARAMS.values()), tspan, ctl.B, x0, v, mode=mode, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return ntraj * N_STEPS / dt, oracle_c.num_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is MATLAB
+    only and neither MATLAB nor Octave is installed, so this times the oracle port (C restatement of
+    RK4Integrator.m / PWLinearControl.m / TestOCProblem.m, OpenMP across trajectories, every host
+    thread), each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    ntraj = 16384
+    for _ in range(args.warmup):
+        cpu_oracle_run(2048)
+    t0 = time.perf_counter()
+    cores = 1
+    for _ in range(args.steps):
+        _, cores = cpu_oracle_run(ntraj)
+    dt = time.perf_counter() - t0
+    value = args.steps * ntraj * N_STEPS / dt
+    sample = f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps per step (fwd + adjoint)"
+    print(json.dumps({
+        "impl": "reference", "metric": "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)", "value": value,
+        "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the RK4 sweeps have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    build = importlib.import_module("optimal-control-solvers_b200.build")
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    ocs = importlib.import_module("optimal-control-solvers_b200")
+    from importlib import import_module
+    distmod = import_module("optimal-control-solvers_b200.host.dist")
+
+    Bt = args.bt
+    tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
+    prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
+    integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+    ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+    integ.attach_control(ctl)
+    stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream: kernels, events and NCCL all use it
+    torch.cuda.set_stream(stream)
+    integ.set_stream(stream.cuda_stream)
+
+    v = np.random.default_rng(1).random(K_PWL)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2 + rank)
+    x0 = (0.5 + 2.0 * torch.rand((1, Bt), dtype=torch.float64, device=dev, generator=gen)).contiguous()
+    J = torch.empty(Bt, dtype=torch.float64, device=dev)
+    xT = torch.empty((1, Bt), dtype=torch.float64, device=dev)
+    status = torch.empty(Bt, dtype=torch.int32, device=dev)
+    dJdv = torch.empty((K_PWL, Bt), dtype=torch.float64, device=dev)
+    lam0 = torch.empty((2, Bt), dtype=torch.float64, device=dev)
+
+    def step():
+        integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(),
+                           status_ptr=status.data_ptr(), dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+        if world > 1:
+            distmod.gather_results(J, xT, world)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    integ.kernel_stats(reset=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = integ.kernel_stats(reset=True)["launches"] + args.steps   # + the dJdv memset per step
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * Bt * N_STEPS * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel device time (CUDA events around every launch, on the launch stream)
+    integ.set_profiling(True)
+    nprof = max(3, min(args.steps, 10))
+    for _ in range(nprof):
+        integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(),
+                           status_ptr=status.data_ptr(), dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+    torch.cuda.synchronize()
+    ks = integ.kernel_stats(reset=True)
+    integ.set_profiling(False)
+    ms_fwd, ms_rev = ks["ms_forward"] / nprof, ks["ms_reverse"] / nprof
+
+    out = None
+    if rank == 0:
+        L = ocs._lib.load()
+        import ctypes
+        tf = ctypes.c_double()
+        L.ocs_b200_measure_fp64_peak(local_rank, ctypes.byref(tf))
+        hbm_peak, hbm_src = _measured_peaks()
+        units = Bt * N_STEPS
+
+        def kern(name, ms_k, flop, byt):
+            return {"kernel": name, "ms": ms_k, "tflops": units * flop / (ms_k * 1e-3) / 1e12,
+                    "gbs": units * byt / (ms_k * 1e-3) / 1e9}
+        kf = kern("ocs_fwd_test_fast_u0_b0_p0", ms_fwd, FLOP_FWD, BYTES_FWD)
+        kr = kern("ocs_rev_test_fast_u0_b1_p0", ms_rev, FLOP_REV, BYTES_REV)
+        dom = kr if ms_rev >= ms_fwd else kf
+        fp_frac, hbm_frac = dom["tflops"] / tf.value, dom["gbs"] / hbm_peak
+        if fp_frac >= hbm_frac:
+            roof = {"bound": "fp64", "achieved": dom["tflops"], "peak": tf.value, "unit": "TFLOP/s", "frac": fp_frac,
+                    "peak_source": "DFMA micro-benchmark in this run (ocs_b200_measure_fp64_peak); no FP64 entry in MEASURED_PEAKS.json"}
+        else:
+            roof = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,
+                    "peak_source": hbm_src}
+        roof.update({"kernel": dom["kernel"], "traffic": None,
+                     "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "peak_source": hbm_src},
+                     "fp64": {"achieved": dom["tflops"], "peak": tf.value, "unit": "TFLOP/s", "frac": fp_frac},
+                     "kernels": [kf, kr],
+                     "algorithmic": {"flop_per_step_fwd": FLOP_FWD, "flop_per_step_rev": FLOP_REV,
+                                     "bytes_per_step_fwd": BYTES_FWD, "bytes_per_step_rev": BYTES_REV}})
+        # whole-evaluation view: (fwd + rev) algorithmic flops over the measured step time
+        roof["step_fp64_frac"] = value / world * (FLOP_FWD + FLOP_REV) / 1e12 / tf.value
+        out = {
+            "metric": "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)", "value": value,
+            "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS,
+                       "l2": "inputs larger than L2 (8.4 GB node-state store per GPU)",
+                       "collective": "all_gather of J and x(T) (NCCL)" if world > 1 else "none"},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
+        }
+
+    # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        x0_h = torch.empty((1, Bt), dtype=torch.float64).pin_memory()
+        x0_h.copy_(x0.cpu())
+        J_h = torch.empty(Bt, dtype=torch.float64).pin_memory()
+        xT_h = torch.empty((1, Bt), dtype=torch.float64).pin_memory()
+        st_h = torch.empty(Bt, dtype=torch.int32).pin_memory()
+        dJdv_h = torch.empty((Bt, K_PWL), dtype=torch.float64).pin_memory()   # MATLAB (nc*K) x Bt, column-major
+        lam0_h = torch.empty((Bt, 2), dtype=torch.float64).pin_memory()
+        lib = ocs._lib
+        vf = lib.f64(v)
+        hnd = integ._h
+        L = lib.load()
+
+        def e2e_step():
+            lib.check(L.ocs_b200_set_control_v(hnd, lib.dp(vf), 1), hnd)
+            lib.check(L.ocs_b200_compute_states(hnd, lib.dp(x0_h.numpy()), Bt, lib.dp(J_h.numpy()), lib.dp(xT_h.numpy()),
+                                                lib.ip(st_h.numpy())), hnd)
+            lib.check(L.ocs_b200_compute_adjoints(hnd, None, 0, lib.dp(dJdv_h.numpy()), lib.dp(lam0_h.numpy())), hnd)
+        ne = max(2, min(args.steps, 5))
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * Bt * N_STEPS * ne / dt, "unit": "trajectory-steps/s",
+               "h2d_bytes_per_step": 8 * Bt + 8 * K_PWL,
+               "d2h_bytes_per_step": 8 * Bt * (1 + 1 + K_PWL + 2) + 4 * Bt,
+               "steps": ne, "ms_per_step": 1e3 * dt / ne,
+               "api": "ocs_b200_compute_states + ocs_b200_compute_adjoints on pinned host buffers (J, xT, status, dJdv, lam0 returned)"}
+
+    if rank == 0:
+        out["e2e"] = e2e
+        if not args.no_cpu:
+            ntraj = 32768
+            val, cores = cpu_oracle_run(ntraj)
+            out["cpu_baseline"] = {"value": val, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+                                   "sample": f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps, fwd + adjoint, "
+                                             "C restatement of the MATLAB reference (no MATLAB/Octave in the image), OpenMP"}
+        print(json.dumps(out))
+    integ.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,11 +4,15 @@
 #pragma once
 
 struct ocs_kernel_table {
-    int n, nc, np, ntt;
+    int n, nc, np;
+    int ntt[3];    // hoisted-table width per hoisting mode (HM_NONE, HM_TIME, HM_TIME_CONTROL)
     int kd;        // compile-time dense-basis size (0 = run-time K <= OCS_KDENSE_MAX)
     int threads;   // block size the kernels were built for
+    int tile;      // RK4 steps per shared-memory tile
     const void *fwd[3][3][2];   // [UMODE][BMODE][params batched]
     const void *rev[3][3][2];
+    const void *fwdg[3][3][2];  // fetch variants: also write the full grids (x with the J row; lam, dJdu)
+    const void *revg[3][3][2];
     const void *fbrev[2];
     const void *tt;
 };

@@ -6,10 +6,10 @@
 
 #if OCS_STRICT
 #define OCS_NS ocs_strict
-#define OCS_TAG(x) x##_strict
+#define OCS_TAGNAME test_strict
 #else
 #define OCS_NS ocs_fast
-#define OCS_TAG(x) x##_fast
+#define OCS_TAGNAME test_fast
 #endif
 
 #include "rk4_kernels.cuh"
@@ -18,37 +18,34 @@
 
 #if OCS_STRICT
 OCS_DEFINE_KERNELS(ocs_strict::TestOCProblem, test_strict, 0)
-#define T(name) (const void *)name##test_strict
 #else
 OCS_DEFINE_KERNELS(ocs_fast::TestOCProblem, test_fast, 0)
-#define T(name) (const void *)name##test_fast
 #endif
 
-#define FWD(UM, BM, PB) (const void *)OCS_CAT5(ocs_fwd_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
-
-#if OCS_STRICT
-#define OCS_TAGNAME test_strict
-#else
-#define OCS_TAGNAME test_fast
-#endif
 #define OCS_CAT5_(a, b, c, d, e) a##b##c##d##e
 #define OCS_CAT5(a, b, c, d, e) OCS_CAT5_(a, b, c, d, e)
+#define OCS_CAT2_(a, b) a##b
+#define OCS_CAT2(a, b) OCS_CAT2_(a, b)
 #define OCS_CAT3_(a, b, c) a##b##c
 #define OCS_CAT3(a, b, c) OCS_CAT3_(a, b, c)
+#define FWD(UM, BM, PB) (const void *)OCS_CAT5(ocs_fwd_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define REV(UM, BM, PB) (const void *)OCS_CAT5(ocs_rev_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
+#define FWDG(UM, BM, PB) (const void *)OCS_CAT5(ocs_fwdg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
+#define REVG(UM, BM, PB) (const void *)OCS_CAT5(ocs_revg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define FBR(PB) (const void *)OCS_CAT3(ocs_fbrev_, OCS_TAGNAME, _p##PB)
 
-static void fill(ocs_kernel_table *t)
+extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
 {
-    t->n = OCS_NS::TestOCProblem::n;
-    t->nc = OCS_NS::TestOCProblem::nc;
-    t->np = OCS_NS::TestOCProblem::np;
-    t->ntt = OCS_NS::TestOCProblem::ntt;
+    typedef OCS_NS::TestOCProblem P;
+    t->n = P::n; t->nc = P::nc; t->np = P::np;
+    for (int hm = 0; hm < 3; ++hm) t->ntt[hm] = P::ntt(hm);
     t->kd = 0;
     t->threads = OCS_THREADS;
+    t->tile = OCS_TILE;
     for (int pb = 0; pb < 2; ++pb)
         for (int um = 0; um < 3; ++um)
-            for (int bm = 0; bm < 3; ++bm) t->fwd[um][bm][pb] = t->rev[um][bm][pb] = nullptr;
+            for (int bm = 0; bm < 3; ++bm)
+                t->fwd[um][bm][pb] = t->rev[um][bm][pb] = t->fwdg[um][bm][pb] = t->revg[um][bm][pb] = nullptr;
     t->fwd[0][0][0] = FWD(0, 0, 0); t->fwd[0][0][1] = FWD(0, 0, 1);
     t->fwd[1][1][0] = FWD(1, 1, 0); t->fwd[1][1][1] = FWD(1, 1, 1);
     t->fwd[1][2][0] = FWD(1, 2, 0); t->fwd[1][2][1] = FWD(1, 2, 1);
@@ -59,12 +56,14 @@ static void fill(ocs_kernel_table *t)
     t->rev[1][1][0] = REV(1, 1, 0); t->rev[1][1][1] = REV(1, 1, 1);
     t->rev[1][2][0] = REV(1, 2, 0); t->rev[1][2][1] = REV(1, 2, 1);
     t->rev[2][0][0] = REV(2, 0, 0); t->rev[2][0][1] = REV(2, 0, 1);
+    t->fwdg[0][0][0] = FWDG(0, 0, 0); t->fwdg[0][0][1] = FWDG(0, 0, 1);
+    t->fwdg[1][1][0] = FWDG(1, 1, 0); t->fwdg[1][1][1] = FWDG(1, 1, 1);
+    t->fwdg[1][2][0] = FWDG(1, 2, 0); t->fwdg[1][2][1] = FWDG(1, 2, 1);
+    t->fwdg[2][0][0] = FWDG(2, 0, 0); t->fwdg[2][0][1] = FWDG(2, 0, 1);
+    t->revg[0][0][0] = REVG(0, 0, 0); t->revg[0][0][1] = REVG(0, 0, 1);
+    t->revg[1][1][0] = REVG(1, 1, 0); t->revg[1][1][1] = REVG(1, 1, 1);
+    t->revg[1][2][0] = REVG(1, 2, 0); t->revg[1][2][1] = REVG(1, 2, 1);
+    t->revg[2][0][0] = REVG(2, 0, 0); t->revg[2][0][1] = REVG(2, 0, 1);
     t->fbrev[0] = FBR(0); t->fbrev[1] = FBR(1);
-    t->tt = (const void *)OCS_CAT3(ocs_tt_, OCS_TAGNAME, );
+    t->tt = (const void *)OCS_CAT2(ocs_tt_, OCS_TAGNAME);
 }
-
-#if OCS_STRICT
-extern "C" void ocs_builtin_table_test_strict(ocs_kernel_table *t) { fill(t); }
-#else
-extern "C" void ocs_builtin_table_test_fast(ocs_kernel_table *t) { fill(t); }
-#endif

@@ -102,7 +102,6 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
     src += "static_assert(ocs_gen::Problem::nc == " + std::to_string(nc) + ", \"control count mismatch\");\n";
     src += "static_assert(ocs_gen::Problem::np == " + std::to_string(np) + ", \"parameter count mismatch\");\n";
     src += "OCS_DEFINE_KERNELS(ocs_gen::Problem, gen, " + std::to_string(kd) + ")\n";
-    src += "extern \"C\" __global__ void ocs_gen_info(int *o) { o[0] = ocs_gen::Problem::ntt; }\n";
 
     nvrtcProgram prog = nullptr;
     nvrtcResult r = rt.CreateProgram(&prog, src.c_str(), "ocs_generated_problem.cu", 0, nullptr, nullptr);
@@ -164,6 +163,10 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
         for (auto &c : combos_f) {
             snprintf(name, sizeof name, "ocs_fwd_gen_u%d_b%d_p%d", c[0], c[1], pb);
             ok &= (table->fwd[c[0]][c[1]][pb] = get(name)) != nullptr;
+            snprintf(name, sizeof name, "ocs_fwdg_gen_u%d_b%d_p%d", c[0], c[1], pb);
+            ok &= (table->fwdg[c[0]][c[1]][pb] = get(name)) != nullptr;
+            snprintf(name, sizeof name, "ocs_revg_gen_u%d_b%d_p%d", c[0], c[1], pb);
+            ok &= (table->revg[c[0]][c[1]][pb] = get(name)) != nullptr;
         }
         for (auto &c : combos_r) {
             snprintf(name, sizeof name, "ocs_rev_gen_u%d_b%d_p%d", c[0], c[1], pb);
@@ -173,19 +176,19 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
         ok &= (table->fbrev[pb] = get(name)) != nullptr;
     }
     ok &= (table->tt = get("ocs_tt_gen")) != nullptr;
-    const void *info = get("ocs_gen_info");
+    const void *info = get("ocs_info_gen");
     if (!ok || !info) {
         *log += "\ncompiled library lacks an expected kernel";
         cudaLibraryUnload(lib);
         return OCS_B200_ERR_COMPILE;
     }
-    // ask the compiled code for its time-table width
-    int *d_info = nullptr, ntt = 0;
-    e = cudaMalloc(&d_info, sizeof(int));
+    // ask the compiled code for its hoisted-table widths and tile constants
+    int *d_info = nullptr, inf[8] = {0};
+    e = cudaMalloc(&d_info, sizeof inf);
     if (e == cudaSuccess) {
         void *args[] = {(void *)&d_info};
         e = cudaLaunchKernel(info, dim3(1), dim3(1), args, 0, nullptr);
-        if (e == cudaSuccess) e = cudaMemcpy(&ntt, d_info, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(inf, d_info, sizeof inf, cudaMemcpyDeviceToHost);
         cudaFree(d_info);
     }
     if (e != cudaSuccess) {
@@ -193,7 +196,9 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
         cudaLibraryUnload(lib);
         return OCS_B200_ERR_CUDA;
     }
-    table->ntt = ntt;
+    for (int hm = 0; hm < 3; ++hm) table->ntt[hm] = inf[3 + hm];
+    table->tile = inf[6];
+    table->threads = inf[7];
     *library = (void *)lib;
     return 0;
 }

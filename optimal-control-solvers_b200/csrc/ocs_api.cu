@@ -42,7 +42,15 @@ std::mutex g_mutex;
 struct Segment {
     int N = 0;
     std::vector<double> tspan, t, h;
-    double *d_gprec = nullptr, *d_steprec = nullptr;
+    double *d_gprec = nullptr, *d_steprec = nullptr, *d_basrec = nullptr;
+    size_t gprec_cap = 0, basrec_cap = 0;   // doubles
+    double *h_rec = nullptr;  // pinned staging of the records (async upload)
+    size_t h_rec_cap = 0;
+    int BW = 0;               // doubles per basis record
+    int hm = 0;               // hoisting mode the records were built for
+    bool basis_dirty = true;
+    cudaEvent_t rec_uploaded = nullptr;
+    bool steps_uploaded = false;
     double *d_xs = nullptr;   // node states [n][N+1][Bt]
     size_t xs_cap = 0;        // doubles
     int R = 0;
@@ -106,6 +114,7 @@ struct ocs_b200_handle {
     size_t frozen_cap = 0;
     double *d_bounds = nullptr;
     double *d_red = nullptr;   // reduction scratch
+    int *d_errflag = nullptr;  // set by a kernel whose compiled record layout disagrees with the host's
 
     // profiling
     bool profiling = false;
@@ -334,15 +343,17 @@ __global__ void broadcast_rows_kernel(const double *__restrict__ col, double *ds
 }
 
 // ---------------------------------------------------------------- records
-inline int even(int x) { return (x + 1) & ~1; }
-
-int basis_width(const H *h, int si)
+int seg_umode(const H *h, int si)
 {
-    if (si != 0) return 0;
-    if (h->basis_kind == BASIS_SPARSE) return 3;
-    if (h->basis_kind == BASIS_DENSE) return h->K;
-    return 0;
+    if (si == 1) return 0;
+    switch (h->ctrl_mode) {
+        case CTRL_V_BATCH: return 1;
+        case CTRL_U_BATCH: return 2;
+        default: return 0;
+    }
 }
+
+int basis_mode(const H *h, int si) { return si == 0 ? h->basis_kind : BASIS_NONE; }
 
 // u(:,j) = reshape(v,nc,[]) * B(:,j) for a shared v -- same operation order as ControlEval::eval
 void shared_u_from_v(const H *h, int j, double *u)
@@ -352,7 +363,7 @@ void shared_u_from_v(const H *h, int j, double *u)
         const int k = h->bk[j];
         for (int c = 0; c < nc; ++c) {
             double s = h->ctrl_shared[(size_t)k * nc + c] * h->bw0[j];
-            if (h->bw1[j] != 0.0) s = s + h->ctrl_shared[(size_t)(k + 1) * nc + c] * h->bw1[j];
+            if (h->bnnz[j] > 1) s = s + h->ctrl_shared[(size_t)(k + 1) * nc + c] * h->bw1[j];
             u[c] = s;
         }
     } else {
@@ -365,52 +376,100 @@ void shared_u_from_v(const H *h, int j, double *u)
     }
 }
 
+// Packs the batch-invariant tables of one segment:
+//   grid-point records [ t | u(nc) | hoisted table | pad ]   (rebuilt when the shared control or parameters change)
+//   step records       [ h, h/2, h/3, h/6 ]                  (once)
+//   basis records      sparse [ (int k, int two) | w0 | w1 | pad ], dense [ B(:,j) | pad ]   (when the basis changes)
 int build_records(H *h, int si)
 {
     Segment &s = h->seg[si];
+    const int N = s.N, G = 2 * N + 1, nc = h->kt.nc;
+    if (s.basis_dirty) {
+        const int bm = basis_mode(h, si);
+        const int BW = ocs_host::ocs_basis_width(bm, h->K);
+        if (BW > 0) {
+            std::vector<double> bas((size_t)G * BW, 0.0);
+            for (int j = 0; j < G; ++j) {
+                double *r = &bas[(size_t)j * BW];
+                if (bm == BASIS_SPARSE) {
+                    // weights by knot parity (wE: the even knot of {k, k+1}); flags bit0 = two non-zeros,
+                    // bit1 = the single non-zero sits on the odd slot
+                    const int k = h->bk[j];
+                    const bool two = h->bnnz[j] > 1, odd = (k & 1) != 0;
+                    int32_t kk[2] = {k, (two ? 1 : 0) | ((!two && odd) ? 2 : 0)};
+                    memcpy(r, kk, sizeof kk);
+                    r[1] = odd ? h->bw1[j] : h->bw0[j];
+                    r[2] = odd ? h->bw0[j] : h->bw1[j];
+                } else {
+                    for (int k = 0; k < h->K; ++k) r[k] = h->bdense[k + (size_t)h->K * j];
+                }
+            }
+            if (s.basrec_cap < bas.size()) {
+                if (s.d_basrec) CK(cudaFree(s.d_basrec));
+                s.d_basrec = nullptr;
+                CK(cudaMalloc(&s.d_basrec, bas.size() * sizeof(double)));
+                s.basrec_cap = bas.size();
+            }
+            CK(cudaMemcpyAsync(s.d_basrec, bas.data(), bas.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));   // bas is a local vector
+        }
+        s.BW = BW;
+        s.basis_dirty = false;
+    }
     if (!s.records_dirty) return 0;
-    const int N = s.N, G = 2 * N + 1, nc = h->kt.nc, ntt = h->kt.ntt;
-    const int off_u = 1 + ntt, off_b = off_u + nc, bw = basis_width(h, si);
-    const int R = even(off_b + bw);
-    std::vector<double> rec((size_t)G * R, 0.0);
+    const int hm = ocs_host::ocs_hoist_mode(seg_umode(h, si), h->params_nbatch > 1);
+    const int ntt = h->kt.ntt[hm];
+    const int R = ocs_host::ocs_rec_width(nc, ntt);
+    const size_t nrec = (size_t)G * R;
+    if (s.h_rec_cap < nrec) {
+        if (s.h_rec) CK(cudaFreeHost(s.h_rec));
+        s.h_rec = nullptr;
+        CK(cudaHostAlloc((void **)&s.h_rec, nrec * sizeof(double), cudaHostAllocDefault));
+        s.h_rec_cap = nrec;
+    }
+    if (s.gprec_cap < nrec) {
+        if (s.d_gprec) CK(cudaFree(s.d_gprec));
+        s.d_gprec = nullptr;
+        CK(cudaMalloc(&s.d_gprec, nrec * sizeof(double)));
+        s.gprec_cap = nrec;
+    }
+    if (!s.rec_uploaded) CK(cudaEventCreateWithFlags(&s.rec_uploaded, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(s.rec_uploaded));   // the previous upload no longer reads the staging buffer
+    double *rec = s.h_rec;
+    memset(rec, 0, nrec * sizeof(double));
     std::vector<double> u(nc);
     for (int j = 0; j < G; ++j) {
         double *r = &rec[(size_t)j * R];
         r[0] = s.t[j];
         if (si == 1) {
-            for (int c = 0; c < nc; ++c) r[off_u + c] = h->uStar[c];   // RK4InfiniteIntegrator.m:15
+            for (int c = 0; c < nc; ++c) r[1 + c] = h->uStar[c];   // RK4InfiniteIntegrator.m:15
         } else if (h->ctrl_mode == CTRL_V_SHARED) {
             shared_u_from_v(h, j, u.data());
-            for (int c = 0; c < nc; ++c) r[off_u + c] = u[c];
+            for (int c = 0; c < nc; ++c) r[1 + c] = u[c];
         } else if (h->ctrl_mode == CTRL_U_SHARED) {
-            for (int c = 0; c < nc; ++c) r[off_u + c] = h->ctrl_shared[c + (size_t)nc * j];
-        }
-        if (bw == 3) {
-            r[off_b] = (double)h->bk[j];
-            r[off_b + 1] = h->bw0[j];
-            r[off_b + 2] = h->bw1[j];
-        } else if (bw > 0) {
-            for (int k = 0; k < h->K; ++k) r[off_b + k] = h->bdense[k + (size_t)h->K * j];
+            for (int c = 0; c < nc; ++c) r[1 + c] = h->ctrl_shared[c + (size_t)nc * j];
         }
     }
-    std::vector<double> st((size_t)N * 4);
-    for (int i = 0; i < N; ++i) {
-        st[4 * i] = s.h[i];
-        st[4 * i + 1] = s.h[i] / 2;   // obj.h(i)/2   RK4Integrator.m:40
-        st[4 * i + 2] = s.h[i] / 3;   // obj.h(i)/3   :77
-        st[4 * i + 3] = s.h[i] / 6;   // obj.h(i)/6   :51
+    CK(cudaMemcpyAsync(s.d_gprec, rec, nrec * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(s.rec_uploaded, h->stream));
+    if (!s.steps_uploaded) {
+        std::vector<double> st((size_t)N * 4);
+        for (int i = 0; i < N; ++i) {
+            st[4 * i] = s.h[i];
+            st[4 * i + 1] = s.h[i] / 2;   // obj.h(i)/2   RK4Integrator.m:40
+            st[4 * i + 2] = s.h[i] / 3;   // obj.h(i)/3   :77
+            st[4 * i + 3] = s.h[i] / 6;   // obj.h(i)/6   :51
+        }
+        CK(cudaMalloc(&s.d_steprec, st.size() * sizeof(double)));
+        CK(cudaMemcpyAsync(s.d_steprec, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // st is a local vector
+        s.steps_uploaded = true;
     }
-    if (s.d_gprec) CK(cudaFree(s.d_gprec));
-    if (s.d_steprec) CK(cudaFree(s.d_steprec));
-    s.d_gprec = s.d_steprec = nullptr;
-    CK(cudaMalloc(&s.d_gprec, rec.size() * sizeof(double)));
-    CK(cudaMalloc(&s.d_steprec, st.size() * sizeof(double)));
-    CK(cudaMemcpyAsync(s.d_gprec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(s.d_steprec, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // rec/st are stack-owned host vectors
     s.R = R;
-    if (ntt > 0 && h->params_nbatch == 1) {
-        void *args[] = {(void *)&s.d_gprec, (void *)&G, (void *)&s.R, (void *)&h->d_params.p};
+    s.hm = hm;
+    if (ntt > 0) {
+        int hmv = hm, Gv = G;
+        void *args[] = {(void *)&s.d_gprec, (void *)&Gv, (void *)&hmv, (void *)&h->d_params.p};
         CK(cudaLaunchKernel(h->kt.tt, dim3((G + 127) / 128), dim3(128), args, 0, h->stream));
     }
     s.records_dirty = false;
@@ -420,6 +479,7 @@ int build_records(H *h, int si)
 void mark_dirty(H *h)
 {
     h->seg[0].records_dirty = h->seg[1].records_dirty = true;
+    h->seg[0].basis_dirty = h->seg[1].basis_dirty = true;
 }
 
 int check_ready(H *h)
@@ -438,21 +498,22 @@ void base_args(H *h, int si, SweepArgs &a)
     Segment &s = h->seg[si];
     memset(&a, 0, sizeof a);
     a.N = s.N;
-    a.R = s.R;
-    a.off_u = 1 + h->kt.ntt;
-    a.off_b = a.off_u + h->kt.nc;
     a.K = h->K;
-    // tile: keep the staged records under ~24 KB so that many blocks stay resident
-    int S = 32;
-    while (S > 4 && ((size_t)(2 * S + 1) * s.R + 4 * S) * sizeof(double) > 24 * 1024) S >>= 1;
-    a.S = S;
+    a.RB = s.R;
+    a.BW = s.BW;
     a.gprec = s.d_gprec;
     a.steprec = s.d_steprec;
+    a.basrec = s.d_basrec;
     a.p = h->d_params.p;
     a.ldp = h->params_nbatch > 1 ? h->params_nbatch : 0;
+    a.error_flag = h->d_errflag;
 }
 
-size_t smem_bytes(const SweepArgs &a) { return ((size_t)(2 * a.S + 1) * a.R + 4 * a.S) * sizeof(double); }
+size_t smem_bytes(const H *h, const SweepArgs &a)
+{
+    const int S = h->kt.tile;
+    return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW) * sizeof(double);
+}
 
 int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward)
 {
@@ -462,7 +523,12 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward)
     const unsigned blocks = (unsigned)((a.nb + threads - 1) / threads);
     void *args[] = {(void *)&a};
     if (h->profiling) CK(cudaEventRecord(h->ev[0], h->stream));
-    CK(cudaLaunchKernel(kernel, dim3(blocks), dim3(threads), args, smem_bytes(a), h->stream));
+    const size_t smem = smem_bytes(h, a);
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return h->fail(OCS_B200_ERR_ARG, "control basis too wide for the shared-memory tile");
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CK(cudaLaunchKernel(kernel, dim3(blocks), dim3(threads), args, smem, h->stream));
     if (h->profiling) {
         CK(cudaEventRecord(h->ev[1], h->stream));
         CK(cudaEventSynchronize(h->ev[1]));
@@ -476,14 +542,7 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward)
 
 int pb_index(const H *h) { return h->params_nbatch > 1 ? 1 : 0; }
 
-int main_umode(const H *h)
-{
-    switch (h->ctrl_mode) {
-        case CTRL_V_BATCH: return 1;
-        case CTRL_U_BATCH: return 2;
-        default: return 0;
-    }
-}
+int main_umode(const H *h) { return seg_umode(h, 0); }
 
 // forward sweep(s) over trajectories [b0, b0+nb) of the resident batch; xgrid optional (fetch)
 int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool write_outputs)
@@ -515,7 +574,7 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         } else if (um == 2) {
             a.ug = h->d_ug.p + b0;
         }
-        TRY(launch(h, h->kt.fwd[um][bm][pb_index(h)], a, true));
+        TRY(launch(h, (d_xgrid ? h->kt.fwdg : h->kt.fwd)[um][bm][pb_index(h)], a, true));
     }
     return 0;
 }
@@ -572,7 +631,9 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             if (d_dJdv && h->basis_kind == BASIS_NONE)
                 return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
         }
-        TRY(launch(h, h->kt.rev[um][bm][pb_index(h)], a, false));
+        const bool grids = a.lamgrid || a.dJdugrid;
+        if (grids && um != 1) bm = 0;   // the fetch variants write dJdu itself; only UMODE_COEF needs the basis
+        TRY(launch(h, (grids ? h->kt.revg : h->kt.rev)[um][bm][pb_index(h)], a, false));
     }
     return 0;
 }
@@ -693,6 +754,8 @@ int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extr
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->ev[k]);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_errflag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_errflag, 0, sizeof(int));
     if (e != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
         delete h;
@@ -725,6 +788,9 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     for (int si = 0; si < 2; ++si) {
         cudaFree(h->seg[si].d_gprec);
         cudaFree(h->seg[si].d_steprec);
+        cudaFree(h->seg[si].d_basrec);
+        if (h->seg[si].h_rec) cudaFreeHost(h->seg[si].h_rec);
+        if (h->seg[si].rec_uploaded) cudaEventDestroy(h->seg[si].rec_uploaded);
         cudaFree(h->seg[si].d_xs);
     }
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
@@ -735,6 +801,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     cudaFree(h->d_sweeps);
     cudaFree(h->d_bounds);
     cudaFree(h->d_red);
+    cudaFree(h->d_errflag);
     for (int k = 0; k < 4; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->gen_library) ocs_unload_problem(h->gen_library);

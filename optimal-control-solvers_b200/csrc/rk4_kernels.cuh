@@ -4,9 +4,11 @@
 // the RK4 stage values live in registers; node states needed by the reverse sweep
 // are stored in HBM in structure-of-arrays layout [component][step][batch] so that
 // a warp's 32 trajectories write/read 256 contiguous bytes.  Everything that is the
-// same for every trajectory of the batch (times, step sizes, time-only
+// same for every trajectory of the batch (times, step sizes, hoisted uniform
 // sub-expressions, shared control values, control basis entries) is packed into
-// per-grid-point records and staged through shared memory tile by tile.
+// fixed-width per-grid-point records and staged through shared memory tile by tile;
+// record widths and the tile size are compile-time constants so that every
+// shared-memory operand is an immediate offset.
 //
 // Arithmetic follows, operation by operation,
 //   Integrator/RK4Integrator.m:28-56   compute_states
@@ -28,6 +30,9 @@
 #ifndef OCS_THREADS
 #define OCS_THREADS 128
 #endif
+#ifndef OCS_TILE
+#define OCS_TILE 32         // RK4 steps per shared-memory tile
+#endif
 #ifndef OCS_KDENSE_MAX
 #define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
 #endif
@@ -40,22 +45,36 @@ enum { UMODE_UNIFORM = 0,   // u_j shared by the batch, read from the grid-point
        UMODE_GRID = 2 };    // per-trajectory values on the G grid points
 // How dJdu is folded into dJdv (and how UMODE_COEF evaluates u).
 enum { BMODE_NONE = 0, BMODE_SPARSE = 1, BMODE_DENSE = 2 };
+// Hoisting mode: which sub-expressions of the right-hand sides are batch-uniform and therefore
+// evaluated once per grid point (into the record's table slots) instead of once per trajectory.
+enum { HM_NONE = 0,         // per-trajectory parameters: nothing is uniform
+       HM_TIME = 1,         // uniform parameters: functions of (t, p)
+       HM_TIME_CONTROL = 2 };   // uniform parameters and control: functions of (t, p, u)
+
+__host__ __device__ constexpr int ocs_even(int x) { return (x + 1) & ~1; }
+// grid-point record: [ t | u(0..nc-1) | table(0..ntt-1) | pad ]
+__host__ __device__ constexpr int ocs_rec_width(int nc, int ntt) { return ocs_even(1 + nc + ntt); }
+// basis record: sparse [ (int k, int two) | w0 | w1 | pad ], dense [ B(0..K-1, j) | pad ]
+__host__ __device__ constexpr int ocs_basis_width(int bmode, int K) { return bmode == 1 ? 4 : (bmode == 2 ? ocs_even(K) : 0); }
+__host__ __device__ constexpr int ocs_hoist_mode(int umode, bool params_batched)
+{
+    return params_batched ? 0 : (umode == 0 ? 2 : 1);
+}
 
 // Argument block of one sweep over one RK4 segment (main horizon or tail).
 // SoA device arrays have leading dimension ldb (the batch stride); the kernel
 // handles trajectories [0, nb) of them, so a sub-range is a pointer offset.
 struct SweepArgs {
     int N;                  // RK4 steps
-    int S;                  // steps per shared-memory tile
-    int R;                  // doubles per grid-point record
-    int off_u;              // record offset of the shared control values (UMODE_UNIFORM)
-    int off_b;              // record offset of the basis part: (k, w0, w1) or B(0..K-1, j)
     int K;                  // basis size
+    int RB;                 // doubles per grid-point record (cross-checked against the kernel's constant)
+    int BW;                 // doubles per basis record
     long nb;                // trajectories handled
     long ldb;               // batch stride of SoA arrays
     long ldp;               // batch stride of per-trajectory params
-    const double *gprec;    // [2N+1][R]  t_j, time-table values, control part
+    const double *gprec;    // [2N+1][RB]
     const double *steprec;  // [N][4]     h, h/2, h/3, h/6
+    const double *basrec;   // [2N+1][BW]
     const double *x0;       // [n][ldb]
     const double *p;        // [np] or [np][ldp]
     const double *v;        // UMODE_COEF: [(k*nc+c)][ldb]
@@ -74,11 +93,12 @@ struct SweepArgs {
     double *lam0;           // [m][ldb] or null
     double *lamgrid;        // MATLAB layout m x (N+1) x nb, or null
     double *dJdugrid;       // MATLAB layout nc x (2N+1) x nb, or null
-    // fb_sweep (reverse kernel with control update; see fb_reverse_body)
+    // fb_sweep (reverse sweep with control update)
     const double *bounds;   // [nc][2]
     double uRelTol, uAbsTol, relax;
     double *max_change;     // [nb]
     const int *frozen;      // [nb] trajectories already converged (skipped), or null
+    int *error_flag;        // set to 1 when the host's record layout disagrees with the kernel's
 };
 
 __device__ __forceinline__ size_t soa(long row, long ld, long b) { return (size_t)row * (size_t)ld + (size_t)b; }
@@ -90,8 +110,10 @@ template <int nc, int UMODE, int BMODE, int KD>
 struct ControlEval {
     static constexpr int KA = (KD > 0 ? KD : OCS_KDENSE_MAX);
     int kcur;
-    double vlo[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
-    double vhi[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
+    // sparse basis: the window {k, k+1} of live coefficients, held by knot parity so that sliding the
+    // window replaces one slot and never shuffles registers
+    double vE[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
+    double vO[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
     double vd[(UMODE == UMODE_COEF && BMODE == BMODE_DENSE) ? KA * nc : 1];
 
     __device__ __forceinline__ void init(const SweepArgs &a, long bb)
@@ -109,52 +131,49 @@ struct ControlEval {
     }
 
     // u(:,j) = reshape(v,nc,[]) * B(:,j)   (PWLinearControl.m:59-62 and twins)
-    __device__ __forceinline__ void eval(const SweepArgs &a, const double *rec, int j, long bb, double *u)
+    //   rec: grid-point record, bas: basis record of grid point j
+    __device__ __forceinline__ void eval(const SweepArgs &a, const double *rec, const double *bas, int j, long bb,
+                                         double *u)
     {
         if constexpr (UMODE == UMODE_UNIFORM) {
 #pragma unroll
-            for (int c = 0; c < nc; ++c) u[c] = rec[a.off_u + c];
+            for (int c = 0; c < nc; ++c) u[c] = rec[1 + c];
         } else if constexpr (UMODE == UMODE_GRID) {
             const int G = 2 * a.N + 1;
 #pragma unroll
             for (int c = 0; c < nc; ++c) u[c] = a.ug[soa((long)c * G + j, a.ldb, bb)];
         } else if constexpr (BMODE == BMODE_SPARSE) {
-            const int k = (int)rec[a.off_b];
-            const double w0 = rec[a.off_b + 1], w1 = rec[a.off_b + 2];
+            const int2 kk = *reinterpret_cast<const int2 *>(bas);
+            const int k = kk.x;
+            const double wE = bas[1], wO = bas[2];
             if (k != kcur) {   // uniform across the block: every trajectory shares the grid
-                const bool up = (k == kcur + 1), down = (k == kcur - 1);
-                if (up) {          // forward sweep: the window slides up by one knot
+                const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
 #pragma unroll
-                    for (int c = 0; c < nc; ++c) vlo[c] = vhi[c];
-                } else if (down) { // reverse sweep: slides down
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) vhi[c] = vlo[c];
-                }
-                if (!up) {
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) vlo[c] = a.v[soa((long)k * nc + c, a.ldb, bb)];
-                }
-                if (!down) {
-#pragma unroll
-                    for (int c = 0; c < nc; ++c)
-                        vhi[c] = (k + 1 < a.K) ? a.v[soa((long)(k + 1) * nc + c, a.ldb, bb)] : 0.0;
+                for (int c = 0; c < nc; ++c) {
+                    vE[c] = (ke < a.K) ? a.v[soa((long)ke * nc + c, a.ldb, bb)] : 0.0;
+                    vO[c] = (ko < a.K) ? a.v[soa((long)ko * nc + c, a.ldb, bb)] : 0.0;
                 }
                 kcur = k;
             }
+            // flags: bit0 = two non-zeros in the column; bit1 = (one non-zero) it sits on the odd slot
+            if (kk.y & 1) {
 #pragma unroll
-            for (int c = 0; c < nc; ++c) {
-                double s = vlo[c] * w0;            // w0 == 1, w1 == 0: exact copy of v (PWConstantControl)
-                if (w1 != 0.0) s = s + vhi[c] * w1;
-                u[c] = s;
+                for (int c = 0; c < nc; ++c) u[c] = (k & 1) ? vO[c] * wO + vE[c] * wE : vE[c] * wE + vO[c] * wO;
+            } else if (kk.y & 2) {
+#pragma unroll
+                for (int c = 0; c < nc; ++c) u[c] = vO[c] * wO;   // weight 1: exact copy of v (PWConstantControl)
+            } else {
+#pragma unroll
+                for (int c = 0; c < nc; ++c) u[c] = vE[c] * wE;
             }
         } else {
             const int K = KD > 0 ? KD : a.K;
 #pragma unroll
-            for (int c = 0; c < nc; ++c) u[c] = vd[c] * rec[a.off_b];
+            for (int c = 0; c < nc; ++c) u[c] = vd[c] * bas[0];
 #pragma unroll
             for (int k = 1; k < KA; ++k)
                 if (k < K) {
-                    const double bk = rec[a.off_b + k];
+                    const double bk = bas[k];
 #pragma unroll
                     for (int c = 0; c < nc; ++c) u[c] = u[c] + vd[k * nc + c] * bk;
                 }
@@ -168,63 +187,60 @@ template <int nc, int BMODE, int KD>
 struct GradAcc {
     static constexpr int KA = (KD > 0 ? KD : OCS_KDENSE_MAX);
     int kcur;
-    double lo[BMODE == BMODE_SPARSE ? nc : 1];
-    double hi[BMODE == BMODE_SPARSE ? nc : 1];
+    // sparse basis: accumulators of the two live knots {k, k+1}, held by knot parity (aE: even knot)
+    double aE[BMODE == BMODE_SPARSE ? nc : 1];
+    double aO[BMODE == BMODE_SPARSE ? nc : 1];
     double ad[BMODE == BMODE_DENSE ? KA * nc : 1];
 
-    __device__ __forceinline__ void init(const SweepArgs &a)
+    __device__ __forceinline__ void init()
     {
         kcur = -0x40000000;
         if constexpr (BMODE == BMODE_SPARSE) {
 #pragma unroll
-            for (int c = 0; c < nc; ++c) lo[c] = hi[c] = 0.0;
+            for (int c = 0; c < nc; ++c) aE[c] = aO[c] = 0.0;
         }
         if constexpr (BMODE == BMODE_DENSE) {
 #pragma unroll
             for (int k = 0; k < KA * nc; ++k) ad[k] = 0.0;
         }
-        (void)a;
     }
 
-    __device__ __forceinline__ void flush(const SweepArgs &a, int k, const double *val, long b, bool active)
+    // writes the finished knot k out and clears its accumulator
+    __device__ __forceinline__ void flush(const SweepArgs &a, int k, long b, bool active)
     {
-        if (k < 0 || k >= a.K || !active) return;
+        double *acc = (k & 1) ? aO : aE;
+        if (k >= 0 && k < a.K && active) {
 #pragma unroll
-        for (int c = 0; c < nc; ++c) {
-            const size_t idx = soa((long)k * nc + c, a.ldb, b);
-            a.dJdv[idx] = a.dJdv[idx] + val[c];   // buffer is zero-initialised; one owner thread per column
+            for (int c = 0; c < nc; ++c) {
+                const size_t idx = soa((long)k * nc + c, a.ldb, b);
+                a.dJdv[idx] = a.dJdv[idx] + acc[c];   // buffer is zero-initialised; one owner thread per column
+            }
         }
+#pragma unroll
+        for (int c = 0; c < nc; ++c) acc[c] = 0.0;
     }
 
-    __device__ __forceinline__ void add(const SweepArgs &a, const double *rec, const double *d, long b, bool active)
+    __device__ __forceinline__ void add(const SweepArgs &a, const double *bas, const double *d, long b, bool active)
     {
         if constexpr (BMODE == BMODE_SPARSE) {
-            const int k = (int)rec[a.off_b];
-            const double w0 = rec[a.off_b + 1], w1 = rec[a.off_b + 2];
-            if (k != kcur) {
-                if (k == kcur - 1) {           // window slides down by one knot
-                    flush(a, kcur + 1, hi, b, active);
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) { hi[c] = lo[c]; lo[c] = 0.0; }
-                } else {
-                    flush(a, kcur + 1, hi, b, active);
-                    flush(a, kcur, lo, b, active);
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) lo[c] = hi[c] = 0.0;
-                }
+            const int k = *reinterpret_cast<const int *>(bas);
+            const double wE = bas[1], wO = bas[2];
+            if (k != kcur) {                    // uniform across the block; ~K times per sweep
+                flush(a, kcur + 1, b, active);  // the window slides down: knot kcur+1 is complete
+                if (k != kcur - 1) flush(a, kcur, b, active);
                 kcur = k;
             }
 #pragma unroll
             for (int c = 0; c < nc; ++c) {
-                lo[c] = lo[c] + d[c] * w0;
-                if (w1 != 0.0) hi[c] = hi[c] + d[c] * w1;
+                aE[c] = aE[c] + d[c] * wE;
+                aO[c] = aO[c] + d[c] * wO;     // a zero weight adds an exact zero
             }
         } else if constexpr (BMODE == BMODE_DENSE) {
             const int K = KD > 0 ? KD : a.K;
 #pragma unroll
             for (int k = 0; k < KA; ++k)
                 if (k < K) {
-                    const double bk = rec[a.off_b + k];
+                    const double bk = bas[k];
 #pragma unroll
                     for (int c = 0; c < nc; ++c) ad[k * nc + c] = ad[k * nc + c] + d[c] * bk;
                 }
@@ -234,8 +250,8 @@ struct GradAcc {
     __device__ __forceinline__ void finish(const SweepArgs &a, long b, bool active)
     {
         if constexpr (BMODE == BMODE_SPARSE) {
-            flush(a, kcur + 1, hi, b, active);
-            flush(a, kcur, lo, b, active);
+            flush(a, kcur + 1, b, active);
+            flush(a, kcur, b, active);
         } else if constexpr (BMODE == BMODE_DENSE) {
             const int K = KD > 0 ? KD : a.K;
             if (active) {
@@ -251,36 +267,52 @@ struct GradAcc {
 };
 
 // ------------------------------------------------------------------ tile staging
-// Copies the grid-point records [2*i0, 2*(i0+ns)] and step records [i0, i0+ns) of one
-// tile into shared memory.  All threads of the block take part.
-__device__ __forceinline__ void stage_tile(const SweepArgs &a, int i0, int ns, double *gp, double *st)
+template <int RB>
+struct TileLayout {
+    static constexpr int S = OCS_TILE;
+    static constexpr int GP = (2 * S + 1) * RB;   // grid-point records
+    static constexpr int ST = 4 * S;              // step records
+};
+
+__device__ __forceinline__ void copy_to_smem(double *dst, const double *src, int ndoubles)
+{
+    // both sides are 16-byte aligned and ndoubles is even
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    const int cnt = ndoubles >> 1;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) d2[k] = s2[k];
+}
+
+// Copies the grid-point records [2*i0, 2*(i0+ns)], step records [i0, i0+ns) and (BW > 0) basis
+// records of one tile into shared memory.  All threads of the block take part.
+template <int RB>
+__device__ __forceinline__ void stage_tile(const SweepArgs &a, int i0, int ns, int BW, double *gp, double *st, double *bs)
 {
     __syncthreads();   // the previous tile has been consumed by every warp
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(a.gprec + (size_t)2 * i0 * a.R);
-        double2 *dst = reinterpret_cast<double2 *>(gp);
-        const int cnt = ((2 * ns + 1) * a.R) >> 1;   // R is even, records are 16-byte aligned
-        for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = src[k];
-    }
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(a.steprec + (size_t)4 * i0);
-        double2 *dst = reinterpret_cast<double2 *>(st);
-        const int cnt = ns * 2;
-        for (int k = threadIdx.x; k < cnt; k += blockDim.x) dst[k] = src[k];
-    }
+    copy_to_smem(gp, a.gprec + (size_t)2 * i0 * RB, (2 * ns + 1) * RB);
+    copy_to_smem(st, a.steprec + (size_t)4 * i0, 4 * ns);
+    if (BW > 0) copy_to_smem(bs, a.basrec + (size_t)2 * i0 * BW, (2 * ns + 1) * BW);
     __syncthreads();
 }
 
 // ------------------------------------------------------------------ forward sweep
 // RK4Integrator.m:28-56 for one trajectory per thread.
-template <class P, int UMODE, int BMODE, bool PB, int KD>
+template <class P, int UMODE, int BMODE, bool PB, int KD, bool GRIDS>
 __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
 {
     constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
-    constexpr bool TT = (!PB) && (P::ntt > 0);
-    const int N = a.N, S = a.S, R = a.R;
-    double *gp = sm;
-    double *st = sm + (size_t)(2 * S + 1) * R;
+    constexpr int HM = ocs_hoist_mode(UMODE, PB);
+    constexpr int RB = ocs_rec_width(nc, P::ntt(HM));
+    constexpr bool NEEDB = (UMODE == UMODE_COEF);
+    constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
+    typedef TileLayout<RB> TL;
+    const int BW = BWc >= 0 ? BWc : a.BW;
+    const int N = a.N;
+    double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
+    if (a.RB != RB || (NEEDB && a.BW != BW)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
+        return;
+    }
 
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = b < a.nb;
@@ -299,45 +331,59 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
     ControlEval<nc, UMODE, BMODE, KD> ctl;
     ctl.init(a, bb);
     double uL[nc], uM[nc], uR[nc];
+    double ttL[P::ntt(HM) > 0 ? P::ntt(HM) : 1];   // table values of the left node, carried from the previous step
+    double tL;
 
-    for (int i0 = 0; i0 < N; i0 += S) {
-        const int ns = (N - i0 < S) ? (N - i0) : S;
-        stage_tile(a, i0, ns, gp, st);
-        if (i0 == 0) ctl.eval(a, gp, 0, bb, uL);
+    double *xsp = a.xs + b;                        // running pointer into the node-state store
+    constexpr bool gridout = GRIDS;   // fetch variant: also writes the full grid, J row included
+
+    for (int i0 = 0; i0 < N; i0 += TL::S) {
+        const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
+        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
+        if (i0 == 0) {
+            ctl.eval(a, gp, bs, 0, bb, uL);
+            tL = gp[0];
+#pragma unroll
+            for (int k = 0; k < P::ntt(HM); ++k) ttL[k] = gp[1 + nc + k];
+        }
+#pragma unroll 4
         for (int s = 0; s < ns; ++s) {
             const int i = i0 + s;
-            const double *rL = gp + (size_t)(2 * s) * R, *rM = rL + R, *rR = rM + R;
+            const double *rM = gp + (2 * s + 1) * RB, *rR = rM + RB;
+            const double *bM = bs + (2 * s + 1) * BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h6 = st[4 * s + 3];
             if (active) {
-                if (a.xs) {
 #pragma unroll
-                    for (int c = 0; c < n; ++c) a.xs[soa((long)c * (N + 1) + i, a.ldb, b)] = y[c];
-                }
-                if (a.xgrid) {
+                for (int c = 0; c < n; ++c) xsp[(size_t)c * (N + 1) * a.ldb] = y[c];
+                if (gridout) {
 #pragma unroll
                     for (int c = 0; c < m; ++c) a.xgrid[c + (size_t)m * (i + (size_t)(N + 1) * b)] = y[c];
                 }
             }
-            ctl.eval(a, rM, 2 * i + 1, bb, uM);
-            ctl.eval(a, rR, 2 * i + 2, bb, uR);
+            xsp += a.ldb;
+            ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
+            ctl.eval(a, rR, bR, 2 * i + 2, bb, uR);
 
             double F[m], acc[m], ys[n];
-            P::template F<TT>(rL + 1, rL[0], y, uL, p, F);                       // F1   :39
+            P::template F<HM>(ttL, tL, y, uL, p, F);                             // F1   :39
 #pragma unroll
             for (int c = 0; c < m; ++c) acc[c] = F[c];
 #pragma unroll
             for (int c = 0; c < n; ++c) ys[c] = y[c] + h2 * F[c];                 // xK2  :40
-            P::template F<TT>(rM + 1, rM[0], ys, uM, p, F);                      // F2   :42
+            P::template F<HM>(rM + 1 + nc, rM[0], ys, uM, p, F);                 // F2   :42
 #pragma unroll
             for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
 #pragma unroll
             for (int c = 0; c < n; ++c) ys[c] = y[c] + h2 * F[c];                 // xK3  :43
-            P::template F<TT>(rM + 1, rM[0], ys, uM, p, F);                      // F3   :45
+            P::template F<HM>(rM + 1 + nc, rM[0], ys, uM, p, F);                 // F3   :45
 #pragma unroll
             for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
 #pragma unroll
             for (int c = 0; c < n; ++c) ys[c] = y[c] + h * F[c];                  // xK4  :46
-            P::template F<TT>(rR + 1, rR[0], ys, uR, p, F);                      // F4   :48
+            tL = rR[0];
+#pragma unroll
+            for (int k = 0; k < P::ntt(HM); ++k) ttL[k] = rR[1 + nc + k];
+            P::template F<HM>(ttL, tL, ys, uR, p, F);                            // F4   :48
 #pragma unroll
             for (int c = 0; c < m; ++c) y[c] = y[c] + h6 * (acc[c] + F[c]);       // :50-51
 #pragma unroll
@@ -346,11 +392,9 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
     }
 
     if (active) {
-        if (a.xs) {
 #pragma unroll
-            for (int c = 0; c < n; ++c) a.xs[soa((long)c * (N + 1) + N, a.ldb, b)] = y[c];
-        }
-        if (a.xgrid) {
+        for (int c = 0; c < n; ++c) xsp[(size_t)c * (N + 1) * a.ldb] = y[c];
+        if (gridout) {
 #pragma unroll
             for (int c = 0; c < m; ++c) a.xgrid[c + (size_t)m * (N + (size_t)(N + 1) * b)] = y[c];
         }
@@ -378,14 +422,24 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
 // sweep (16 B/step of HBM traffic instead of 64).  FB = fb_sweep variant: no dJdu; the
 // control on the grid is replaced by ControlChar(t, x, lam) and the normalised change
 // is reduced per trajectory (functions/fb_sweep.m:96,107-110).
-template <class P, int UMODE, int BMODE, bool PB, int KD, bool FB>
+template <class P, int UMODE, int BMODE, bool PB, int KD, bool FB, bool GRIDS>
 __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 {
     constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
-    constexpr bool TT = (!PB) && (P::ntt > 0);
-    const int N = a.N, S = a.S, R = a.R, G = 2 * N + 1;
-    double *gp = sm;
-    double *st = sm + (size_t)(2 * S + 1) * R;
+    constexpr int HM = ocs_hoist_mode(UMODE, PB);
+    constexpr int NT = P::ntt(HM);
+    constexpr int RB = ocs_rec_width(nc, NT);
+    constexpr bool NEEDB = (BMODE != BMODE_NONE);
+    constexpr bool GACC = NEEDB && !GRIDS && !FB;   // fold dJdu into dJdv (the fetch variant writes dJdu itself)
+    constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
+    typedef TileLayout<RB> TL;
+    const int BW = BWc >= 0 ? BWc : a.BW;
+    const int N = a.N, G = 2 * N + 1;
+    double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
+    if (a.RB != RB || (NEEDB && a.BW != BW)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
+        return;
+    }
 
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = b < a.nb;
@@ -400,103 +454,114 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
     for (int c = 0; c < m; ++c)
         lam[c] = a.lamT ? a.lamT[soa(c, a.ldl, a.ldl ? bb : 0)] : (c == n ? 1.0 : 0.0);   // :63-66
-    if (a.lamgrid && active) {
+    const bool lamout = GRIDS && a.lamgrid != nullptr, duout = GRIDS && a.dJdugrid != nullptr;
+    const bool want_du = GACC || duout;
+    if (lamout && active) {
 #pragma unroll
         for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (N + (size_t)(N + 1) * b)] = lam[c];
     }
 
     ControlEval<nc, UMODE, BMODE, KD> ctl;
     ctl.init(a, bb);
-    GradAcc<nc, BMODE, KD> gacc;
-    gacc.init(a);
+    GradAcc<nc, GACC ? BMODE : BMODE_NONE, KD> gacc;
+    gacc.init();
 
     double uL[nc], uM[nc], uR[nc], dcar[nc];
+    double ttR[NT > 0 ? NT : 1], tR;   // record values of the right node, carried from the previous iteration
     double y1[n], ynext[n];
-    double xR[n];            // FB: node state and costate to the right (for midpoint averages)
+    double xR[n];                      // FB: node state to the right (for midpoint averages)
     double maxchg = 0.0;
 #pragma unroll
     for (int c = 0; c < nc; ++c) dcar[c] = 0.0;
+    const double *xsp = a.xs + (size_t)(N - 1) * a.ldb + bb;   // node N-1
 #pragma unroll
-    for (int c = 0; c < n; ++c) ynext[c] = a.xs[soa((long)c * (N + 1) + (N - 1), a.ldb, bb)];
+    for (int c = 0; c < n; ++c) ynext[c] = xsp[(size_t)c * (N + 1) * a.ldb];
     if constexpr (FB) {
 #pragma unroll
-        for (int c = 0; c < n; ++c) xR[c] = a.xs[soa((long)c * (N + 1) + N, a.ldb, bb)];
+        for (int c = 0; c < n; ++c) xR[c] = xsp[(size_t)c * (N + 1) * a.ldb + a.ldb];
     }
 
-    const int i0_last = ((N - 1) / S) * S;
-    for (int i0 = i0_last; i0 >= 0; i0 -= S) {
-        const int ns = (N - i0 < S) ? (N - i0) : S;
-        stage_tile(a, i0, ns, gp, st);
-        if (i0 == i0_last) ctl.eval(a, gp + (size_t)(2 * ns) * R, 2 * N, bb, uR);
+    const int i0_last = ((N - 1) / TL::S) * TL::S;
+    for (int i0 = i0_last; i0 >= 0; i0 -= TL::S) {
+        const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
+        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
+        if (i0 == i0_last) {
+            const double *rE = gp + (2 * ns) * RB;
+            ctl.eval(a, rE, bs + (2 * ns) * BW, 2 * N, bb, uR);
+            tR = rE[0];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) ttR[k] = rE[1 + nc + k];
+        }
+#pragma unroll 2
         for (int s = ns - 1; s >= 0; --s) {
             const int i = i0 + s;
-            const double *rL = gp + (size_t)(2 * s) * R, *rM = rL + R, *rR = rM + R;
+            const double *rL = gp + (2 * s) * RB, *rM = rL + RB;
+            const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
 #pragma unroll
             for (int c = 0; c < n; ++c) y1[c] = ynext[c];
+            xsp -= a.ldb;
             if (i > 0) {   // prefetch the next node state: its HBM latency overlaps this step's arithmetic
 #pragma unroll
-                for (int c = 0; c < n; ++c) ynext[c] = a.xs[soa((long)c * (N + 1) + (i - 1), a.ldb, bb)];
+                for (int c = 0; c < n; ++c) ynext[c] = xsp[(size_t)c * (N + 1) * a.ldb];
             }
-            ctl.eval(a, rM, 2 * i + 1, bb, uM);
-            ctl.eval(a, rL, 2 * i, bb, uL);
+            ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
+            ctl.eval(a, rL, bL, 2 * i, bb, uL);
+            const double *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
+            const double tM = rM[0], tL = rL[0];
 
             // stage states of the forward step (RK4Integrator.m:39-46), recomputed
             double F[m], y2[n], y3[n], y4[n];
-            P::template F<TT>(rL + 1, rL[0], y1, uL, p, F);
+            P::template F<HM>(ttL, tL, y1, uL, p, F);
 #pragma unroll
             for (int c = 0; c < n; ++c) y2[c] = y1[c] + h2 * F[c];
-            P::template F<TT>(rM + 1, rM[0], y2, uM, p, F);
+            P::template F<HM>(ttM, tM, y2, uM, p, F);
 #pragma unroll
             for (int c = 0; c < n; ++c) y3[c] = y1[c] + h2 * F[c];
-            P::template F<TT>(rM + 1, rM[0], y3, uM, p, F);
+            P::template F<HM>(ttM, tM, y3, uM, p, F);
 #pragma unroll
             for (int c = 0; c < n; ++c) y4[c] = y1[c] + h * F[c];
 
             double k4[m], k3[m], k2[m], k1[m], g3[n], g2[n], g1[n], g0[n];
 #pragma unroll
             for (int c = 0; c < m; ++c) k4[c] = h6 * lam[c];                              // :73
-            P::template X<TT>(rR + 1, rR[0], y4, uR, p, k4, g3);                         // :74-75
+            P::template X<HM>(ttR, tR, y4, uR, p, k4, g3);                               // :74-75
 #pragma unroll
             for (int c = 0; c < n; ++c) k3[c] = h3 * lam[c] + h * g3[c];                  // :77
             k3[n] = h3 * lam[n];
-            P::template X<TT>(rM + 1, rM[0], y3, uM, p, k3, g2);                         // :78-79
+            P::template X<HM>(ttM, tM, y3, uM, p, k3, g2);                               // :78-79
 #pragma unroll
             for (int c = 0; c < n; ++c) k2[c] = h3 * lam[c] + h2 * g2[c];                 // :81
             k2[n] = h3 * lam[n];
-            P::template X<TT>(rM + 1, rM[0], y2, uM, p, k2, g1);                         // :82-83
+            P::template X<HM>(ttM, tM, y2, uM, p, k2, g1);                               // :82-83
 #pragma unroll
             for (int c = 0; c < n; ++c) k1[c] = h6 * lam[c] + h2 * g1[c];                 // :85
             k1[n] = h6 * lam[n];
-            P::template X<TT>(rL + 1, rL[0], y1, uL, p, k1, g0);                         // :86-88
+            P::template X<HM>(ttL, tL, y1, uL, p, k1, g0);                               // :86-88
 
-            if constexpr (!FB) {
-                if (BMODE != BMODE_NONE || a.dJdugrid) {
-                    // dJdu at the right node: stage 1 of step i+1 (carried) + stage 4 of step i   :112-120
-                    double d[nc], e[nc];
-                    P::template U<TT>(rR + 1, rR[0], y4, uR, p, k4, d);
-                    if (i < N - 1) {
+            if (want_du) {
+                // dJdu at the right node: stage 1 of step i+1 (carried) + stage 4 of step i   :112-120
+                double d[nc], e[nc];
+                P::template U<HM>(ttR, tR, y4, uR, p, k4, d);
 #pragma unroll
-                        for (int c = 0; c < nc; ++c) d[c] = dcar[c] + d[c];
-                    }
-                    gacc.add(a, rR, d, b, active);
-                    if (a.dJdugrid && active) {
+                for (int c = 0; c < nc; ++c) d[c] = dcar[c] + d[c];   // dcar == 0 at the right end
+                gacc.add(a, bR, d, b, active);
+                if (duout && active) {
 #pragma unroll
-                        for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 2) + (size_t)G * b)] = d[c];
-                    }
-                    // midpoint: stages 2 and 3   :105-109
-                    P::template U<TT>(rM + 1, rM[0], y2, uM, p, k2, d);
-                    P::template U<TT>(rM + 1, rM[0], y3, uM, p, k3, e);
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) d[c] = d[c] + e[c];
-                    gacc.add(a, rM, d, b, active);
-                    if (a.dJdugrid && active) {
-#pragma unroll
-                        for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 1) + (size_t)G * b)] = d[c];
-                    }
-                    // left node: stage 1 of this step, completed by the next iteration (or the left end :101-102)
-                    P::template U<TT>(rL + 1, rL[0], y1, uL, p, k1, dcar);
+                    for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 2) + (size_t)G * b)] = d[c];
                 }
+                // midpoint: stages 2 and 3   :105-109
+                P::template U<HM>(ttM, tM, y2, uM, p, k2, d);
+                P::template U<HM>(ttM, tM, y3, uM, p, k3, e);
+#pragma unroll
+                for (int c = 0; c < nc; ++c) d[c] = d[c] + e[c];
+                gacc.add(a, bM, d, b, active);
+                if (duout && active) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 1) + (size_t)G * b)] = d[c];
+                }
+                // left node: stage 1 of this step, completed by the next iteration (or the left end :101-102)
+                P::template U<HM>(ttL, tL, y1, uL, p, k1, dcar);
             }
 
             double lamR[n];
@@ -505,7 +570,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 lamR[c] = lam[c];
                 lam[c] = lam[c] + g1[c] + g2[c] + g3[c] + g0[c];                           // :86
             }
-            if (a.lamgrid && active) {
+            if (lamout && active) {
 #pragma unroll
                 for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (i + (size_t)(N + 1) * b)] = lam[c];
             }
@@ -514,7 +579,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 // uNew at the right node and at the midpoint of step i (midpoint x, lam = mean of the
                 // neighbouring nodes, the same formula the grid uses for t, RK4Integrator.m:23)
                 double un[nc], xm[n], lm[n];
-                P::template ControlChar<TT>(rR + 1, rR[0], xR, lamR, p, a.bounds, un);
+                P::template ControlChar<HM>(ttR, tR, xR, lamR, p, a.bounds, un);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);   // fb_sweep.m:107-108
@@ -524,7 +589,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 }
 #pragma unroll
                 for (int c = 0; c < n; ++c) { xm[c] = (y1[c] + xR[c]) / 2; lm[c] = (lam[c] + lamR[c]) / 2; }
-                P::template ControlChar<TT>(rM + 1, rM[0], xm, lm, p, a.bounds, un);
+                P::template ControlChar<HM>(ttM, tM, xm, lm, p, a.bounds, un);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     const double w = fabs(un[c] - uM[c]) / (a.uRelTol * fabs(uM[c]) + a.uAbsTol);
@@ -537,13 +602,16 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
             }
 #pragma unroll
             for (int c = 0; c < nc; ++c) uR[c] = uL[c];
+            tR = tL;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) ttR[k] = ttL[k];
         }
     }
 
     if constexpr (!FB) {
-        if (BMODE != BMODE_NONE || a.dJdugrid) {
-            gacc.add(a, gp, dcar, b, active);                                              // left end :101-102
-            if (a.dJdugrid && active) {
+        if (want_du) {
+            gacc.add(a, bs, dcar, b, active);                                              // left end :101-102
+            if (duout && active) {
 #pragma unroll
                 for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((size_t)G * b)] = dcar[c];
             }
@@ -554,7 +622,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         double lam0[n];
 #pragma unroll
         for (int c = 0; c < n; ++c) lam0[c] = lam[c];
-        P::template ControlChar<TT>(gp + 1, gp[0], xR, lam0, p, a.bounds, un);
+        P::template ControlChar<HM>(ttR, tR, xR, lam0, p, a.bounds, un);
 #pragma unroll
         for (int c = 0; c < nc; ++c) {
             const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);
@@ -572,21 +640,36 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 
 // ------------------------------------------------------------------ small helper kernels
 
-// Fills the time-table slots of the grid-point records: every sub-expression of the
-// right-hand sides that depends only on t and batch-uniform parameters is evaluated once
-// per grid point here (with the same device code the in-thread variant would run).
+// Fills the table slots of the grid-point records: every sub-expression of the right-hand
+// sides that is batch-uniform -- a function of t and shared parameters (HM_TIME) and, when
+// the control is shared too, of u (HM_TIME_CONTROL) -- is evaluated once per grid point here,
+// with the same device code the in-thread variant would run.
 template <class P>
-__device__ __forceinline__ void time_table_body(double *gprec, int G, int R, const double *p)
+__device__ __forceinline__ void table_body(double *gprec, int G, int hm, const double *p)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= G) return;
+    constexpr int nc = P::nc;
     double pr[P::np > 0 ? P::np : 1];
 #pragma unroll
     for (int k = 0; k < P::np; ++k) pr[k] = p[k];
-    double tt[P::ntt > 0 ? P::ntt : 1];
-    P::time_table(gprec[(size_t)j * R], pr, tt);
+    if (hm == HM_TIME) {
+        constexpr int NT = P::ntt(HM_TIME), RB = ocs_rec_width(nc, NT);
+        double *r = gprec + (size_t)j * RB;
+        double tt[NT > 0 ? NT : 1];
+        P::template table<HM_TIME>(r[0], r + 1, pr, tt);
 #pragma unroll
-    for (int k = 0; k < P::ntt; ++k) gprec[(size_t)j * R + 1 + k] = tt[k];
+        for (int k = 0; k < NT; ++k) r[1 + nc + k] = tt[k];
+    } else if (hm == HM_TIME_CONTROL) {
+        constexpr int NT = P::ntt(HM_TIME_CONTROL), RB = ocs_rec_width(nc, NT);
+        double *r = gprec + (size_t)j * RB;
+        double tt[NT > 0 ? NT : 1], u[nc];
+#pragma unroll
+        for (int c = 0; c < nc; ++c) u[c] = r[1 + c];
+        P::template table<HM_TIME_CONTROL>(r[0], u, pr, tt);
+#pragma unroll
+        for (int k = 0; k < NT; ++k) r[1 + nc + k] = tt[k];
+    }
 }
 
 }  // namespace OCS_NS
@@ -598,26 +681,45 @@ __device__ __forceinline__ void time_table_body(double *gprec, int G, int R, con
         ocs_fwd_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
     {                                                                                                  \
         extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::forward_body<P, UM, BM, (PB != 0), KD>(a, reinterpret_cast<double *>(ocs_smem2));      \
+        OCS_NS::forward_body<P, UM, BM, (PB != 0), KD, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
+    }                                                                                                  \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
+        ocs_fwdg_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                              \
+    {                                                                                                  \
+        extern __shared__ double2 ocs_smem2[];                                                         \
+        OCS_NS::forward_body<P, UM, BM, (PB != 0), KD, true>(a, reinterpret_cast<double *>(ocs_smem2)); \
     }
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD)                                                        \
     extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
         ocs_rev_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
     {                                                                                                  \
         extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::reverse_body<P, UM, BM, (PB != 0), KD, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
+        OCS_NS::reverse_body<P, UM, BM, (PB != 0), KD, false, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
+    }
+#define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD)                                                       \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
+        ocs_revg_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                              \
+    {                                                                                                  \
+        extern __shared__ double2 ocs_smem2[];                                                         \
+        OCS_NS::reverse_body<P, UM, BM, (PB != 0), KD, false, true>(a, reinterpret_cast<double *>(ocs_smem2)); \
     }
 #define OCS_FB_KERNEL(P, tag, PB)                                                                     \
     extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
         ocs_fbrev_##tag##_p##PB(const OCS_NS::SweepArgs a)                                             \
     {                                                                                                  \
         extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::reverse_body<P, 2, 0, (PB != 0), 0, true>(a, reinterpret_cast<double *>(ocs_smem2));   \
+        OCS_NS::reverse_body<P, 2, 0, (PB != 0), 0, true, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
     }
 #define OCS_TT_KERNEL(P, tag)                                                                         \
-    extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int R, const double *p)              \
+    extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int hm, const double *p)             \
     {                                                                                                  \
-        OCS_NS::time_table_body<P>(gprec, G, R, p);                                                    \
+        OCS_NS::table_body<P>(gprec, G, hm, p);                                                        \
+    }                                                                                                  \
+    extern "C" __global__ void ocs_info_##tag(int *o)                                                  \
+    {                                                                                                  \
+        o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
+        o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2);                                          \
+        o[6] = OCS_TILE; o[7] = OCS_THREADS;                                                           \
     }
 
 #define OCS_DEFINE_KERNELS_PB(P, tag, PB, KD)   \
@@ -631,6 +733,10 @@ __device__ __forceinline__ void time_table_body(double *gprec, int G, int R, con
     OCS_REV_KERNEL(P, tag, 1, 1, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 1, 2, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 2, 0, PB, KD)        \
+    OCS_REVG_KERNEL(P, tag, 0, 0, PB, KD)       \
+    OCS_REVG_KERNEL(P, tag, 1, 1, PB, KD)       \
+    OCS_REVG_KERNEL(P, tag, 1, 2, PB, KD)       \
+    OCS_REVG_KERNEL(P, tag, 2, 0, PB, KD)       \
     OCS_FB_KERNEL(P, tag, PB)
 
 #define OCS_DEFINE_KERNELS(P, tag, KD)   \

@@ -226,6 +226,34 @@ class CudaRK4Integrator:
                                                          _lib.dp(out["lam0"])))
         return out
 
+    # ------------------------------------------------------------------ device-resident variants
+    def set_stream(self, cuda_stream):
+        """Launch on the given cudaStream_t (an int, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self._lib.ocs_b200_set_stream(self._h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def synchronize(self):
+        self._ck(self._lib.ocs_b200_synchronize(self._h))
+
+    def evaluate_dev(self, prob, x0_ptr, Bt, v=None, v_ptr=None, J_ptr=0, xT_ptr=0, status_ptr=0,
+                     dJdv_ptr=0, lam0_ptr=0, lamT_ptr=0, lamT_nbatch=0, gradient=True):
+        """evaluate() on caller-owned DEVICE buffers in SoA layout [row][Bt] (raw pointers as ints):
+        nothing crosses PCIe.  v: shared host coefficients, or v_ptr: device [(nc*K)][Bt].
+        Asynchronous on the handle's stream."""
+        if self._control is None:
+            raise RuntimeError("attach_control(control) first")
+        self._bind(prob)
+        if v_ptr:
+            self._ck(self._lib.ocs_b200_set_control_v_dev(self._h, ctypes.c_void_p(int(v_ptr)), int(Bt)))
+        else:
+            self._set_v(v)
+        self._last_u = None
+        P = lambda a: ctypes.c_void_p(int(a)) if a else None
+        self._ck(self._lib.ocs_b200_compute_states_dev(self._h, P(x0_ptr), int(Bt), P(J_ptr), P(xT_ptr), P(status_ptr)))
+        self._Bt, self._single = int(Bt), False
+        if gradient:
+            self._ck(self._lib.ocs_b200_compute_adjoints_dev(self._h, P(lamT_ptr), int(lamT_nbatch), P(dJdv_ptr),
+                                                             P(lam0_ptr)))
+
     # ------------------------------------------------------------------ grids on request
     def fetch_states(self, b0=0, nb=None, segment=0):
         """x of RK4Integrator.m:54 for trajectories [b0, b0+nb): (m, N+1, nb)."""
