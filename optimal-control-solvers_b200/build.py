@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-                 "-Xptxas", "-v"]
+                 "-Xptxas", "-v"] + os.environ.get("OCS_EXTRA_NVCC_FLAGS", "").split()
 
 # (object name, source, extra flags)
 UNITS = [

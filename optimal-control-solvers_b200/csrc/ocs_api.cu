@@ -51,8 +51,9 @@ struct Segment {
     bool basis_dirty = true;
     cudaEvent_t rec_uploaded = nullptr;
     bool steps_uploaded = false;
-    double *d_xs = nullptr;   // node states [n][N+1][Bt]
-    size_t xs_cap = 0;        // doubles
+    double *d_xs_base = nullptr;   // allocation: 2*Bt doubles of slack, then node states [n][N+1][Bt]
+    double *d_xs = nullptr;        // = d_xs_base + 2*Bt
+    size_t xs_cap = 0;             // doubles (whole allocation)
     int R = 0;
     bool records_dirty = true;
 };
@@ -396,7 +397,14 @@ int build_records(H *h, int si)
                     // bit1 = the single non-zero sits on the odd slot
                     const int k = h->bk[j];
                     const bool two = h->bnnz[j] > 1, odd = (k & 1) != 0;
-                    int32_t kk[2] = {k, (two ? 1 : 0) | ((!two && odd) ? 2 : 0)};
+                    // bit2 (on midpoint records): the reverse sweep's knot window moves while it handles this
+                    // step's right node or midpoint, i.e. k differs from the grid point processed just before
+                    int moves = 0;
+                    if (j & 1) {
+                        const int kprev = (j + 2 < G) ? h->bk[j + 2] : -0x40000000;   // handled before point j+1
+                        moves = (h->bk[j + 1] != kprev) || (h->bk[j] != h->bk[j + 1]);
+                    }
+                    int32_t kk[2] = {k, (two ? 1 : 0) | ((!two && odd) ? 2 : 0) | (moves ? 4 : 0)};
                     memcpy(r, kk, sizeof kk);
                     r[1] = odd ? h->bw1[j] : h->bw0[j];
                     r[2] = odd ? h->bw0[j] : h->bw1[j];
@@ -652,7 +660,8 @@ int alloc_batch(H *h, long Bt)
     }
     for (int si = 0; si < (h->has_tail ? 2 : 1); ++si) {
         Segment &s = h->seg[si];
-        TRY(ensure_raw(h, &s.d_xs, &s.xs_cap, (size_t)n * (s.N + 1) * Bt));
+        TRY(ensure_raw(h, &s.d_xs_base, &s.xs_cap, (size_t)n * (s.N + 1) * Bt + 2 * (size_t)Bt));
+        s.d_xs = s.d_xs_base + 2 * (size_t)Bt;
     }
     (void)m;
     return 0;
@@ -791,7 +800,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
         cudaFree(h->seg[si].d_basrec);
         if (h->seg[si].h_rec) cudaFreeHost(h->seg[si].h_rec);
         if (h->seg[si].rec_uploaded) cudaEventDestroy(h->seg[si].rec_uploaded);
-        cudaFree(h->seg[si].d_xs);
+        cudaFree(h->seg[si].d_xs_base);
     }
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
                       &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg};

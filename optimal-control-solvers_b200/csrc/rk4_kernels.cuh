@@ -33,6 +33,9 @@
 #ifndef OCS_TILE
 #define OCS_TILE 32         // RK4 steps per shared-memory tile
 #endif
+#ifndef OCS_MINBLOCKS_REV
+#define OCS_MINBLOCKS_REV 1 // __launch_bounds__ min blocks/SM of the reverse kernels (register cap)
+#endif
 #ifndef OCS_KDENSE_MAX
 #define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
 #endif
@@ -79,7 +82,8 @@ struct SweepArgs {
     const double *p;        // [np] or [np][ldp]
     const double *v;        // UMODE_COEF: [(k*nc+c)][ldb]
     double *ug;             // UMODE_GRID: [nc][2N+1][ldb]   (fb_sweep updates it in place)
-    double *xs;             // node-state store [n][N+1][ldb]
+    double *xs;             // node-state store [n][N+1][ldb]; 2*ldb doubles of slack precede it so that the
+                            // reverse sweep's two-node prefetch never needs a bounds check
     // forward outputs
     double *J;              // [nb]
     int J_accumulate;       // J = J_in + J_segment (RK4InfiniteIntegrator.m:23)
@@ -247,6 +251,19 @@ struct GradAcc {
         }
     }
 
+    // sparse basis, window known not to move at this grid point
+    __device__ __forceinline__ void add_fast(const double *bas, const double *d)
+    {
+        if constexpr (BMODE == BMODE_SPARSE) {
+            const double wE = bas[1], wO = bas[2];
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+                aE[c] = aE[c] + d[c] * wE;
+                aO[c] = aO[c] + d[c] * wO;
+            }
+        }
+    }
+
     __device__ __forceinline__ void finish(const SweepArgs &a, long b, bool active)
     {
         if constexpr (BMODE == BMODE_SPARSE) {
@@ -331,8 +348,6 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
     ControlEval<nc, UMODE, BMODE, KD> ctl;
     ctl.init(a, bb);
     double uL[nc], uM[nc], uR[nc];
-    double ttL[P::ntt(HM) > 0 ? P::ntt(HM) : 1];   // table values of the left node, carried from the previous step
-    double tL;
 
     double *xsp = a.xs + b;                        // running pointer into the node-state store
     constexpr bool gridout = GRIDS;   // fetch variant: also writes the full grid, J row included
@@ -340,18 +355,14 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
     for (int i0 = 0; i0 < N; i0 += TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
-        if (i0 == 0) {
-            ctl.eval(a, gp, bs, 0, bb, uL);
-            tL = gp[0];
-#pragma unroll
-            for (int k = 0; k < P::ntt(HM); ++k) ttL[k] = gp[1 + nc + k];
-        }
+        if (i0 == 0) ctl.eval(a, gp, bs, 0, bb, uL);
 #pragma unroll 4
         for (int s = 0; s < ns; ++s) {
             const int i = i0 + s;
-            const double *rM = gp + (2 * s + 1) * RB, *rR = rM + RB;
+            const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bM = bs + (2 * s + 1) * BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h6 = st[4 * s + 3];
+            if constexpr (UMODE == UMODE_UNIFORM) ctl.eval(a, rL, bs, 2 * i, bb, uL);   // a shared-memory read
             if (active) {
 #pragma unroll
                 for (int c = 0; c < n; ++c) xsp[(size_t)c * (N + 1) * a.ldb] = y[c];
@@ -365,7 +376,7 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
             ctl.eval(a, rR, bR, 2 * i + 2, bb, uR);
 
             double F[m], acc[m], ys[n];
-            P::template F<HM>(ttL, tL, y, uL, p, F);                             // F1   :39
+            P::template F<HM>(rL + 1 + nc, rL[0], y, uL, p, F);                  // F1   :39
 #pragma unroll
             for (int c = 0; c < m; ++c) acc[c] = F[c];
 #pragma unroll
@@ -380,14 +391,13 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
             for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
 #pragma unroll
             for (int c = 0; c < n; ++c) ys[c] = y[c] + h * F[c];                  // xK4  :46
-            tL = rR[0];
-#pragma unroll
-            for (int k = 0; k < P::ntt(HM); ++k) ttL[k] = rR[1 + nc + k];
-            P::template F<HM>(ttL, tL, ys, uR, p, F);                            // F4   :48
+            P::template F<HM>(rR + 1 + nc, rR[0], ys, uR, p, F);                 // F4   :48
 #pragma unroll
             for (int c = 0; c < m; ++c) y[c] = y[c] + h6 * (acc[c] + F[c]);       // :50-51
+            if constexpr (UMODE != UMODE_UNIFORM) {   // per-trajectory controls are carried, not re-evaluated
 #pragma unroll
-            for (int c = 0; c < nc; ++c) uL[c] = uR[c];
+                for (int c = 0; c < nc; ++c) uL[c] = uR[c];
+            }
         }
     }
 
@@ -467,48 +477,46 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     gacc.init();
 
     double uL[nc], uM[nc], uR[nc], dcar[nc];
-    double ttR[NT > 0 ? NT : 1], tR;   // record values of the right node, carried from the previous iteration
-    double y1[n], ynext[n];
+    double y1[n], yn1[n], yn2[n];      // node states: current, and the next two (prefetched)
     double xR[n];                      // FB: node state to the right (for midpoint averages)
     double maxchg = 0.0;
 #pragma unroll
     for (int c = 0; c < nc; ++c) dcar[c] = 0.0;
     const double *xsp = a.xs + (size_t)(N - 1) * a.ldb + bb;   // node N-1
 #pragma unroll
-    for (int c = 0; c < n; ++c) ynext[c] = xsp[(size_t)c * (N + 1) * a.ldb];
+    for (int c = 0; c < n; ++c) {
+        yn1[c] = xsp[(size_t)c * (N + 1) * a.ldb];
+        yn2[c] = xsp[(size_t)c * (N + 1) * a.ldb - a.ldb];   // node N-2 (slack when N == 1)
+    }
     if constexpr (FB) {
 #pragma unroll
         for (int c = 0; c < n; ++c) xR[c] = xsp[(size_t)c * (N + 1) * a.ldb + a.ldb];
     }
+    xsp -= a.ldb;                                              // node N-2: the deepest prefetch so far
 
     const int i0_last = ((N - 1) / TL::S) * TL::S;
     for (int i0 = i0_last; i0 >= 0; i0 -= TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
-        if (i0 == i0_last) {
-            const double *rE = gp + (2 * ns) * RB;
-            ctl.eval(a, rE, bs + (2 * ns) * BW, 2 * N, bb, uR);
-            tR = rE[0];
-#pragma unroll
-            for (int k = 0; k < NT; ++k) ttR[k] = rE[1 + nc + k];
-        }
+        if (i0 == i0_last) ctl.eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb, uR);
 #pragma unroll 2
         for (int s = ns - 1; s >= 0; --s) {
             const int i = i0 + s;
-            const double *rL = gp + (2 * s) * RB, *rM = rL + RB;
+            const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
 #pragma unroll
-            for (int c = 0; c < n; ++c) y1[c] = ynext[c];
+            for (int c = 0; c < n; ++c) { y1[c] = yn1[c]; yn1[c] = yn2[c]; }
             xsp -= a.ldb;
-            if (i > 0) {   // prefetch the next node state: its HBM latency overlaps this step's arithmetic
+            // prefetch two nodes ahead (node i-2): the HBM latency overlaps two steps of arithmetic.
+            // Unconditional: for i < 2 it reads the slack in front of the store and is never used.
 #pragma unroll
-                for (int c = 0; c < n; ++c) ynext[c] = xsp[(size_t)c * (N + 1) * a.ldb];
-            }
+            for (int c = 0; c < n; ++c) yn2[c] = xsp[(size_t)c * (N + 1) * a.ldb];
+            if constexpr (UMODE == UMODE_UNIFORM) ctl.eval(a, rR, bR, 2 * i + 2, bb, uR);   // shared-memory reads
             ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
             ctl.eval(a, rL, bL, 2 * i, bb, uL);
-            const double *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
-            const double tM = rM[0], tL = rL[0];
+            const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
+            const double tR = rR[0], tM = rM[0], tL = rL[0];
 
             // stage states of the forward step (RK4Integrator.m:39-46), recomputed
             double F[m], y2[n], y3[n], y4[n];
@@ -545,7 +553,9 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 P::template U<HM>(ttR, tR, y4, uR, p, k4, d);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) d[c] = dcar[c] + d[c];   // dcar == 0 at the right end
-                gacc.add(a, bR, d, b, active);
+                // the host flags the steps in which the knot window moves; all others take the straight path
+                const bool moves = GACC && BMODE == BMODE_SPARSE ? (reinterpret_cast<const int *>(bM)[1] & 4) != 0 : true;
+                if (moves) gacc.add(a, bR, d, b, active); else gacc.add_fast(bR, d);
                 if (duout && active) {
 #pragma unroll
                     for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 2) + (size_t)G * b)] = d[c];
@@ -555,7 +565,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 P::template U<HM>(ttM, tM, y3, uM, p, k3, e);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) d[c] = d[c] + e[c];
-                gacc.add(a, bM, d, b, active);
+                if (moves) gacc.add(a, bM, d, b, active); else gacc.add_fast(bM, d);
                 if (duout && active) {
 #pragma unroll
                     for (int c = 0; c < nc; ++c) a.dJdugrid[c + (size_t)nc * ((2 * i + 1) + (size_t)G * b)] = d[c];
@@ -600,11 +610,10 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
                 for (int c = 0; c < n; ++c) xR[c] = y1[c];
             }
+            if constexpr (UMODE != UMODE_UNIFORM) {   // per-trajectory controls are carried, not re-evaluated
 #pragma unroll
-            for (int c = 0; c < nc; ++c) uR[c] = uL[c];
-            tR = tL;
-#pragma unroll
-            for (int k = 0; k < NT; ++k) ttR[k] = ttL[k];
+                for (int c = 0; c < nc; ++c) uR[c] = uL[c];
+            }
         }
     }
 
@@ -622,7 +631,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         double lam0[n];
 #pragma unroll
         for (int c = 0; c < n; ++c) lam0[c] = lam[c];
-        P::template ControlChar<HM>(ttR, tR, xR, lam0, p, a.bounds, un);
+        P::template ControlChar<HM>(gp + 1 + nc, gp[0], xR, lam0, p, a.bounds, un);
 #pragma unroll
         for (int c = 0; c < nc; ++c) {
             const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);
@@ -690,7 +699,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
         OCS_NS::forward_body<P, UM, BM, (PB != 0), KD, true>(a, reinterpret_cast<double *>(ocs_smem2)); \
     }
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD)                                                        \
-    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS, OCS_MINBLOCKS_REV)                                        \
         ocs_rev_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
     {                                                                                                  \
         extern __shared__ double2 ocs_smem2[];                                                         \
