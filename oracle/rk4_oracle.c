@@ -2,10 +2,10 @@
  *
  * TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load this library.
- * PARITY PINNING: see the header of oracle/rk4_oracle.py (no MATLAB/Octave in the
- * image; pinned by the reference's backprop property, golden vectors from the
- * reference .m files run under oracle/mlab, and agreement with the NumPy
- * restatement).
+ * PARITY PINNING: pinned against golden vectors produced by executing the reference's
+ * unmodified .m files under oracle/mlab (tests/golden/*.npz, tests/test_oracle_golden.py);
+ * see the header of oracle/rk4_oracle.py for what that does and does not cover (no
+ * MATLAB/Octave in the image; MATLAB's built-ins are restated).
  *
  * Plain C, one trajectory at a time, the exact operation order of
  *   Integrator/RK4Integrator.m:28-56   (compute_states)

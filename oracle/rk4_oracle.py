@@ -10,15 +10,21 @@ of /root/reference it follows.  Every routine accepts a trailing batch axis
 (``y`` of shape (m,) or (m, Bt)) because the reference's own F / dFdx_times_vec /
 dFdu_times_vec are written column-vectorised (tests/TestOCProblem.m:23,30).
 
-PARITY PINNING STATUS: the reference ships no numeric golden vectors and neither
-MATLAB nor Octave exists in this image.  This oracle is pinned
-by (1) the properties the reference's own tests/backprop_test.m checks (adjoint
-gradient == finite differences), (2) tests/TestOCProblem.m's closed forms,
-(3) golden vectors in tests/golden/ produced by executing the reference's
-UNMODIFIED .m files with the MATLAB-subset interpreter in oracle/mlab (generator
-script committed beside them) and (4) an mpmath 50-digit forward sweep.  MATLAB's
-builtins (linspace rounding, mtimes summation order, exp) are restated, not run:
-where that matters the test tolerances say so.
+PARITY PINNING STATUS: pinned against the reference's own source.  The reference
+ships no numeric golden vectors and neither MATLAB nor Octave exists in this image
+(SURVEY.md section 8c), so the reference's UNMODIFIED .m files (RK4Integrator.m,
+RK4InfiniteIntegrator.m, the three Control classes, TestOCProblem.m and the script
+tests/backprop_test.m) are executed by the MATLAB-subset interpreter in oracle/mlab;
+their outputs are committed as tests/golden/*.npz (generator:
+tests/golden/generate_golden.py) and tests/test_oracle_golden.py holds this module and
+the C restatement to them: grids, step sizes, basis matrices and control-grid indices
+bit-identical, sweeps to 1e-13.  What that run does NOT pin are MATLAB's built-ins,
+which oracle/mlab/builtins.py restates (linspace rounding, mtimes summation order, exp,
+griddedInterpolant's formula): a genuine MATLAB run could differ from these vectors by a
+few ulp in exp()/BLAS products, far inside the 1e-10 bar, and -- only if MathWorks'
+linspace rounded differently from the documented formula -- in PWConstant indices.
+Further self-checks: tests/test_oracle_properties.py (adjoint == finite differences as
+tests/backprop_test.m prints, RK4 order, an mpmath 40-digit forward sweep).
 """
 from __future__ import annotations
 

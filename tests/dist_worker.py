@@ -1,0 +1,37 @@
+"""Worker of tests/test_host_logic.py::test_gather_over_gloo_world_size_2 (CPU, gloo)."""
+import importlib
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world = int(sys.argv[1]), int(sys.argv[2])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("optimal-control-solvers_b200.host.dist")
+    total = 1001                                   # ragged on purpose
+    b0, b1 = d.shard_range(total, rank, world)
+    J_full = torch.arange(total, dtype=torch.float64) * 0.5
+    J = J_full[b0:b1].clone()
+    got = d.gather_ragged(J, world, rank, total)
+    assert torch.equal(got, J_full)
+    # equal shards (the bench's weak-scaling layout)
+    Bt = 64
+    Jl = torch.full((Bt,), float(rank), dtype=torch.float64)
+    xT = torch.full((2, Bt), float(rank) + 0.25, dtype=torch.float64)
+    J_all, xT_all = d.gather_results(Jl, xT, world)
+    assert J_all.shape == (world * Bt,) and xT_all.shape == (world, 2, Bt)
+    for r in range(world):
+        assert torch.all(J_all[r * Bt:(r + 1) * Bt] == r) and torch.all(xT_all[r] == r + 0.25)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("gather ok", rank)
+
+
+if __name__ == "__main__":
+    main()
