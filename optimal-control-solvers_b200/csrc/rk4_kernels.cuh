@@ -463,7 +463,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     double lam[m];
 #pragma unroll
     for (int c = 0; c < m; ++c)
-        lam[c] = a.lamT ? a.lamT[soa(c, a.ldl, a.ldl ? bb : 0)] : (c == n ? 1.0 : 0.0);   // :63-66
+        lam[c] = a.lamT ? (a.ldl ? a.lamT[soa(c, a.ldl, bb)] : a.lamT[c]) : (c == n ? 1.0 : 0.0);   // :63-66
     const bool lamout = GRIDS && a.lamgrid != nullptr, duout = GRIDS && a.dJdugrid != nullptr;
     const bool want_du = GACC || duout;
     if (lamout && active) {

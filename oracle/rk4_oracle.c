@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load this library.
  * PARITY PINNING: pinned against golden vectors produced by executing the reference's
- * unmodified .m files under oracle/mlab (tests/golden/*.npz, tests/test_oracle_golden.py);
+ * unmodified .m files under oracle/mlab (the .npz files in tests/golden, tests/test_oracle_golden.py);
  * see the header of oracle/rk4_oracle.py for what that does and does not cover (no
  * MATLAB/Octave in the image; MATLAB's built-ins are restated).
  *
