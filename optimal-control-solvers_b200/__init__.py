@@ -6,5 +6,7 @@ from ._lib import OcsError
 from .host import (ChebyshevControl, Control, CudaRK4InfiniteIntegrator, CudaRK4Integrator, OCProblem,
                    PWConstantControl, PWLinearControl, TestOCProblem, matlab_linspace)
 
-__all__ = ["OcsError", "CudaRK4Integrator", "CudaRK4InfiniteIntegrator", "Control", "PWConstantControl",
+from .codegen import CodegenProblem, harvest_chain_problem, make_from_symbolic, test_problem_symbolic  # noqa: E402
+
+__all__ = ["make_from_symbolic", "CodegenProblem", "test_problem_symbolic", "harvest_chain_problem","OcsError", "CudaRK4Integrator", "CudaRK4InfiniteIntegrator", "Control", "PWConstantControl",
            "PWLinearControl", "ChebyshevControl", "OCProblem", "TestOCProblem", "matlab_linspace"]

@@ -1,0 +1,296 @@
+"""CUDA backend of make_from_symbolic (functions/make_from_symbolic.m).
+
+The reference derives, with the Symbolic Math Toolbox, the Hamiltonian H = f + lam*g
+(:11), the adjoint right-hand side -grad_x H (:14), dH/du (:17) and the control
+characterisation solving dH/du = 0 (:20-23, clamped to the bounds at :111), and turns
+them into MATLAB function handles with matlabFunction (:27-31).  This backend performs
+the same derivations with SymPy and prints them as CUDA `__device__` functions -- the
+`struct Problem` that csrc/rk4_kernels.cuh is instantiated on -- which the library
+compiles for sm_100a with NVRTC (ocs_b200_set_problem_source).  It emits the v2 plugin
+triple the RK4 path consumes (OCProblem/OCProblem.m:3-21):
+
+    F                = [g; f]                                       (objective integrand in the last row)
+    dFdx_times_vec   = (dg/dx)' v_x + v_J df/dx                      (last row 0)
+    dFdu_times_vec   = (dg/du)' v_x + v_J df/du
+    ControlChar      = clamp(solve(dFdu_times_vec(t,y,u,[lam;1]) = 0, u), bounds)
+
+Input contract = the reference's (:1-8): symbolic objective and state right-hand side in
+the variables t, x1..xn, lam1..lamn, u1..um and the parameters named by the fields of the
+params struct, in field order.
+
+Hoisting: every maximal sub-expression that is batch-uniform -- a function of (t, params)
+when the parameters are shared by the batch (HM_TIME), additionally of u when the control
+is shared too (HM_TIME_CONTROL) -- is evaluated once per grid point into the record's
+table instead of once per trajectory (see rk4_kernels.cuh).
+"""
+from __future__ import annotations
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+from ..host.problems import OCProblem
+from .. import _lib
+
+__all__ = ["make_from_symbolic", "CodegenProblem"]
+
+
+class _CudaPrinter(C99CodePrinter):
+    """C printer with small integer powers as products (pow(double, int) is slow and inexact)."""
+
+    def _print_Pow(self, expr):
+        b, e = expr.base, expr.exp
+        if e.is_Integer and 2 <= int(e) <= 4:
+            s = self.parenthesize(b, 50)
+            return "(" + "*".join([s] * int(e)) + ")"
+        if e.is_Integer and -4 <= int(e) <= -1:
+            s = self.parenthesize(b, 50)
+            return "(1.0/(" + "*".join([s] * (-int(e))) + "))"
+        if e == sp.Rational(1, 2):
+            return f"sqrt({self._print(b)})"
+        return super()._print_Pow(expr)
+
+    def _print_Rational(self, expr):
+        return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+    def _print_Integer(self, expr):
+        return f"{int(expr)}.0" if abs(int(expr)) < 2 ** 53 else super()._print_Integer(expr)
+
+
+def _count_ops(exprs):
+    """FLOPs of the CSE'd DAG: add/sub/mul/div/function = 1 each."""
+    repl, red = sp.cse(list(exprs), optimizations="basic")
+    total = 0
+    for e in [r for _, r in repl] + list(red):
+        total += int(sp.count_ops(e, visual=False))
+    return total
+
+
+class CodegenProblem(OCProblem):
+    """An OCProblem whose right-hand sides exist as generated CUDA source."""
+
+    def __init__(self, nStates, nControls, params, ControlBounds, source, sym, flops, MinMax="Min"):
+        self.nStates, self.nControls = nStates, nControls
+        self.param_names = list(params.keys())
+        self.params = dict(params)
+        import numpy as np
+        self.ControlBounds = np.asarray(ControlBounds, dtype=np.float64).reshape(-1, 2)
+        self.source = source
+        self.sym = sym            # dict of SymPy objects (for tests / documentation)
+        self.flops = flops        # dict C_F, C_X, C_U
+        self.MinMax = MinMax
+
+    def param_array(self):
+        import numpy as np
+        vals = [np.atleast_1d(np.asarray(self.params[k], dtype=np.float64)) for k in self.param_names]
+        nb = max(v.size for v in vals) if vals else 1
+        if nb == 1:
+            return np.array([v[0] for v in vals])
+        return np.stack([np.broadcast_to(v, (nb,)) for v in vals])
+
+    def bind(self, lib, handle):
+        _lib.check(lib.ocs_b200_set_problem_source(handle, self.source.encode(), self.nStates, self.nControls,
+                                                   len(self.param_names), None), handle)
+
+
+def _hoist(exprs, uniform_syms, grid_syms, table, prefix="tt"):
+    """Replaces, in every expression, the maximal sub-expressions whose free symbols are all
+    uniform and that depend on at least one grid symbol (t or a shared control) by table symbols.
+    `table` (list of (symbol, expr)) is extended in place and shared between functions."""
+    known = {e: s for s, e in table}
+
+    def visit(e):
+        fs = e.free_symbols
+        if not e.is_Atom and fs and fs <= uniform_syms and (fs & grid_syms):
+            if e not in known:
+                s = sp.Symbol(f"{prefix}{len(table)}")
+                table.append((s, e))
+                known[e] = s
+            return known[e]
+        if e.is_Atom:
+            return e
+        # for Add/Mul keep the uniform part of the argument list together so that it is hoisted as one
+        if isinstance(e, (sp.Add, sp.Mul)):
+            uni = [a for a in e.args if a.free_symbols <= uniform_syms and not a.is_Number]
+            rest = [a for a in e.args if a not in uni]
+            grid_uni = [a for a in uni if a.free_symbols & grid_syms]
+            if len(grid_uni) >= 1 and len(uni) >= 2 and rest:
+                packed = e.func(*uni)
+                return e.func(visit(packed), *[visit(a) for a in rest])
+        return e.func(*[visit(a) for a in e.args])
+    return [visit(sp.sympify(e)) for e in exprs]
+
+
+def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, ControlBounds, MinMax="Min",
+                       solve_control=True):
+    """CUDA-backend twin of functions/make_from_symbolic.m:1.
+
+    symObjective : SymPy expression (or string) of the running cost f(t, x, u)
+    symStateRHS  : sequence of nStates expressions g_i(t, x, u)
+    params       : dict name -> value (scalar, or an array of per-trajectory values); the order of the
+                   keys is the order of the generated parameter vector p (make_from_symbolic.m:3-4)
+    ControlBounds: nControls x 2
+    """
+    n, nc = int(nStates), int(nControls)
+    t = sp.Symbol("t")
+    x = sp.symbols(f"x1:{n + 1}")
+    lam = sp.symbols(f"lam1:{n + 1}")
+    u = sp.symbols(f"u1:{nc + 1}")
+    pnames = list(params.keys())
+    psyms = [sp.Symbol(k) for k in pnames]
+    local = {s.name: s for s in (t, *x, *lam, *u, *psyms)}
+    f = sp.sympify(symObjective, locals=local)
+    g = [sp.sympify(e, locals=local) for e in symStateRHS]
+    if len(g) != n:
+        raise ValueError("symStateRHS must have nStates rows")
+
+    vJ = sp.Symbol("vJ")
+    vx = sp.symbols(f"v1:{n + 1}")
+    # F = [g; f]
+    F = list(g) + [f]
+    # dFdx_times_vec(v) = (dg/dx)' v_x + v_J df/dx            (make_from_symbolic.m:11-14 with lam -> v_x, 1 -> v_J)
+    X = [sum(sp.diff(g[i], x[k]) * vx[i] for i in range(n)) + vJ * sp.diff(f, x[k]) for k in range(n)]
+    # dFdu_times_vec(v) = (dg/du)' v_x + v_J df/du            (:17)
+    U = [sum(sp.diff(g[i], u[c]) * vx[i] for i in range(n)) + vJ * sp.diff(f, u[c]) for c in range(nc)]
+    # ControlChar: dH/du = 0 with H = f + lam*g               (:11,:17,:20-23)
+    H = f + sum(lam[i] * g[i] for i in range(n))
+    dHdu = [sp.diff(H, u[c]) for c in range(nc)]
+    CC = None
+    if solve_control:
+        try:
+            sol = sp.solve(dHdu, list(u), dict=True)
+            if sol:
+                CC = [sp.simplify(sol[0][u[c]]) for c in range(nc)]
+        except Exception:
+            CC = None
+
+    pr = _CudaPrinter()
+    subs_common = {}
+    for i in range(n):
+        subs_common[x[i]] = sp.Symbol(f"y[{i}]")
+        subs_common[vx[i]] = sp.Symbol(f"v[{i}]")
+        subs_common[lam[i]] = sp.Symbol(f"lam[{i}]")
+    subs_common[vJ] = sp.Symbol(f"v[{n}]")
+    for c in range(nc):
+        subs_common[u[c]] = sp.Symbol(f"u[{c}]")
+    for k, s in enumerate(psyms):
+        subs_common[s] = sp.Symbol(f"p[{k}]")
+
+    def emit_body(exprs, out, table_syms):
+        sub = dict(subs_common)
+        for k, s in enumerate(table_syms):
+            sub[s] = sp.Symbol(f"tt[{k}]")
+        repl, red = sp.cse(list(exprs), symbols=sp.numbered_symbols("z"), optimizations="basic")
+        lines = []
+        for s, e in repl:
+            lines.append(f"            const double {s} = {pr.doprint(e.xreplace(sub))};")
+        for k, e in enumerate(red):
+            lines.append(f"            {out}[{k}] = {pr.doprint(e.xreplace(sub))};")
+        return "\n".join(lines)
+
+    uniform = {1: {t, *psyms}, 2: {t, *psyms, *u}}
+    grid = {1: {t}, 2: {t, *u}}
+    variants = {}
+    tables = {}
+    for hm in (0, 1, 2):
+        if hm == 0:
+            variants[hm] = dict(F=F, X=X, U=U, CC=CC)
+            tables[hm] = []
+            continue
+        table = []
+        Fh = _hoist(F, uniform[hm], grid[hm], table)
+        Xh = _hoist(X, uniform[hm], grid[hm], table)
+        Uh = _hoist(U, uniform[hm], grid[hm], table)
+        CCh = _hoist(CC, uniform[hm], grid[hm], table) if CC is not None else None
+        variants[hm] = dict(F=Fh, X=Xh, U=Uh, CC=CCh)
+        tables[hm] = table
+
+    def per_hm(fn, out):
+        parts = []
+        for hm in (0, 1, 2):
+            exprs = variants[hm][fn]
+            kw = "if" if hm == 0 else "else if"
+            parts.append(f"        {kw} constexpr (HM == {hm}) {{\n{emit_body(exprs, out, [s for s, _ in tables[hm]])}\n        }}")
+        return "\n".join(parts)
+
+    def table_code():
+        parts = []
+        for hm in (1, 2):
+            kw = "if" if hm == 1 else "else if"
+            exprs = [e for _, e in tables[hm]]
+            body = emit_body(exprs, "tt", []) if exprs else ""
+            parts.append(f"        {kw} constexpr (HM == {hm}) {{\n{body}\n        }}")
+        return "\n".join(parts)
+
+    sig = "const double *tt, double t, const double *y, const double *u, const double *p"
+    unused = "(void)tt; (void)t; (void)y; (void)u; (void)p;"
+    lo_hi = "\n".join(f"            o[{c}] = fmin(bounds[{2 * c + 1}], fmax(bounds[{2 * c}], o[{c}]));" for c in range(nc))
+    if CC is not None:
+        cc_body = per_hm("CC", "o")
+        cc_src = f"""    template <int HM>
+    __device__ __forceinline__ static void ControlChar(const double *tt, double t, const double *y, const double *lam,
+                                                       const double *p, const double *bounds, double *o)
+    {{
+        (void)tt; (void)t; (void)y; (void)lam; (void)p;
+        const double *u = nullptr; (void)u;
+{cc_body}
+        {{
+{lo_hi}
+        }}
+    }}"""
+    else:
+        cc_src = """    template <int HM>
+    __device__ __forceinline__ static void ControlChar(const double *, double, const double *, const double *,
+                                                       const double *, const double *, double *o)
+    {
+        for (int c = 0; c < nc; ++c) o[c] = nan("");   // dH/du = 0 has no closed-form solution: fb_sweep unavailable
+    }"""
+    source = f"""// generated by optimal-control-solvers_b200/codegen/make_from_symbolic.py -- do not edit
+// states: {', '.join(map(str, x))}   controls: {', '.join(map(str, u))}   params: {', '.join(pnames)}
+// f = {f}
+// g = {g}
+namespace ocs_gen {{
+struct Problem {{
+    static constexpr int n = {n}, nc = {nc}, np = {len(pnames)};
+    __host__ __device__ static constexpr int ntt(int hm) {{ return hm == 1 ? {len(tables[1])} : (hm == 2 ? {len(tables[2])} : 0); }}
+
+    // batch-uniform sub-expressions, once per grid point
+    template <int HM>
+    __device__ __forceinline__ static void table(double t, const double *u, const double *p, double *tt)
+    {{
+        (void)t; (void)u; (void)p; (void)tt;
+{table_code()}
+    }}
+
+    // F = [g; f]   (OCProblem.m:9-11)
+    template <int HM>
+    __device__ __forceinline__ static void F({sig}, double *o)
+    {{
+        {unused}
+{per_hm("F", "o")}
+    }}
+
+    // dFdx' * v, last row (zero) implicit   (OCProblem.m:13-16)
+    template <int HM>
+    __device__ __forceinline__ static void X({sig}, const double *v, double *o)
+    {{
+        {unused} (void)v;
+{per_hm("X", "o")}
+    }}
+
+    // dFdu' * v   (OCProblem.m:18-19)
+    template <int HM>
+    __device__ __forceinline__ static void U({sig}, const double *v, double *o)
+    {{
+        {unused} (void)v;
+{per_hm("U", "o")}
+    }}
+
+    // argmin_u H clamped to ControlBounds   (make_from_symbolic.m:20-23,111)
+{cc_src}
+}};
+}}  // namespace ocs_gen
+"""
+    flops = dict(C_F=_count_ops(F), C_X=_count_ops(X), C_U=_count_ops(U))
+    sym = dict(t=t, x=x, lam=lam, u=u, params=psyms, vx=vx, vJ=vJ, f=f, g=g, F=F, X=X, U=U, H=H, dHdu=dHdu, CC=CC,
+               tables=tables)
+    return CodegenProblem(n, nc, params, ControlBounds, source, sym, flops, MinMax=MinMax)

@@ -32,7 +32,7 @@ OCS_DEFINE_KERNELS(ocs_fast::TestOCProblem, test_fast, 0)
 #define REV(UM, BM, PB) (const void *)OCS_CAT5(ocs_rev_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define FWDG(UM, BM, PB) (const void *)OCS_CAT5(ocs_fwdg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define REVG(UM, BM, PB) (const void *)OCS_CAT5(ocs_revg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
-#define FBR(PB) (const void *)OCS_CAT3(ocs_fbrev_, OCS_TAGNAME, _p##PB)
+#define FBR(PB) (const void *)OCS_CAT3(ocs_fbrev_, OCS_TAGNAME, _u2_b0_p##PB)
 
 extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
 {

@@ -86,10 +86,12 @@ std::string default_include_dir()
 
 }  // namespace
 
-// Compiles `source` (which defines `namespace ocs_gen { struct Problem {...}; }` with static
-// constexpr n, nc, np, ntt) and fills `table` with the kernels of the resulting library.
-int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int strict, const char *include_dir,
-                        ocs_kernel_table *table, void **library, std::string *log)
+// Compiles `source` (which defines `namespace ocs_gen { struct Problem {...}; }`) followed by
+// `unit` -- one or more OCS_*_KERNEL macro invocations -- and returns the named kernels of the
+// resulting library.  Sweep variants are compiled one at a time, on first use: a 6-state problem
+// takes a second or two per variant instead of a minute for all of them.
+int ocs_compile_unit(const char *source, const char *unit, int strict, const char *include_dir,
+                     const char *const *names, int nnames, const void **kernels, void **library, std::string *log)
 {
     Nvrtc rt;
     if (!load_nvrtc(rt, log)) return OCS_B200_ERR_COMPILE;
@@ -98,10 +100,9 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
     src += "#define OCS_NS ocs_gen\n";
     src += "#include \"rk4_kernels.cuh\"\n";
     src += source;
-    src += "\nstatic_assert(ocs_gen::Problem::n == " + std::to_string(n) + ", \"state count mismatch\");\n";
-    src += "static_assert(ocs_gen::Problem::nc == " + std::to_string(nc) + ", \"control count mismatch\");\n";
-    src += "static_assert(ocs_gen::Problem::np == " + std::to_string(np) + ", \"parameter count mismatch\");\n";
-    src += "OCS_DEFINE_KERNELS(ocs_gen::Problem, gen, " + std::to_string(kd) + ")\n";
+    src += "\n";
+    src += unit;
+    src += "\n";
 
     nvrtcProgram prog = nullptr;
     nvrtcResult r = rt.CreateProgram(&prog, src.c_str(), "ocs_generated_problem.cu", 0, nullptr, nullptr);
@@ -111,7 +112,7 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
     }
     const std::string inc = std::string("-I") + (include_dir ? std::string(include_dir) : default_include_dir());
     std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", inc.c_str(),
-                                      strict ? "--fmad=false" : "--fmad=true", "-default-device"};
+                                      strict ? "--fmad=false" : "--fmad=true"};
     r = rt.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t logsz = 0;
     rt.GetProgramLogSize(prog, &logsz);
@@ -134,72 +135,63 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int s
         *log += "\nnvrtcGetCUBIN returned nothing";
         return OCS_B200_ERR_COMPILE;
     }
-
     cudaLibrary_t lib = nullptr;
     cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) {
         *log += std::string("\ncudaLibraryLoadData: ") + cudaGetErrorString(e);
         return OCS_B200_ERR_CUDA;
     }
-    auto get = [&](const std::string &name) -> const void * {
-        cudaKernel_t k = nullptr;
-        if (cudaLibraryGetKernel(&k, lib, name.c_str()) != cudaSuccess) {
+    for (int k = 0; k < nnames; ++k) {
+        cudaKernel_t kern = nullptr;
+        if (cudaLibraryGetKernel(&kern, lib, names[k]) != cudaSuccess) {
             cudaGetLastError();
-            return nullptr;
+            *log += std::string("\ncompiled library lacks kernel ") + names[k];
+            cudaLibraryUnload(lib);
+            return OCS_B200_ERR_COMPILE;
         }
-        return (const void *)k;
-    };
+        kernels[k] = (const void *)kern;
+    }
+    *library = (void *)lib;
+    return 0;
+}
+
+// Base unit of a generated problem: the table-fill and info kernels; fills the problem constants
+// of `table` (every sweep entry stays null until ocs_compile_unit resolves it).
+int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, const char *include_dir,
+                        ocs_kernel_table *table, void **library, std::string *log)
+{
+    std::string unit;
+    unit += "static_assert(ocs_gen::Problem::n == " + std::to_string(n) + ", \"state count mismatch\");\n";
+    unit += "static_assert(ocs_gen::Problem::nc == " + std::to_string(nc) + ", \"control count mismatch\");\n";
+    unit += "static_assert(ocs_gen::Problem::np == " + std::to_string(np) + ", \"parameter count mismatch\");\n";
+    unit += "OCS_TT_KERNEL(ocs_gen::Problem, gen)\n";
+    const char *names[2] = {"ocs_tt_gen", "ocs_info_gen"};
+    const void *kern[2] = {nullptr, nullptr};
+    int rc = ocs_compile_unit(source, unit.c_str(), strict, include_dir, names, 2, kern, library, log);
+    if (rc != 0) return rc;
     memset(table, 0, sizeof *table);
-    table->n = n;
-    table->nc = nc;
-    table->np = np;
-    table->kd = kd;
-    table->threads = 128;
-    const int combos_f[4][2] = {{0, 0}, {1, 1}, {1, 2}, {2, 0}};
-    const int combos_r[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 0}};
-    bool ok = true;
-    for (int pb = 0; pb < 2; ++pb) {
-        char name[96];
-        for (auto &c : combos_f) {
-            snprintf(name, sizeof name, "ocs_fwd_gen_u%d_b%d_p%d", c[0], c[1], pb);
-            ok &= (table->fwd[c[0]][c[1]][pb] = get(name)) != nullptr;
-            snprintf(name, sizeof name, "ocs_fwdg_gen_u%d_b%d_p%d", c[0], c[1], pb);
-            ok &= (table->fwdg[c[0]][c[1]][pb] = get(name)) != nullptr;
-            snprintf(name, sizeof name, "ocs_revg_gen_u%d_b%d_p%d", c[0], c[1], pb);
-            ok &= (table->revg[c[0]][c[1]][pb] = get(name)) != nullptr;
-        }
-        for (auto &c : combos_r) {
-            snprintf(name, sizeof name, "ocs_rev_gen_u%d_b%d_p%d", c[0], c[1], pb);
-            ok &= (table->rev[c[0]][c[1]][pb] = get(name)) != nullptr;
-        }
-        snprintf(name, sizeof name, "ocs_fbrev_gen_p%d", pb);
-        ok &= (table->fbrev[pb] = get(name)) != nullptr;
-    }
-    ok &= (table->tt = get("ocs_tt_gen")) != nullptr;
-    const void *info = get("ocs_info_gen");
-    if (!ok || !info) {
-        *log += "\ncompiled library lacks an expected kernel";
-        cudaLibraryUnload(lib);
-        return OCS_B200_ERR_COMPILE;
-    }
-    // ask the compiled code for its hoisted-table widths and tile constants
+    table->tt = kern[0];
     int *d_info = nullptr, inf[8] = {0};
-    e = cudaMalloc(&d_info, sizeof inf);
+    cudaError_t e = cudaMalloc(&d_info, sizeof inf);
     if (e == cudaSuccess) {
         void *args[] = {(void *)&d_info};
-        e = cudaLaunchKernel(info, dim3(1), dim3(1), args, 0, nullptr);
+        e = cudaLaunchKernel(kern[1], dim3(1), dim3(1), args, 0, nullptr);
         if (e == cudaSuccess) e = cudaMemcpy(inf, d_info, sizeof inf, cudaMemcpyDeviceToHost);
         cudaFree(d_info);
     }
     if (e != cudaSuccess) {
-        *log += std::string("\nocs_gen_info launch: ") + cudaGetErrorString(e);
-        cudaLibraryUnload(lib);
+        *log += std::string("\nocs_info_gen launch: ") + cudaGetErrorString(e);
+        cudaLibraryUnload((cudaLibrary_t)*library);
+        *library = nullptr;
         return OCS_B200_ERR_CUDA;
     }
+    table->n = inf[0];
+    table->nc = inf[1];
+    table->np = inf[2];
     for (int hm = 0; hm < 3; ++hm) table->ntt[hm] = inf[3 + hm];
     table->tile = inf[6];
     table->threads = inf[7];
-    *library = (void *)lib;
+    table->kd = 0;
     return 0;
 }
 

@@ -30,8 +30,10 @@ using ocs_host::SweepArgs;
 extern "C" void ocs_builtin_table_test_fast(ocs_kernel_table *t);
 extern "C" void ocs_builtin_table_test_strict(ocs_kernel_table *t);
 // nvrtc_problem.cu
-int ocs_compile_problem(const char *source, int n, int nc, int np, int kd, int strict, const char *include_dir,
+int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, const char *include_dir,
                         ocs_kernel_table *table, void **library, std::string *log);
+int ocs_compile_unit(const char *source, const char *unit, int strict, const char *include_dir,
+                     const char *const *names, int nnames, const void **kernels, void **library, std::string *log);
 void ocs_unload_problem(void *library);
 
 namespace {
@@ -81,7 +83,7 @@ struct ocs_b200_handle {
     // problem
     bool have_problem = false;
     ocs_kernel_table kt{};
-    void *gen_library = nullptr;
+    std::vector<void *> gen_libraries;
     std::string gen_source, gen_include;
     int gen_n = 0, gen_nc = 0, gen_np = 0;
     bool is_generated = false;
@@ -550,6 +552,43 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward)
 
 int pb_index(const H *h) { return h->params_nbatch > 1 ? 1 : 0; }
 
+enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB };
+
+// The kernel of one sweep variant.  Built-in problems have every variant compiled in; generated
+// problems compile the variant with NVRTC the first time it is needed.
+int resolve(H *h, int kind, int um, int bm, int pb, const void **out)
+{
+    const void **slot = kind == KIND_FWD ? &h->kt.fwd[um][bm][pb]
+                      : kind == KIND_FWDG ? &h->kt.fwdg[um][bm][pb]
+                      : kind == KIND_REV ? &h->kt.rev[um][bm][pb]
+                      : kind == KIND_REVG ? &h->kt.revg[um][bm][pb] : &h->kt.fbrev[pb];
+    if (!*slot && h->is_generated) {
+        static const char *macro[] = {"OCS_FWD_KERNEL", "OCS_FWDG_KERNEL", "OCS_REV_KERNEL", "OCS_REVG_KERNEL", "OCS_FB_KERNEL"};
+        static const char *prefix[] = {"ocs_fwd_", "ocs_fwdg_", "ocs_rev_", "ocs_revg_", "ocs_fbrev_"};
+        char unit[256], name[96];
+        const int kd = bm == 2 ? h->K : 0;
+        if (kind == KIND_FB) {
+            snprintf(unit, sizeof unit, "%s(ocs_gen::Problem, gen, %d)", macro[kind], pb);
+            snprintf(name, sizeof name, "%sgen_u2_b0_p%d", prefix[kind], pb);
+        } else {
+            snprintf(unit, sizeof unit, "%s(ocs_gen::Problem, gen, %d, %d, %d, %d)", macro[kind], um, bm, pb, kd);
+            snprintf(name, sizeof name, "%sgen_u%d_b%d_p%d", prefix[kind], um, bm, pb);
+        }
+        const char *names[1] = {name};
+        const void *kern[1] = {nullptr};
+        void *lib = nullptr;
+        std::string log;
+        int rc = ocs_compile_unit(h->gen_source.c_str(), unit, h->math_mode == OCS_B200_MATH_STRICT,
+                                  h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log);
+        if (rc != 0) return h->fail(rc, "kernel %s of the generated problem did not compile:\n%s", name, log.c_str());
+        h->gen_libraries.push_back(lib);
+        *slot = kern[0];
+    }
+    if (!*slot) return h->fail(OCS_B200_ERR_ARG, "this control/basis/parameter combination has no kernel variant");
+    *out = *slot;
+    return 0;
+}
+
 int main_umode(const H *h) { return seg_umode(h, 0); }
 
 // forward sweep(s) over trajectories [b0, b0+nb) of the resident batch; xgrid optional (fetch)
@@ -582,7 +621,9 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         } else if (um == 2) {
             a.ug = h->d_ug.p + b0;
         }
-        TRY(launch(h, (d_xgrid ? h->kt.fwdg : h->kt.fwd)[um][bm][pb_index(h)], a, true));
+        const void *kern = nullptr;
+        TRY(resolve(h, d_xgrid ? KIND_FWDG : KIND_FWD, um, bm, pb_index(h), &kern));
+        TRY(launch(h, kern, a, true));
     }
     return 0;
 }
@@ -641,7 +682,9 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         }
         const bool grids = a.lamgrid || a.dJdugrid;
         if (grids && um != 1) bm = 0;   // the fetch variants write dJdu itself; only UMODE_COEF needs the basis
-        TRY(launch(h, (grids ? h->kt.revg : h->kt.rev)[um][bm][pb_index(h)], a, false));
+        const void *kern = nullptr;
+        TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
+        TRY(launch(h, kern, a, false));
     }
     return 0;
 }
@@ -813,7 +856,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     cudaFree(h->d_errflag);
     for (int k = 0; k < 4; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
-    if (h->gen_library) ocs_unload_problem(h->gen_library);
+    for (void *lib : h->gen_libraries) ocs_unload_problem(lib);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
     delete h;
@@ -856,15 +899,15 @@ int ocs_b200_set_problem_source(ocs_b200_handle *h, const char *cuda_source, int
         h->gen_n = n;
         h->gen_nc = nc;
         h->gen_np = np;
-        const int kd = (h->basis_kind == BASIS_DENSE) ? h->K : 0;
         std::string log;
         ocs_kernel_table kt{};
         void *lib = nullptr;
-        int rc = ocs_compile_problem(cuda_source, n, nc, np, kd, h->math_mode == OCS_B200_MATH_STRICT,
+        int rc = ocs_compile_problem(cuda_source, n, nc, np, h->math_mode == OCS_B200_MATH_STRICT,
                                      h->gen_include.empty() ? nullptr : h->gen_include.c_str(), &kt, &lib, &log);
         if (rc != 0) return h->fail(rc, "generated problem did not compile:\n%s", log.c_str());
-        if (h->gen_library) ocs_unload_problem(h->gen_library);
-        h->gen_library = lib;
+        for (void *old : h->gen_libraries) ocs_unload_problem(old);
+        h->gen_libraries.clear();
+        h->gen_libraries.push_back(lib);
         h->kt = kt;
         h->have_problem = true;
         h->is_generated = true;
@@ -964,10 +1007,12 @@ int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
             h->bk.assign(G, 0);
             for (int j = 0; j < G; ++j) h->bnnz[j] = K;
         }
-        // a generated problem is specialised on the dense basis size
+        // a generated problem's dense-basis kernels are specialised on K: forget them when K changes
         if (h->is_generated && h->basis_kind == BASIS_DENSE && h->kt.kd != K) {
-            std::string src = h->gen_source, inc = h->gen_include;
-            TRY(ocs_b200_set_problem_source(h, src.c_str(), h->gen_n, h->gen_nc, h->gen_np, inc.empty() ? nullptr : inc.c_str()));
+            for (int um = 0; um < 3; ++um)
+                for (int pb = 0; pb < 2; ++pb)
+                    h->kt.fwd[um][2][pb] = h->kt.rev[um][2][pb] = h->kt.fwdg[um][2][pb] = h->kt.revg[um][2][pb] = nullptr;
+            h->kt.kd = K;
         }
         h->ctrl_mode = CTRL_NONE;   // coefficients belong to the previous basis
         mark_dirty(h);
@@ -1331,7 +1376,10 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             a.xT = h->d_xT.p;
             a.status = h->d_status;
             a.frozen = h->d_frozen;
-            TRY(launch(h, h->kt.fwd[2][0][pb_index(h)], a, true));
+            const void *kf = nullptr, *kr = nullptr;
+            TRY(resolve(h, KIND_FWD, 2, 0, pb_index(h), &kf));
+            TRY(resolve(h, KIND_FB, 2, 0, pb_index(h), &kr));
+            TRY(launch(h, kf, a, true));
             SweepArgs r;
             base_args(h, 0, r);
             r.nb = Bt;
@@ -1344,7 +1392,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             r.relax = relax;
             r.max_change = h->d_maxchg.p;
             r.frozen = h->d_frozen;
-            TRY(launch(h, h->kt.fbrev[pb_index(h)], r, false));
+            TRY(launch(h, kr, r, false));
             CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
             fb_update_kernel<<<(unsigned)((Bt + 255) / 256), 256, 0, h->stream>>>(h->d_maxchg.p, h->d_frozen, h->d_sweeps,
                                                                                 sweep, Bt, d_nopen);

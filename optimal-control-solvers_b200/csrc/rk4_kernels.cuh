@@ -683,42 +683,27 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
 
 }  // namespace OCS_NS
 
-// Kernel entry points.  OCS_DEFINE_KERNELS(P, tag) emits the extern "C" __global__
-// wrappers of every sweep variant for problem P; the host looks them up by name.
-#define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD)                                                        \
-    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
-        ocs_fwd_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
+// Kernel entry points.  Each macro emits one extern "C" __global__ wrapper; the host looks the
+// kernels up by name (built-in problems: OCS_DEFINE_KERNELS instantiates every variant at build
+// time; generated problems: nvrtc_problem.cu compiles single variants on demand).
+#define OCS_KERNEL_(prefix, body_call, tag, UM, BM, PB, LB)                                            \
+    extern "C" __global__ void __launch_bounds__(OCS_THREADS, LB)                                      \
+        prefix##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                                 \
     {                                                                                                  \
         extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::forward_body<P, UM, BM, (PB != 0), KD, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
-    }                                                                                                  \
-    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
-        ocs_fwdg_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                              \
-    {                                                                                                  \
-        extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::forward_body<P, UM, BM, (PB != 0), KD, true>(a, reinterpret_cast<double *>(ocs_smem2)); \
+        OCS_NS::body_call(a, reinterpret_cast<double *>(ocs_smem2));                                   \
     }
-#define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD)                                                        \
-    extern "C" __global__ void __launch_bounds__(OCS_THREADS, OCS_MINBLOCKS_REV)                                        \
-        ocs_rev_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                               \
-    {                                                                                                  \
-        extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::reverse_body<P, UM, BM, (PB != 0), KD, false, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
-    }
-#define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD)                                                       \
-    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
-        ocs_revg_##tag##_u##UM##_b##BM##_p##PB(const OCS_NS::SweepArgs a)                              \
-    {                                                                                                  \
-        extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::reverse_body<P, UM, BM, (PB != 0), KD, false, true>(a, reinterpret_cast<double *>(ocs_smem2)); \
-    }
-#define OCS_FB_KERNEL(P, tag, PB)                                                                     \
-    extern "C" __global__ void __launch_bounds__(OCS_THREADS)                                          \
-        ocs_fbrev_##tag##_p##PB(const OCS_NS::SweepArgs a)                                             \
-    {                                                                                                  \
-        extern __shared__ double2 ocs_smem2[];                                                         \
-        OCS_NS::reverse_body<P, 2, 0, (PB != 0), 0, true, false>(a, reinterpret_cast<double *>(ocs_smem2)); \
-    }
+#define OCS_COMMA ,
+#define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD) \
+    OCS_KERNEL_(ocs_fwd_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false>, tag, UM, BM, PB, 1)
+#define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
+    OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
+#define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
+    OCS_KERNEL_(ocs_rev_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA false>, tag, UM, BM, PB, OCS_MINBLOCKS_REV)
+#define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
+    OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA true>, tag, UM, BM, PB, 1)
+#define OCS_FB_KERNEL(P, tag, PB) \
+    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA true OCS_COMMA false>, tag, 2, 0, PB, 1)
 #define OCS_TT_KERNEL(P, tag)                                                                         \
     extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int hm, const double *p)             \
     {                                                                                                  \
@@ -736,6 +721,10 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     OCS_FWD_KERNEL(P, tag, 1, 1, PB, KD)        \
     OCS_FWD_KERNEL(P, tag, 1, 2, PB, KD)        \
     OCS_FWD_KERNEL(P, tag, 2, 0, PB, KD)        \
+    OCS_FWDG_KERNEL(P, tag, 0, 0, PB, KD)       \
+    OCS_FWDG_KERNEL(P, tag, 1, 1, PB, KD)       \
+    OCS_FWDG_KERNEL(P, tag, 1, 2, PB, KD)       \
+    OCS_FWDG_KERNEL(P, tag, 2, 0, PB, KD)       \
     OCS_REV_KERNEL(P, tag, 0, 0, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 0, 1, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 0, 2, PB, KD)        \

@@ -1,0 +1,136 @@
+"""make_from_symbolic CUDA backend: derivations and emitted source (CPU) and NVRTC-compiled
+sweeps against the oracle (GPU)."""
+import importlib
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import sympy as sp
+
+from gen_util import oracle_problem
+from util import TEST_PARAMS, TOL, relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cg(ocs):
+    return importlib.import_module("optimal-control-solvers_b200.codegen")
+
+
+def test_derivations_reproduce_TestOCProblem(cg):
+    """SymPy derives exactly the hand-written products of tests/TestOCProblem.m:29-38 and
+    the control characterisation lam exp(rt)/(2c)."""
+    p = cg.test_problem_symbolic()
+    s = p.sym
+    x, u, v1, vJ = s["x"][0], s["u"][0], s["vx"][0], s["vJ"]
+    c, m, r = s["params"]
+    t = s["t"]
+    assert sp.simplify(s["F"][0] - (x * (m - x) - u)) == 0
+    assert sp.simplify(s["F"][1] - sp.exp(-r * t) * (x ** 2 + c * u ** 2)) == 0
+    assert sp.simplify(s["X"][0] - ((m - 2 * x) * v1 + 2 * sp.exp(-r * t) * x * vJ)) == 0
+    assert sp.simplify(s["U"][0] - (-v1 + 2 * c * sp.exp(-r * t) * u * vJ)) == 0
+    assert sp.simplify(s["CC"][0] - s["lam"][0] * sp.exp(r * t) / (2 * c)) == 0
+    assert p.flops == dict(C_F=10, C_X=8, C_U=7)
+    assert "struct Problem" in p.source and "static constexpr int n = 1, nc = 1, np = 3;" in p.source
+    assert p.param_names == ["c", "m", "r"] and np.array_equal(p.param_array(), [1.5, 3.0, 0.05])
+
+
+def test_six_state_problem_source_compiles_for_sm100a(cg):
+    """The generated source is valid CUDA for sm_100a together with the sweep kernels (nvcc here;
+    NVRTC does the same at run time on the GPU box)."""
+    p = cg.harvest_chain_problem()
+    assert p.nStates == 6 and p.nControls == 2 and len(p.param_names) == 6
+    assert p.sym["CC"] is not None
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "gen.cu")
+        with open(src, "w") as f:
+            f.write('#define OCS_NS ocs_gen\n#include "rk4_kernels.cuh"\n' + p.source +
+                    "\nOCS_TT_KERNEL(ocs_gen::Problem, gen)\nOCS_FWD_KERNEL(ocs_gen::Problem, gen, 0, 0, 0, 0)\n"
+                    "OCS_REV_KERNEL(ocs_gen::Problem, gen, 0, 1, 0, 0)\n")
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1",
+                            "-I", os.path.join(ROOT, "optimal-control-solvers_b200", "csrc"), "-cubin", "-o",
+                            os.path.join(d, "gen.cubin"), src], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_oracle_twin_of_generated_problem(cg, oracle):
+    """The lambdified SymPy twin agrees with the oracle's hand-written TestOCProblem."""
+    p = cg.test_problem_symbolic()
+    g = oracle_problem(oracle, p)
+    ref = oracle.TestOCProblem(**TEST_PARAMS)
+    rng = np.random.default_rng(0)
+    y, u, v = rng.random((2, 5)), rng.random((1, 5)), rng.random((2, 5))
+    assert relerr(g.F(0.7, y, u), ref.F(0.7, y, u)) < 1e-15
+    assert relerr(g.dFdx_times_vec(0.7, y, u, v), ref.dFdx_times_vec(0.7, y, u, v)) < 1e-15
+    assert relerr(g.dFdu_times_vec(0.7, y, u, v), ref.dFdu_times_vec(0.7, y, u, v)) < 1e-15
+
+
+# ------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("math", ["fast", "strict"])
+def test_generated_test_problem_matches_builtin_and_oracle(ocs, oracle, cg, math):
+    tspan = ocs.matlab_linspace(0.0, 10.0, 301)
+    gen, builtin = cg.test_problem_symbolic(), ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(.5, 2.5, (1, 500))
+    res = {}
+    for name, prob in (("gen", gen), ("builtin", builtin)):
+        integ = ocs.CudaRK4Integrator(tspan, math=math)
+        ctl = ocs.PWLinearControl(integ.t, 31, 1)
+        integ.attach_control(ctl)
+        v = np.random.default_rng(1).random(31)
+        res[name] = integ.evaluate(prob, x0, v)
+        res[name + "_pv"] = integ.evaluate(prob, x0, np.random.default_rng(2).random((31, 500)))
+        integ.close()
+    ref = oracle.C.evaluate(list(TEST_PARAMS.values()), tspan, ctl.B, x0, v)
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(res["gen"][key], ref[key]) < TOL, key
+        assert relerr(res["gen"][key], res["builtin"][key]) < TOL, key
+        assert relerr(res["gen_pv"][key], res["builtin_pv"][key]) < TOL, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,K", [("PWLinearControl", 11), ("ChebyshevControl", 17)])
+def test_six_state_problem_vs_oracle(ocs, oracle, cg, kind, K):
+    """cfg3's problem (6 states, 2 controls) at a size the NumPy oracle finishes in seconds."""
+    prob = cg.harvest_chain_problem()
+    oprob = oracle_problem(oracle, prob)
+    N, Bt = 120, 40
+    tspan = ocs.matlab_linspace(0.0, 6.0, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ointeg = oracle.RK4Integrator(tspan)
+    ctl = getattr(ocs, kind)(integ.t, K, 2)
+    octl = getattr(oracle, kind)(ointeg.t, K, 2)
+    assert np.array_equal(ctl.B, octl.B)
+    integ.attach_control(ctl)
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    if kind == "ChebyshevControl":
+        v = np.vstack([rng.uniform(.2, .8, (2, Bt)), 0.05 * rng.standard_normal((2 * (K - 1), Bt))])
+    else:
+        v = rng.random((2 * K, Bt))
+    out = integ.evaluate(prob, x0, v)
+    u = octl.compute_u(v)
+    x, J = ointeg.compute_states(oprob, x0, u)
+    lam, dJdu = ointeg.compute_adjoints(oprob, u)
+    dJdv = octl.compute_dJdv(dJdu)
+    assert relerr(out["J"], J) < TOL and relerr(out["xT"], x[:-1, -1]) < TOL
+    assert relerr(out["dJdv"], dJdv) < TOL and relerr(out["lam0"], lam[:, 0]) < TOL
+    # shared control + grids through the literal Integrator API
+    xg, Jg = integ.compute_states(prob, x0[:, 0], v=v[:, 0])
+    lg, dug = integ.compute_adjoints(prob, grids=True)
+    assert relerr(xg, x[:, :, 0]) < TOL and relerr(lg, lam[:, :, 0]) < TOL and relerr(dug, dJdu[:, :, 0]) < TOL
+    # fb_sweep with the generated ControlChar
+    G = 2 * N + 1
+    u0 = np.full((2, G), 0.4)
+    fb = integ.fb_sweep(prob, x0[:, :4], u0, nSWEEPS=40, relax=0.5)
+    ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, 0], u0.copy(), oprob.control_char, nSWEEPS=40, relax=0.5)
+    assert bool(fb["converged"][0]) == ref["converged"] and fb["sweeps"][0] == ref["sweeps"]
+    assert relerr(fb["J"][0], ref["J"]) < 1e-8
