@@ -1,0 +1,240 @@
+/* ocs_b200_mex.c -- MEX gateway between the MATLAB classes in this directory and the C ABI of
+ * include/ocs_b200.h (libocs_b200.so).
+ *
+ *     out = ocs_b200_mex(command, args...)
+ *
+ * One thin dispatcher: every command unpacks mxArrays into plain pointers, calls exactly one
+ * ocs_b200_* entry point, and packs the outputs.  MATLAB owns every prhs (read-only) and every
+ * plhs created here; the library never keeps a host pointer past a call.  A non-zero status is
+ * turned into a MATLAB error (mexErrMsgIdAndTxt) AFTER temporaries are released; nothing
+ * throws across the C ABI.  The handle travels as a uint64 scalar and is freed by
+ * delete(obj) -> 'destroy' (CudaRK4Integrator.m).
+ *
+ * Build (MATLAB):  mex -I../../include ocs_b200_mex.c -L.. -locs_b200          (see build_mex.m)
+ * Not compiled in this repository's image (no MATLAB / mex.h); tests/test_mex_gateway.py compiles it
+ * against a stub mex.h and drives it end to end.
+ */
+#include <stdint.h>
+#include <string.h>
+
+#include "mex.h"
+#include "ocs_b200.h"
+
+#define FAIL_IF(cond, id, msg)                     \
+    do {                                           \
+        if (cond) mexErrMsgIdAndTxt(id, "%s", msg);\
+    } while (0)
+
+static ocs_b200_handle *get_handle(const mxArray *a)
+{
+    FAIL_IF(!mxIsUint64(a) || mxGetNumberOfElements(a) != 1, "ocs_b200:handle", "handle must be a uint64 scalar");
+    uint64_t v = *(const uint64_t *)mxGetData(a);
+    FAIL_IF(v == 0, "ocs_b200:handle", "integrator handle was already deleted");
+    return (ocs_b200_handle *)(uintptr_t)v;
+}
+
+static const double *dbl(const mxArray *a, const char *what)
+{
+    if (mxIsEmpty(a)) return NULL;
+    if (!mxIsDouble(a) || mxIsComplex(a)) mexErrMsgIdAndTxt("ocs_b200:type", "%s must be a real double array", what);
+    return mxGetPr(a);
+}
+
+static double scalar(const mxArray *a) { return mxGetScalar(a); }
+
+/* pages along the last dimension: size(a, d) for d = ndims wanted (1 if absent) */
+static long dim(const mxArray *a, int d)
+{
+    mwSize nd = mxGetNumberOfDimensions(a);
+    const mwSize *s = mxGetDimensions(a);
+    return d < (int)nd ? (long)s[d] : 1;
+}
+
+static void check(int rc, ocs_b200_handle *h)
+{
+    if (rc != 0) mexErrMsgIdAndTxt("ocs_b200:failed", "ocs_b200 error %d: %s", rc, ocs_b200_last_error(h));
+}
+
+static mxArray *int32_row(long n)
+{
+    mwSize d[2];
+    d[0] = 1;
+    d[1] = (mwSize)n;
+    return mxCreateNumericArray(2, d, mxINT32_CLASS, mxREAL);
+}
+
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    char cmd[64];
+    FAIL_IF(nrhs < 1 || !mxIsChar(prhs[0]) || mxGetString(prhs[0], cmd, sizeof cmd) != 0, "ocs_b200:command",
+            "first argument must be a command string");
+
+    /* ---- h = mex('create', tspan, tspanExtra | [], device, math_mode)      RK4Integrator.m:16-25 */
+    if (!strcmp(cmd, "create")) {
+        FAIL_IF(nrhs < 5, "ocs_b200:nargin", "create(tspan, tspanExtra, device, math_mode)");
+        const double *ts = dbl(prhs[1], "tspan"), *te = dbl(prhs[2], "tspanExtra");
+        int N = (int)mxGetNumberOfElements(prhs[1]) - 1;
+        int N2 = te ? (int)mxGetNumberOfElements(prhs[2]) - 1 : 0;
+        ocs_b200_handle *h = NULL;
+        int rc = ocs_b200_create(N, ts, N2, te, (int)scalar(prhs[3]), (int)scalar(prhs[4]), &h);
+        if (rc != 0) mexErrMsgIdAndTxt("ocs_b200:create", "ocs_b200 error %d: %s", rc, ocs_b200_last_error(NULL));
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *(uint64_t *)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)h;
+        return;
+    }
+    FAIL_IF(nrhs < 2, "ocs_b200:nargin", "missing handle");
+    ocs_b200_handle *h = get_handle(prhs[1]);
+
+    if (!strcmp(cmd, "destroy")) {                                   /* delete(obj) */
+        ocs_b200_destroy(h);
+        return;
+    }
+    if (!strcmp(cmd, "get_grid")) {                                  /* [t, h] = mex('get_grid', h, segment) */
+        int seg = nrhs > 2 ? (int)scalar(prhs[2]) : 0;
+        int N = 0;
+        /* sizes come from the caller's tspan: ask for t with a generous first call */
+        FAIL_IF(nrhs < 4, "ocs_b200:nargin", "get_grid(h, segment, N)");
+        N = (int)scalar(prhs[3]);
+        plhs[0] = mxCreateDoubleMatrix(1, 2 * N + 1, mxREAL);
+        mxArray *hh = mxCreateDoubleMatrix(1, N, mxREAL);
+        int rc = ocs_b200_get_grid(h, seg, mxGetPr(plhs[0]), mxGetPr(hh));
+        if (nlhs > 1) plhs[1] = hh; else mxDestroyArray(hh);
+        check(rc, h);
+        return;
+    }
+    if (!strcmp(cmd, "set_problem_builtin")) {
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_problem_builtin(h, id)");
+        check(ocs_b200_set_problem_builtin(h, (int)scalar(prhs[2])), h);
+        return;
+    }
+    if (!strcmp(cmd, "set_problem_source")) {                        /* (h, source, n, nc, np, include_dir) */
+        FAIL_IF(nrhs < 6, "ocs_b200:nargin", "set_problem_source(h, source, n, nc, np [, include_dir])");
+        char *src = mxArrayToString(prhs[2]);
+        char *inc = (nrhs > 6 && !mxIsEmpty(prhs[6])) ? mxArrayToString(prhs[6]) : NULL;
+        int rc = ocs_b200_set_problem_source(h, src, (int)scalar(prhs[3]), (int)scalar(prhs[4]), (int)scalar(prhs[5]), inc);
+        mxFree(src);
+        if (inc) mxFree(inc);
+        check(rc, h);
+        return;
+    }
+    if (!strcmp(cmd, "set_params")) {                                /* (h, params [np x nbatch]) */
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_params(h, params)");
+        check(ocs_b200_set_params(h, dbl(prhs[2], "params"), (int)mxGetM(prhs[2]), (long)mxGetN(prhs[2])), h);
+        return;
+    }
+    if (!strcmp(cmd, "set_tail_control")) {
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_tail_control(h, uStar)");
+        check(ocs_b200_set_tail_control(h, dbl(prhs[2], "uStar"), (int)mxGetNumberOfElements(prhs[2])), h);
+        return;
+    }
+    if (!strcmp(cmd, "set_control_basis")) {                         /* (h, B [K x G]) ; [] detaches */
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_control_basis(h, B)");
+        check(ocs_b200_set_control_basis(h, (int)mxGetM(prhs[2]), dbl(prhs[2], "B")), h);
+        return;
+    }
+    if (!strcmp(cmd, "set_control_v")) {                             /* (h, v [(nc*K) x nbatch]) */
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_control_v(h, v)");
+        check(ocs_b200_set_control_v(h, dbl(prhs[2], "v"), (long)mxGetN(prhs[2])), h);
+        return;
+    }
+    if (!strcmp(cmd, "set_control_u")) {                             /* (h, u [nc x G x nbatch]) */
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_control_u(h, u)");
+        check(ocs_b200_set_control_u(h, dbl(prhs[2], "u"), dim(prhs[2], 2)), h);
+        return;
+    }
+    /* ---- [J, xT, status] = mex('compute_states', h, x0 [n x Bt])            RK4Integrator.m:28-56 */
+    if (!strcmp(cmd, "compute_states")) {
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "compute_states(h, x0)");
+        long n = (long)mxGetM(prhs[2]), Bt = (long)mxGetN(prhs[2]);
+        plhs[0] = mxCreateDoubleMatrix(1, Bt, mxREAL);
+        mxArray *xT = mxCreateDoubleMatrix(n, Bt, mxREAL);
+        mxArray *st = int32_row(Bt);
+        int rc = ocs_b200_compute_states(h, dbl(prhs[2], "x0"), Bt, mxGetPr(plhs[0]), mxGetPr(xT), (int32_t *)mxGetData(st));
+        if (nlhs > 1) plhs[1] = xT; else mxDestroyArray(xT);
+        if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
+        check(rc, h);
+        return;
+    }
+    /* ---- [lam0, dJdv] = mex('compute_adjoints', h, lamT | [], m, Bt, nv)    RK4Integrator.m:59-121 */
+    if (!strcmp(cmd, "compute_adjoints")) {
+        FAIL_IF(nrhs < 6, "ocs_b200:nargin", "compute_adjoints(h, lamT, m, Bt, nv)");
+        const double *lamT = dbl(prhs[2], "lamT");
+        long m = (long)scalar(prhs[3]), Bt = (long)scalar(prhs[4]), nv = (long)scalar(prhs[5]);
+        plhs[0] = mxCreateDoubleMatrix(m, Bt, mxREAL);
+        mxArray *dJdv = (nlhs > 1 && nv > 0) ? mxCreateDoubleMatrix(nv, Bt, mxREAL) : NULL;
+        int rc = ocs_b200_compute_adjoints(h, lamT, lamT ? (long)mxGetN(prhs[2]) : 0, dJdv ? mxGetPr(dJdv) : NULL,
+                                           mxGetPr(plhs[0]));
+        if (nlhs > 1) plhs[1] = dJdv ? dJdv : mxCreateDoubleMatrix(0, 0, mxREAL);
+        check(rc, h);
+        return;
+    }
+    /* ---- x = mex('fetch_states', h, segment, b0, nb, m, N)                  x of RK4Integrator.m:54 */
+    if (!strcmp(cmd, "fetch_states")) {
+        FAIL_IF(nrhs < 7, "ocs_b200:nargin", "fetch_states(h, segment, b0, nb, m, N)");
+        mwSize d[3];
+        d[0] = (mwSize)scalar(prhs[5]);
+        d[1] = (mwSize)scalar(prhs[6]) + 1;
+        d[2] = (mwSize)scalar(prhs[4]);
+        plhs[0] = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL);
+        check(ocs_b200_fetch_states(h, (int)scalar(prhs[2]), (long)scalar(prhs[3]), (long)scalar(prhs[4]), mxGetPr(plhs[0])), h);
+        return;
+    }
+    /* ---- [lam, dJdu] = mex('fetch_adjoints', h, segment, b0, nb, m, N, nc) */
+    if (!strcmp(cmd, "fetch_adjoints")) {
+        FAIL_IF(nrhs < 8, "ocs_b200:nargin", "fetch_adjoints(h, segment, b0, nb, m, N, nc)");
+        mwSize d[3];
+        long N = (long)scalar(prhs[6]);
+        d[0] = (mwSize)scalar(prhs[5]);
+        d[1] = (mwSize)N + 1;
+        d[2] = (mwSize)scalar(prhs[4]);
+        plhs[0] = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL);
+        mxArray *du = NULL;
+        if (nlhs > 1) {
+            d[0] = (mwSize)scalar(prhs[7]);
+            d[1] = (mwSize)(2 * N + 1);
+            du = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL);
+            plhs[1] = du;
+        }
+        check(ocs_b200_fetch_adjoints(h, (int)scalar(prhs[2]), (long)scalar(prhs[3]), (long)scalar(prhs[4]),
+                                      mxGetPr(plhs[0]), du ? mxGetPr(du) : NULL), h);
+        return;
+    }
+    /* ---- u = mex('get_control_u', h, b0, nb, nc, G) */
+    if (!strcmp(cmd, "get_control_u")) {
+        FAIL_IF(nrhs < 6, "ocs_b200:nargin", "get_control_u(h, b0, nb, nc, G)");
+        mwSize d[3];
+        d[0] = (mwSize)scalar(prhs[4]);
+        d[1] = (mwSize)scalar(prhs[5]);
+        d[2] = (mwSize)scalar(prhs[3]);
+        plhs[0] = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL);
+        check(ocs_b200_get_control_u(h, (long)scalar(prhs[2]), (long)scalar(prhs[3]), mxGetPr(plhs[0])), h);
+        return;
+    }
+    /* ---- [J, sweeps, converged, maxChange] = mex('fb_sweep', h, x0, u0, bounds, uRelTol, uAbsTol, nSWEEPS, relax)
+     *      functions/fb_sweep.m:79-115 on the RK4 grid */
+    if (!strcmp(cmd, "fb_sweep")) {
+        FAIL_IF(nrhs < 9, "ocs_b200:nargin", "fb_sweep(h, x0, u0, bounds, uRelTol, uAbsTol, nSWEEPS, relax)");
+        long Bt = (long)mxGetN(prhs[2]);
+        plhs[0] = mxCreateDoubleMatrix(1, Bt, mxREAL);
+        mxArray *sw = int32_row(Bt), *cv = int32_row(Bt), *mc = mxCreateDoubleMatrix(1, Bt, mxREAL);
+        int rc = ocs_b200_fb_sweep(h, dbl(prhs[2], "x0"), Bt, dbl(prhs[3], "u0"), dim(prhs[3], 2), dbl(prhs[4], "bounds"),
+                                   scalar(prhs[5]), scalar(prhs[6]), (int)scalar(prhs[7]), scalar(prhs[8]),
+                                   mxGetPr(plhs[0]), (int32_t *)mxGetData(sw), (int32_t *)mxGetData(cv), mxGetPr(mc));
+        if (nlhs > 1) plhs[1] = sw; else mxDestroyArray(sw);
+        if (nlhs > 2) plhs[2] = cv; else mxDestroyArray(cv);
+        if (nlhs > 3) plhs[3] = mc; else mxDestroyArray(mc);
+        check(rc, h);
+        return;
+    }
+    /* ---- [value, index] = mex('reduce_J', h, op)   op: 0 sum, 1 min, 2 max (index 1-based) */
+    if (!strcmp(cmd, "reduce_J")) {
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "reduce_J(h, op)");
+        double val = 0;
+        long idx = -1;
+        check(ocs_b200_reduce_J(h, (int)scalar(prhs[2]), &val, &idx), h);
+        plhs[0] = mxCreateDoubleScalar(val);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(idx >= 0 ? (double)(idx + 1) : 0.0);
+        return;
+    }
+    mexErrMsgIdAndTxt("ocs_b200:command", "unknown command '%s'", cmd);
+}

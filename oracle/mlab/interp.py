@@ -367,7 +367,7 @@ class Parser:
         return out
 
     def to_lvalue(self, e):
-        if e[0] in ("name", "index", "field"):
+        if e[0] in ("name", "index", "field", "dynfield", "cellindex"):
             return e
         raise SyntaxError(f"{self.fname}: invalid assignment target {e[0]}")
 
@@ -485,6 +485,23 @@ class Parser:
             elif tok.val == "." and self.peek(1).kind == "id" and not tok.sp:
                 self.next()
                 e = ("field", e, self.next().val)
+            elif tok.val == "." and self.peek(1).val == "(" and not tok.sp:
+                self.next()                      # dynamic field s.(name): parsed, not evaluated
+                self.next()
+                name = self.parse_expr()
+                self.expect(")")
+                e = ("dynfield", e, name)
+            elif tok.val == "{" and not (self.in_matrix and tok.sp):
+                self.next()                      # cell indexing c{...}: parsed, not evaluated
+                args = self.parse_args("}")
+                e = ("cellindex", e, args)
+            elif tok.val == "@" and e[0] == "name" and self.peek(1).kind == "id" and not tok.sp:
+                self.next()                      # superclass call  obj@Super(...) / method@Super(...)
+                sup = self.next().val
+                while self.at("."):
+                    self.next()
+                    sup += "." + self.next().val
+                e = ("name", e[1] + "@" + sup)
             elif tok.val in ("'", ".'"):
                 self.next()
                 e = ("un", "'", e)
