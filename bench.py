@@ -49,6 +49,55 @@ BYTES_FWD = 8                                 # node state written once (n = 1)
 BYTES_REV = 8                                 # ... and read once
 
 
+# ---- other BASELINE.json configs, selectable with --config (parity cases; cfg2 is the bench line)
+def make_workload(name, ocs, local_rank, bt_override=None):
+    """Returns dict(integ, prob, ctl, n, K_rows, Bt, N_total, v (host, shared) or None, v_batch_shape,
+    flop_fwd, flop_rev, bytes_fwd, bytes_rev, label, store_gb)."""
+    if name == "cfg2":
+        Bt = bt_override or BT
+        tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
+        integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+        ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+        return dict(integ=integ, prob=ocs.TestOCProblem(PARAMS, [[0.0, 1.0]]), ctl=ctl, n=1, rows=K_PWL, Bt=Bt,
+                    N_total=N_STEPS, v=np.random.default_rng(1).random(K_PWL), v_batch=None,
+                    flop_fwd=FLOP_FWD, flop_rev=FLOP_REV, bytes_fwd=BYTES_FWD, bytes_rev=BYTES_REV, label=WORKLOAD,
+                    kernels=("ocs_fwd_test_fast_u0_b0_p0", "ocs_rev_test_fast_u0_b1_p0"),
+                    x0_lo=0.5, x0_hi=2.5)
+    if name == "cfg3":
+        # 6-state generated problem, one Chebyshev (degree 16) coefficient set per control candidate
+        Bt = bt_override or 100_000
+        K = 17
+        tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
+        integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+        prob = ocs.harvest_chain_problem()
+        ctl = ocs.ChebyshevControl(integ.t, K, 2)
+        fl = prob.flops
+        cu = cv = 2 * K * 2
+        return dict(integ=integ, prob=prob, ctl=ctl, n=6, rows=2 * K, Bt=Bt, N_total=N_STEPS, v=None,
+                    v_batch=(2 * K, Bt),
+                    flop_fwd=4 * fl["C_F"] + 13 * 7 + 2 * cu, flop_rev=4 * fl["C_X"] + 14 * 7 + 4 * fl["C_U"] + 2 * 2 + 2 * cv,
+                    bytes_fwd=48, bytes_rev=48,
+                    label="cfg3: generated 6-state/6-costate harvest-chain problem (make_from_symbolic CUDA backend, NVRTC), "
+                          "100k control candidates x 1000 RK4 steps, per-candidate ChebyshevControl degree 16, forward + adjoint",
+                    kernels=("ocs_fwd_gen_u1_b2_p0", "ocs_rev_gen_u1_b2_p0"), x0_lo=1.0, x0_hi=2.5)
+    if name == "cfg4":
+        # RK4InfiniteIntegrator: main horizon + tail under uStar, stored state grids of both in HBM
+        Bt = bt_override or 262_144
+        N = 10_000
+        tspan = ocs.matlab_linspace(0.0, 100.0, N + 1)
+        tspanE = ocs.matlab_linspace(100.0, 200.0, N + 1)
+        integ = ocs.CudaRK4InfiniteIntegrator(tspan, tspanE, 0.723368780097983, device=local_rank)
+        ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+        return dict(integ=integ, prob=ocs.TestOCProblem(PARAMS, [[0.0, 1.0]]), ctl=ctl, n=1, rows=K_PWL, Bt=Bt,
+                    N_total=2 * N, v=np.full(K_PWL, 0.723368780097983), v_batch=None,
+                    flop_fwd=FLOP_FWD, flop_rev=FLOP_REV, bytes_fwd=BYTES_FWD, bytes_rev=BYTES_REV,
+                    label="cfg4: RK4InfiniteIntegrator, 262144 trajectories x (10000 main + 10000 tail) RK4 steps, "
+                          "shared PWLinearControl K=101, forward + adjoint, stored state grids in HBM",
+                    kernels=("ocs_fwd_test_fast_u0_b0_p0", "ocs_rev_test_fast_u0_b1_p0 (+ u0_b0 tail)"),
+                    x0_lo=0.5, x0_hi=2.5)
+    raise SystemExit(f"unknown --config {name}")
+
+
 def _measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,6 +212,8 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+                    help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,29 +244,36 @@ def main():
     from importlib import import_module
     distmod = import_module("optimal-control-solvers_b200.host.dist")
 
-    Bt = args.bt
-    tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
-    prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
-    integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
-    ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+    wl = make_workload(args.config, ocs, local_rank, None if args.bt == BT else args.bt)
+    integ, prob, ctl, Bt, n_st, rows, NT = wl["integ"], wl["prob"], wl["ctl"], wl["Bt"], wl["n"], wl["rows"], wl["N_total"]
     integ.attach_control(ctl)
     stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream: kernels, events and NCCL all use it
     torch.cuda.set_stream(stream)
     integ.set_stream(stream.cuda_stream)
 
-    v = np.random.default_rng(1).random(K_PWL)
+    v = wl["v"]
     gen = torch.Generator(device=dev)
     gen.manual_seed(2 + rank)
-    x0 = (0.5 + 2.0 * torch.rand((1, Bt), dtype=torch.float64, device=dev, generator=gen)).contiguous()
+    x0 = (wl["x0_lo"] + (wl["x0_hi"] - wl["x0_lo"]) *
+          torch.rand((n_st, Bt), dtype=torch.float64, device=dev, generator=gen)).contiguous()
+    v_dev = None
+    if wl["v_batch"] is not None:     # per-trajectory coefficients: constant term U[0.2,0.8], higher ones N(0, 0.05^2)
+        v_dev = 0.05 * torch.randn(wl["v_batch"], dtype=torch.float64, device=dev, generator=gen)
+        v_dev[:2] = 0.2 + 0.6 * torch.rand((2, Bt), dtype=torch.float64, device=dev, generator=gen)
+        v_dev = v_dev.contiguous()
     J = torch.empty(Bt, dtype=torch.float64, device=dev)
-    xT = torch.empty((1, Bt), dtype=torch.float64, device=dev)
+    xT = torch.empty((n_st, Bt), dtype=torch.float64, device=dev)
     status = torch.empty(Bt, dtype=torch.int32, device=dev)
-    dJdv = torch.empty((K_PWL, Bt), dtype=torch.float64, device=dev)
-    lam0 = torch.empty((2, Bt), dtype=torch.float64, device=dev)
+    dJdv = torch.empty((rows, Bt), dtype=torch.float64, device=dev)
+    lam0 = torch.empty((n_st + 1, Bt), dtype=torch.float64, device=dev)
+
+    def evaluate_dev():
+        integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, v_ptr=(v_dev.data_ptr() if v_dev is not None else 0),
+                           J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(), status_ptr=status.data_ptr(),
+                           dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
 
     def step():
-        integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(),
-                           status_ptr=status.data_ptr(), dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+        evaluate_dev()
         if world > 1:
             distmod.gather_results(J, xT, world)
 
@@ -245,14 +303,13 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * Bt * N_STEPS * args.steps / (ms * 1e-3)
+    value = world * Bt * NT * args.steps / (ms * 1e-3)
 
     # ---- per-kernel device time (CUDA events around every launch, on the launch stream)
     integ.set_profiling(True)
     nprof = max(3, min(args.steps, 10))
     for _ in range(nprof):
-        integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(),
-                           status_ptr=status.data_ptr(), dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+        evaluate_dev()
     torch.cuda.synchronize()
     ks = integ.kernel_stats(reset=True)
     integ.set_profiling(False)
@@ -265,13 +322,13 @@ def main():
         tf = ctypes.c_double()
         L.ocs_b200_measure_fp64_peak(local_rank, ctypes.byref(tf))
         hbm_peak, hbm_src = _measured_peaks()
-        units = Bt * N_STEPS
+        units = Bt * NT
 
         def kern(name, ms_k, flop, byt):
             return {"kernel": name, "ms": ms_k, "tflops": units * flop / (ms_k * 1e-3) / 1e12,
                     "gbs": units * byt / (ms_k * 1e-3) / 1e9}
-        kf = kern("ocs_fwd_test_fast_u0_b0_p0", ms_fwd, FLOP_FWD, BYTES_FWD)
-        kr = kern("ocs_rev_test_fast_u0_b1_p0", ms_rev, FLOP_REV, BYTES_REV)
+        kf = kern(wl["kernels"][0], ms_fwd, wl["flop_fwd"], wl["bytes_fwd"])
+        kr = kern(wl["kernels"][1], ms_rev, wl["flop_rev"], wl["bytes_rev"])
         dom = kr if ms_rev >= ms_fwd else kf
         fp_frac, hbm_frac = dom["tflops"] / tf.value, dom["gbs"] / hbm_peak
         if fp_frac >= hbm_frac:
@@ -284,24 +341,24 @@ def main():
                      "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "peak_source": hbm_src},
                      "fp64": {"achieved": dom["tflops"], "peak": tf.value, "unit": "TFLOP/s", "frac": fp_frac},
                      "kernels": [kf, kr],
-                     "algorithmic": {"flop_per_step_fwd": FLOP_FWD, "flop_per_step_rev": FLOP_REV,
-                                     "bytes_per_step_fwd": BYTES_FWD, "bytes_per_step_rev": BYTES_REV}})
+                     "algorithmic": {"flop_per_step_fwd": wl["flop_fwd"], "flop_per_step_rev": wl["flop_rev"],
+                                     "bytes_per_step_fwd": wl["bytes_fwd"], "bytes_per_step_rev": wl["bytes_rev"]}})
         # whole-evaluation view: (fwd + rev) algorithmic flops over the measured step time
-        roof["step_fp64_frac"] = value / world * (FLOP_FWD + FLOP_REV) / 1e12 / tf.value
+        roof["step_fp64_frac"] = value / world * (wl["flop_fwd"] + wl["flop_rev"]) / 1e12 / tf.value
         out = {
             "metric": "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)", "value": value,
             "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS,
-                       "l2": "inputs larger than L2 (8.4 GB node-state store per GPU)",
+            "config": {"workload": wl["label"], "trajectories_per_gpu": Bt, "rk4_steps": NT,
+                       "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * n_st * NT * Bt),
                        "collective": "all_gather of J and x(T) (NCCL)" if world > 1 else "none"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
         }
 
     # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.config == "cfg2":
         x0_h = torch.empty((1, Bt), dtype=torch.float64).pin_memory()
         x0_h.copy_(x0.cpu())
         J_h = torch.empty(Bt, dtype=torch.float64).pin_memory()
@@ -339,7 +396,7 @@ def main():
 
     if rank == 0:
         out["e2e"] = e2e
-        if not args.no_cpu:
+        if not args.no_cpu and args.config == "cfg2":
             ntraj = 32768
             val, cores = cpu_oracle_run(ntraj)
             out["cpu_baseline"] = {"value": val, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
