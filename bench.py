@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = args.steps * ntraj * N_STEPS / dt
     sample = f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps per step (fwd + adjoint)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)", "value": value,
         "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -200,7 +200,19 @@ def run_reference(args, rank, world):
                          "sample": sample},
         "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -219,6 +231,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner, ...)
+    # is sent to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -402,7 +420,7 @@ def main():
             out["cpu_baseline"] = {"value": val, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
                                    "sample": f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps, fwd + adjoint, "
                                              "C restatement of the MATLAB reference (no MATLAB/Octave in the image), OpenMP"}
-        print(json.dumps(out))
+        emit(out)
     integ.close()
     if world > 1:
         dist.barrier()

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libocs_b200.so")
+# OCS_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("OCS_B200_LIB") or os.path.join(_HERE, "libocs_b200.so")
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int32)

@@ -12,6 +12,9 @@
 #define OCS_TAGNAME test_fast
 #endif
 
+// 9 resident blocks/SM (56 registers) measured fastest for the test problem's reverse sweep on B200
+// (profiles/r1_notes.md); larger generated problems keep the default (no register cap).
+#define OCS_MINBLOCKS_REV 9
 #include "rk4_kernels.cuh"
 #include "problem_test.cuh"
 #include "kernel_table.h"

@@ -111,6 +111,9 @@ struct ocs_b200_handle {
     long Bt = 0;
     bool have_states = false;
     DevBuf d_x0, d_J, d_xT, d_lamT_tail, d_lamT_user, d_dJdv, d_lam0, d_stage, d_stage2, d_maxchg;
+    DevBuf d_pipe[2];                 // double-buffered transpose staging of the chunked dJdv download
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[2] = {nullptr, nullptr};
     int *d_status = nullptr;
     size_t status_cap = 0;
     int *d_frozen = nullptr, *d_sweeps = nullptr;
@@ -232,11 +235,12 @@ int to_soa(H *h, const double *d_src, double *d_dst, long rows, long nb, long ld
     CK(cudaGetLastError());
     return 0;
 }
-int from_soa(H *h, const double *d_src, double *d_dst, long rows, long nb, long lds, int nc = 1)
+int from_soa(H *h, const double *d_src, double *d_dst, long rows, long nb, long lds, int nc = 1,
+             cudaStream_t stream = nullptr)
 {
     if (rows == 0 || nb == 0) return 0;
     dim3 grid((unsigned)((nb + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
-    from_soa_kernel<<<grid, block, 0, h->stream>>>(d_src, d_dst, rows, nb, lds, nc);
+    from_soa_kernel<<<grid, block, 0, stream ? stream : h->stream>>>(d_src, d_dst, rows, nb, lds, nc);
     CK(cudaGetLastError());
     return 0;
 }
@@ -846,7 +850,11 @@ int ocs_b200_destroy(ocs_b200_handle *h)
         cudaFree(h->seg[si].d_xs_base);
     }
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
-                      &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg};
+                      &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg,
+                      &h->d_pipe[0], &h->d_pipe[1]};
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int k = 0; k < 2; ++k)
+        if (h->chunk_done[k]) cudaEventDestroy(h->chunk_done[k]);
     for (DevBuf *b : bufs) cudaFree(b->p);
     cudaFree(h->d_status);
     cudaFree(h->d_frozen);
@@ -1237,11 +1245,39 @@ int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_
         }
         TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
         d_lam0 = h->d_lam0.p;
-        TRY(adjoints_common(h, d_lamT, lamT && lamT_nbatch > 1 ? Bt : 0, d_dJdv, d_lam0));
-        if (dJdv) TRY(download_soa(h, d_dJdv, Bt, 0, dJdv, (long)nc * h->K, Bt));
-        if (lam0) {
-            // d_stage may be in use by the dJdv transpose above: stream order keeps it safe
-            TRY(download_soa(h, d_lam0, Bt, 0, lam0, m, Bt));
+        const long rows = (long)nc * h->K;
+        const long ldl = lamT && lamT_nbatch > 1 ? Bt : 0;
+        if (!dJdv || Bt < 262144) {
+            TRY(adjoints_common(h, d_lamT, ldl, d_dJdv, d_lam0));
+            if (dJdv) TRY(download_soa(h, d_dJdv, Bt, 0, dJdv, rows, Bt));
+            if (lam0) TRY(download_soa(h, d_lam0, Bt, 0, lam0, m, Bt));   // d_stage reuse is ordered by the stream
+        } else {
+            // Large batch: the gradient download (rows*Bt doubles over PCIe) dominates the call.  Sweep the batch
+            // in trajectory chunks on the compute stream while a second stream transposes and downloads the
+            // previous chunk, so the transfer overlaps the arithmetic.
+            if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k)
+                if (!h->chunk_done[k]) CK(cudaEventCreateWithFlags(&h->chunk_done[k], cudaEventDisableTiming));
+            const long chunk = (((Bt + 7) / 8) + 127) / 128 * 128;
+            for (int k = 0; k < 2; ++k) TRY(ensure(h, h->d_pipe[k], (size_t)(rows + m) * chunk));
+            CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * rows * Bt, h->stream));
+            int k = 0;
+            for (long b0 = 0; b0 < Bt; b0 += chunk, ++k) {
+                const long nb = std::min(chunk, Bt - b0);
+                TRY(run_reverse(h, b0, nb, -1, d_lamT, ldl, d_dJdv + b0, d_lam0 + b0, nullptr, nullptr));
+                CK(cudaEventRecord(h->chunk_done[k & 1], h->stream));
+                CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[k & 1], 0));
+                double *stg = h->d_pipe[k & 1].p;     // its previous download precedes this one on copy_stream
+                TRY(from_soa(h, d_dJdv + b0, stg, rows, nb, Bt, 1, h->copy_stream));
+                CK(cudaMemcpyAsync(dJdv + (size_t)rows * b0, stg, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost,
+                                   h->copy_stream));
+                if (lam0) {
+                    TRY(from_soa(h, d_lam0 + b0, stg + (size_t)rows * chunk, m, nb, Bt, 1, h->copy_stream));
+                    CK(cudaMemcpyAsync(lam0 + (size_t)m * b0, stg + (size_t)rows * chunk, sizeof(double) * m * nb,
+                                       cudaMemcpyDeviceToHost, h->copy_stream));
+                }
+            }
+            CK(cudaStreamSynchronize(h->copy_stream));
         }
         CK(cudaStreamSynchronize(h->stream));
         return 0;
