@@ -12,9 +12,15 @@
 #define OCS_TAGNAME test_fast
 #endif
 
-// 9 resident blocks/SM (56 registers) measured fastest for the test problem's reverse sweep on B200
-// (profiles/r1_notes.md); larger generated problems keep the default (no register cap).
-#define OCS_MINBLOCKS_REV 9
+// Two trajectories per thread at 5 resident blocks/SM (92 registers) measured fastest for the test problem's
+// reverse sweep on B200 (profiles/r1_notes.md); generated problems keep the defaults (one trajectory per
+// thread, no register cap).
+#ifndef OCS_MINBLOCKS_REV
+#define OCS_MINBLOCKS_REV 5
+#endif
+#ifndef OCS_TPT_REV
+#define OCS_TPT_REV 2
+#endif
 #include "rk4_kernels.cuh"
 #include "problem_test.cuh"
 #include "kernel_table.h"
@@ -45,6 +51,7 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->kd = 0;
     t->threads = OCS_THREADS;
     t->tile = OCS_TILE;
+    t->tpt_rev = OCS_TPT_REV;
     for (int pb = 0; pb < 2; ++pb)
         for (int um = 0; um < 3; ++um)
             for (int bm = 0; bm < 3; ++bm)

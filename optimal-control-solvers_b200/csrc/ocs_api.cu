@@ -529,12 +529,12 @@ size_t smem_bytes(const H *h, const SweepArgs &a)
     return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW) * sizeof(double);
 }
 
-int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward)
+int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1)
 {
     if (!kernel) return h->fail(OCS_B200_ERR_ARG, "this control/basis/parameter combination has no kernel variant");
     if (a.nb <= 0) return 0;
     const int threads = h->kt.threads;
-    const unsigned blocks = (unsigned)((a.nb + threads - 1) / threads);
+    const unsigned blocks = (unsigned)((a.nb + (long)threads * tpt - 1) / ((long)threads * tpt));
     void *args[] = {(void *)&a};
     if (h->profiling) CK(cudaEventRecord(h->ev[0], h->stream));
     const size_t smem = smem_bytes(h, a);
@@ -688,7 +688,8 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         if (grids && um != 1) bm = 0;   // the fetch variants write dJdu itself; only UMODE_COEF needs the basis
         const void *kern = nullptr;
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
-        TRY(launch(h, kern, a, false));
+        // dense-basis kernels keep K coefficients and K accumulators per trajectory in registers: one per thread
+        TRY(launch(h, kern, a, false, (grids || bm == 2) ? 1 : std::max(h->kt.tpt_rev, 1)));
     }
     return 0;
 }

@@ -33,6 +33,9 @@
 #ifndef OCS_TILE
 #define OCS_TILE 32         // RK4 steps per shared-memory tile
 #endif
+#ifndef OCS_TPT_REV
+#define OCS_TPT_REV 1       // trajectories per thread of the reverse (gradient) kernels
+#endif
 #ifndef OCS_MINBLOCKS_REV
 #define OCS_MINBLOCKS_REV 1 // __launch_bounds__ min blocks/SM of the reverse kernels (register cap)
 #endif
@@ -647,6 +650,172 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     }
 }
 
+// ------------------------------------------------------------------ reverse sweep, T trajectories per thread
+// The plain gradient sweep (no grids, no fb_sweep) with T independent trajectories per thread:
+// thread tid of a block handles trajectories blockIdx*blockDim*T + q*blockDim + tid, q = 0..T-1, so
+// every q-slice is coalesced.  Everything read from shared memory (records, weights, step sizes) and
+// all address / loop / branch instructions are issued once for T trajectories, and the T dependency
+// chains interleave in the FP64 pipe.  Same arithmetic, operation for operation, as reverse_body.
+template <class P, int UMODE, int BMODE, bool PB, int KD, int T>
+__device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *sm)
+{
+    constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
+    constexpr int HM = ocs_hoist_mode(UMODE, PB);
+    constexpr int NT = P::ntt(HM);
+    constexpr int RB = ocs_rec_width(nc, NT);
+    constexpr bool NEEDB = (BMODE != BMODE_NONE);
+    constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
+    typedef TileLayout<RB> TL;
+    const int BW = BWc >= 0 ? BWc : a.BW;
+    const int N = a.N;
+    double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
+    if (a.RB != RB || (NEEDB && a.BW != BW)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
+        return;
+    }
+
+    long b[T], bb[T];
+    bool active[T];
+    double p[T][np > 0 ? np : 1];
+    double lam[T][m];
+    ControlEval<nc, UMODE, BMODE, KD> ctl[T];
+    GradAcc<nc, BMODE, KD> gacc[T];
+    double uL[T][nc], uM[T][nc], uR[T][nc], dcar[T][nc], dR[T][nc], dM[T][nc];
+    double y1[T][n], yn1[T][n], yn2[T][n];
+    const double *xsp[T];
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        b[q] = ((long)blockIdx.x * T + q) * blockDim.x + threadIdx.x;
+        active[q] = b[q] < a.nb;
+        bb[q] = active[q] ? b[q] : a.nb - 1;
+        if (a.frozen && a.frozen[bb[q]]) active[q] = false;
+#pragma unroll
+        for (int k = 0; k < np; ++k) p[q][k] = PB ? a.p[soa(k, a.ldp, bb[q])] : a.p[k];
+#pragma unroll
+        for (int c = 0; c < m; ++c)
+            lam[q][c] = a.lamT ? (a.ldl ? a.lamT[soa(c, a.ldl, bb[q])] : a.lamT[c]) : (c == n ? 1.0 : 0.0);
+        ctl[q].init(a, bb[q]);
+        gacc[q].init();
+#pragma unroll
+        for (int c = 0; c < nc; ++c) dcar[q][c] = 0.0;
+        xsp[q] = a.xs + (size_t)(N - 1) * a.ldb + bb[q];
+#pragma unroll
+        for (int c = 0; c < n; ++c) {
+            yn1[q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
+            yn2[q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb - a.ldb];
+        }
+        xsp[q] -= a.ldb;
+    }
+
+    const int i0_last = ((N - 1) / TL::S) * TL::S;
+    for (int i0 = i0_last; i0 >= 0; i0 -= TL::S) {
+        const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
+        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
+        if (i0 == i0_last) {
+#pragma unroll
+            for (int q = 0; q < T; ++q) ctl[q].eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb[q], uR[q]);
+        }
+#pragma unroll 2
+        for (int s = ns - 1; s >= 0; --s) {
+            const int i = i0 + s;
+            const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
+            const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
+            const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
+            const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
+            const double tR = rR[0], tM = rM[0], tL = rL[0];
+            const bool moves = BMODE == BMODE_SPARSE ? (reinterpret_cast<const int *>(bM)[1] & 4) != 0 : true;
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+#pragma unroll
+                for (int c = 0; c < n; ++c) { y1[q][c] = yn1[q][c]; yn1[q][c] = yn2[q][c]; }
+                xsp[q] -= a.ldb;
+#pragma unroll
+                for (int c = 0; c < n; ++c) yn2[q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
+            }
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+                if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
+                ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
+                ctl[q].eval(a, rL, bL, 2 * i, bb[q], uL[q]);
+
+                double F[m], y2[n], y3[n], y4[n];
+                P::template F<HM>(ttL, tL, y1[q], uL[q], p[q], F);
+#pragma unroll
+                for (int c = 0; c < n; ++c) y2[c] = y1[q][c] + h2 * F[c];
+                P::template F<HM>(ttM, tM, y2, uM[q], p[q], F);
+#pragma unroll
+                for (int c = 0; c < n; ++c) y3[c] = y1[q][c] + h2 * F[c];
+                P::template F<HM>(ttM, tM, y3, uM[q], p[q], F);
+#pragma unroll
+                for (int c = 0; c < n; ++c) y4[c] = y1[q][c] + h * F[c];
+
+                double k4[m], k3[m], k2[m], k1[m], g3[n], g2[n], g1[n], g0[n];
+#pragma unroll
+                for (int c = 0; c < m; ++c) k4[c] = h6 * lam[q][c];                          // :73
+                P::template X<HM>(ttR, tR, y4, uR[q], p[q], k4, g3);                        // :74-75
+#pragma unroll
+                for (int c = 0; c < n; ++c) k3[c] = h3 * lam[q][c] + h * g3[c];              // :77
+                k3[n] = h3 * lam[q][n];
+                P::template X<HM>(ttM, tM, y3, uM[q], p[q], k3, g2);                        // :78-79
+#pragma unroll
+                for (int c = 0; c < n; ++c) k2[c] = h3 * lam[q][c] + h2 * g2[c];             // :81
+                k2[n] = h3 * lam[q][n];
+                P::template X<HM>(ttM, tM, y2, uM[q], p[q], k2, g1);                        // :82-83
+#pragma unroll
+                for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
+                k1[n] = h6 * lam[q][n];
+                P::template X<HM>(ttL, tL, y1[q], uL[q], p[q], k1, g0);                     // :86-88
+
+                if constexpr (BMODE != BMODE_NONE) {
+                    double e[nc];
+                    P::template U<HM>(ttR, tR, y4, uR[q], p[q], k4, dR[q]);                 // :112-120
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) dR[q][c] = dcar[q][c] + dR[q][c];
+                    P::template U<HM>(ttM, tM, y2, uM[q], p[q], k2, dM[q]);                 // :105-109
+                    P::template U<HM>(ttM, tM, y3, uM[q], p[q], k3, e);
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) dM[q][c] = dM[q][c] + e[c];
+                    P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);            // :101-102 / :112-116
+                }
+#pragma unroll
+                for (int c = 0; c < n; ++c) lam[q][c] = lam[q][c] + g1[c] + g2[c] + g3[c] + g0[c];   // :86
+                if constexpr (UMODE != UMODE_UNIFORM) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) uR[q][c] = uL[q][c];
+                }
+            }
+            // fold dJdu of the right node and the midpoint into dJdv: ONE uniform branch for all T trajectories,
+            // outside the arithmetic above so that the T dependency chains share a basic block and interleave
+            if constexpr (BMODE != BMODE_NONE) {
+                if (moves) {
+#pragma unroll
+                    for (int q = 0; q < T; ++q) {
+                        gacc[q].add(a, bR, dR[q], b[q], active[q]);
+                        gacc[q].add(a, bM, dM[q], b[q], active[q]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < T; ++q) {
+                        gacc[q].add_fast(bR, dR[q]);
+                        gacc[q].add_fast(bM, dM[q]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        if constexpr (BMODE != BMODE_NONE) {
+            gacc[q].add(a, bs, dcar[q], b[q], active[q]);                                    // left end :101-102
+            gacc[q].finish(a, b[q], active[q]);
+        }
+        if (a.lam0 && active[q]) {
+#pragma unroll
+            for (int c = 0; c < m; ++c) a.lam0[soa(c, a.ldb, b[q])] = lam[q][c];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ small helper kernels
 
 // Fills the table slots of the grid-point records: every sub-expression of the right-hand
@@ -699,7 +868,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_rev_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA false>, tag, UM, BM, PB, OCS_MINBLOCKS_REV)
+    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_REV)>, tag, UM, BM, PB, OCS_MINBLOCKS_REV)
 #define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_FB_KERNEL(P, tag, PB) \
@@ -713,7 +882,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
         o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2);                                          \
-        o[6] = OCS_TILE; o[7] = OCS_THREADS;                                                           \
+        o[6] = OCS_TILE; o[7] = OCS_THREADS | (OCS_TPT_REV << 16);                                     \
     }
 
 #define OCS_DEFINE_KERNELS_PB(P, tag, PB, KD)   \
