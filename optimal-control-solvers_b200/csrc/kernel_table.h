@@ -10,6 +10,7 @@ struct ocs_kernel_table {
     int threads;   // block size the kernels were built for
     int tile;      // RK4 steps per shared-memory tile
     int tpt_rev;   // trajectories per thread of the reverse (gradient) kernels
+    int tpt_fwd;   // ... and of the forward kernels
     const void *fwd[3][3][2];   // [UMODE][BMODE][params batched]
     const void *rev[3][3][2];
     const void *fwdg[3][3][2];  // fetch variants: also write the full grids (x with the J row; lam, dJdu)

@@ -21,6 +21,9 @@
 #ifndef OCS_TPT_REV
 #define OCS_TPT_REV 2
 #endif
+#ifndef OCS_TPT_FWD
+#define OCS_TPT_FWD 3
+#endif
 #include "rk4_kernels.cuh"
 #include "problem_test.cuh"
 #include "kernel_table.h"
@@ -52,6 +55,7 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->threads = OCS_THREADS;
     t->tile = OCS_TILE;
     t->tpt_rev = OCS_TPT_REV;
+    t->tpt_fwd = OCS_TPT_FWD;
     for (int pb = 0; pb < 2; ++pb)
         for (int um = 0; um < 3; ++um)
             for (int bm = 0; bm < 3; ++bm)

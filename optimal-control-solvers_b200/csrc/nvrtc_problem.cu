@@ -191,7 +191,8 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, c
     for (int hm = 0; hm < 3; ++hm) table->ntt[hm] = inf[3 + hm];
     table->tile = inf[6];
     table->threads = inf[7] & 0xffff;
-    table->tpt_rev = inf[7] >> 16;
+    table->tpt_rev = (inf[7] >> 16) & 0xff;
+    table->tpt_fwd = (inf[7] >> 24) & 0xff;
     table->kd = 0;
     return 0;
 }

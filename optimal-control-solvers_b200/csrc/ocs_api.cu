@@ -627,7 +627,7 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         }
         const void *kern = nullptr;
         TRY(resolve(h, d_xgrid ? KIND_FWDG : KIND_FWD, um, bm, pb_index(h), &kern));
-        TRY(launch(h, kern, a, true));
+        TRY(launch(h, kern, a, true, (d_xgrid || bm == 2) ? 1 : std::max(h->kt.tpt_fwd, 1)));
     }
     return 0;
 }
@@ -1416,7 +1416,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             const void *kf = nullptr, *kr = nullptr;
             TRY(resolve(h, KIND_FWD, 2, 0, pb_index(h), &kf));
             TRY(resolve(h, KIND_FB, 2, 0, pb_index(h), &kr));
-            TRY(launch(h, kf, a, true));
+            TRY(launch(h, kf, a, true, std::max(h->kt.tpt_fwd, 1)));
             SweepArgs r;
             base_args(h, 0, r);
             r.nb = Bt;

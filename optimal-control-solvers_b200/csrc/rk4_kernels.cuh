@@ -33,6 +33,12 @@
 #ifndef OCS_TILE
 #define OCS_TILE 32         // RK4 steps per shared-memory tile
 #endif
+#ifndef OCS_TPT_FWD
+#define OCS_TPT_FWD 1       // trajectories per thread of the forward kernels
+#endif
+#ifndef OCS_MINBLOCKS_FWD
+#define OCS_MINBLOCKS_FWD 1
+#endif
 #ifndef OCS_TPT_REV
 #define OCS_TPT_REV 1       // trajectories per thread of the reverse (gradient) kernels
 #endif
@@ -425,6 +431,124 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
 #pragma unroll
             for (int c = 0; c < n; ++c) ok = ok && isfinite(y[c]);
             a.status[b] = (a.J_accumulate ? a.status[b] : 0) | (ok ? 0 : 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward sweep, T trajectories per thread
+// RK4Integrator.m:28-56 with T independent trajectories per thread (see reverse_multi_body for the
+// mapping): record reads, address arithmetic and loop control are issued once for T trajectories and
+// the T dependency chains interleave.  Same arithmetic as forward_body; no grid output (fetch uses
+// forward_body).
+template <class P, int UMODE, int BMODE, bool PB, int KD, int T>
+__device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *sm)
+{
+    constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
+    constexpr int HM = ocs_hoist_mode(UMODE, PB);
+    constexpr int RB = ocs_rec_width(nc, P::ntt(HM));
+    constexpr bool NEEDB = (UMODE == UMODE_COEF);
+    constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
+    typedef TileLayout<RB> TL;
+    const int BW = BWc >= 0 ? BWc : a.BW;
+    const int N = a.N;
+    double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
+    if (a.RB != RB || (NEEDB && a.BW != BW)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
+        return;
+    }
+
+    long b[T], bb[T];
+    bool active[T];
+    double p[T][np > 0 ? np : 1];
+    double y[T][m];
+    ControlEval<nc, UMODE, BMODE, KD> ctl[T];
+    double uL[T][nc], uM[T][nc], uR[T][nc];
+    double *xsp[T];
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        b[q] = ((long)blockIdx.x * T + q) * blockDim.x + threadIdx.x;
+        active[q] = b[q] < a.nb;
+        bb[q] = active[q] ? b[q] : a.nb - 1;
+        if (a.frozen && a.frozen[bb[q]]) active[q] = false;
+#pragma unroll
+        for (int k = 0; k < np; ++k) p[q][k] = PB ? a.p[soa(k, a.ldp, bb[q])] : a.p[k];
+#pragma unroll
+        for (int c = 0; c < n; ++c) y[q][c] = a.x0[soa(c, a.ldb, bb[q])];
+        y[q][n] = 0.0;                                                // xK(:,1,1) = [x0; 0]   :33
+        ctl[q].init(a, bb[q]);
+        xsp[q] = a.xs + b[q];
+    }
+
+    for (int i0 = 0; i0 < N; i0 += TL::S) {
+        const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
+        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
+        if (i0 == 0) {
+#pragma unroll
+            for (int q = 0; q < T; ++q) ctl[q].eval(a, gp, bs, 0, bb[q], uL[q]);
+        }
+#pragma unroll 4
+        for (int s = 0; s < ns; ++s) {
+            const int i = i0 + s;
+            const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
+            const double *bM = bs + (2 * s + 1) * BW, *bR = bM + BW;
+            const double h = st[4 * s], h2 = st[4 * s + 1], h6 = st[4 * s + 3];
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+                if (active[q]) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) xsp[q][(size_t)c * (N + 1) * a.ldb] = y[q][c];
+                }
+                xsp[q] += a.ldb;
+                if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rL, bs, 2 * i, bb[q], uL[q]);
+                ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
+                ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
+
+                double F[m], acc[m], ys[n];
+                P::template F<HM>(rL + 1 + nc, rL[0], y[q], uL[q], p[q], F);         // F1   :39
+#pragma unroll
+                for (int c = 0; c < m; ++c) acc[c] = F[c];
+#pragma unroll
+                for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h2 * F[c];             // xK2  :40
+                P::template F<HM>(rM + 1 + nc, rM[0], ys, uM[q], p[q], F);           // F2   :42
+#pragma unroll
+                for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
+#pragma unroll
+                for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h2 * F[c];             // xK3  :43
+                P::template F<HM>(rM + 1 + nc, rM[0], ys, uM[q], p[q], F);           // F3   :45
+#pragma unroll
+                for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
+#pragma unroll
+                for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h * F[c];              // xK4  :46
+                P::template F<HM>(rR + 1 + nc, rR[0], ys, uR[q], p[q], F);           // F4   :48
+#pragma unroll
+                for (int c = 0; c < m; ++c) y[q][c] = y[q][c] + h6 * (acc[c] + F[c]);   // :50-51
+                if constexpr (UMODE != UMODE_UNIFORM) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) uL[q][c] = uR[q][c];
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        if (!active[q]) continue;
+#pragma unroll
+        for (int c = 0; c < n; ++c) xsp[q][(size_t)c * (N + 1) * a.ldb] = y[q][c];
+        if (a.xT) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) a.xT[soa(c, a.ldb, b[q])] = y[q][c];
+        }
+        double Jv = y[q][n];                                          // J = x(end,end)   :55
+        if (a.J) {
+            if (a.J_accumulate) Jv = a.J[b[q]] + Jv;                  // J = J1 + J2  (RK4InfiniteIntegrator.m:23)
+            a.J[b[q]] = Jv;
+        }
+        if (a.status) {
+            bool ok = isfinite(Jv);
+#pragma unroll
+            for (int c = 0; c < n; ++c) ok = ok && isfinite(y[q][c]);
+            a.status[b[q]] = (a.J_accumulate ? a.status[b[q]] : 0) | (ok ? 0 : 1);
         }
     }
 }
@@ -864,7 +988,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     }
 #define OCS_COMMA ,
 #define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_fwd_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false>, tag, UM, BM, PB, 1)
+    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_FWD)>, tag, UM, BM, PB, OCS_MINBLOCKS_FWD)
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
@@ -882,7 +1006,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
         o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2);                                          \
-        o[6] = OCS_TILE; o[7] = OCS_THREADS | (OCS_TPT_REV << 16);                                     \
+        o[6] = OCS_TILE; o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24);               \
     }
 
 #define OCS_DEFINE_KERNELS_PB(P, tag, PB, KD)   \
