@@ -355,7 +355,15 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,
                     "peak_source": hbm_src}
-        roof.update({"kernel": dom["kernel"], "traffic": None,
+        traffic = None
+        try:    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload only)
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if Bt == BT:
+                traffic = tj.get(args.config, {}).get(dom["kernel"], {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+        roof.update({"kernel": dom["kernel"], "traffic": traffic,
                      "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "peak_source": hbm_src},
                      "fp64": {"achieved": dom["tflops"], "peak": tf.value, "unit": "TFLOP/s", "frac": fp_frac},
                      "kernels": [kf, kr],

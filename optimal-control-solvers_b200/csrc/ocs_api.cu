@@ -53,8 +53,8 @@ struct Segment {
     bool basis_dirty = true;
     cudaEvent_t rec_uploaded = nullptr;
     bool steps_uploaded = false;
-    double *d_xs_base = nullptr;   // allocation: 2*Bt doubles of slack, then node states [n][N+1][Bt]
-    double *d_xs = nullptr;        // = d_xs_base + 2*Bt
+    double *d_xs_base = nullptr;   // allocation: OCS_XS_SLACK*Bt doubles of slack, then node states [n][N+1][Bt]
+    double *d_xs = nullptr;        // = d_xs_base + OCS_XS_SLACK*Bt
     size_t xs_cap = 0;             // doubles (whole allocation)
     int R = 0;
     bool records_dirty = true;
@@ -708,8 +708,8 @@ int alloc_batch(H *h, long Bt)
     }
     for (int si = 0; si < (h->has_tail ? 2 : 1); ++si) {
         Segment &s = h->seg[si];
-        TRY(ensure_raw(h, &s.d_xs_base, &s.xs_cap, (size_t)n * (s.N + 1) * Bt + 2 * (size_t)Bt));
-        s.d_xs = s.d_xs_base + 2 * (size_t)Bt;
+        TRY(ensure_raw(h, &s.d_xs_base, &s.xs_cap, (size_t)n * (s.N + 1) * Bt + OCS_XS_SLACK * (size_t)Bt));
+        s.d_xs = s.d_xs_base + OCS_XS_SLACK * (size_t)Bt;
     }
     (void)m;
     return 0;

@@ -33,6 +33,10 @@
 #ifndef OCS_TILE
 #define OCS_TILE 32         // RK4 steps per shared-memory tile
 #endif
+#define OCS_XS_SLACK 8      // nodes of slack in front of the node-state store (>= any OCS_PREFETCH)
+#ifndef OCS_PREFETCH
+#define OCS_PREFETCH 2      // node states prefetched ahead by the reverse sweep (slack in front of the store)
+#endif
 #ifndef OCS_TPT_FWD
 #define OCS_TPT_FWD 1       // trajectories per thread of the forward kernels
 #endif
@@ -91,8 +95,8 @@ struct SweepArgs {
     const double *p;        // [np] or [np][ldp]
     const double *v;        // UMODE_COEF: [(k*nc+c)][ldb]
     double *ug;             // UMODE_GRID: [nc][2N+1][ldb]   (fb_sweep updates it in place)
-    double *xs;             // node-state store [n][N+1][ldb]; 2*ldb doubles of slack precede it so that the
-                            // reverse sweep's two-node prefetch never needs a bounds check
+    double *xs;             // node-state store [n][N+1][ldb]; OCS_XS_SLACK*ldb doubles of slack precede it so
+                            // that the reverse sweep's prefetch never needs a bounds check
     // forward outputs
     double *J;              // [nb]
     int J_accumulate;       // J = J_in + J_segment (RK4InfiniteIntegrator.m:23)
@@ -805,7 +809,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     ControlEval<nc, UMODE, BMODE, KD> ctl[T];
     GradAcc<nc, BMODE, KD> gacc[T];
     double uL[T][nc], uM[T][nc], uR[T][nc], dcar[T][nc], dR[T][nc], dM[T][nc];
-    double y1[T][n], yn1[T][n], yn2[T][n];
+    constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
+    double y1[T][n], yn[D][T][n];
     const double *xsp[T];
 #pragma unroll
     for (int q = 0; q < T; ++q) {
@@ -822,13 +827,13 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
         gacc[q].init();
 #pragma unroll
         for (int c = 0; c < nc; ++c) dcar[q][c] = 0.0;
-        xsp[q] = a.xs + (size_t)(N - 1) * a.ldb + bb[q];
+        xsp[q] = a.xs + (size_t)(N - 1) * a.ldb + bb[q];     // node N-1; nodes below 0 fall into the slack
 #pragma unroll
-        for (int c = 0; c < n; ++c) {
-            yn1[q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
-            yn2[q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb - a.ldb];
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) yn[d][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb - (size_t)d * a.ldb];
         }
-        xsp[q] -= a.ldb;
+        xsp[q] -= (size_t)(D - 1) * a.ldb;
     }
 
     const int i0_last = ((N - 1) / TL::S) * TL::S;
@@ -839,7 +844,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
             for (int q = 0; q < T; ++q) ctl[q].eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb[q], uR[q]);
         }
-#pragma unroll 2
+#pragma unroll D
         for (int s = ns - 1; s >= 0; --s) {
             const int i = i0 + s;
             const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
@@ -850,11 +855,18 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             const bool moves = BMODE == BMODE_SPARSE ? (reinterpret_cast<const int *>(bM)[1] & 4) != 0 : true;
 #pragma unroll
             for (int q = 0; q < T; ++q) {
+                // rotate the ring (register renaming under the unroll) and issue the load D nodes ahead;
+                // unconditional: below node 0 it reads the slack in front of the store and is never used
 #pragma unroll
-                for (int c = 0; c < n; ++c) { y1[q][c] = yn1[q][c]; yn1[q][c] = yn2[q][c]; }
+                for (int c = 0; c < n; ++c) y1[q][c] = yn[0][q][c];
+#pragma unroll
+                for (int d = 0; d + 1 < D; ++d) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) yn[d][q][c] = yn[d + 1][q][c];
+                }
                 xsp[q] -= a.ldb;
 #pragma unroll
-                for (int c = 0; c < n; ++c) yn2[q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
+                for (int c = 0; c < n; ++c) yn[D - 1][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
             }
 #pragma unroll
             for (int q = 0; q < T; ++q) {
