@@ -177,6 +177,25 @@ OCS_B200_API int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt
                                    double uRelTol, double uAbsTol, int nSWEEPS, double relax,
                                    double *J, int32_t *sweeps, int32_t *converged, double *max_change);
 
+/* Batched single shooting: the solve behind functions/single_shooting.m:114
+ *     [vOpt, J] = fmincon(@nlpObjective, v0, [], [], [], [], Lb, Ub)
+ * for every trajectory at once, entirely on the device.  fmincon (SQP, serial, host) is replaced by a
+ * spectral projected-gradient method (Barzilai-Borwein step, non-monotone Armijo safeguard, box projection
+ * onto [Lb, Ub] from control.compute_nlp_bounds): each iteration is one fused objective/gradient evaluation
+ * (compute_states + compute_adjoints) of the whole batch plus one update kernel; trajectories converge and
+ * freeze independently.  The minimiser, not the iterate path, is what is comparable with fmincon.
+ *   x0 [n x Bt]; v0 [(nc*K) x nbatch] (nbatch in {1, Bt}); Lb, Ub [(nc*K)]
+ *   free_states [nfree] 0-based rows of x0 that are optimised too (single_shooting.m:82-97,143-149) with
+ *   bounds free_lb/free_ub [nfree]; nfree = 0 and NULLs for none
+ *   tol: stop when the projected-gradient max-norm ||v - P(v - dJdv)|| <= tol;  max_iter evaluations at most
+ *   v_opt [(nc*K + nfree) x Bt], J [Bt], iters [Bt], converged [Bt]: any may be NULL
+ * Requires an attached basis.  States/adjoints of the minimisers stay on the device for fetch_*. */
+OCS_B200_API int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt,
+                                          const double *v0, long v0_nbatch, const double *Lb, const double *Ub,
+                                          int nfree, const int32_t *free_states, const double *free_lb,
+                                          const double *free_ub, int max_iter, double tol,
+                                          double *v_opt, double *J, int32_t *iters, int32_t *converged);
+
 /* Batch reduction of the last J (warp-shuffle tree): value and arg index (index may be NULL). */
 OCS_B200_API int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, long *index);
 

@@ -104,6 +104,7 @@ struct ocs_b200_handle {
     long ctrl_nbatch = 0;
     DevBuf d_v, d_ug;
     const double *v_ext = nullptr;     // caller-owned device v (set_control_v_dev)
+    const int *fb_frozen = nullptr;    // trajectories the sweeps must leave untouched (single_shooting / fb_sweep)
     bool user_lamT = false;            // last compute_adjoints carried an explicit lamT (kept in d_lamT_user)
     long user_lamT_ld = 0;
 
@@ -111,6 +112,7 @@ struct ocs_b200_handle {
     long Bt = 0;
     bool have_states = false;
     DevBuf d_x0, d_J, d_xT, d_lamT_tail, d_lamT_user, d_dJdv, d_lam0, d_stage, d_stage2, d_maxchg;
+    DevBuf d_z, d_g, d_zt, d_gt, d_Jacc, d_Jhist, d_alpha, d_lbub;   // single_shooting (SPG) state
     DevBuf d_pipe[2];                 // double-buffered transpose staging of the chunked dJdv download
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
@@ -342,6 +344,71 @@ __global__ void fb_update_kernel(const double *__restrict__ maxchg, int *frozen,
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_open, __popc(bal));
 }
 
+// Spectral projected gradient update, one trajectory per thread (rows of z are coalesced across threads).
+//   z, g, J   : accepted point, its gradient and objective
+//   zt, gt, Jt: trial point the sweeps just evaluated
+//   Jhist     : the last SPG_M accepted objectives (non-monotone reference value)
+// first != 0: the trial IS the starting point (accepted unconditionally).
+#define SPG_M 5
+__global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double *zt, const double *gt, double *J,
+                                  const double *Jt, double *Jhist, double *alpha, const double *lb, const double *ub,
+                                  int *frozen, int *iters, int iter, double tol, int first, int *n_open)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int open = 0;
+    if (b < nb && !frozen[b]) {
+        bool accept = first != 0;
+        double a = alpha[b];
+        if (!first) {
+            double pred = 0.0;                                   // g.(z - zt) >= 0 for a projected step
+            for (long k = 0; k < nz; ++k) pred += g[k * nb + b] * (z[k * nb + b] - zt[k * nb + b]);
+            double Jref = -INFINITY;
+            for (int j = 0; j < SPG_M; ++j) Jref = fmax(Jref, Jhist[j * nb + b]);
+            accept = isfinite(Jt[b]) && Jt[b] <= Jref - 1e-4 * pred;
+        }
+        if (accept) {
+            double sts = 0.0, sty = 0.0, pg = 0.0, gmax = 0.0;
+            for (long k = 0; k < nz; ++k) {
+                const size_t i = (size_t)k * nb + b;
+                const double zn = zt[i], gn = gt[i];
+                const double sk = zn - z[i], yk = gn - g[i];
+                sts += sk * sk;
+                sty += sk * yk;
+                z[i] = zn;
+                g[i] = gn;
+                const double proj = fmin(ub[k], fmax(lb[k], zn - gn));
+                pg = fmax(pg, fabs(zn - proj));
+                gmax = fmax(gmax, fabs(gn));
+            }
+            J[b] = Jt[b];
+            Jhist[(size_t)(iter % SPG_M) * nb + b] = Jt[b];
+            if (first) {
+                for (int j = 0; j < SPG_M; ++j) Jhist[(size_t)j * nb + b] = Jt[b];
+                a = 1.0 / fmax(gmax, 1e-8);
+            } else {
+                a = sty > 0.0 ? fmin(1e10, fmax(1e-10, sts / sty)) : fmin(1e10, 10.0 * a);
+            }
+            if (pg <= tol) frozen[b] = 1;
+        } else {
+            a *= 0.25;                                           // rejected: shorter step from the same point
+            if (a < 1e-14) frozen[b] = 2;                        // stalled
+        }
+        alpha[b] = a;
+        iters[b] = iter;
+        if (!frozen[b]) {
+            open = 1;
+            for (long k = 0; k < nz; ++k) {
+                const size_t i = (size_t)k * nb + b;
+                zt[i] = fmin(ub[k], fmax(lb[k], z[i] - a * g[i]));
+            }
+        } else {
+            for (long k = 0; k < nz; ++k) zt[(size_t)k * nb + b] = z[(size_t)k * nb + b];   // leave the minimiser in place
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, open);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_open, __popc(bal));
+}
+
 __global__ void broadcast_rows_kernel(const double *__restrict__ col, double *dst, long rows, long nb)
 {
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,6 +588,7 @@ void base_args(H *h, int si, SweepArgs &a)
     a.p = h->d_params.p;
     a.ldp = h->params_nbatch > 1 ? h->params_nbatch : 0;
     a.error_flag = h->d_errflag;
+    a.frozen = h->fb_frozen;
 }
 
 size_t smem_bytes(const H *h, const SweepArgs &a)
@@ -852,7 +920,8 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     }
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
                       &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg,
-                      &h->d_pipe[0], &h->d_pipe[1]};
+                      &h->d_pipe[0], &h->d_pipe[1], &h->d_z, &h->d_g, &h->d_zt, &h->d_gt, &h->d_Jacc, &h->d_Jhist,
+                      &h->d_alpha, &h->d_lbub};
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int k = 0; k < 2; ++k)
         if (h->chunk_done[k]) cudaEventDestroy(h->chunk_done[k]);
@@ -1444,6 +1513,127 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
         if (sweeps) CK(cudaMemcpyAsync(sweeps, h->d_sweeps, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
         if (converged) CK(cudaMemcpyAsync(converged, h->d_frozen, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
         if (max_change) CK(cudaMemcpyAsync(max_change, h->d_maxchg.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, const double *v0, long v0_nbatch,
+                             const double *Lb, const double *Ub, int nfree, const int32_t *free_states,
+                             const double *free_lb, const double *free_ub, int max_iter, double tol, double *v_opt,
+                             double *J, int32_t *iters, int32_t *converged)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!x0 || !v0 || !Lb || !Ub || Bt < 1 || max_iter < 1 || (v0_nbatch != 1 && v0_nbatch != Bt) || nfree < 0 ||
+        (nfree > 0 && (!free_states || !free_lb || !free_ub)))
+        return h->fail(OCS_B200_ERR_ARG, "bad single_shooting arguments");
+    if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "single_shooting needs an attached control basis");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+        const long nv = (long)nc * h->K, nz = nv + nfree;
+        for (int f = 0; f < nfree; ++f)
+            if (free_states[f] < 0 || free_states[f] >= n) return h->fail(OCS_B200_ERR_ARG, "free state index out of range");
+        if (h->params_nbatch > 1 && h->params_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "params batch mismatch");
+        h->Bt = Bt;
+        TRY(alloc_batch(h, Bt));
+        TRY(upload_soa(h, x0, h->d_x0, n, Bt));
+        TRY(ensure(h, h->d_z, (size_t)nz * Bt));
+        TRY(ensure(h, h->d_g, (size_t)nz * Bt));
+        TRY(ensure(h, h->d_zt, (size_t)nz * Bt));
+        TRY(ensure(h, h->d_gt, (size_t)nz * Bt));
+        TRY(ensure(h, h->d_Jacc, Bt));
+        TRY(ensure(h, h->d_Jhist, (size_t)SPG_M * Bt));
+        TRY(ensure(h, h->d_alpha, Bt));
+        TRY(ensure(h, h->d_lbub, 2 * (size_t)nz));
+        TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
+        // starting point: zt = [v0; x0(free)] projected onto the box
+        {
+            std::vector<double> lbub(2 * (size_t)nz);
+            for (long k = 0; k < nv; ++k) { lbub[k] = Lb[k]; lbub[nz + k] = Ub[k]; }
+            for (int f = 0; f < nfree; ++f) { lbub[nv + f] = free_lb[f]; lbub[nz + nv + f] = free_ub[f]; }
+            CK(cudaMemcpyAsync(h->d_lbub.p, lbub.data(), sizeof(double) * 2 * nz, cudaMemcpyHostToDevice, h->stream));
+            if (v0_nbatch == Bt) {
+                TRY(ensure(h, h->d_stage, (size_t)nv * Bt));
+                CK(cudaMemcpyAsync(h->d_stage.p, v0, sizeof(double) * nv * Bt, cudaMemcpyHostToDevice, h->stream));
+                TRY(to_soa(h, h->d_stage.p, h->d_zt.p, nv, Bt, Bt));
+            } else {
+                std::vector<double> v0p(v0, v0 + nv);
+                for (long k = 0; k < nv; ++k) v0p[k] = std::min(Ub[k], std::max(Lb[k], v0p[k]));
+                TRY(ensure(h, h->d_stage, (size_t)nv));
+                CK(cudaMemcpyAsync(h->d_stage.p, v0p.data(), sizeof(double) * nv, cudaMemcpyHostToDevice, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                broadcast_rows_kernel<<<(unsigned)((Bt + 255) / 256), 256, 0, h->stream>>>(h->d_stage.p, h->d_zt.p, nv, Bt);
+                CK(cudaGetLastError());
+            }
+            for (int f = 0; f < nfree; ++f)
+                CK(cudaMemcpyAsync(h->d_zt.p + (size_t)(nv + f) * Bt, h->d_x0.p + (size_t)free_states[f] * Bt,
+                                   sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));   // lbub is a local vector
+        }
+        if (h->frozen_cap < (size_t)Bt) {
+            cudaFree(h->d_frozen);
+            cudaFree(h->d_sweeps);
+            h->d_frozen = h->d_sweeps = nullptr;
+            CK(cudaMalloc(&h->d_frozen, sizeof(int) * (Bt + 1)));
+            CK(cudaMalloc(&h->d_sweeps, sizeof(int) * Bt));
+            h->frozen_cap = Bt;
+        }
+        int *d_nopen = h->d_frozen + Bt;
+        CK(cudaMemsetAsync(h->d_frozen, 0, sizeof(int) * (Bt + 1), h->stream));
+        CK(cudaMemsetAsync(h->d_sweeps, 0, sizeof(int) * Bt, h->stream));
+        // the sweeps read the trial coefficients in place
+        h->v_ext = h->d_zt.p;
+        h->ctrl_mode = CTRL_V_BATCH;
+        h->ctrl_nbatch = Bt;
+        h->seg[0].records_dirty = true;
+        for (int iter = 0; iter < max_iter; ++iter) {
+            for (int f = 0; f < nfree; ++f)      // x0(FreeInitStates) = v(end-nFREE_STATES+1:end)   single_shooting.m:145
+                CK(cudaMemcpyAsync(h->d_x0.p + (size_t)free_states[f] * Bt, h->d_zt.p + (size_t)(nv + f) * Bt,
+                                   sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+            // nlpObjective for the whole batch; converged trajectories are skipped by the kernels (frozen)
+            {
+                const int n_seg = h->has_tail ? 2 : 1;
+                for (int si = 0; si < n_seg; ++si) {
+                    TRY(build_records(h, si));
+                }
+            }
+            h->fb_frozen = h->d_frozen;
+            int rc = run_forward(h, 0, Bt, -1, nullptr, true);
+            if (rc == 0) {
+                CK(cudaMemsetAsync(h->d_gt.p, 0, sizeof(double) * nv * Bt, h->stream));
+                rc = run_reverse(h, 0, Bt, -1, nullptr, 0, h->d_gt.p, h->d_lam0.p, nullptr, nullptr);
+            }
+            h->fb_frozen = nullptr;
+            if (rc != 0) return rc;
+            for (int f = 0; f < nfree; ++f)      // dJdv = [compute_dJdv(dJdu); lam(FreeInitStates,1)]   :148
+                CK(cudaMemcpyAsync(h->d_gt.p + (size_t)(nv + f) * Bt, h->d_lam0.p + (size_t)free_states[f] * Bt,
+                                   sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
+            spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
+                nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
+                h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+            CK(cudaGetLastError());
+            int nopen = 0;
+            CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (nopen == 0) break;
+        }
+        // leave the device state at the minimisers: one last evaluation of the accepted points (zt == z for
+        // frozen trajectories; the others get their best accepted point)
+        CK(cudaMemcpyAsync(h->d_zt.p, h->d_z.p, sizeof(double) * nz * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        for (int f = 0; f < nfree; ++f)
+            CK(cudaMemcpyAsync(h->d_x0.p + (size_t)free_states[f] * Bt, h->d_zt.p + (size_t)(nv + f) * Bt,
+                               sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        TRY(run_forward(h, 0, Bt, -1, nullptr, true));
+        h->have_states = true;
+        if (v_opt) TRY(download_soa(h, h->d_z.p, Bt, 0, v_opt, nz, Bt));
+        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (iters) CK(cudaMemcpyAsync(iters, h->d_sweeps, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (converged) CK(cudaMemcpyAsync(converged, h->d_frozen, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     } catch (const std::exception &ex) {

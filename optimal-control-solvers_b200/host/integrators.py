@@ -308,6 +308,39 @@ class CudaRK4Integrator:
         self._last_u = None
         return out
 
+    # ------------------------------------------------------------------ batched single shooting on the device
+    def single_shooting(self, prob, x0, v0, Lb, Ub, FreeInitStates=(), FreeStateBounds=None, max_iter=200, tol=1e-6):
+        """The fmincon solve of functions/single_shooting.m:114 for every trajectory at once, on the device
+        (spectral projected gradient; see ocs_b200_single_shooting).  v0: (nc*K,) shared or (nc*K, Bt).
+        Returns dict(v, J, iters, converged): v is (nc*K + nfree, Bt)."""
+        if self._control is None:
+            raise RuntimeError("attach_control(control) first")
+        self._bind(prob)
+        x0f, single = self._x0(x0)
+        Bt = x0f.shape[1]
+        v0 = np.asarray(v0, dtype=np.float64)
+        nb0 = 1 if v0.ndim == 1 else v0.shape[1]
+        v0f = _lib.f64(v0)
+        nv = self._nc * self._control.nBasis
+        Lbf, Ubf = _lib.f64(np.asarray(Lb, dtype=np.float64).ravel()), _lib.f64(np.asarray(Ub, dtype=np.float64).ravel())
+        if Lbf.size != nv or Ubf.size != nv:
+            raise ValueError("Lb / Ub must have nControls*K entries (control.compute_nlp_bounds)")
+        free = np.asarray(list(FreeInitStates), dtype=np.int32)
+        nf = free.size
+        flb = fub = None
+        if nf:
+            fb = np.asarray(FreeStateBounds, dtype=np.float64).reshape(nf, 2)
+            flb, fub = _lib.f64(fb[:, 0].copy()), _lib.f64(fb[:, 1].copy())
+        out = dict(v=np.empty((nv + nf, Bt), order="F"), J=np.empty(Bt), iters=np.empty(Bt, dtype=np.int32),
+                   converged=np.empty(Bt, dtype=np.int32))
+        self._ck(self._lib.ocs_b200_single_shooting(
+            self._h, _lib.dp(x0f), Bt, _lib.dp(v0f), nb0, _lib.dp(Lbf), _lib.dp(Ubf), nf,
+            _lib.ip(free) if nf else None, _lib.dp(flb), _lib.dp(fub), int(max_iter), float(tol),
+            _lib.dp(out["v"]), _lib.dp(out["J"]), _lib.ip(out["iters"]), _lib.ip(out["converged"])))
+        self._Bt, self._single = Bt, single
+        self._last_u = None
+        return out
+
     # ------------------------------------------------------------------ measurement
     def set_profiling(self, on=True):
         self._ck(self._lib.ocs_b200_set_profiling(self._h, int(on)))

@@ -104,6 +104,24 @@ classdef CudaRK4Integrator < Integrator
                                              size(obj.control.B, 1)*obj.nControls);
       end
 
+      function out = single_shooting(obj, prob, x0, v0, Lb, Ub, varargin)
+         % The fmincon solve of functions/single_shooting.m:114 for every column of x0, on the device
+         % (spectral projected gradient with the box [Lb, Ub] of control.compute_nlp_bounds).
+         p = inputParser;
+         p.addParameter('FreeInitStates', []);    % 1-based, as in single_shooting.m:28
+         p.addParameter('FreeStateBounds', []);
+         p.addParameter('MaxIter', 300);
+         p.addParameter('TolX', 1e-6);
+         parse(p, varargin{:});
+         obj.bind(prob);
+         free = int32(p.Results.FreeInitStates(:)') - 1;
+         fb = p.Results.FreeStateBounds;
+         if isempty(free), flb = []; fub = []; else, flb = fb(:,1); fub = fb(:,2); end
+         [out.v, out.J, out.iters, out.converged] = ocs_b200_mex('single_shooting', obj.handle, x0, v0, Lb, Ub, ...
+            free, flb, fub, p.Results.MaxIter, p.Results.TolX);
+         obj.Bt = size(x0, 2);
+      end
+
       function out = fb_sweep(obj, prob, x0, u0, varargin)
          % The sweep loop of functions/fb_sweep.m:79-115 on the RK4 grid, for every column of x0.
          p = inputParser;

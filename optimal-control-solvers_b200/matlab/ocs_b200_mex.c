@@ -226,6 +226,27 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         check(rc, h);
         return;
     }
+    /* ---- [v, J, iters, converged] = mex('single_shooting', h, x0, v0, Lb, Ub, free (0-based int32 | []), freeLb, freeUb, maxIter, tol)
+     *      the fmincon solve of functions/single_shooting.m:114 for every column of x0, on the device */
+    if (!strcmp(cmd, "single_shooting")) {
+        FAIL_IF(nrhs < 11, "ocs_b200:nargin", "single_shooting(h, x0, v0, Lb, Ub, free, freeLb, freeUb, maxIter, tol)");
+        long Bt = (long)mxGetN(prhs[2]);
+        long nv = (long)mxGetNumberOfElements(prhs[4]);
+        int nfree = (int)mxGetNumberOfElements(prhs[6]);
+        FAIL_IF(nfree > 0 && mxGetClassID(prhs[6]) != mxINT32_CLASS, "ocs_b200:type", "free state indices must be int32 (0-based)");
+        plhs[0] = mxCreateDoubleMatrix(nv + nfree, Bt, mxREAL);
+        mxArray *Jo = mxCreateDoubleMatrix(1, Bt, mxREAL), *it = int32_row(Bt), *cv = int32_row(Bt);
+        int rc = ocs_b200_single_shooting(h, dbl(prhs[2], "x0"), Bt, dbl(prhs[3], "v0"), (long)mxGetN(prhs[3]),
+                                          dbl(prhs[4], "Lb"), dbl(prhs[5], "Ub"), nfree,
+                                          nfree ? (const int32_t *)mxGetData(prhs[6]) : NULL, dbl(prhs[7], "freeLb"),
+                                          dbl(prhs[8], "freeUb"), (int)scalar(prhs[9]), scalar(prhs[10]),
+                                          mxGetPr(plhs[0]), mxGetPr(Jo), (int32_t *)mxGetData(it), (int32_t *)mxGetData(cv));
+        if (nlhs > 1) plhs[1] = Jo; else mxDestroyArray(Jo);
+        if (nlhs > 2) plhs[2] = it; else mxDestroyArray(it);
+        if (nlhs > 3) plhs[3] = cv; else mxDestroyArray(cv);
+        check(rc, h);
+        return;
+    }
     /* ---- [value, index] = mex('reduce_J', h, op)   op: 0 sum, 1 min, 2 max (index 1-based) */
     if (!strcmp(cmd, "reduce_J")) {
         FAIL_IF(nrhs < 3, "ocs_b200:nargin", "reduce_J(h, op)");

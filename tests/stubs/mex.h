@@ -25,6 +25,7 @@ int mxIsDouble(const mxArray *a);
 int mxIsChar(const mxArray *a);
 int mxIsComplex(const mxArray *a);
 int mxIsEmpty(const mxArray *a);
+mxClassID mxGetClassID(const mxArray *a);
 size_t mxGetNumberOfElements(const mxArray *a);
 mwSize mxGetNumberOfDimensions(const mxArray *a);
 const mwSize *mxGetDimensions(const mxArray *a);

@@ -20,6 +20,7 @@ int mxIsUint64(const mxArray *a) { return a->cls == mxUINT64_CLASS; }
 int mxIsDouble(const mxArray *a) { return a->cls == mxDOUBLE_CLASS; }
 int mxIsChar(const mxArray *a) { return a->cls == mxCHAR_CLASS; }
 int mxIsComplex(const mxArray *a) { (void)a; return 0; }
+mxClassID mxGetClassID(const mxArray *a) { return a->cls; }
 size_t mxGetNumberOfElements(const mxArray *a) { size_t n = 1; for (mwSize k = 0; k < a->ndim; ++k) n *= a->dims[k]; return n; }
 int mxIsEmpty(const mxArray *a) { return mxGetNumberOfElements(a) == 0; }
 mwSize mxGetNumberOfDimensions(const mxArray *a) { return a->ndim; }
