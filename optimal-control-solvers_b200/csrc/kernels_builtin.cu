@@ -66,9 +66,7 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->fwd[2][0][0] = FWD(2, 0, 0); t->fwd[2][0][1] = FWD(2, 0, 1);
     t->rev[0][0][0] = REV(0, 0, 0); t->rev[0][0][1] = REV(0, 0, 1);
     t->rev[0][1][0] = REV(0, 1, 0); t->rev[0][1][1] = REV(0, 1, 1);
-    t->rev[0][2][0] = REV(0, 2, 0); t->rev[0][2][1] = REV(0, 2, 1);
     t->rev[1][1][0] = REV(1, 1, 0); t->rev[1][1][1] = REV(1, 1, 1);
-    t->rev[1][2][0] = REV(1, 2, 0); t->rev[1][2][1] = REV(1, 2, 1);
     t->rev[2][0][0] = REV(2, 0, 0); t->rev[2][0][1] = REV(2, 0, 1);
     t->fwdg[0][0][0] = FWDG(0, 0, 0); t->fwdg[0][0][1] = FWDG(0, 0, 1);
     t->fwdg[1][1][0] = FWDG(1, 1, 0); t->fwdg[1][1][1] = FWDG(1, 1, 1);

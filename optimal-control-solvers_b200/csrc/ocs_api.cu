@@ -112,6 +112,7 @@ struct ocs_b200_handle {
     long Bt = 0;
     bool have_states = false;
     DevBuf d_x0, d_J, d_xT, d_lamT_tail, d_lamT_user, d_dJdv, d_lam0, d_stage, d_stage2, d_maxchg;
+    DevBuf d_dug;                     // dJdu grid [nc][G][Bt] of the dense-basis gradient path
     DevBuf d_z, d_g, d_zt, d_gt, d_Jacc, d_Jhist, d_alpha, d_lbub;   // single_shooting (SPG) state
     DevBuf d_pipe[2];                 // double-buffered transpose staging of the chunked dJdv download
     cudaStream_t copy_stream = nullptr;
@@ -409,6 +410,71 @@ __global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_open, __popc(bal));
 }
 
+// dJdv = dJdu * B' for a dense basis (ChebyshevControl.m:34-37):
+// dug [nc][G][ldb] (SoA, written by the reverse sweep), basrec [G][BW] = B(:,j), dJdv [(k*nc+c)][ldb].
+// The block stages B for a tile of grid points in shared memory.  A thread owns PROJ_T trajectories and keeps
+// KC accumulators for each in registers (K is walked in chunks of KC): one row B(:,j) read from shared memory
+// feeds PROJ_T*KC FMAs, and the dJdu loads of 4 grid points are issued ahead of their use.  Summation runs
+// over ascending j.
+#define PROJ_JT 64
+#define PROJ_T 4
+template <int KC>
+__global__ void __launch_bounds__(128) dense_project_kernel(const double *__restrict__ dug, const double *__restrict__ basrec,
+                                                            int BW, int K, int nc, int G, long nb, long ldb, double *dJdv)
+{
+    extern __shared__ double2 proj_smem2[];
+    double *Bs = reinterpret_cast<double *>(proj_smem2);      // [PROJ_JT][BW]
+    long b[PROJ_T], bb[PROJ_T];
+#pragma unroll
+    for (int q = 0; q < PROJ_T; ++q) {
+        b[q] = ((long)blockIdx.x * PROJ_T + q) * blockDim.x + threadIdx.x;
+        bb[q] = b[q] < nb ? b[q] : nb - 1;
+    }
+    for (int c = 0; c < nc; ++c)
+        for (int k0 = 0; k0 < K; k0 += KC) {
+            double acc[PROJ_T][KC];
+#pragma unroll
+            for (int q = 0; q < PROJ_T; ++q)
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) acc[q][kk] = 0.0;
+            const double *dp = dug + (size_t)c * G * ldb;
+            for (int j0 = 0; j0 < G; j0 += PROJ_JT) {
+                const int nj = G - j0 < PROJ_JT ? G - j0 : PROJ_JT;
+                __syncthreads();
+                for (int k = threadIdx.x; k < PROJ_JT * BW; k += blockDim.x)
+                    Bs[k] = k < nj * BW ? basrec[(size_t)j0 * BW + k] : 0.0;   // rows past the grid multiply by zero
+                __syncthreads();
+                for (int jj = 0; jj < PROJ_JT; jj += 4) {
+                    if (jj >= nj) break;
+                    double d[4][PROJ_T];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = j0 + jj + r < G ? j0 + jj + r : G - 1;   // clamped rows meet a zero B row
+#pragma unroll
+                        for (int q = 0; q < PROJ_T; ++q) d[r][q] = dp[(size_t)j * ldb + bb[q]];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        double Bj[KC];
+#pragma unroll
+                        for (int kk = 0; kk < KC; ++kk) Bj[kk] = (k0 + kk < BW) ? Bs[(jj + r) * BW + k0 + kk] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < PROJ_T; ++q)
+#pragma unroll
+                            for (int kk = 0; kk < KC; ++kk) acc[q][kk] = acc[q][kk] + d[r][q] * Bj[kk];
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PROJ_T; ++q)
+                if (b[q] < nb) {
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk)
+                        if (k0 + kk < K) dJdv[(size_t)((k0 + kk) * nc + c) * ldb + b[q]] = acc[q][kk];
+                }
+        }
+}
+
 __global__ void broadcast_rows_kernel(const double *__restrict__ col, double *dst, long rows, long nb)
 {
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -591,13 +657,14 @@ void base_args(H *h, int si, SweepArgs &a)
     a.frozen = h->fb_frozen;
 }
 
-size_t smem_bytes(const H *h, const SweepArgs &a)
+size_t smem_bytes(const H *h, const SweepArgs &a, size_t acc_doubles)
 {
     const int S = h->kt.tile;
-    return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW) * sizeof(double);
+    return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW + acc_doubles) * sizeof(double);
 }
 
-int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1)
+// acc_doubles: shared-memory doubles per block beyond the record tiles (dense-basis gradient accumulators)
+int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1, size_t acc_doubles = 0)
 {
     if (!kernel) return h->fail(OCS_B200_ERR_ARG, "this control/basis/parameter combination has no kernel variant");
     if (a.nb <= 0) return 0;
@@ -605,7 +672,7 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1)
     const unsigned blocks = (unsigned)((a.nb + (long)threads * tpt - 1) / ((long)threads * tpt));
     void *args[] = {(void *)&a};
     if (h->profiling) CK(cudaEventRecord(h->ev[0], h->stream));
-    const size_t smem = smem_bytes(h, a);
+    const size_t smem = smem_bytes(h, a, acc_doubles);
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return h->fail(OCS_B200_ERR_ARG, "control basis too wide for the shared-memory tile");
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -690,6 +757,10 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         if (um == 1) {
             bm = h->basis_kind;
             a.v = (h->v_ext ? h->v_ext : h->d_v.p) + b0;
+            if (bm == BASIS_DENSE) {     // keep the evaluated control grid for the reverse sweep
+                TRY(ensure(h, h->d_ug, (size_t)h->kt.nc * (2 * s.N + 1) * Bt));
+                a.ug_out = h->d_ug.p + b0;
+            }
         } else if (um == 2) {
             a.ug = h->d_ug.p + b0;
         }
@@ -720,6 +791,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         if (a.ldp) a.p = h->d_params.p + b0;
         a.xs = s.d_xs + b0;
         int um = 0, bm = 0;
+        bool project = false;
         if (si == 1) {
             TRY(ensure(h, h->d_lamT_tail, (size_t)m * Bt));
             a.lam0 = h->d_lamT_tail.p + b0;
@@ -740,17 +812,32 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             a.lamgrid = d_lamgrid;
             a.dJdugrid = d_dJdugrid;
             um = main_umode(h);
-            if (um == 1) {
+            const bool grids_req = d_lamgrid || d_dJdugrid;
+            if (d_dJdv && h->basis_kind == BASIS_NONE)
+                return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
+            if (um == 2 && d_dJdv)
+                return h->fail(OCS_B200_ERR_ARG, "dJdv needs coefficients v, not a per-trajectory u grid");
+            if (h->basis_kind == BASIS_DENSE && !grids_req) {
+                // dense basis: the sweep writes dJdu (SoA) and dense_project_kernel forms dJdu*B' afterwards;
+                // a per-trajectory control is read from the grid the forward sweep evaluated (d_ug)
+                if (um == 1) {
+                    um = 2;
+                    a.ug = h->d_ug.p + b0;
+                }
+                if (d_dJdv) {
+                    TRY(ensure(h, h->d_dug, (size_t)h->kt.nc * (2 * s.N + 1) * Bt));
+                    a.dug = h->d_dug.p + b0;
+                    a.dJdv = nullptr;
+                    project = true;
+                }
+            } else if (um == 1) {
                 bm = h->basis_kind;
                 a.v = (h->v_ext ? h->v_ext : h->d_v.p) + b0;
             } else if (um == 2) {
                 a.ug = h->d_ug.p + b0;
-                if (d_dJdv) return h->fail(OCS_B200_ERR_ARG, "dJdv needs coefficients v, not a per-trajectory u grid");
             } else if (d_dJdv) {
                 bm = h->basis_kind;
             }
-            if (d_dJdv && h->basis_kind == BASIS_NONE)
-                return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
         }
         const bool grids = a.lamgrid || a.dJdugrid;
         if (grids && um != 1) bm = 0;   // the fetch variants write dJdu itself; only UMODE_COEF needs the basis
@@ -758,6 +845,26 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
         // dense-basis kernels keep K coefficients and K accumulators per trajectory in registers: one per thread
         TRY(launch(h, kern, a, false, (grids || bm == 2) ? 1 : std::max(h->kt.tpt_rev, 1)));
+        if (project) {
+            const int G = 2 * s.N + 1;
+            if (h->profiling) CK(cudaEventRecord(h->ev[2], h->stream));
+            const size_t psm = (size_t)PROJ_JT * s.BW * sizeof(double);
+            const unsigned pblocks = (unsigned)((nb + 128 * PROJ_T - 1) / (128 * PROJ_T));
+            // K <= 18: one pass with 18 accumulators per trajectory; larger K in chunks of 16
+            if (h->K <= 18)
+                dense_project_kernel<18><<<pblocks, 128, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
+            else
+                dense_project_kernel<16><<<pblocks, 128, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
+            CK(cudaGetLastError());
+            if (h->profiling) {
+                CK(cudaEventRecord(h->ev[3], h->stream));
+                CK(cudaEventSynchronize(h->ev[3]));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+                h->ms_rev += ms;
+            }
+            h->launches++;
+        }
     }
     return 0;
 }
@@ -921,7 +1028,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
                       &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg,
                       &h->d_pipe[0], &h->d_pipe[1], &h->d_z, &h->d_g, &h->d_zt, &h->d_gt, &h->d_Jacc, &h->d_Jhist,
-                      &h->d_alpha, &h->d_lbub};
+                      &h->d_alpha, &h->d_lbub, &h->d_dug};
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int k = 0; k < 2; ++k)
         if (h->chunk_done[k]) cudaEventDestroy(h->chunk_done[k]);

@@ -95,6 +95,9 @@ struct SweepArgs {
     const double *p;        // [np] or [np][ldp]
     const double *v;        // UMODE_COEF: [(k*nc+c)][ldb]
     double *ug;             // UMODE_GRID: [nc][2N+1][ldb]   (fb_sweep updates it in place)
+    double *ug_out;         // dense UMODE_COEF forward sweep: the evaluated control grid is kept here for the
+                            // reverse sweep ([nc][2N+1][ldb]), or null
+    double *dug;            // BMODE_NONE reverse sweep: dJdu in SoA layout [nc][2N+1][ldb], or null
     double *xs;             // node-state store [n][N+1][ldb]; OCS_XS_SLACK*ldb doubles of slack precede it so
                             // that the reverse sweep's prefetch never needs a bounds check
     // forward outputs
@@ -207,7 +210,8 @@ struct GradAcc {
     // sparse basis: accumulators of the two live knots {k, k+1}, held by knot parity (aE: even knot)
     double aE[BMODE == BMODE_SPARSE ? nc : 1];
     double aO[BMODE == BMODE_SPARSE ? nc : 1];
-    double ad[BMODE == BMODE_DENSE ? KA * nc : 1];
+    // (a dense basis is not folded in the sweep: the reverse kernel writes dJdu and a separate projection
+    //  kernel forms dJdu*B', see dense_project_kernel in ocs_api.cu)
 
     __device__ __forceinline__ void init()
     {
@@ -215,10 +219,6 @@ struct GradAcc {
         if constexpr (BMODE == BMODE_SPARSE) {
 #pragma unroll
             for (int c = 0; c < nc; ++c) aE[c] = aO[c] = 0.0;
-        }
-        if constexpr (BMODE == BMODE_DENSE) {
-#pragma unroll
-            for (int k = 0; k < KA * nc; ++k) ad[k] = 0.0;
         }
     }
 
@@ -252,15 +252,6 @@ struct GradAcc {
                 aE[c] = aE[c] + d[c] * wE;
                 aO[c] = aO[c] + d[c] * wO;     // a zero weight adds an exact zero
             }
-        } else if constexpr (BMODE == BMODE_DENSE) {
-            const int K = KD > 0 ? KD : a.K;
-#pragma unroll
-            for (int k = 0; k < KA; ++k)
-                if (k < K) {
-                    const double bk = bas[k];
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) ad[k * nc + c] = ad[k * nc + c] + d[c] * bk;
-                }
         }
     }
 
@@ -282,16 +273,6 @@ struct GradAcc {
         if constexpr (BMODE == BMODE_SPARSE) {
             flush(a, kcur + 1, b, active);
             flush(a, kcur, b, active);
-        } else if constexpr (BMODE == BMODE_DENSE) {
-            const int K = KD > 0 ? KD : a.K;
-            if (active) {
-#pragma unroll
-                for (int k = 0; k < KA; ++k)
-                    if (k < K) {
-#pragma unroll
-                        for (int c = 0; c < nc; ++c) a.dJdv[soa((long)k * nc + c, a.ldb, b)] = ad[k * nc + c];
-                    }
-            }
         }
     }
 };
@@ -368,7 +349,15 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
     for (int i0 = 0; i0 < N; i0 += TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
-        if (i0 == 0) ctl.eval(a, gp, bs, 0, bb, uL);
+        if (i0 == 0) {
+            ctl.eval(a, gp, bs, 0, bb, uL);
+            if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
+                if (a.ug_out && active) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) a.ug_out[soa((long)c * (2 * N + 1), a.ldb, b)] = uL[c];
+                }
+            }
+        }
 #pragma unroll 4
         for (int s = 0; s < ns; ++s) {
             const int i = i0 + s;
@@ -387,6 +376,15 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
             xsp += a.ldb;
             ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
             ctl.eval(a, rR, bR, 2 * i + 2, bb, uR);
+            if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
+                if (a.ug_out && active) {   // the reverse sweep reads the grid instead of re-evaluating v*B
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) {
+                        a.ug_out[soa((long)c * (2 * N + 1) + 2 * i + 1, a.ldb, b)] = uM[c];
+                        a.ug_out[soa((long)c * (2 * N + 1) + 2 * i + 2, a.ldb, b)] = uR[c];
+                    }
+                }
+            }
 
             double F[m], acc[m], ys[n];
             P::template F<HM>(rL + 1 + nc, rL[0], y, uL, p, F);                  // F1   :39
@@ -488,7 +486,15 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
         if (i0 == 0) {
 #pragma unroll
-            for (int q = 0; q < T; ++q) ctl[q].eval(a, gp, bs, 0, bb[q], uL[q]);
+            for (int q = 0; q < T; ++q) {
+                ctl[q].eval(a, gp, bs, 0, bb[q], uL[q]);
+                if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
+                    if (a.ug_out && active[q]) {
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) a.ug_out[soa((long)c * (2 * N + 1), a.ldb, b[q])] = uL[q][c];
+                    }
+                }
+            }
         }
 #pragma unroll 4
         for (int s = 0; s < ns; ++s) {
@@ -506,6 +512,15 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rL, bs, 2 * i, bb[q], uL[q]);
                 ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
                 ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
+                if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
+                    if (a.ug_out && active[q]) {   // the reverse sweep reads the grid instead of re-evaluating v*B
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) {
+                            a.ug_out[soa((long)c * (2 * N + 1) + 2 * i + 1, a.ldb, b[q])] = uM[q][c];
+                            a.ug_out[soa((long)c * (2 * N + 1) + 2 * i + 2, a.ldb, b[q])] = uR[q][c];
+                        }
+                    }
+                }
 
                 double F[m], acc[m], ys[n];
                 P::template F<HM>(rL + 1 + nc, rL[0], y[q], uL[q], p[q], F);         // F1   :39
@@ -795,7 +810,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
     typedef TileLayout<RB> TL;
     const int BW = BWc >= 0 ? BWc : a.BW;
-    const int N = a.N;
+    const int N = a.N, G = 2 * N + 1;
+    const bool dugout = a.dug != nullptr;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
     if (a.RB != RB || (NEEDB && a.BW != BW)) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
@@ -885,33 +901,50 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                 for (int c = 0; c < n; ++c) y4[c] = y1[q][c] + h * F[c];
 
+                // Adjoint chain :73-88 with each dFdu_times_vec (:101-120) evaluated as soon as its stage costate
+                // dJdk is known, so that stage states and dJdk's die early (the sums are formed in the reference's
+                // order; only the evaluation order of independent terms differs).
+                constexpr bool GA = (BMODE != BMODE_NONE);
+                const bool du = GA || dugout;
                 double k4[m], k3[m], k2[m], k1[m], g3[n], g2[n], g1[n], g0[n];
+                double dRq[nc], dM3[nc], dM2[nc];
 #pragma unroll
                 for (int c = 0; c < m; ++c) k4[c] = h6 * lam[q][c];                          // :73
+                if (du) P::template U<HM>(ttR, tR, y4, uR[q], p[q], k4, dRq);               // :119-120 / :116
                 P::template X<HM>(ttR, tR, y4, uR[q], p[q], k4, g3);                        // :74-75
 #pragma unroll
                 for (int c = 0; c < n; ++c) k3[c] = h3 * lam[q][c] + h * g3[c];              // :77
                 k3[n] = h3 * lam[q][n];
+                if (du) P::template U<HM>(ttM, tM, y3, uM[q], p[q], k3, dM3);               // :108-109
                 P::template X<HM>(ttM, tM, y3, uM[q], p[q], k3, g2);                        // :78-79
 #pragma unroll
                 for (int c = 0; c < n; ++c) k2[c] = h3 * lam[q][c] + h2 * g2[c];             // :81
                 k2[n] = h3 * lam[q][n];
+                if (du) P::template U<HM>(ttM, tM, y2, uM[q], p[q], k2, dM2);               // :106-107
                 P::template X<HM>(ttM, tM, y2, uM[q], p[q], k2, g1);                        // :82-83
 #pragma unroll
                 for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
                 k1[n] = h6 * lam[q][n];
                 P::template X<HM>(ttL, tL, y1[q], uL[q], p[q], k1, g0);                     // :86-88
 
-                if constexpr (BMODE != BMODE_NONE) {
-                    double e[nc];
-                    P::template U<HM>(ttR, tR, y4, uR[q], p[q], k4, dR[q]);                 // :112-120
+                if constexpr (GA) {
 #pragma unroll
-                    for (int c = 0; c < nc; ++c) dR[q][c] = dcar[q][c] + dR[q][c];
-                    P::template U<HM>(ttM, tM, y2, uM[q], p[q], k2, dM[q]);                 // :105-109
-                    P::template U<HM>(ttM, tM, y3, uM[q], p[q], k3, e);
-#pragma unroll
-                    for (int c = 0; c < nc; ++c) dM[q][c] = dM[q][c] + e[c];
+                    for (int c = 0; c < nc; ++c) {
+                        dR[q][c] = dcar[q][c] + dRq[c];        // stage 1 of step i+1 (carried) + stage 4 of step i
+                        dM[q][c] = dM2[c] + dM3[c];            // stages 2 + 3
+                    }
                     P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);            // :101-102 / :112-116
+                } else {
+                    if (dugout) {            // dJdu itself, SoA [nc][G][batch], coalesced (dense bases project it later)
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) {
+                            if (active[q]) {
+                                a.dug[soa((long)c * G + 2 * i + 2, a.ldb, b[q])] = dcar[q][c] + dRq[c];
+                                a.dug[soa((long)c * G + 2 * i + 1, a.ldb, b[q])] = dM2[c] + dM3[c];
+                            }
+                        }
+                        P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < n; ++c) lam[q][c] = lam[q][c] + g1[c] + g2[c] + g3[c] + g0[c];   // :86
@@ -944,6 +977,11 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
         if constexpr (BMODE != BMODE_NONE) {
             gacc[q].add(a, bs, dcar[q], b[q], active[q]);                                    // left end :101-102
             gacc[q].finish(a, b[q], active[q]);
+        } else {
+            if (dugout && active[q]) {
+#pragma unroll
+                for (int c = 0; c < nc; ++c) a.dug[soa((long)c * G, a.ldb, b[q])] = dcar[q][c];
+            }
         }
         if (a.lam0 && active[q]) {
 #pragma unroll
@@ -1004,7 +1042,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_REV)>, tag, UM, BM, PB, OCS_MINBLOCKS_REV)
+    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_REV)>, tag, UM, BM, PB, ((BM) == 2 ? 1 : OCS_MINBLOCKS_REV))
 #define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_FB_KERNEL(P, tag, PB) \
@@ -1032,9 +1070,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     OCS_FWDG_KERNEL(P, tag, 2, 0, PB, KD)       \
     OCS_REV_KERNEL(P, tag, 0, 0, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 0, 1, PB, KD)        \
-    OCS_REV_KERNEL(P, tag, 0, 2, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 1, 1, PB, KD)        \
-    OCS_REV_KERNEL(P, tag, 1, 2, PB, KD)        \
     OCS_REV_KERNEL(P, tag, 2, 0, PB, KD)        \
     OCS_REVG_KERNEL(P, tag, 0, 0, PB, KD)       \
     OCS_REVG_KERNEL(P, tag, 1, 1, PB, KD)       \
