@@ -279,21 +279,24 @@ def main():
         v_dev = 0.05 * torch.randn(wl["v_batch"], dtype=torch.float64, device=dev, generator=gen)
         v_dev[:2] = 0.2 + 0.6 * torch.rand((2, Bt), dtype=torch.float64, device=dev, generator=gen)
         v_dev = v_dev.contiguous()
-    J = torch.empty(Bt, dtype=torch.float64, device=dev)
-    xT = torch.empty((n_st, Bt), dtype=torch.float64, device=dev)
+    # J and x(T) live in one packed (1+n) x Bt buffer so that one all-gather moves both; double-buffered and
+    # gathered on a side stream so that the collective overlaps the next evaluation (host/dist.py)
+    pg = distmod.PipelinedGather(n_st, Bt, world, dev)
     status = torch.empty(Bt, dtype=torch.int32, device=dev)
     dJdv = torch.empty((rows, Bt), dtype=torch.float64, device=dev)
     lam0 = torch.empty((n_st + 1, Bt), dtype=torch.float64, device=dev)
 
     def evaluate_dev():
+        res = pg.next_buffer()
         integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, v_ptr=(v_dev.data_ptr() if v_dev is not None else 0),
-                           J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(), status_ptr=status.data_ptr(),
+                           J_ptr=res[0].data_ptr(), xT_ptr=res[1:].data_ptr(), status_ptr=status.data_ptr(),
                            dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+        return res
 
     def step():
-        evaluate_dev()
+        res = evaluate_dev()
         if world > 1:
-            distmod.gather_results(J, xT, world)
+            pg.gather(res)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -312,6 +315,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    pg.finish()                 # every gather of the timed steps has completed before the closing event
     ev1.record(stream)
     sync_all()
     ms = ev0.elapsed_time(ev1)

@@ -41,3 +41,59 @@ def gather_ragged(J, world: int, rank: int, Bt_total: int, group=None):
     out = torch.empty(world * big, dtype=J.dtype, device=J.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * big: r * big + (b1 - b0)] for r, (b0, b1) in enumerate(sizes)])
+
+
+class PipelinedGather:
+    """All-gather of the packed per-trajectory results [J; x(T)] ((1+n) x Bt_local per rank) that overlaps
+    with the next evaluation: results are double-buffered, the collective runs on its own CUDA stream behind
+    an event of the compute stream, and a buffer is only handed out again once its gather has completed.
+
+        pg = PipelinedGather(n, Bt, world, device)
+        for step in ...:
+            res = pg.next_buffer()          # (1+n, Bt) tensor: row 0 = J, rows 1.. = x(T)
+            ... sweeps write res ...
+            pg.gather(res)                  # asynchronous
+        pg.finish()                         # pg.out[k] (world, 1+n, Bt) holds the gathered results of buffer k
+    """
+
+    def __init__(self, n, Bt, world, device, group=None):
+        import torch
+        self.world, self.group = world, group
+        self.bufs = [torch.empty((1 + n, Bt), dtype=torch.float64, device=device) for _ in range(2)]
+        self.out = [torch.empty((world, 1 + n, Bt), dtype=torch.float64, device=device) for _ in range(2)]
+        self.cuda = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+        self.done = [None, None]
+        self.k = 1
+
+    def next_buffer(self):
+        import torch
+        self.k ^= 1
+        if self.cuda and self.done[self.k] is not None:
+            torch.cuda.current_stream().wait_event(self.done[self.k])   # its previous gather has read it
+        return self.bufs[self.k]
+
+    def gather(self, res):
+        import torch
+        import torch.distributed as dist
+        k = self.k
+        assert res is self.bufs[k]
+        if self.world == 1:
+            self.out[k][0].copy_(res)
+            return
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.out[k].view(-1), res.view(-1), group=self.group)
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            dist.all_gather_into_tensor(self.out[k].view(-1), res.view(-1), group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.done[k] = ev
+
+    def finish(self):
+        import torch
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
