@@ -37,6 +37,9 @@
 #ifndef OCS_PREFETCH
 #define OCS_PREFETCH 2      // node states prefetched ahead by the reverse sweep (slack in front of the store)
 #endif
+#ifndef OCS_REV_UNROLL
+#define OCS_REV_UNROLL 2    // unroll factor of the reverse step loop
+#endif
 #ifndef OCS_TPT_FWD
 #define OCS_TPT_FWD 1       // trajectories per thread of the forward kernels
 #endif
@@ -123,6 +126,11 @@ struct SweepArgs {
 
 __device__ __forceinline__ size_t soa(long row, long ld, long b) { return (size_t)row * (size_t)ld + (size_t)b; }
 
+// The first slot of a sparse basis record packs two ints (knot index k, flags) into one double; they are
+// taken apart with a bit cast of the loaded double, never through an int-typed pointer (no aliasing games).
+__device__ __forceinline__ int rec_k(const double *bas) { return (int)(__double_as_longlong(bas[0]) & 0xffffffffLL); }
+__device__ __forceinline__ int rec_flags(const double *bas) { return (int)(__double_as_longlong(bas[0]) >> 32); }
+
 // ------------------------------------------------------------------ control evaluation
 // Evaluates u(:,j) for one trajectory while the sweep walks the grid monotonically
 // (up in the forward sweep, down in the reverse sweep).
@@ -163,8 +171,7 @@ struct ControlEval {
 #pragma unroll
             for (int c = 0; c < nc; ++c) u[c] = a.ug[soa((long)c * G + j, a.ldb, bb)];
         } else if constexpr (BMODE == BMODE_SPARSE) {
-            const int2 kk = *reinterpret_cast<const int2 *>(bas);
-            const int k = kk.x;
+            const int k = rec_k(bas), kflags = rec_flags(bas);
             const double wE = bas[1], wO = bas[2];
             if (k != kcur) {   // uniform across the block: every trajectory shares the grid
                 const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
@@ -176,10 +183,10 @@ struct ControlEval {
                 kcur = k;
             }
             // flags: bit0 = two non-zeros in the column; bit1 = (one non-zero) it sits on the odd slot
-            if (kk.y & 1) {
+            if (kflags & 1) {
 #pragma unroll
                 for (int c = 0; c < nc; ++c) u[c] = (k & 1) ? vO[c] * wO + vE[c] * wE : vE[c] * wE + vO[c] * wO;
-            } else if (kk.y & 2) {
+            } else if (kflags & 2) {
 #pragma unroll
                 for (int c = 0; c < nc; ++c) u[c] = vO[c] * wO;   // weight 1: exact copy of v (PWConstantControl)
             } else {
@@ -222,25 +229,38 @@ struct GradAcc {
         }
     }
 
-    // writes the finished knot k out and clears its accumulator
+    // writes the finished knot k out and clears its accumulator (explicit branches on the knot parity: the
+    // accumulators must stay in registers, so they are never selected through a run-time pointer)
     __device__ __forceinline__ void flush(const SweepArgs &a, int k, long b, bool active)
     {
-        double *acc = (k & 1) ? aO : aE;
-        if (k >= 0 && k < a.K && active) {
+        const bool write = k >= 0 && k < a.K && active;
+        if (k & 1) {
+            if (write) {
 #pragma unroll
-            for (int c = 0; c < nc; ++c) {
-                const size_t idx = soa((long)k * nc + c, a.ldb, b);
-                a.dJdv[idx] = a.dJdv[idx] + acc[c];   // buffer is zero-initialised; one owner thread per column
+                for (int c = 0; c < nc; ++c) {
+                    const size_t idx = soa((long)k * nc + c, a.ldb, b);
+                    a.dJdv[idx] = a.dJdv[idx] + aO[c];   // buffer is zero-initialised; one owner thread per column
+                }
             }
-        }
 #pragma unroll
-        for (int c = 0; c < nc; ++c) acc[c] = 0.0;
+            for (int c = 0; c < nc; ++c) aO[c] = 0.0;
+        } else {
+            if (write) {
+#pragma unroll
+                for (int c = 0; c < nc; ++c) {
+                    const size_t idx = soa((long)k * nc + c, a.ldb, b);
+                    a.dJdv[idx] = a.dJdv[idx] + aE[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < nc; ++c) aE[c] = 0.0;
+        }
     }
 
     __device__ __forceinline__ void add(const SweepArgs &a, const double *bas, const double *d, long b, bool active)
     {
         if constexpr (BMODE == BMODE_SPARSE) {
-            const int k = *reinterpret_cast<const int *>(bas);
+            const int k = rec_k(bas);
             const double wE = bas[1], wO = bas[2];
             if (k != kcur) {                    // uniform across the block; ~K times per sweep
                 flush(a, kcur + 1, b, active);  // the window slides down: knot kcur+1 is complete
@@ -700,7 +720,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
                 for (int c = 0; c < nc; ++c) d[c] = dcar[c] + d[c];   // dcar == 0 at the right end
                 // the host flags the steps in which the knot window moves; all others take the straight path
-                const bool moves = GACC && BMODE == BMODE_SPARSE ? (reinterpret_cast<const int *>(bM)[1] & 4) != 0 : true;
+                const bool moves = GACC && BMODE == BMODE_SPARSE ? (rec_flags(bM) & 4) != 0 : true;
                 if (moves) gacc.add(a, bR, d, b, active); else gacc.add_fast(bR, d);
                 if (duout && active) {
 #pragma unroll
@@ -826,6 +846,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     GradAcc<nc, BMODE, KD> gacc[T];
     double uL[T][nc], uM[T][nc], uR[T][nc], dcar[T][nc], dR[T][nc], dM[T][nc];
     constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
+    constexpr int UNR = OCS_REV_UNROLL;
     double y1[T][n], yn[D][T][n];
     const double *xsp[T];
 #pragma unroll
@@ -860,15 +881,17 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
             for (int q = 0; q < T; ++q) ctl[q].eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb[q], uR[q]);
         }
-#pragma unroll D
-        for (int s = ns - 1; s >= 0; --s) {
+        // one RK4 step (all T trajectories) as a lambda, so that the step loop below can be unrolled by hand:
+        // `#pragma unroll 2` on this loop miscompiled the peeled remainder iteration for odd step counts
+        // (nvcc 12.9, caught by tests/test_gpu_edges.py); pairs + one explicit odd step are equivalent and safe.
+        auto rk4_reverse_step = [&](const int s) {
             const int i = i0 + s;
             const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
             const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
             const double tR = rR[0], tM = rM[0], tL = rL[0];
-            const bool moves = BMODE == BMODE_SPARSE ? (reinterpret_cast<const int *>(bM)[1] & 4) != 0 : true;
+            const bool moves = BMODE == BMODE_SPARSE ? (rec_flags(bM) & 4) != 0 : true;
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 // rotate the ring (register renaming under the unroll) and issue the load D nodes ahead;
@@ -970,7 +993,17 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                     }
                 }
             }
+        };
+        int s = ns - 1;
+        if constexpr (UNR >= 2) {
+#pragma unroll 1
+            for (; s >= 1; s -= 2) {
+                rk4_reverse_step(s);
+                rk4_reverse_step(s - 1);
+            }
         }
+#pragma unroll 1
+        for (; s >= 0; --s) rk4_reverse_step(s);
     }
 #pragma unroll
     for (int q = 0; q < T; ++q) {

@@ -127,6 +127,8 @@ class CudaRK4Integrator:
     def _set_v(self, v):
         v = np.asarray(v, dtype=np.float64)
         nb = 1 if v.ndim == 1 else v.shape[1]
+        if self._control is not None and v.shape[0] != self._nc * self._control.nBasis:
+            raise ValueError(f"v must have nControls*K = {self._nc * self._control.nBasis} rows, got {v.shape[0]}")
         vf = _lib.f64(v)
         self._ck(self._lib.ocs_b200_set_control_v(self._h, _lib.dp(vf), nb))
 

@@ -1,0 +1,115 @@
+"""Edge cases of the batched sweeps: smallest and ragged sizes, tiles that do not divide N, single
+knots, divergent trajectories (status word), argument validation.  All against the CPU oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from util import TEST_PARAMS, TOL, relerr
+
+pytestmark = pytest.mark.gpu
+P = list(TEST_PARAMS.values())
+
+
+def _eval_both(ocs, oracle, N, T, kind, K, Bt, seed=0, per_traj_v=False):
+    tspan = ocs.matlab_linspace(0.0, T, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ctl = getattr(ocs, kind)(integ.t, K, 1)
+    integ.attach_control(ctl)
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(.5, 2.5, (1, Bt))
+    v = rng.random((K, Bt)) if per_traj_v else rng.random(K)
+    if kind == "ChebyshevControl":
+        v = v * 0.1
+    out = integ.evaluate(ocs.TestOCProblem(TEST_PARAMS, [[0, 1]]), x0, v)
+    ref = oracle.C.evaluate(P, tspan, ctl.B, x0, v)
+    integ.close()
+    return out, ref
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 31, 32, 33, 63, 64, 65, 95, 97])
+@pytest.mark.parametrize("per_traj_v", [False, True])
+def test_step_counts_around_the_tile_size(ocs, oracle, N, per_traj_v):
+    """N below, at and just above multiples of the 32-step shared-memory tile, and N = 1
+    (one RK4 step: the reverse sweep's prefetch reads only slack)."""
+    out, ref = _eval_both(ocs, oracle, N, 1.0 + 0.1 * N, "PWLinearControl", min(5, N + 1), 50, per_traj_v=per_traj_v)
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(out[key], ref[key]) < TOL, (key, N)
+
+
+@pytest.mark.parametrize("Bt", [1, 2, 31, 127, 128, 129, 255, 256, 257, 383, 384, 385, 769])
+def test_ragged_batch_sizes(ocs, oracle, Bt):
+    """Batches around the block tilings (128 threads x 2 or 3 trajectories per thread)."""
+    out, ref = _eval_both(ocs, oracle, 40, 2.0, "PWLinearControl", 7, Bt, seed=Bt)
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert out[key].shape == ref[key].shape
+        assert relerr(out[key], ref[key]) < TOL, (key, Bt)
+
+
+@pytest.mark.parametrize("kind,K", [("PWConstantControl", 1), ("PWConstantControl", 2), ("PWLinearControl", 2),
+                                    ("PWLinearControl", 3), ("ChebyshevControl", 1), ("ChebyshevControl", 2),
+                                    ("ChebyshevControl", 33), ("PWConstantControl", 150), ("PWLinearControl", 161)])
+def test_smallest_and_largest_bases(ocs, oracle, kind, K):
+    """One interval / two knots / a constant Chebyshev basis, and bases with more knots than RK4 steps
+    (the knot window jumps by more than one per grid point)."""
+    for per in (False, True):
+        if kind == "ChebyshevControl" and K > 32 and per:
+            continue          # run-time dense K > 32 needs a generated problem (compile-time K)
+        out, ref = _eval_both(ocs, oracle, 60, 3.0, kind, K, 37, seed=K, per_traj_v=per)
+        for key in ("J", "xT", "dJdv", "lam0"):
+            assert relerr(out[key], ref[key]) < TOL, (key, kind, K, per)
+
+
+def test_divergent_trajectories_are_flagged(ocs):
+    """The reference has no NaN/Inf guard: a trajectory that blows up just propagates
+    Inf/NaN into J.  Here it additionally sets its status word; the others are unaffected."""
+    tspan = ocs.matlab_linspace(0.0, 10.0, 201)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ctl = ocs.PWLinearControl(integ.t, 5, 1)
+    integ.attach_control(ctl)
+    x0 = np.full((1, 300), 1.0)
+    x0[0, 17] = -50.0          # x' = x(m - x) - u runs away to -inf
+    x0[0, 299] = -1e3
+    out = integ.evaluate(ocs.TestOCProblem(TEST_PARAMS, [[0, 1]]), x0, np.full(5, .5))
+    assert out["status"][17] == 1 and out["status"][299] == 1
+    assert not np.isfinite(out["J"][17])
+    ok = np.ones(300, bool)
+    ok[[17, 299]] = False
+    assert not out["status"][ok].any() and np.all(out["J"][ok] == out["J"][0])
+
+
+def test_argument_validation(ocs):
+    L = ocs._lib
+    tspan = ocs.matlab_linspace(0.0, 1.0, 11)
+    integ = ocs.CudaRK4Integrator(tspan)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    ctl = ocs.PWLinearControl(integ.t, 4, 1)
+    with pytest.raises(RuntimeError):
+        integ.evaluate(prob, 1.0, np.zeros(4))                       # no control attached
+    integ.attach_control(ctl)
+    with pytest.raises(ocs.OcsError) as e:
+        integ.evaluate(prob, np.ones((1, 5)), np.zeros((4, 3)))       # v batch != x0 batch
+    assert e.value.code == L.ERR_ARG
+    with pytest.raises(ValueError):
+        integ.evaluate(prob, 1.0, np.zeros(7))                       # wrong coefficient count (host-side check)
+    with pytest.raises(ValueError):
+        integ.attach_control(ocs.PWLinearControl(np.linspace(0, 1, 11), 4, 1))   # basis on another grid
+    bad = np.zeros((4, integ.t.size))
+    bad[0, 0] = np.nan
+    lib = L.load()
+    assert lib.ocs_b200_set_control_basis(integ._h, 4, L.dp(L.f64(bad))) == L.ERR_ARG
+    # per-trajectory parameters must match the batch
+    prob_b = ocs.TestOCProblem(dict(c=np.ones(3), m=3.0, r=.05), [[0, 1]])
+    integ.attach_control(ctl)
+    with pytest.raises(ocs.OcsError):
+        integ.evaluate(prob_b, np.ones((1, 5)), np.zeros(4))
+    # fetch range checks
+    integ.evaluate(prob, np.ones((1, 5)), np.zeros(4))
+    with pytest.raises(ocs.OcsError):
+        integ.fetch_states(3, 10)
+    # the handle is still usable after errors (only CUDA errors are sticky)
+    out = integ.evaluate(prob, np.ones((1, 5)), np.zeros(4))
+    assert np.all(np.isfinite(out["J"]))
+    # double destroy through the Python wrapper is harmless
+    integ.close()
+    integ.close()
