@@ -206,6 +206,66 @@ def run_reference(args, rank, world):
 _REAL_STDOUT = None
 
 
+def run_fbsweep(args, ocs, local_rank, rank, world):
+    """--config fbsweep: the forward-backward sweep iteration (functions/fb_sweep.m:79-115 on the RK4 grid) on
+    cfg2's batch: per sweep one forward sweep and one costate sweep with the control of EVERY trajectory on the
+    G grid points in HBM (16 B/step read + 16 B/step written on top of the 16 B/step state stream), ControlChar
+    update and convergence measure fused into the reverse kernel.  Tolerances 0 => exactly S sweeps per step.
+    One sweep of one RK4 step of one trajectory = one trajectory-step."""
+    import ctypes
+    import torch
+    Bt, S = args.bt, 4
+    tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
+    integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+    prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
+    x0 = np.random.default_rng(2 + rank).uniform(0.5, 2.5, (1, Bt))
+    u0 = np.full((1, 2 * N_STEPS + 1), 0.5)
+    integ.set_profiling(True)
+    for _ in range(max(1, min(args.warmup, 2))):
+        integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S)
+    integ.kernel_stats(reset=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nrep = max(1, min(args.steps, 5))
+    for _ in range(nrep):
+        out = integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S)
+    dt = time.perf_counter() - t0
+    ks = integ.kernel_stats(reset=True)
+    assert (out["sweeps"] == S).all()
+    ms_f, ms_r = ks["ms_forward"] / (nrep * S), ks["ms_reverse"] / (nrep * S)
+    units = Bt * N_STEPS
+    hbm_peak, hbm_src = _measured_peaks()
+    L = ocs._lib.load()
+    tf = ctypes.c_double()
+    L.ocs_b200_measure_fp64_peak(local_rank, ctypes.byref(tf))
+    # algorithmic per trajectory-step: forward 4*C_F + 13*m (control read from the grid) and 8 B state write +
+    # 16 B control read; costate sweep 4*C_X + 14*m + 2 ControlChar (4 flop each) + change measure (2 x 5) and
+    # 8 B state read + 16 B control read + 16 B control write
+    ff, fr, bf, br = 4 * 10 + 13 * 2, 4 * 8 + 14 * 2 + 2 * 4 + 10, 24, 40
+    kf = {"kernel": "ocs_fwd_test_fast_u2_b0_p0", "ms": ms_f, "tflops": units * ff / ms_f / 1e9, "gbs": units * bf / ms_f / 1e6}
+    kr = {"kernel": "ocs_fbrev_test_fast_u2_b0_p0", "ms": ms_r, "tflops": units * fr / ms_r / 1e9, "gbs": units * br / ms_r / 1e6}
+    dom = kr if ms_r >= ms_f else kf
+    fp_frac, hbm_frac = dom["tflops"] / tf.value, dom["gbs"] / hbm_peak
+    bound = "hbm" if hbm_frac >= fp_frac else "fp64"
+    emit({
+        "metric": "FP64 trajectory-steps/sec (fb_sweep iteration on the RK4 grid)",
+        "value": units * 1e3 / (ms_f + ms_r), "unit": "trajectory-steps/s", "n_gpus": 1, "steps": nrep, "warmup": 1,
+        "ms_per_step": (ms_f + ms_r) * S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "fbsweep: fb_sweep iteration of tests/TestOCProblem.m, 2^20 random x0 x 1000 RK4 steps, "
+                               "per-trajectory control on the grid, %d sweeps per step" % S,
+                   "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS, "l2": "inputs larger than L2 (8.4 GB states + 16.8 GB controls)"},
+        "gpu_launches": int(ks["launches"]),
+        "roofline": {"bound": bound, "achieved": dom["gbs"] if bound == "hbm" else dom["tflops"],
+                     "peak": hbm_peak if bound == "hbm" else tf.value, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                     "frac": max(hbm_frac, fp_frac), "kernel": dom["kernel"], "traffic": None, "peak_source": hbm_src,
+                     "kernels": [kf, kr]},
+        "e2e": {"value": nrep * S * units / dt, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 * Bt + 8 * u0.size,
+                "d2h_bytes_per_step": 8 * Bt * 2 + 4 * Bt * 2, "api": "ocs_b200_fb_sweep on host buffers"},
+    })
+    integ.close()
+
+
 def emit(obj):
     line = (json.dumps(obj) + "\n").encode()
     if _REAL_STDOUT is None:
@@ -224,7 +284,7 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "fbsweep"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
@@ -262,6 +322,9 @@ def main():
     from importlib import import_module
     distmod = import_module("optimal-control-solvers_b200.host.dist")
 
+    if args.config == "fbsweep":
+        run_fbsweep(args, ocs, local_rank, rank, world)
+        return
     wl = make_workload(args.config, ocs, local_rank, None if args.bt == BT else args.bt)
     integ, prob, ctl, Bt, n_st, rows, NT = wl["integ"], wl["prob"], wl["ctl"], wl["Bt"], wl["n"], wl["rows"], wl["N_total"]
     integ.attach_control(ctl)

@@ -6,7 +6,7 @@
 // evaluated once per grid point with the very operations (and order) of the in-thread
 // form, so hoisting does not change a single bit of the result:
 //   HM_TIME          tt[0] = exp(-r t)        (F :25, dFdx_times_vec :31, dFdu_times_vec :37)
-//                    tt[1] = exp(r t)         (ControlChar: u* = lam exp(r t) / (2c))
+//                    tt[1] = exp(r t)/(2c)    (ControlChar: u* = lam * (exp(r t) / (2c)))
 //   HM_TIME_CONTROL  tt[0] = exp(-r t)
 //                    tt[1] = c*u.^2           (F :25)
 //                    tt[2] = 2*exp(-r t)      (dFdx_times_vec :31, left-to-right prefix)
@@ -24,7 +24,7 @@ struct TestOCProblem {
     {
         if constexpr (HM == 1) {
             tt[0] = exp(-p[2] * t);
-            tt[1] = exp(p[2] * t);
+            tt[1] = exp(p[2] * t) / (2.0 * p[0]);
         } else if constexpr (HM == 2) {
             const double E = exp(-p[2] * t);
             tt[0] = E;
@@ -70,15 +70,16 @@ struct TestOCProblem {
     }
 
     // u solving dFdu_times_vec(t, y, u, [lam; 1]) = 0, clamped to ControlBounds
-    // (functions/make_from_symbolic.m:17-23,111):  u* = lam*exp(r*t)/(2*c)
+    // (functions/make_from_symbolic.m:17-23,111):  u* = lam*exp(r*t)/(2*c), written as lam * (exp(r*t)/(2*c)) so
+    // that the batch-uniform factor is one table entry (the reference's form is whatever `solve` prints)
     template <int HM>
     __device__ __forceinline__ static void ControlChar(const double *tt, double t, const double *x,
                                                        const double *lam, const double *p,
                                                        const double *bounds, double *o)
     {
         (void)x;
-        const double Ei = HM == 1 ? tt[1] : exp(p[2] * t);
-        const double uu = lam[0] * Ei / (2.0 * p[0]);
+        const double Ei2c = HM == 1 ? tt[1] : exp(p[2] * t) / (2.0 * p[0]);
+        const double uu = lam[0] * Ei2c;
         o[0] = fmin(bounds[1], fmax(bounds[0], uu));
     }
 };

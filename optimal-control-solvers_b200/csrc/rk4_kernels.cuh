@@ -297,6 +297,19 @@ struct GradAcc {
     }
 };
 
+// Running maximum of ratios num/den (den >= 0) without a division per sample: the current maximiser is
+// kept as a (num, den) pair and compared by cross-multiplication; one division at the end.  A zero
+// denominator with a positive numerator is +inf and dominates; 0/0 samples are NaN in the reference's
+// formula and are ignored here like fmax ignores NaN.
+struct MaxRatio {
+    double num = 0.0, den = 1.0;
+    __device__ __forceinline__ void update(double n_, double d_)
+    {
+        if (n_ * den > num * d_) { num = n_; den = d_; }
+    }
+    __device__ __forceinline__ double value() const { return num / den; }
+};
+
 // ------------------------------------------------------------------ tile staging
 template <int RB>
 struct TileLayout {
@@ -485,6 +498,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
     double y[T][m];
     ControlEval<nc, UMODE, BMODE, KD> ctl[T];
     double uL[T][nc], uM[T][nc], uR[T][nc];
+    double uMn[T][nc], uRn[T][nc];      // UMODE_GRID: control of the next step, loaded one step ahead
     double *xsp[T];
 #pragma unroll
     for (int q = 0; q < T; ++q) {
@@ -508,6 +522,10 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 ctl[q].eval(a, gp, bs, 0, bb[q], uL[q]);
+                if constexpr (UMODE == UMODE_GRID) {
+                    ctl[q].eval(a, gp, bs, 1, bb[q], uMn[q]);
+                    ctl[q].eval(a, gp, bs, 2, bb[q], uRn[q]);
+                }
                 if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
                     if (a.ug_out && active[q]) {
 #pragma unroll
@@ -530,8 +548,18 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 }
                 xsp[q] += a.ldb;
                 if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rL, bs, 2 * i, bb[q], uL[q]);
-                ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
-                ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
+                if constexpr (UMODE == UMODE_GRID) {
+                    // per-trajectory grid control: use the values loaded during the previous step and issue the
+                    // loads of the next step now (clamped at the last grid point), hiding the HBM latency
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) { uM[q][c] = uMn[q][c]; uR[q][c] = uRn[q][c]; }
+                    const int jm = 2 * i + 3 < 2 * N ? 2 * i + 3 : 2 * N, jr = 2 * i + 4 < 2 * N ? 2 * i + 4 : 2 * N;
+                    ctl[q].eval(a, rM, bM, jm, bb[q], uMn[q]);
+                    ctl[q].eval(a, rR, bR, jr, bb[q], uRn[q]);
+                } else {
+                    ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
+                    ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
+                }
                 if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
                     if (a.ug_out && active[q]) {   // the reverse sweep reads the grid instead of re-evaluating v*B
 #pragma unroll
@@ -643,9 +671,10 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     gacc.init();
 
     double uL[nc], uM[nc], uR[nc], dcar[nc];
+    double uMn[nc], uLn[nc];           // UMODE_GRID: control of the next step, loaded one step ahead
     double y1[n], yn1[n], yn2[n];      // node states: current, and the next two (prefetched)
     double xR[n];                      // FB: node state to the right (for midpoint averages)
-    double maxchg = 0.0;
+    MaxRatio chg;                      // FB: running max of |uNew-u| / (uRelTol |u| + uAbsTol)
 #pragma unroll
     for (int c = 0; c < nc; ++c) dcar[c] = 0.0;
     const double *xsp = a.xs + (size_t)(N - 1) * a.ldb + bb;   // node N-1
@@ -664,7 +693,13 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     for (int i0 = i0_last; i0 >= 0; i0 -= TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
-        if (i0 == i0_last) ctl.eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb, uR);
+        if (i0 == i0_last) {
+            ctl.eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb, uR);
+            if constexpr (UMODE == UMODE_GRID) {
+                ctl.eval(a, gp, bs, 2 * N - 1, bb, uMn);
+                ctl.eval(a, gp, bs, 2 * N - 2, bb, uLn);
+            }
+        }
 #pragma unroll 2
         for (int s = ns - 1; s >= 0; --s) {
             const int i = i0 + s;
@@ -679,8 +714,18 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
             for (int c = 0; c < n; ++c) yn2[c] = xsp[(size_t)c * (N + 1) * a.ldb];
             if constexpr (UMODE == UMODE_UNIFORM) ctl.eval(a, rR, bR, 2 * i + 2, bb, uR);   // shared-memory reads
-            ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
-            ctl.eval(a, rL, bL, 2 * i, bb, uL);
+            if constexpr (UMODE == UMODE_GRID) {
+                // per-trajectory grid control: loaded one step ahead (fb_sweep only overwrites grid points of the
+                // current step after they were read, so the early loads never see an updated value)
+#pragma unroll
+                for (int c = 0; c < nc; ++c) { uM[c] = uMn[c]; uL[c] = uLn[c]; }
+                const int jm = 2 * i - 1 > 0 ? 2 * i - 1 : 0, jl = 2 * i - 2 > 0 ? 2 * i - 2 : 0;
+                ctl.eval(a, rM, bM, jm, bb, uMn);
+                ctl.eval(a, rL, bL, jl, bb, uLn);
+            } else {
+                ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
+                ctl.eval(a, rL, bL, 2 * i, bb, uL);
+            }
             const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
             const double tR = rR[0], tM = rM[0], tL = rL[0];
 
@@ -758,8 +803,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 P::template ControlChar<HM>(ttR, tR, xR, lamR, p, a.bounds, un);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
-                    const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);   // fb_sweep.m:107-108
-                    maxchg = fmax(maxchg, w);
+                    chg.update(fabs(un[c] - uR[c]), a.uRelTol * fabs(uR[c]) + a.uAbsTol);          // fb_sweep.m:107-108
                     const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
                     if (active) a.ug[soa((long)c * G + (2 * i + 2), a.ldb, b)] = uw;
                 }
@@ -768,8 +812,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 P::template ControlChar<HM>(ttM, tM, xm, lm, p, a.bounds, un);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
-                    const double w = fabs(un[c] - uM[c]) / (a.uRelTol * fabs(uM[c]) + a.uAbsTol);
-                    maxchg = fmax(maxchg, w);
+                    chg.update(fabs(un[c] - uM[c]), a.uRelTol * fabs(uM[c]) + a.uAbsTol);
                     const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uM[c] + a.relax * un[c];
                     if (active) a.ug[soa((long)c * G + (2 * i + 1), a.ldb, b)] = uw;
                 }
@@ -800,12 +843,11 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         P::template ControlChar<HM>(gp + 1 + nc, gp[0], xR, lam0, p, a.bounds, un);
 #pragma unroll
         for (int c = 0; c < nc; ++c) {
-            const double w = fabs(un[c] - uR[c]) / (a.uRelTol * fabs(uR[c]) + a.uAbsTol);
-            maxchg = fmax(maxchg, w);
+            chg.update(fabs(un[c] - uR[c]), a.uRelTol * fabs(uR[c]) + a.uAbsTol);
             const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
             if (active) a.ug[soa((long)c * G, a.ldb, b)] = uw;
         }
-        if (active && a.max_change) a.max_change[b] = maxchg;
+        if (active && a.max_change) a.max_change[b] = chg.value();
     }
     if (a.lam0 && active) {
 #pragma unroll
@@ -845,6 +887,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     ControlEval<nc, UMODE, BMODE, KD> ctl[T];
     GradAcc<nc, BMODE, KD> gacc[T];
     double uL[T][nc], uM[T][nc], uR[T][nc], dcar[T][nc], dR[T][nc], dM[T][nc];
+    double uMn[T][nc], uLn[T][nc];      // UMODE_GRID: control of the next step, loaded one step ahead
     constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
     constexpr int UNR = OCS_REV_UNROLL;
     double y1[T][n], yn[D][T][n];
@@ -879,7 +922,13 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
         if (i0 == i0_last) {
 #pragma unroll
-            for (int q = 0; q < T; ++q) ctl[q].eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb[q], uR[q]);
+            for (int q = 0; q < T; ++q) {
+                ctl[q].eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb[q], uR[q]);
+                if constexpr (UMODE == UMODE_GRID) {
+                    ctl[q].eval(a, gp, bs, 2 * N - 1, bb[q], uMn[q]);
+                    ctl[q].eval(a, gp, bs, 2 * N - 2, bb[q], uLn[q]);
+                }
+            }
         }
         // one RK4 step (all T trajectories) as a lambda, so that the step loop below can be unrolled by hand:
         // `#pragma unroll 2` on this loop miscompiled the peeled remainder iteration for odd step counts
@@ -910,8 +959,16 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
-                ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
-                ctl[q].eval(a, rL, bL, 2 * i, bb[q], uL[q]);
+                if constexpr (UMODE == UMODE_GRID) {     // loaded one step ahead, see reverse_body
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) { uM[q][c] = uMn[q][c]; uL[q][c] = uLn[q][c]; }
+                    const int jm = 2 * i - 1 > 0 ? 2 * i - 1 : 0, jl = 2 * i - 2 > 0 ? 2 * i - 2 : 0;
+                    ctl[q].eval(a, rM, bM, jm, bb[q], uMn[q]);
+                    ctl[q].eval(a, rL, bL, jl, bb[q], uLn[q]);
+                } else {
+                    ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
+                    ctl[q].eval(a, rL, bL, 2 * i, bb[q], uL[q]);
+                }
 
                 double F[m], y2[n], y3[n], y4[n];
                 P::template F<HM>(ttL, tL, y1[q], uL[q], p[q], F);
@@ -1071,7 +1128,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     }
 #define OCS_COMMA ,
 #define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_FWD)>, tag, UM, BM, PB, OCS_MINBLOCKS_FWD)
+    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_FWD)>, tag, UM, BM, PB, ((UM) == 2 ? 4 : OCS_MINBLOCKS_FWD))
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \

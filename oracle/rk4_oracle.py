@@ -383,8 +383,9 @@ def nlp_objective(prob, integrator, control, x0, v, FreeInitStates=()):
 def control_char_test_problem(prob, t, x, lam):
     """ControlChar for tests/TestOCProblem.m: the u solving dFdu_times_vec(t,y,u,[lam;1])=0
     (make_from_symbolic.m:17-23), clamped to ControlBounds (:111):
-    ``u* = clamp(lam*exp(r t)/(2c), umin, umax)``."""
-    u = lam * np.exp(prob.r * t) / (2 * prob.c)
+    ``u* = clamp(lam*(exp(r t)/(2c)), umin, umax)``; the batch-uniform factor
+    exp(r t)/(2c) is grouped, the form the device code tabulates."""
+    u = lam * (np.exp(prob.r * t) / (2 * prob.c))
     return np.minimum(prob.ControlBounds[0, 1], np.maximum(prob.ControlBounds[0, 0], u))
 
 
