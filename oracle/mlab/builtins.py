@@ -304,6 +304,46 @@ def _dims(args):
     return tuple(int(scalar(a)) for a in args)
 
 
+class InputParser:
+    """inputParser with addParameter / parse / Results (name-value pairs only)."""
+    METHODS = ("addParameter", "parse")
+
+    def __init__(self):
+        from .interp import MStruct
+        self.defaults = {}
+        self.Results = MStruct()
+
+    def call_method(self, name, args, nargout):
+        from .interp import MStruct
+        if name == "addParameter":
+            self.defaults[args[0]] = args[1]
+            return []
+        if name == "parse":
+            res = MStruct(self.defaults)
+            if len(args) % 2:
+                raise ValueError("inputParser.parse: name-value arguments must come in pairs")
+            for k in range(0, len(args), 2):
+                if args[k] not in self.defaults:
+                    raise ValueError(f"inputParser: unknown parameter {args[k]!r}")
+                res[args[k]] = args[k + 1]
+            self.Results = res
+            return []
+        raise ValueError(name)
+
+    def getfield(self, name):
+        if name == "Results":
+            return self.Results
+        raise ValueError(f"inputParser has no field {name}")
+
+
+class MatlabRaised(RuntimeError):
+    """error(id, msg) raised by interpreted code."""
+
+    def __init__(self, ident, msg):
+        super().__init__(f"{ident}: {msg}")
+        self.ident = ident
+
+
 def named_handle(interp, name, frame):
     def call(*args, nargout=1):
         return tuple(interp.call_named(name, list(args), nargout, frame))
@@ -440,7 +480,38 @@ def make_builtins(interp):
         gi = GriddedInterpolant(x, v, method, extrap)
         return lambda q: gi(q)
 
+    def isa(a, cls):
+        from .interp import MObject
+        if isinstance(a, MObject):
+            return np.array([[float(any(c["name"] == cls for c in interp.class_chain(a.cls)) or
+                                    cls in [s_ for c in interp.class_chain(a.cls) for s_ in c["supers"]])]])
+        if cls in ("numeric", "double", "float"):
+            return np.array([[float(isinstance(a, np.ndarray))]])
+        return np.array([[0.0]])
+
+    def isequal(a, b):
+        from .interp import MObject
+        if isinstance(a, MObject) or isinstance(b, MObject):
+            return np.array([[float(a is b)]])
+        if isinstance(a, str) or isinstance(b, str):
+            return np.array([[float(a == b)]])
+        a, b = as_array(a), as_array(b)
+        return np.array([[float(a.shape == b.shape and bool(np.all(a == b)))]])
+
+    def merror(ident, *rest):
+        msg = rest[0] if rest else ident
+        raise MatlabRaised(ident, msg if isinstance(msg, str) else str(msg))
+
+    def fieldnames(s_):
+        from .interp import MCell
+        return MCell(list(s_.keys()))
+
     bi = {
+        "inputParser": lambda: InputParser(),
+        "isequal": isequal, "error": merror, "fieldnames": fieldnames,
+        "uint64": lambda a: np.asarray(as_array(a), dtype=np.float64).copy(),
+        "int32": lambda a: np.round(as_array(a)),
+        "logical": lambda a: as_logical(as_array(a) != 0),
         "zeros": lambda *d: np.zeros(_dims(d)),
         "ones": lambda *d: np.ones(_dims(d)),
         "nan": lambda *d: np.full(_dims(d), np.nan),
@@ -452,8 +523,10 @@ def make_builtins(interp):
         "eps": lambda: np.array([[np.finfo(float).eps]]),
         "true": lambda: as_logical(np.array([[1.0]])),
         "false": lambda: as_logical(np.array([[0.0]])),
-        "size": size, "length": length, "numel": lambda a: np.array([[float(as_array(a).size)]]),
-        "isempty": lambda a: np.array([[float((len(a) == 0) if isinstance(a, (str, dict)) else as_array(a).size == 0)]]),
+        "size": size, "length": length,
+        "numel": lambda a: np.array([[float(len(a) if isinstance(a, (list, str)) else as_array(a).size)]]),
+        "isempty": lambda a: np.array([[float((len(a) == 0) if isinstance(a, (str, dict, list)) else
+                                             (as_array(a).size == 0 if isinstance(a, (np.ndarray, int, float)) else False))]]),
         "reshape": reshape, "repmat": repmat, "diff": diff, "linspace": matlab_linspace,
         "double": lambda a: np.asarray(as_array(a), dtype=np.float64).copy(),
         "exp": lambda a: np.exp(as_array(a)), "log": lambda a: np.log(as_array(a)),
@@ -467,7 +540,7 @@ def make_builtins(interp):
         "rand": rand, "rng": rng, "fprintf": fprintf, "disp": lambda a: interp.output.append(str(a)) or empty(),
         "struct": struct, "isprop": isprop, "ismethod": ismethod, "isfield": isfield,
         "griddedInterpolant": griddedInterpolant,
-        "isa": lambda a, cls: np.array([[float(cls == "numeric" and isinstance(a, np.ndarray))]]),
+        "isa": isa,
         "strcmp": lambda a, b: np.array([[float(a == b)]]),
         "any": lambda a: np.array([[float(np.any(as_array(a) != 0))]]),
         "all": lambda a: np.array([[float(np.all(as_array(a) != 0))]]),

@@ -623,6 +623,10 @@ class MStruct(dict):
     pass
 
 
+class MCell(list):
+    """A MATLAB cell array (row)."""
+
+
 class Closure:
     def __init__(self, interp, fdef, parent_frame=None, bound_obj=None, cls=None):
         self.interp, self.fdef, self.parent, self.bound, self.cls = interp, fdef, parent_frame, bound_obj, cls
@@ -736,7 +740,12 @@ class Interpreter:
             fr.nargout = 1
             out = ctor["outs"][0]
             fr.vars[out] = obj
-            for p, a in zip(ctor["params"], args):
+            cparams = ctor["params"]
+            if cparams and cparams[-1] == "varargin":
+                fr.vars["varargin"] = MCell(args[len(cparams) - 1:])
+                args = args[:len(cparams) - 1]
+                cparams = cparams[:-1]
+            for p, a in zip(cparams, args):
                 if p != "~":
                     fr.vars[p] = a
             fr.nested = ctor["nested"]
@@ -747,16 +756,65 @@ class Interpreter:
             obj = fr.vars[out]
         return obj
 
+    def eval_args(self, arg_nodes, fr):
+        """Evaluates call arguments; c{:} expands into several arguments."""
+        out = []
+        for a in arg_nodes:
+            if a[0] == "cellindex" and len(a[2]) == 1 and a[2][0][0] == "colon":
+                out.extend(self.eval(a[1], fr))
+            else:
+                out.append(self.eval(a, fr))
+        return out
+
+    def super_call(self, name, args, nargout, fr):
+        """obj@Super(args...) inside a constructor, or method@Super(obj, args...)."""
+        left, sup = name.split("@", 1)
+        ent = self.find(sup)
+        if ent is None or ent[0] != "classdef":
+            raise MatlabError(f"unknown superclass {sup}")
+        cls = ent[1]
+        if left in fr.vars and isinstance(fr.vars[left], MObject):       # superclass constructor
+            obj = fr.vars[left]
+            ctor = cls["methods"].get(cls["name"])
+            if ctor is not None:
+                f2 = Frame()
+                f2.vars[ctor["outs"][0]] = obj
+                cparams = ctor["params"]
+                if cparams and cparams[-1] == "varargin":
+                    f2.vars["varargin"] = MCell(args[len(cparams) - 1:])
+                    args = args[:len(cparams) - 1]
+                    cparams = cparams[:-1]
+                for p_, a_ in zip(cparams, args):
+                    if p_ != "~":
+                        f2.vars[p_] = a_
+                f2.nargin, f2.nargout = len(args), 1
+                f2.nested = ctor["nested"]
+                try:
+                    self.exec_block(ctor["body"], f2)
+                except _Return:
+                    pass
+            return [obj]
+        meth, owner = self.find_method(cls, left)                         # superclass method
+        if meth is None:
+            raise MatlabError(f"{sup} has no method {left}")
+        return self.call_function(meth, args, nargout, None, owner)
+
     # -- calls
     def call_function(self, fdef, args, nargout, parent_frame=None, cls=None):
         fr = Frame()
         if parent_frame is not None:     # nested function: shares the parent's workspace
             fr.vars = parent_frame.vars
             fr.parent = parent_frame
-        if len(args) > len(fdef["params"]):
+        params = fdef["params"]
+        if params and params[-1] == "varargin":
+            nfix = len(params) - 1
+            fr.vars["varargin"] = MCell(args[nfix:])
+            args = args[:nfix]
+            params = params[:nfix]
+        if len(args) > len(params):
             raise MatlabError(f"too many input arguments to {fdef['name']}")
         saved = {}
-        for p, a in zip(fdef["params"], args):
+        for p, a in zip(params, args):
             if p != "~":
                 if parent_frame is not None and p in fr.vars:
                     saved[p] = fr.vars[p]
@@ -787,6 +845,8 @@ class Interpreter:
         raise MatlabError("value is not callable")
 
     def call_named(self, name, args, nargout, frame):
+        if "@" in name:
+            return self.super_call(name, args, nargout, frame)
         # nested / local functions
         fr = frame
         if name in frame.nested:
@@ -796,6 +856,8 @@ class Interpreter:
             meth, owner = self.find_method(args[0].cls, name)
             if meth is not None:
                 return self.call_function(meth, args, nargout, None, owner)
+        if args and hasattr(args[0], "call_method") and name in getattr(args[0], "METHODS", ()):
+            return args[0].call_method(name, args[1:], nargout)
         if name in self.builtins:
             return self.call_value(self.builtins[name], args, nargout)
         ent = self.find(name)
@@ -943,18 +1005,20 @@ class Interpreter:
             base = e[1]
             # obj.method(args) / struct.fhandle(args) / name(args)
             if base[0] == "name" and base[1] not in fr.vars:
-                args = [self.eval(a, fr) for a in e[2]]
+                args = self.eval_args(e[2], fr)
                 return self.call_named(base[1], args, nargout, fr)
             if base[0] == "field":
                 owner = self.eval(base[1], fr)
                 if isinstance(owner, MObject):
                     meth, cls = self.find_method(owner.cls, base[2])
                     if meth is not None and base[2] not in owner.props:
-                        args = [owner] + [self.eval(a, fr) for a in e[2]]
+                        args = [owner] + self.eval_args(e[2], fr)
                         return self.call_function(meth, args, nargout, None, cls)
+                if hasattr(owner, "call_method"):                  # built-in objects (inputParser)
+                    return owner.call_method(base[2], self.eval_args(e[2], fr), nargout)
             target = self.eval(base, fr)
             if isinstance(target, (Closure, Anon)) or (callable(target) and not isinstance(target, np.ndarray)):
-                args = [self.eval(a, fr) for a in e[2]]
+                args = self.eval_args(e[2], fr)
                 return self.call_value(target, args, nargout)
             arr = B.as_array(target)
             idx = [self.eval_index(a, fr, arr, d, len(e[2])) for d, a in enumerate(e[2])]
@@ -1045,12 +1109,28 @@ class Interpreter:
                 return owner[e[2]]
             if hasattr(owner, "getfield"):
                 return owner.getfield(e[2])
+            if hasattr(owner, "call_method") and e[2] in getattr(owner, "METHODS", ()):
+                return (owner.call_method(e[2], [], 1) or [B.empty()])[0]
             raise MatlabError(f"cannot take field {e[2]!r} of {type(owner).__name__}")
         if k == "index":
             r = self.eval_multi(e, fr, nargout)
             if not r:
                 raise MatlabError("expression produced no value")
             return r[0]
+        if k == "cellindex":
+            c = self.eval(e[1], fr)
+            if not isinstance(c, MCell):
+                raise MatlabError("brace indexing into a non-cell")
+            idx = self.eval(e[2][0], fr)
+            return c[int(B.scalar(idx)) - 1]
+        if k == "dynfield":
+            owner = self.eval(e[1], fr)
+            name = self.eval(e[2], fr)
+            if isinstance(owner, MStruct):
+                return owner[name]
+            if isinstance(owner, MObject):
+                return owner.props[name]
+            raise MatlabError("dynamic field of a non-struct")
         if k == "anon":
             return Anon(self, e[1], e[2], fr.vars)
         if k == "fhandle":

@@ -66,3 +66,22 @@ def test_gateway_matches_golden(driver):
     assert relerr(x.reshape(2, N + 1, order="F"), g["x"]) < TOL
     assert relerr(lam.reshape(2, N + 1, order="F"), g["lam"]) < TOL
     assert relerr(dJdu, g["dJdu"].reshape(-1)) < TOL
+
+
+def test_matlab_classes_run_under_the_interpreter_up_to_the_device(ocs):
+    """CPU: the MATLAB host classes parse and execute under oracle/mlab (constructor, inputParser, property
+    access) until the first C-ABI call, which reports the missing device exactly like the MEX gateway would."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mlab_reference_stubs
+    from mlab_mex_bridge import make_mex
+    from oracle.mlab.interp import Interpreter
+    it = Interpreter([os.path.join(PKG, "matlab"), os.path.join(ROOT, "tests", "matlab")])
+    it.builtins["ocs_b200_mex"] = make_mex(ocs)
+    mlab_reference_stubs.install(it, ocs)
+    if has_cuda():
+        fr = it.run_script("backprop_test_cuda")
+        assert "J" in fr.vars
+    else:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            it.run_script("backprop_test_cuda")
