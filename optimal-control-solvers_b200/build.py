@@ -73,5 +73,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, flags: list[str]) -> str:
+    """Kernel tuning experiments: recompile only the FMA-contracted kernel unit with extra -D flags and link it
+    with the objects of the regular build into build/variants/libocs_<name>.so (select it with OCS_B200_LIB)."""
+    build()
+    vdir = os.path.join(OBJ, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    obj = os.path.join(vdir, f"kernels_fast_{name}.o")
+    cmd = [NVCC] + COMMON + ["-DOCS_STRICT=0", "-fmad=true"] + flags + ["-c", os.path.join(CSRC, "kernels_builtin.cu"), "-o", obj]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    with open(obj + ".ptxas.log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)
+    if p.returncode != 0:
+        raise RuntimeError(p.stdout + p.stderr)
+    lib = os.path.join(vdir, f"libocs_{name}.so")
+    others = [os.path.join(OBJ, u[0]) for u in UNITS if u[0] != "kernels_fast.o"]
+    p = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib, obj] + others + ["-ldl"], capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError(p.stdout + p.stderr)
+    return lib
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":      # build.py --variant NAME -DFOO=1 ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(force="--force" in sys.argv, verbose=True)

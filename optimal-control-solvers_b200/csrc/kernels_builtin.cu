@@ -21,6 +21,12 @@
 #ifndef OCS_TPT_REV
 #define OCS_TPT_REV 2
 #endif
+// fb_sweep costate kernel (HBM-bound, 40 B/step): occupancy is the lever.  Same-box A/B of (min blocks/SM,
+// control prefetch depth): (1,1: 92 regs) 10.35 ms / (6,1) 9.71 / (7,2) 8.90 / (8,1: 64 regs) 8.38 / (8,2) 8.79 /
+// (9,1) 8.56 / (10,1: spills) 8.79.
+#ifndef OCS_MINBLOCKS_FB
+#define OCS_MINBLOCKS_FB 8
+#endif
 #ifndef OCS_TPT_FWD
 #define OCS_TPT_FWD 3
 #endif

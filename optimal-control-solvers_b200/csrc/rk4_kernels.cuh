@@ -52,6 +52,12 @@
 #ifndef OCS_MINBLOCKS_REV
 #define OCS_MINBLOCKS_REV 1 // __launch_bounds__ min blocks/SM of the reverse kernels (register cap)
 #endif
+#ifndef OCS_MINBLOCKS_FB
+#define OCS_MINBLOCKS_FB 1  // __launch_bounds__ min blocks/SM of the fb_sweep costate kernels
+#endif
+#ifndef OCS_UPREFETCH
+#define OCS_UPREFETCH 1     // steps of per-trajectory grid control loaded ahead by reverse_body (UMODE_GRID)
+#endif
 #ifndef OCS_KDENSE_MAX
 #define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
 #endif
@@ -671,7 +677,8 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     gacc.init();
 
     double uL[nc], uM[nc], uR[nc], dcar[nc];
-    double uMn[nc], uLn[nc];           // UMODE_GRID: control of the next step, loaded one step ahead
+    constexpr int DU = OCS_UPREFETCH;
+    double uMn[DU][nc], uLn[DU][nc];   // UMODE_GRID: controls of the next DU steps, loaded ahead (ring, [0] = next)
     double y1[n], yn1[n], yn2[n];      // node states: current, and the next two (prefetched)
     double xR[n];                      // FB: node state to the right (for midpoint averages)
     MaxRatio chg;                      // FB: running max of |uNew-u| / (uRelTol |u| + uAbsTol)
@@ -696,8 +703,13 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         if (i0 == i0_last) {
             ctl.eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb, uR);
             if constexpr (UMODE == UMODE_GRID) {
-                ctl.eval(a, gp, bs, 2 * N - 1, bb, uMn);
-                ctl.eval(a, gp, bs, 2 * N - 2, bb, uLn);
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int jm = 2 * (N - 1 - d) + 1 > 0 ? 2 * (N - 1 - d) + 1 : 0;
+                    const int jl = 2 * (N - 1 - d) > 0 ? 2 * (N - 1 - d) : 0;
+                    ctl.eval(a, gp, bs, jm, bb, uMn[d]);
+                    ctl.eval(a, gp, bs, jl, bb, uLn[d]);
+                }
             }
         }
 #pragma unroll 2
@@ -718,10 +730,15 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 // per-trajectory grid control: loaded one step ahead (fb_sweep only overwrites grid points of the
                 // current step after they were read, so the early loads never see an updated value)
 #pragma unroll
-                for (int c = 0; c < nc; ++c) { uM[c] = uMn[c]; uL[c] = uLn[c]; }
-                const int jm = 2 * i - 1 > 0 ? 2 * i - 1 : 0, jl = 2 * i - 2 > 0 ? 2 * i - 2 : 0;
-                ctl.eval(a, rM, bM, jm, bb, uMn);
-                ctl.eval(a, rL, bL, jl, bb, uLn);
+                for (int c = 0; c < nc; ++c) { uM[c] = uMn[0][c]; uL[c] = uLn[0][c]; }
+#pragma unroll
+                for (int d = 0; d + 1 < DU; ++d) {
+#pragma unroll
+                    for (int c = 0; c < nc; ++c) { uMn[d][c] = uMn[d + 1][c]; uLn[d][c] = uLn[d + 1][c]; }
+                }
+                const int jm = 2 * (i - DU) + 1 > 0 ? 2 * (i - DU) + 1 : 0, jl = 2 * (i - DU) > 0 ? 2 * (i - DU) : 0;
+                ctl.eval(a, rM, bM, jm, bb, uMn[DU - 1]);
+                ctl.eval(a, rL, bL, jl, bb, uLn[DU - 1]);
             } else {
                 ctl.eval(a, rM, bM, 2 * i + 1, bb, uM);
                 ctl.eval(a, rL, bL, 2 * i, bb, uL);
@@ -1136,7 +1153,7 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
 #define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_FB_KERNEL(P, tag, PB) \
-    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA true OCS_COMMA false>, tag, 2, 0, PB, 1)
+    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA true OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
 #define OCS_TT_KERNEL(P, tag)                                                                         \
     extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int hm, const double *p)             \
     {                                                                                                  \
