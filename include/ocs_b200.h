@@ -177,6 +177,17 @@ OCS_B200_API int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt
                                    double uRelTol, double uAbsTol, int nSWEEPS, double relax,
                                    double *J, int32_t *sweeps, int32_t *converged, double *max_change);
 
+/* Which costate the fb_sweep iteration uses (default DISCRETE).
+ *   DISCRETE:   lam = the v2 Integrator's discrete adjoint of the RK4 scheme (Integrator/RK4Integrator.m:59-94).
+ *   CONTINUOUS: the v1 struct API's costate equation  lam' = prob.adjointRHS(t, x, lam, u) = -gradient(H, x)
+ *               (functions/make_from_symbolic.m:11-14, functions/compute_x_lam.m:11-12, compute_x_lam_J.m:18-19)
+ *               integrated backwards from lam(T) = 0 by classical RK4 on the fixed grid (the reference integrates
+ *               it with the absent odevr7); midpoint state = mean of the neighbouring nodes.  adjointRHS is
+ *               evaluated as -dFdx_times_vec(t, y, u, [lam; 1]), the same expression. */
+#define OCS_B200_COSTATE_DISCRETE 0
+#define OCS_B200_COSTATE_CONTINUOUS 1
+OCS_B200_API int ocs_b200_set_fb_costate(ocs_b200_handle *h, int mode);
+
 /* Batched single shooting: the solve behind functions/single_shooting.m:114
  *     [vOpt, J] = fmincon(@nlpObjective, v0, [], [], [], [], Lb, Ub)
  * for every trajectory at once, entirely on the device.  fmincon (SQP, serial, host) is replaced by a

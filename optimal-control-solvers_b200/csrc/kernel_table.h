@@ -16,5 +16,6 @@ struct ocs_kernel_table {
     const void *fwdg[3][3][2];  // fetch variants: also write the full grids (x with the J row; lam, dJdu)
     const void *revg[3][3][2];
     const void *fbrev[2];
+    const void *fbcont[2];      // fb_sweep with the continuous costate equation (v1 adjointRHS) instead of the discrete adjoint
     const void *tt;
 };

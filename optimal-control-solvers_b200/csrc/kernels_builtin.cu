@@ -51,6 +51,7 @@ OCS_DEFINE_KERNELS(ocs_fast::TestOCProblem, test_fast, 0)
 #define FWDG(UM, BM, PB) (const void *)OCS_CAT5(ocs_fwdg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define REVG(UM, BM, PB) (const void *)OCS_CAT5(ocs_revg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define FBR(PB) (const void *)OCS_CAT3(ocs_fbrev_, OCS_TAGNAME, _u2_b0_p##PB)
+#define FBC(PB) (const void *)OCS_CAT3(ocs_fbcont_, OCS_TAGNAME, _u2_b0_p##PB)
 
 extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
 {
@@ -83,5 +84,6 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->revg[1][2][0] = REVG(1, 2, 0); t->revg[1][2][1] = REVG(1, 2, 1);
     t->revg[2][0][0] = REVG(2, 0, 0); t->revg[2][0][1] = REVG(2, 0, 1);
     t->fbrev[0] = FBR(0); t->fbrev[1] = FBR(1);
+    t->fbcont[0] = FBC(0); t->fbcont[1] = FBC(1);
     t->tt = (const void *)OCS_CAT2(ocs_tt_, OCS_TAGNAME);
 }

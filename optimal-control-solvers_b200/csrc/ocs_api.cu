@@ -105,6 +105,7 @@ struct ocs_b200_handle {
     DevBuf d_v, d_ug;
     const double *v_ext = nullptr;     // caller-owned device v (set_control_v_dev)
     const int *fb_frozen = nullptr;    // trajectories the sweeps must leave untouched (single_shooting / fb_sweep)
+    int fb_costate = 0;                // OCS_B200_COSTATE_* used by ocs_b200_fb_sweep
     bool user_lamT = false;            // last compute_adjoints carried an explicit lamT (kept in d_lamT_user)
     long user_lamT_ld = 0;
 
@@ -691,7 +692,7 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1,
 
 int pb_index(const H *h) { return h->params_nbatch > 1 ? 1 : 0; }
 
-enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB };
+enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB, KIND_FBC };
 
 // The kernel of one sweep variant.  Built-in problems have every variant compiled in; generated
 // problems compile the variant with NVRTC the first time it is needed.
@@ -700,13 +701,15 @@ int resolve(H *h, int kind, int um, int bm, int pb, const void **out)
     const void **slot = kind == KIND_FWD ? &h->kt.fwd[um][bm][pb]
                       : kind == KIND_FWDG ? &h->kt.fwdg[um][bm][pb]
                       : kind == KIND_REV ? &h->kt.rev[um][bm][pb]
-                      : kind == KIND_REVG ? &h->kt.revg[um][bm][pb] : &h->kt.fbrev[pb];
+                      : kind == KIND_REVG ? &h->kt.revg[um][bm][pb]
+                      : kind == KIND_FB ? &h->kt.fbrev[pb] : &h->kt.fbcont[pb];
     if (!*slot && h->is_generated) {
-        static const char *macro[] = {"OCS_FWD_KERNEL", "OCS_FWDG_KERNEL", "OCS_REV_KERNEL", "OCS_REVG_KERNEL", "OCS_FB_KERNEL"};
-        static const char *prefix[] = {"ocs_fwd_", "ocs_fwdg_", "ocs_rev_", "ocs_revg_", "ocs_fbrev_"};
+        static const char *macro[] = {"OCS_FWD_KERNEL", "OCS_FWDG_KERNEL", "OCS_REV_KERNEL", "OCS_REVG_KERNEL", "OCS_FB_KERNEL",
+                                      "OCS_FBC_KERNEL"};
+        static const char *prefix[] = {"ocs_fwd_", "ocs_fwdg_", "ocs_rev_", "ocs_revg_", "ocs_fbrev_", "ocs_fbcont_"};
         char unit[256], name[96];
         const int kd = bm == 2 ? h->K : 0;
-        if (kind == KIND_FB) {
+        if (kind == KIND_FB || kind == KIND_FBC) {
             snprintf(unit, sizeof unit, "%s(ocs_gen::Problem, gen, %d)", macro[kind], pb);
             snprintf(name, sizeof name, "%sgen_u2_b0_p%d", prefix[kind], pb);
         } else {
@@ -1591,7 +1594,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             a.frozen = h->d_frozen;
             const void *kf = nullptr, *kr = nullptr;
             TRY(resolve(h, KIND_FWD, 2, 0, pb_index(h), &kf));
-            TRY(resolve(h, KIND_FB, 2, 0, pb_index(h), &kr));
+            TRY(resolve(h, h->fb_costate == OCS_B200_COSTATE_CONTINUOUS ? KIND_FBC : KIND_FB, 2, 0, pb_index(h), &kr));
             TRY(launch(h, kf, a, true, std::max(h->kt.tpt_fwd, 1)));
             SweepArgs r;
             base_args(h, 0, r);
@@ -1625,6 +1628,15 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
+}
+
+int ocs_b200_set_fb_costate(ocs_b200_handle *h, int mode)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (mode != OCS_B200_COSTATE_DISCRETE && mode != OCS_B200_COSTATE_CONTINUOUS)
+        return h->fail(OCS_B200_ERR_ARG, "costate mode must be OCS_B200_COSTATE_DISCRETE or _CONTINUOUS");
+    h->fb_costate = mode;
+    return 0;
 }
 
 int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, const double *v0, long v0_nbatch,

@@ -629,10 +629,15 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
 // ------------------------------------------------------------------ reverse sweep
 // RK4Integrator.m:59-121 for one trajectory per thread.  Stage states 2..4 are
 // recomputed from the stored node state with the same device functions as the forward
-// sweep (16 B/step of HBM traffic instead of 64).  FB = fb_sweep variant: no dJdu; the
+// sweep (16 B/step of HBM traffic instead of 64).  FB != 0 = fb_sweep variant: no dJdu; the
 // control on the grid is replaced by ControlChar(t, x, lam) and the normalised change
-// is reduced per trajectory (functions/fb_sweep.m:96,107-110).
-template <class P, int UMODE, int BMODE, bool PB, int KD, bool FB, bool GRIDS>
+// is reduced per trajectory (functions/fb_sweep.m:96,107-110).  FB == 1: lam is the discrete
+// adjoint of the RK4 scheme (the v2 Integrator's).  FB == 2: lam solves the continuous costate
+// equation lam' = adjointRHS(t, x, lam, u) = -gradient(H, x) (functions/make_from_symbolic.m:11-14,
+// functions/compute_x_lam.m:11-12) backwards from lam(T) = 0 by classical RK4 on the same grid, with
+// the midpoint state taken as the mean of the neighbouring nodes (the textbook forward-backward sweep);
+// with H = f + lam*g, -gradient(H, x) is -dFdx_times_vec(t, y, u, [lam; 1]).
+template <class P, int UMODE, int BMODE, bool PB, int KD, int FB, bool GRIDS>
 __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 {
     constexpr int n = P::n, m = n + 1, nc = P::nc, np = P::np;
@@ -640,7 +645,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     constexpr int NT = P::ntt(HM);
     constexpr int RB = ocs_rec_width(nc, NT);
     constexpr bool NEEDB = (BMODE != BMODE_NONE);
-    constexpr bool GACC = NEEDB && !GRIDS && !FB;   // fold dJdu into dJdv (the fetch variant writes dJdu itself)
+    constexpr bool GACC = NEEDB && !GRIDS && FB == 0;   // fold dJdu into dJdv (the fetch variant writes dJdu itself)
     constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
     typedef TileLayout<RB> TL;
     const int BW = BWc >= 0 ? BWc : a.BW;
@@ -690,7 +695,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         yn1[c] = xsp[(size_t)c * (N + 1) * a.ldb];
         yn2[c] = xsp[(size_t)c * (N + 1) * a.ldb - a.ldb];   // node N-2 (slack when N == 1)
     }
-    if constexpr (FB) {
+    if constexpr (FB != 0) {
 #pragma unroll
         for (int c = 0; c < n; ++c) xR[c] = xsp[(size_t)c * (N + 1) * a.ldb + a.ldb];
     }
@@ -746,6 +751,30 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
             const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
             const double tR = rR[0], tM = rM[0], tL = rL[0];
 
+            double lamR[n];
+          if constexpr (FB == 2) {
+            // k_s = adjointRHS = -g_s;  lam - (h/2) k = lam + (h/2) g  (sign flips are exact)
+            double xm[n], vs[m], g1[n], g2[n], g3[n], g4[n];
+            vs[n] = lam[n];
+#pragma unroll
+            for (int c = 0; c < n; ++c) { vs[c] = lam[c]; xm[c] = (y1[c] + xR[c]) / 2; }
+            P::template X<HM>(ttR, tR, xR, uR, p, vs, g1);
+#pragma unroll
+            for (int c = 0; c < n; ++c) vs[c] = lam[c] + h2 * g1[c];
+            P::template X<HM>(ttM, tM, xm, uM, p, vs, g2);
+#pragma unroll
+            for (int c = 0; c < n; ++c) vs[c] = lam[c] + h2 * g2[c];
+            P::template X<HM>(ttM, tM, xm, uM, p, vs, g3);
+#pragma unroll
+            for (int c = 0; c < n; ++c) vs[c] = lam[c] + h * g3[c];
+            P::template X<HM>(ttL, tL, y1, uL, p, vs, g4);
+#pragma unroll
+            for (int c = 0; c < n; ++c) {
+                lamR[c] = lam[c];
+                lam[c] = lam[c] + h6 * (g1[c] + 2.0 * g2[c] + 2.0 * g3[c] + g4[c]);
+            }
+            (void)h3;
+          } else {
             // stage states of the forward step (RK4Integrator.m:39-46), recomputed
             double F[m], y2[n], y3[n], y4[n];
             P::template F<HM>(ttL, tL, y1, uL, p, F);
@@ -802,18 +831,18 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 P::template U<HM>(ttL, tL, y1, uL, p, k1, dcar);
             }
 
-            double lamR[n];
 #pragma unroll
             for (int c = 0; c < n; ++c) {
                 lamR[c] = lam[c];
                 lam[c] = lam[c] + g1[c] + g2[c] + g3[c] + g0[c];                           // :86
             }
+          }
             if (lamout && active) {
 #pragma unroll
                 for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (i + (size_t)(N + 1) * b)] = lam[c];
             }
 
-            if constexpr (FB) {
+            if constexpr (FB != 0) {
                 // uNew at the right node and at the midpoint of step i (midpoint x, lam = mean of the
                 // neighbouring nodes, the same formula the grid uses for t, RK4Integrator.m:23)
                 double un[nc], xm[n], lm[n];
@@ -843,7 +872,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         }
     }
 
-    if constexpr (!FB) {
+    if constexpr (FB == 0) {
         if (want_du) {
             gacc.add(a, bs, dcar, b, active);                                              // left end :101-102
             if (duout && active) {
@@ -1151,9 +1180,11 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_REV)>, tag, UM, BM, PB, ((BM) == 2 ? 1 : OCS_MINBLOCKS_REV))
 #define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA false OCS_COMMA true>, tag, UM, BM, PB, 1)
+    OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA 0 OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_FB_KERNEL(P, tag, PB) \
-    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA true OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
+    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 1 OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
+#define OCS_FBC_KERNEL(P, tag, PB) \
+    OCS_KERNEL_(ocs_fbcont_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 2 OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
 #define OCS_TT_KERNEL(P, tag)                                                                         \
     extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int hm, const double *p)             \
     {                                                                                                  \
@@ -1183,7 +1214,8 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     OCS_REVG_KERNEL(P, tag, 1, 1, PB, KD)       \
     OCS_REVG_KERNEL(P, tag, 1, 2, PB, KD)       \
     OCS_REVG_KERNEL(P, tag, 2, 0, PB, KD)       \
-    OCS_FB_KERNEL(P, tag, PB)
+    OCS_FB_KERNEL(P, tag, PB)                   \
+    OCS_FBC_KERNEL(P, tag, PB)
 
 #define OCS_DEFINE_KERNELS(P, tag, KD)   \
     OCS_DEFINE_KERNELS_PB(P, tag, 0, KD) \

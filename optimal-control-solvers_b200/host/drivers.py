@@ -70,7 +70,7 @@ def fb_sweep(prob, integrator, x0, u0=None, options=None):
     reference's pure replacement).  Returns a dict with J, u (grid values of the converged control, = soln.u
     sampled on integrator.t), x, lam (grids on request via integrator.fetch_*), sweeps, converged; like the
     reference, a trajectory that did not converge within nSWEEPS reports converged = 0 (fb_sweep.m:77-87)."""
-    opt = dict(uRelTol=1e-7, uAbsTol=1e-7, nSWEEPS=50, relax=1.0)
+    opt = dict(uRelTol=1e-7, uAbsTol=1e-7, nSWEEPS=50, relax=1.0, costate="discrete")
     opt.update(options or {})
     nc = prob.nControls
     G = integrator.t.size
@@ -83,7 +83,7 @@ def fb_sweep(prob, integrator, x0, u0=None, options=None):
     u0 = np.minimum(cb[:, 1].reshape((nc,) + (1,) * (u0.ndim - 1)),
                     np.maximum(cb[:, 0].reshape((nc,) + (1,) * (u0.ndim - 1)), u0))
     out = integrator.fb_sweep(prob, x0, u0, uRelTol=opt["uRelTol"], uAbsTol=opt["uAbsTol"],
-                              nSWEEPS=opt["nSWEEPS"], relax=opt["relax"])
+                              nSWEEPS=opt["nSWEEPS"], relax=opt["relax"], costate=opt["costate"])
     out["u"] = integrator.get_control_u(0, out["J"].size)
     return out
 

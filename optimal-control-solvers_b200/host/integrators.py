@@ -288,10 +288,15 @@ class CudaRK4Integrator:
         return val.value, idx.value
 
     # ------------------------------------------------------------------ fb_sweep on the RK4 grid
-    def fb_sweep(self, prob, x0, u0, uRelTol=1e-7, uAbsTol=1e-7, nSWEEPS=50, relax=1.0):
+    def fb_sweep(self, prob, x0, u0, uRelTol=1e-7, uAbsTol=1e-7, nSWEEPS=50, relax=1.0, costate="discrete"):
         """The sweep loop of functions/fb_sweep.m:79-115 with the RK4 forward / discrete-adjoint
-        sweeps in place of odevr7, for every trajectory.  u0: nc x G shared or nc x G x Bt."""
+        sweeps in place of odevr7, for every trajectory.  u0: nc x G shared or nc x G x Bt.
+        costate="continuous" integrates the v1 API's adjointRHS (make_from_symbolic.m:11-14,
+        compute_x_lam.m:11-12) backwards by RK4 instead of using the discrete adjoint."""
         self._bind(prob)
+        if costate not in ("discrete", "continuous"):
+            raise ValueError("costate must be 'discrete' or 'continuous'")
+        self._ck(self._lib.ocs_b200_set_fb_costate(self._h, 1 if costate == "continuous" else 0))
         x0f, single = self._x0(x0)
         Bt = x0f.shape[1]
         u0 = np.asarray(u0, dtype=np.float64)

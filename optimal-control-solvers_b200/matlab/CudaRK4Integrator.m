@@ -129,10 +129,12 @@ classdef CudaRK4Integrator < Integrator
          p.addParameter('uAbsTol', 1e-7);
          p.addParameter('nSWEEPS', 50);     % fb_sweep.m:20
          p.addParameter('relax', 1);        % 1 = the reference's pure replacement (fb_sweep.m:96)
+         p.addParameter('costate', 'discrete');   % 'continuous' = v1 adjointRHS by RK4 (compute_x_lam.m:11-12)
          parse(p, varargin{:});
          obj.bind(prob);
          [out.J, out.sweeps, out.converged, out.maxChange] = ocs_b200_mex('fb_sweep', obj.handle, x0, u0, ...
-            prob.ControlBounds, p.Results.uRelTol, p.Results.uAbsTol, p.Results.nSWEEPS, p.Results.relax);
+            prob.ControlBounds, p.Results.uRelTol, p.Results.uAbsTol, p.Results.nSWEEPS, p.Results.relax, ...
+            double(strcmp(p.Results.costate, 'continuous')));
          obj.Bt = size(x0, 2);
          out.u = ocs_b200_mex('get_control_u', obj.handle, 0, obj.Bt, obj.nControls, length(obj.t));
       end

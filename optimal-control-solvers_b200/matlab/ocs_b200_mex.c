@@ -210,10 +210,12 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         check(ocs_b200_get_control_u(h, (long)scalar(prhs[2]), (long)scalar(prhs[3]), mxGetPr(plhs[0])), h);
         return;
     }
-    /* ---- [J, sweeps, converged, maxChange] = mex('fb_sweep', h, x0, u0, bounds, uRelTol, uAbsTol, nSWEEPS, relax)
-     *      functions/fb_sweep.m:79-115 on the RK4 grid */
+    /* ---- [J, sweeps, converged, maxChange] = mex('fb_sweep', h, x0, u0, bounds, uRelTol, uAbsTol, nSWEEPS, relax[, costate])
+     *      functions/fb_sweep.m:79-115 on the RK4 grid; costate 0 = discrete adjoint (default), 1 = the v1 API's
+     *      adjointRHS integrated backwards (functions/compute_x_lam.m:11-12) */
     if (!strcmp(cmd, "fb_sweep")) {
-        FAIL_IF(nrhs < 9, "ocs_b200:nargin", "fb_sweep(h, x0, u0, bounds, uRelTol, uAbsTol, nSWEEPS, relax)");
+        FAIL_IF(nrhs < 9, "ocs_b200:nargin", "fb_sweep(h, x0, u0, bounds, uRelTol, uAbsTol, nSWEEPS, relax[, costate])");
+        check(ocs_b200_set_fb_costate(h, nrhs > 9 ? (int)scalar(prhs[9]) : OCS_B200_COSTATE_DISCRETE), h);
         long Bt = (long)mxGetN(prhs[2]);
         plhs[0] = mxCreateDoubleMatrix(1, Bt, mxREAL);
         mxArray *sw = int32_row(Bt), *cv = int32_row(Bt), *mc = mxCreateDoubleMatrix(1, Bt, mxREAL);

@@ -389,13 +389,43 @@ def control_char_test_problem(prob, t, x, lam):
     return np.minimum(prob.ControlBounds[0, 1], np.maximum(prob.ControlBounds[0, 0], u))
 
 
+def adjoint_rhs(prob, t, x, lam, u):
+    """prob.adjointRHS of the v1 struct API: -gradient(H, x) with H = objective + lam*stateRHS
+    (functions/make_from_symbolic.m:11-14).  In terms of the v2 callbacks this is
+    -dFdx_times_vec(t, [x; .], u, [lam; 1]) restricted to the state rows."""
+    y = np.concatenate([x, np.zeros((1,) + x.shape[1:])])
+    v = np.concatenate([lam, np.ones((1,) + lam.shape[1:])])
+    return -prob.dFdx_times_vec(t, y, u, v)[:-1]
+
+
+def costate_rk4_continuous(prob, integrator, x, u):
+    """The backward costate solve of functions/compute_x_lam.m:11-12 / compute_x_lam_J.m:18-19
+    (lam' = adjointRHS(t, x(t), lam, u(t)), lam(T) = 0) with classical RK4 on the integrator's
+    fixed grid in place of odevr7.  x: (n, N+1) node states, u: (nc, G).  Midpoint state = mean
+    of the neighbouring nodes (the textbook forward-backward sweep).  Returns lam (n, N+1)."""
+    t, h = integrator.t, integrator.h
+    n, N = x.shape[0], h.size
+    lam = np.zeros((n, N + 1) + x.shape[2:])
+    for i in range(N - 1, -1, -1):
+        lR, xR, xL = lam[:, i + 1], x[:, i + 1], x[:, i]
+        xm = (xL + xR) / 2
+        hh, h2, h6 = h[i], h[i] / 2, h[i] / 6
+        k1 = adjoint_rhs(prob, t[2 * i + 2], xR, lR, _col(u, 2 * i + 2))
+        k2 = adjoint_rhs(prob, t[2 * i + 1], xm, lR - h2 * k1, _col(u, 2 * i + 1))
+        k3 = adjoint_rhs(prob, t[2 * i + 1], xm, lR - h2 * k2, _col(u, 2 * i + 1))
+        k4 = adjoint_rhs(prob, t[2 * i], xL, lR - hh * k3, _col(u, 2 * i))
+        lam[:, i] = lR - h6 * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+    return lam
+
+
 def fb_sweep_rk4(prob, integrator, x0, u0_grid, control_char, uRelTol=1e-7, uAbsTol=1e-7,
-                 nSWEEPS=50, relax=1.0):
+                 nSWEEPS=50, relax=1.0, costate="discrete"):
     """The fb_sweep iteration (functions/fb_sweep.m:79-115) composed on the RK4 grid
     (SURVEY.md App. A.6 -- a NEW composition; the reference's own fb_sweep integrates
     with odevr7).  Control lives on the integrator's G grid points.
 
-    per sweep (:94-97)   x = forward(u); lam = discrete adjoint(u);
+    per sweep (:94-97)   x = forward(u); lam = discrete adjoint(u)  (costate="continuous":
+                         lam from costate_rk4_continuous, the v1 adjointRHS);
                          uNew_j = ControlChar(t_j, x_j, lam_j)
     midpoint x/lam are the averages of the two neighbouring nodes (documented
     deviation: the reference interpolates ODE output with pchip).
@@ -406,7 +436,10 @@ def fb_sweep_rk4(prob, integrator, x0, u0_grid, control_char, uRelTol=1e-7, uAbs
     out = dict(converged=False, sweeps=0)
     for sweep in range(1, nSWEEPS + 1):
         x, J = integrator.compute_states(prob, x0, u)
-        lam = integrator.compute_adjoints(prob, u, want_dJdu=False)
+        if costate == "continuous":     # v1 API: adjointRHS integrated backwards (compute_x_lam.m:11-12)
+            lam = np.concatenate([costate_rk4_continuous(prob, integrator, x[:-1], u), np.ones((1, x.shape[1]))])
+        else:
+            lam = integrator.compute_adjoints(prob, u, want_dJdu=False)
         xg = _nodes_to_grid(x[:-1])
         lg = _nodes_to_grid(lam[:-1])
         uNew = control_char(t, xg, lg)

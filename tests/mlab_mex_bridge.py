@@ -121,6 +121,7 @@ def make_mex(ocs):
             u0f = L.f64(u0)
             J, mc = np.empty((1, Bt)), np.empty((1, Bt))
             sw, cv = np.empty(Bt, dtype=np.int32), np.empty(Bt, dtype=np.int32)
+            check(lib.ocs_b200_set_fb_costate(h, int(sc(a[8])) if len(a) > 8 else 0), h)
             check(lib.ocs_b200_fb_sweep(h, L.dp(x0), Bt, L.dp(u0f), nbu, L.dp(bounds), sc(a[4]), sc(a[5]), int(sc(a[6])),
                                         sc(a[7]), L.dp(J), L.ip(sw), L.ip(cv), L.dp(mc)), h)
             return (J, sw.astype(float).reshape(1, -1), cv.astype(float).reshape(1, -1), mc)[:max(nargout, 1)]

@@ -179,6 +179,32 @@ def test_fb_sweep_rk4_grid(ocs, oracle):
         assert np.max(np.abs(un - ref["u"])) < 1e-6   # soln.u = ControlChar of the final sweep (fb_sweep.m:123)
 
 
+def test_fb_sweep_continuous_costate(ocs, oracle):
+    """fb_sweep with the v1 API's costate equation (adjointRHS, compute_x_lam.m:11-12) integrated
+    backwards by RK4 on the grid, vs the oracle's costate_rk4_continuous composition."""
+    tspan, integ, prob, oprob, ointeg, ctl, octl = _setup(ocs, oracle, N=200, T=4.0)
+    G = 401
+    u0 = np.full((1, G), 0.5)
+    cc = lambda t, x, lam: oracle.control_char_test_problem(oprob, t, x, lam)
+    x0 = np.random.default_rng(12).uniform(.5, 2.5, (1, 333))
+    one = integ.fb_sweep(prob, x0, u0, nSWEEPS=1, costate="continuous")       # a single sweep: pure kernel parity
+    for b in (0, 77, 332):
+        ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, b], u0.copy(), cc, nSWEEPS=1, costate="continuous")
+        un = integ.get_control_u(b, 1)[:, :, 0]
+        assert relerr(un, ref["u"]) < TOL
+        assert relerr(one["maxChange"][b], ref["maxChange"]) < 1e-9
+    out = integ.fb_sweep(prob, x0, u0, nSWEEPS=60, costate="continuous")
+    dis = integ.fb_sweep(prob, x0, u0, nSWEEPS=60, costate="discrete")
+    for b in (0, 77, 332):
+        ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, b], u0.copy(), cc, nSWEEPS=60, costate="continuous")
+        assert bool(out["converged"][b]) == ref["converged"] and out["sweeps"][b] == ref["sweeps"]
+        assert relerr(out["J"][b], ref["J"]) < 1e-9
+    # both costates approximate the same continuous problem: the optimal J agree to discretisation accuracy
+    assert np.max(np.abs(out["J"] - dis["J"]) / np.abs(dis["J"])) < 1e-4
+    with pytest.raises(ValueError):
+        integ.fb_sweep(prob, x0, u0, costate="odevr7")
+
+
 def test_reduce_J(ocs, oracle):
     tspan, integ, prob, oprob, ointeg, ctl, octl = _setup(ocs, oracle, N=50, K=11)
     integ.attach_control(ctl)

@@ -115,3 +115,24 @@ def test_equilibrium_and_fb_sweep_composition(oracle):
     # at the fixed point the control satisfies its characterisation
     xg, lg = oracle._nodes_to_grid(out["x"][:-1]), oracle._nodes_to_grid(out["lam"][:-1])
     assert np.max(np.abs(cc(integ.t, xg, lg) - out["u"])) < 1e-6
+
+
+def test_continuous_costate_matches_an_adaptive_solve(oracle):
+    """costate_rk4_continuous (the v1 adjointRHS integrated on the RK4 grid) against scipy's adaptive
+    integration of the same ODE through a dense interpolant of x: the fixed-grid solve is O(h^2)
+    (midpoint state = mean of the nodes), so the gap shrinks 4x per grid halving."""
+    from scipy.integrate import solve_ivp
+    from scipy.interpolate import CubicSpline
+    prob = oracle.TestOCProblem(*P)
+    errs = []
+    for N in (100, 200, 400):
+        integ = oracle.RK4Integrator(oracle.matlab_linspace(0, 4, N + 1))
+        u = 0.3 + 0.2 * np.sin(integ.t)[None, :]
+        x, _ = integ.compute_states(prob, [1.3], u)
+        lam = oracle.costate_rk4_continuous(prob, integ, x[:-1], u)
+        xs = CubicSpline(integ.t[0::2], x[0])
+        uf = lambda t: 0.3 + 0.2 * np.sin(t)
+        rhs = lambda t, l: oracle.adjoint_rhs(prob, t, np.array([xs(t)]), l, np.array([uf(t)]))
+        sol = solve_ivp(rhs, [4.0, 0.0], [0.0], rtol=1e-11, atol=1e-13, dense_output=True)
+        errs.append(np.max(np.abs(sol.sol(integ.t[0::2])[0] - lam[0])))
+    assert errs[0] < 1e-3 and errs[1] < errs[0] / 3.5 and errs[2] < errs[1] / 3.5
