@@ -207,6 +207,23 @@ OCS_B200_API int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, 
                                           const double *free_ub, int max_iter, double tol,
                                           double *v_opt, double *J, int32_t *iters, int32_t *converged);
 
+/* Batched compute_equilibrium (functions/compute_equilibrium.m:1-33): for every parameter set, the steady state
+ * [xStar; lamStar; uStar] of the infinite-horizon problem, i.e. the solution within [lb, ub] of (:10-21)
+ *     F(0,x,u)(1:n) = 0;   r*lam - dFdx_times_vec(0,x,u,[lam;1])(1:n) = 0;   dFdu_times_vec(0,x,u,[lam;1]) = 0.
+ * The reference solves ONE system per call with lsqnonlin (:23-27); here every parameter set is solved by its own
+ * thread (Levenberg-Marquardt, central-difference Jacobian, steps projected onto the bounds), using the bound
+ * problem's device functions -- parameter sweeps of RK4InfiniteIntegrator need one uStar per set.
+ *   params [np x nparams], nparams in {1, nsets}; guess [(2n+nc) x nguess] = [xGuess; lamGuess; uGuess], nguess in {1, nsets};
+ *   lb, ub [(2n+nc)] or NULL (unbounded); r [nr] discount rate(s), nr in {1, nsets};
+ *   max_iter (reference: MaxIter 4000), tol: stop when max_k |step_k| <= tol (1 + |y_k|) or resnorm <= tol^2.
+ *   y [(2n+nc) x nsets]; resnorm [nsets] = sum(residual.^2); residual [(2n+nc) x nsets];
+ *   exitflag [nsets] (1 converged, 0 iteration limit, -1 not finite); iters [nsets].  All but y may be NULL.
+ * Needs a bound problem only (no grid data is used). */
+OCS_B200_API int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int np, long nparams, long nsets,
+                                              const double *guess, long nguess, const double *lb, const double *ub,
+                                              const double *r, long nr, int max_iter, double tol, double *y,
+                                              double *resnorm, double *residual, int32_t *exitflag, int32_t *iters);
+
 /* Batch reduction of the last J (warp-shuffle tree): value and arg index (index may be NULL). */
 OCS_B200_API int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, long *index);
 

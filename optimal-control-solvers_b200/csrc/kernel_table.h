@@ -18,4 +18,5 @@ struct ocs_kernel_table {
     const void *fbrev[2];
     const void *fbcont[2];      // fb_sweep with the continuous costate equation (v1 adjointRHS) instead of the discrete adjoint
     const void *tt;
+    const void *eq;             // batched compute_equilibrium (one parameter set per thread)
 };

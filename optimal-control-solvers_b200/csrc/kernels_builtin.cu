@@ -86,4 +86,5 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->fbrev[0] = FBR(0); t->fbrev[1] = FBR(1);
     t->fbcont[0] = FBC(0); t->fbcont[1] = FBC(1);
     t->tt = (const void *)OCS_CAT2(ocs_tt_, OCS_TAGNAME);
+    t->eq = (const void *)OCS_CAT2(ocs_eq_, OCS_TAGNAME);
 }

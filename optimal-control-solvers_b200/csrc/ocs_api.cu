@@ -26,6 +26,7 @@
 #define OCS_NS ocs_host
 #include "rk4_kernels.cuh"
 using ocs_host::SweepArgs;
+using ocs_host::EqArgs;
 
 extern "C" void ocs_builtin_table_test_fast(ocs_kernel_table *t);
 extern "C" void ocs_builtin_table_test_strict(ocs_kernel_table *t);
@@ -1623,6 +1624,80 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
         if (sweeps) CK(cudaMemcpyAsync(sweeps, h->d_sweeps, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
         if (converged) CK(cudaMemcpyAsync(converged, h->d_frozen, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
         if (max_change) CK(cudaMemcpyAsync(max_change, h->d_maxchg.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int np, long nparams, long nsets, const double *guess,
+                                 long nguess, const double *lb, const double *ub, const double *r, long nr, int max_iter,
+                                 double tol, double *y, double *resnorm, double *residual, int32_t *exitflag, int32_t *iters)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->sticky) return h->sticky;
+    if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "no problem bound (ocs_b200_set_problem_*)");
+    if (np != h->kt.np) return h->fail(OCS_B200_ERR_ARG, "the problem has %d parameters, got %d", h->kt.np, np);
+    if ((np > 0 && !params) || !guess || !r || !y || nsets < 1 || (nguess != 1 && nguess != nsets) ||
+        (nr != 1 && nr != nsets) || (nparams != 1 && nparams != nsets) || max_iter < 1 || !(tol > 0.0))
+        return h->fail(OCS_B200_ERR_ARG, "bad compute_equilibrium arguments");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int NY = 2 * h->kt.n + h->kt.nc;
+        if (!h->kt.eq && h->is_generated) {
+            const char *names[1] = {"ocs_eq_gen"};
+            const void *kern[1] = {nullptr};
+            void *lib = nullptr;
+            std::string log;
+            int rc = ocs_compile_unit(h->gen_source.c_str(), "OCS_EQ_KERNEL(ocs_gen::Problem, gen)",
+                                      h->math_mode == OCS_B200_MATH_STRICT,
+                                      h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log);
+            if (rc != 0) return h->fail(rc, "equilibrium kernel of the generated problem did not compile:\n%s", log.c_str());
+            h->gen_libraries.push_back(lib);
+            h->kt.eq = kern[0];
+        }
+        if (!h->kt.eq) return h->fail(OCS_B200_ERR_ARG, "the bound problem has no equilibrium kernel");
+        // one scratch allocation: params | guess | lb | ub | r | y | resnorm | residual | (int) exitflag, iters
+        const size_t n_par = (size_t)std::max(np, 1) * nparams, n_gs = (size_t)NY * nguess, n_y = (size_t)NY * nsets;
+        const size_t total = n_par + n_gs + 2 * NY + (size_t)nr + n_y + (size_t)nsets + n_y + (size_t)nsets + 2;
+        TRY(ensure(h, h->d_stage2, total));
+        double *d = h->d_stage2.p;
+        double *d_par = d, *d_gs = d_par + n_par, *d_lb = d_gs + n_gs, *d_ub = d_lb + NY, *d_r = d_ub + NY, *d_y = d_r + nr,
+               *d_rn = d_y + n_y, *d_res = d_rn + nsets;
+        int *d_flag = reinterpret_cast<int *>(d_res + n_y), *d_it = d_flag + nsets;
+        if (np > 0) CK(cudaMemcpyAsync(d_par, params, sizeof(double) * np * nparams, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d_gs, guess, sizeof(double) * n_gs, cudaMemcpyHostToDevice, h->stream));
+        if (lb) CK(cudaMemcpyAsync(d_lb, lb, sizeof(double) * NY, cudaMemcpyHostToDevice, h->stream));
+        if (ub) CK(cudaMemcpyAsync(d_ub, ub, sizeof(double) * NY, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d_r, r, sizeof(double) * nr, cudaMemcpyHostToDevice, h->stream));
+        EqArgs a;
+        memset(&a, 0, sizeof a);
+        a.nsets = nsets;
+        a.np = np;
+        a.params = d_par;
+        a.nparams = nparams;
+        a.guess = d_gs;
+        a.nguess = nguess;
+        a.lb = lb ? d_lb : nullptr;
+        a.ub = ub ? d_ub : nullptr;
+        a.r = d_r;
+        a.nr = nr;
+        a.max_iter = max_iter;
+        a.tol = tol;
+        a.y = d_y;
+        a.resnorm = d_rn;
+        a.residual = d_res;
+        a.exitflag = d_flag;
+        a.iters = d_it;
+        void *args[] = {(void *)&a};
+        CK(cudaLaunchKernel(h->kt.eq, dim3((unsigned)((nsets + 127) / 128)), dim3(128), args, 0, h->stream));
+        h->launches++;
+        CK(cudaMemcpyAsync(y, d_y, sizeof(double) * n_y, cudaMemcpyDeviceToHost, h->stream));
+        if (resnorm) CK(cudaMemcpyAsync(resnorm, d_rn, sizeof(double) * nsets, cudaMemcpyDeviceToHost, h->stream));
+        if (residual) CK(cudaMemcpyAsync(residual, d_res, sizeof(double) * n_y, cudaMemcpyDeviceToHost, h->stream));
+        if (exitflag) CK(cudaMemcpyAsync(exitflag, d_flag, sizeof(int) * nsets, cudaMemcpyDeviceToHost, h->stream));
+        if (iters) CK(cudaMemcpyAsync(iters, d_it, sizeof(int) * nsets, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     } catch (const std::exception &ex) {

@@ -1160,6 +1160,174 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
     }
 }
 
+// ------------------------------------------------------------------ batched compute_equilibrium
+// functions/compute_equilibrium.m:1-33 for one parameter set per thread.  The reference hands the
+// residual system (:10-21)
+//     value(x)   = F(0, x, u)(1:n)
+//     value(lam) = r*lam - dFdx_times_vec(0, x, u, [lam; 1])(1:n)
+//     value(u)   = dFdu_times_vec(0, x, u, [lam; 1])
+// to lsqnonlin with bounds (:23-27).  Here every thread runs a Levenberg-Marquardt iteration on its
+// own system (central-difference Jacobian, Cholesky solve of the damped normal equations, active-set
+// treatment of [lb, ub] plus projection of the step); the root, not the iterate path, is what compares
+// with lsqnonlin.  exitflag 1 = converged to a (possibly local) minimiser of sum(residual.^2): resnorm
+// tells whether it is a root.
+// All host-layout arrays are MATLAB column-major with one column per parameter set.
+struct EqArgs {
+    long nsets;
+    int np;
+    const double *params;   // [np x nparams]
+    long nparams;           // 1 or nsets
+    const double *guess;    // [(2n+nc) x nguess]
+    long nguess;            // 1 or nsets
+    const double *lb, *ub;  // [(2n+nc)] or null
+    const double *r;        // [nr]
+    long nr;                // 1 or nsets
+    int max_iter;
+    double tol;             // stop when max |step_k| <= tol*(1+|y_k|) or sum(residual.^2) <= tol^2
+    double *y;              // [(2n+nc) x nsets]  = [xStar; lamStar; uStar]
+    double *resnorm;        // [nsets] sum(residual.^2)
+    double *residual;       // [(2n+nc) x nsets] or null
+    int *exitflag;          // [nsets] 1 converged, 0 iteration limit, -1 not finite
+    int *iters;             // [nsets] or null
+};
+
+template <class P>
+__device__ __forceinline__ void eq_residual(const double *y, const double *p, double r, double *f)
+{
+    constexpr int n = P::n, m = n + 1, nc = P::nc;
+    double ya[m], v[m], Fo[m], gx[n], gu[nc], u[nc];
+    const double dummy[2] = {0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < n; ++c) { ya[c] = y[c]; v[c] = y[n + c]; }
+    ya[n] = 0.0;
+    v[n] = 1.0;                                                        // [lam; 1]   :16,:19
+#pragma unroll
+    for (int c = 0; c < nc; ++c) u[c] = y[2 * n + c];
+    P::template F<HM_NONE>(dummy, 0.0, ya, u, p, Fo);                  // :13
+    P::template X<HM_NONE>(dummy, 0.0, ya, u, p, v, gx);               // :16
+    P::template U<HM_NONE>(dummy, 0.0, ya, u, p, v, gu);               // :19
+#pragma unroll
+    for (int c = 0; c < n; ++c) { f[c] = Fo[c]; f[n + c] = r * y[n + c] - gx[c]; }   // :14,:17
+#pragma unroll
+    for (int c = 0; c < nc; ++c) f[2 * n + c] = gu[c];
+}
+
+template <class P>
+__device__ __forceinline__ void equilibrium_body(const EqArgs &a)
+{
+    constexpr int n = P::n, nc = P::nc, np = P::np, NY = 2 * n + nc;
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nsets) return;
+    double p[np > 0 ? np : 1];
+    for (int k = 0; k < np; ++k) p[k] = a.params[k + (size_t)np * (a.nparams > 1 ? b : 0)];
+    const double r = a.r[a.nr > 1 ? b : 0];
+    double y[NY], f[NY], yt[NY], ft[NY], fm[NY], g[NY], dy[NY], lo[NY], hi[NY];
+    double Jm[NY][NY], A[NY][NY], Lc[NY][NY];
+    for (int k = 0; k < NY; ++k) {
+        lo[k] = a.lb ? a.lb[k] : -1.0e308 * 10.0;
+        hi[k] = a.ub ? a.ub[k] : 1.0e308 * 10.0;
+        y[k] = fmin(hi[k], fmax(lo[k], a.guess[k + (size_t)NY * (a.nguess > 1 ? b : 0)]));
+    }
+    eq_residual<P>(y, p, r, f);
+    double Fv = 0.0;
+    for (int k = 0; k < NY; ++k) Fv += f[k] * f[k];
+    double mu = -1.0, nu = 2.0;
+    int flag = 0, it = 0;
+    bool need_jac = true;
+    for (it = 0; it < a.max_iter; ++it) {
+        if (!(Fv == Fv) || Fv > 1.0e300) { flag = -1; break; }
+        if (Fv <= a.tol * a.tol) { flag = 1; break; }
+        if (need_jac) {
+            for (int k = 0; k < NY; ++k) yt[k] = y[k];
+            for (int k = 0; k < NY; ++k) {
+                const double d = 6.0e-6 * fmax(1.0, fabs(y[k]));     // ~eps^(1/3): central differences
+                yt[k] = y[k] + d;
+                eq_residual<P>(yt, p, r, ft);
+                yt[k] = y[k] - d;
+                eq_residual<P>(yt, p, r, fm);
+                yt[k] = y[k];
+                const double inv = 1.0 / (2.0 * d);
+                for (int q = 0; q < NY; ++q) Jm[q][k] = (ft[q] - fm[q]) * inv;
+            }
+            double amax = 0.0;
+            for (int i = 0; i < NY; ++i) {
+                double s = 0.0;
+                for (int q = 0; q < NY; ++q) s += Jm[q][i] * f[q];
+                g[i] = s;
+                for (int j = 0; j <= i; ++j) {
+                    double t = 0.0;
+                    for (int q = 0; q < NY; ++q) t += Jm[q][i] * Jm[q][j];
+                    A[i][j] = A[j][i] = t;
+                }
+                amax = fmax(amax, A[i][i]);
+            }
+            if (mu < 0.0) mu = 1.0e-3 * fmax(amax, 1.0e-300);
+            need_jac = false;
+        }
+        // active set: a variable on a bound whose gradient points outwards is held there for this step
+        bool act[NY];
+        for (int k = 0; k < NY; ++k) act[k] = (y[k] <= lo[k] && g[k] > 0.0) || (y[k] >= hi[k] && g[k] < 0.0);
+        // (A + mu I) dy = -g on the free variables by Cholesky; a failed factorisation raises the damping
+        bool spd = true;
+        for (int i = 0; i < NY && spd; ++i) {
+            for (int j = 0; j <= i; ++j) {
+                double s = (i == j) ? (act[i] ? 1.0 : A[i][i]) + mu : ((act[i] || act[j]) ? 0.0 : A[i][j]);
+                for (int q = 0; q < j; ++q) s -= Lc[i][q] * Lc[j][q];
+                if (i == j) {
+                    if (!(s > 0.0)) { spd = false; break; }
+                    Lc[i][i] = sqrt(s);
+                } else {
+                    Lc[i][j] = s / Lc[j][j];
+                }
+            }
+        }
+        if (!spd) { mu *= nu; nu *= 2.0; continue; }
+        for (int i = 0; i < NY; ++i) {
+            double s = act[i] ? 0.0 : -g[i];
+            for (int q = 0; q < i; ++q) s -= Lc[i][q] * dy[q];
+            dy[i] = s / Lc[i][i];
+        }
+        for (int i = NY - 1; i >= 0; --i) {
+            double s = dy[i];
+            for (int q = i + 1; q < NY; ++q) s -= Lc[q][i] * dy[q];
+            dy[i] = s / Lc[i][i];
+        }
+        bool tiny = true;
+        for (int k = 0; k < NY; ++k) {
+            yt[k] = fmin(hi[k], fmax(lo[k], y[k] + dy[k]));           // projected step
+            dy[k] = yt[k] - y[k];
+            if (fabs(dy[k]) > a.tol * (1.0 + fabs(y[k]))) tiny = false;
+        }
+        eq_residual<P>(yt, p, r, ft);
+        double Fn = 0.0;
+        for (int k = 0; k < NY; ++k) Fn += ft[k] * ft[k];
+        if (Fn < Fv) {
+            // gain ratio against the damped model: F - model = dy'(mu dy - g) for the unprojected step
+            double pred = 0.0;
+            for (int k = 0; k < NY; ++k) pred += dy[k] * (mu * dy[k] - (act[k] ? 0.0 : g[k]));
+            const double rho = pred > 0.0 ? (Fv - Fn) / (2.0 * pred) : 1.0;   // F = |f|^2 = 2 * (|f|^2 / 2)
+            const double c = 2.0 * rho - 1.0;
+            mu *= fmax(1.0 / 3.0, 1.0 - c * c * c);
+            nu = 2.0;
+            for (int k = 0; k < NY; ++k) { y[k] = yt[k]; f[k] = ft[k]; }
+            Fv = Fn;
+            need_jac = true;
+            if (tiny) { flag = 1; ++it; break; }
+        } else {
+            if (tiny) { flag = 1; break; }     // no further decrease within the step tolerance
+            mu *= nu;
+            nu *= 2.0;
+        }
+    }
+    for (int k = 0; k < NY; ++k) {
+        a.y[k + (size_t)NY * b] = y[k];
+        if (a.residual) a.residual[k + (size_t)NY * b] = f[k];
+    }
+    a.resnorm[b] = Fv;
+    a.exitflag[b] = flag;
+    if (a.iters) a.iters[b] = it;
+}
+
 }  // namespace OCS_NS
 
 // Kernel entry points.  Each macro emits one extern "C" __global__ wrapper; the host looks the
@@ -1197,6 +1365,12 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
         o[6] = OCS_TILE; o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24);               \
     }
 
+#define OCS_EQ_KERNEL(P, tag)                                                                         \
+    extern "C" __global__ void __launch_bounds__(128) ocs_eq_##tag(const OCS_NS::EqArgs a)            \
+    {                                                                                                  \
+        OCS_NS::equilibrium_body<P>(a);                                                               \
+    }
+
 #define OCS_DEFINE_KERNELS_PB(P, tag, PB, KD)   \
     OCS_FWD_KERNEL(P, tag, 0, 0, PB, KD)        \
     OCS_FWD_KERNEL(P, tag, 1, 1, PB, KD)        \
@@ -1220,4 +1394,5 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
 #define OCS_DEFINE_KERNELS(P, tag, KD)   \
     OCS_DEFINE_KERNELS_PB(P, tag, 0, KD) \
     OCS_DEFINE_KERNELS_PB(P, tag, 1, KD) \
-    OCS_TT_KERNEL(P, tag)
+    OCS_TT_KERNEL(P, tag)                \
+    OCS_EQ_KERNEL(P, tag)

@@ -4,12 +4,15 @@ They contain no arithmetic of their own: every sweep runs on the GPU through the
   nlp_objective                  functions/single_shooting.m:137-150 (the fmincon callback)
   compute_states_and_objective   functions/compute_states_and_objective.m (legacy v1 forward sweep)
   fb_sweep                       functions/fb_sweep.m:79-125 composed on the RK4 grid
+  compute_equilibrium            functions/compute_equilibrium.m, one steady state per parameter set
 """
 from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["nlp_objective", "compute_states_and_objective", "fb_sweep", "single_shooting"]
+from .. import _lib
+
+__all__ = ["nlp_objective", "compute_states_and_objective", "fb_sweep", "single_shooting", "compute_equilibrium"]
 
 
 def nlp_objective(prob, integrator, control, x0, v, FreeInitStates=()):
@@ -86,6 +89,47 @@ def fb_sweep(prob, integrator, x0, u0=None, options=None):
                               nSWEEPS=opt["nSWEEPS"], relax=opt["relax"], costate=opt["costate"])
     out["u"] = integrator.get_control_u(0, out["J"].size)
     return out
+
+
+def compute_equilibrium(prob, xGuess, lamGuess, uGuess, lb=None, ub=None, r=0.0, params=None, device=0, math="fast",
+                        MaxIter=4000, tol=1e-13, integrator=None):
+    """[xStar, lamStar, uStar, resnorm, residual, exitflag] = compute_equilibrium(prob, xGuess, lamGuess, uGuess,
+    lb, ub, r) (functions/compute_equilibrium.m:1-33), batched: one steady state per parameter set, each solved
+    by its own GPU thread (ocs_b200_compute_equilibrium).  `params` (np, nsets) overrides prob's parameters for
+    a sweep; guesses may be columns (shared) or (., nsets); r scalar or (nsets,).  With one parameter set the
+    outputs have the reference's shapes (column vectors, scalar resnorm/exitflag)."""
+    from .integrators import CudaRK4Integrator
+    own = integrator is None
+    integ = integrator or CudaRK4Integrator(np.array([0.0, 1.0]), device=device, math=math)
+    try:
+        integ._bind(prob)
+        n, nc = prob.nStates, prob.nControls
+        P = np.asarray(prob.param_array() if params is None else params, dtype=np.float64)
+        P = P.reshape(P.shape[0], -1)
+        g = [np.asarray(a, dtype=np.float64).reshape(k, -1) for a, k in ((xGuess, n), (lamGuess, n), (uGuess, nc))]
+        ng = max(a.shape[1] for a in g)
+        guess = _lib.f64(np.concatenate([np.broadcast_to(a, (a.shape[0], ng)) for a in g], axis=0))
+        rr = _lib.f64(np.atleast_1d(np.asarray(r, dtype=np.float64)).ravel())
+        nsets = max(P.shape[1], ng, rr.size)
+        Pf = _lib.f64(P)
+        NY = 2 * n + nc
+        lbf = None if lb is None else _lib.f64(np.asarray(lb, dtype=np.float64).ravel())
+        ubf = None if ub is None else _lib.f64(np.asarray(ub, dtype=np.float64).ravel())
+        for a in (lbf, ubf):
+            if a is not None and a.size != NY:
+                raise ValueError("lb / ub must have 2*nStates + nControls entries")
+        y = np.empty((NY, nsets), order="F")
+        resnorm, residual = np.empty(nsets), np.empty((NY, nsets), order="F")
+        flag, iters = np.empty(nsets, dtype=np.int32), np.empty(nsets, dtype=np.int32)
+        integ._ck(integ._lib.ocs_b200_compute_equilibrium(
+            integ._h, _lib.dp(Pf), Pf.shape[0], Pf.shape[1], nsets, _lib.dp(guess), ng, _lib.dp(lbf), _lib.dp(ubf), _lib.dp(rr), rr.size,
+            int(MaxIter), float(tol), _lib.dp(y), _lib.dp(resnorm), _lib.dp(residual), _lib.ip(flag), _lib.ip(iters)))
+    finally:
+        if own:
+            integ.close()
+    if nsets == 1:
+        return y[:n, 0].copy(), y[n:2 * n, 0].copy(), y[2 * n:, 0].copy(), float(resnorm[0]), residual[:, 0].copy(), int(flag[0])
+    return y[:n], y[n:2 * n], y[2 * n:], resnorm, residual, flag
 
 
 def single_shooting(prob, x0, tspan, nCONTROL_PTS, Control=None, Integrator=None, u0=0.0, FreeInitStates=(),

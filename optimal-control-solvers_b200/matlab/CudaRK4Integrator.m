@@ -122,6 +122,17 @@ classdef CudaRK4Integrator < Integrator
          obj.Bt = size(x0, 2);
       end
 
+      function [xStar, lamStar, uStar, resnorm, residual, exitflag] = compute_equilibrium(obj, prob, xGuess, lamGuess, uGuess, lb, ub, r, params)
+         % functions/compute_equilibrium.m for every parameter set at once (one GPU thread per set).
+         % params (np x nsets) overrides prob's parameters for a sweep; guesses may be columns or (. x nsets).
+         obj.bind(prob);
+         if nargin < 9 || isempty(params), params = obj.boundParams; end
+         [y, resnorm, residual, exitflag] = ocs_b200_mex('compute_equilibrium', obj.handle, params, ...
+            [xGuess; lamGuess; uGuess], lb, ub, r, 4000, 1e-13);     % MaxIter 4000: compute_equilibrium.m:24
+         n = obj.nStates;
+         xStar = y(1:n, :);  lamStar = y(n+1:2*n, :);  uStar = y(2*n+1:end, :);
+      end
+
       function out = fb_sweep(obj, prob, x0, u0, varargin)
          % The sweep loop of functions/fb_sweep.m:79-115 on the RK4 grid, for every column of x0.
          p = inputParser;

@@ -228,6 +228,29 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         check(rc, h);
         return;
     }
+    /* ---- [y, resnorm, residual, exitflag] = mex('compute_equilibrium', h, params, guess, lb, ub, r, maxIter, tol)
+     *      functions/compute_equilibrium.m:1-33, one steady state per column of params */
+    if (!strcmp(cmd, "compute_equilibrium")) {
+        FAIL_IF(nrhs < 9, "ocs_b200:nargin", "compute_equilibrium(h, params, guess, lb, ub, r, maxIter, tol)");
+        long nsets = (long)mxGetN(prhs[2]);
+        long ny = (long)mxGetM(prhs[3]);
+        if (nsets < 1) nsets = 1;
+        if ((long)mxGetN(prhs[3]) > nsets) nsets = (long)mxGetN(prhs[3]);
+        if ((long)mxGetNumberOfElements(prhs[6]) > nsets) nsets = (long)mxGetNumberOfElements(prhs[6]);
+        FAIL_IF(mxGetN(prhs[2]) > 1 && (long)mxGetN(prhs[2]) != nsets, "ocs_b200:size", "params must have one column per set");
+        plhs[0] = mxCreateDoubleMatrix(ny, nsets, mxREAL);
+        mxArray *rn = mxCreateDoubleMatrix(1, nsets, mxREAL), *rs = mxCreateDoubleMatrix(ny, nsets, mxREAL), *fl = int32_row(nsets);
+        int rc = ocs_b200_compute_equilibrium(h, dbl(prhs[2], "params"), (int)mxGetM(prhs[2]),
+                                              mxGetN(prhs[2]) > 1 ? (long)mxGetN(prhs[2]) : 1, nsets, dbl(prhs[3], "guess"), (long)mxGetN(prhs[3]),
+                                              dbl(prhs[4], "lb"), dbl(prhs[5], "ub"), dbl(prhs[6], "r"),
+                                              (long)mxGetNumberOfElements(prhs[6]), (int)scalar(prhs[7]), scalar(prhs[8]),
+                                              mxGetPr(plhs[0]), mxGetPr(rn), mxGetPr(rs), (int32_t *)mxGetData(fl), NULL);
+        if (nlhs > 1) plhs[1] = rn; else mxDestroyArray(rn);
+        if (nlhs > 2) plhs[2] = rs; else mxDestroyArray(rs);
+        if (nlhs > 3) plhs[3] = fl; else mxDestroyArray(fl);
+        check(rc, h);
+        return;
+    }
     /* ---- [v, J, iters, converged] = mex('single_shooting', h, x0, v0, Lb, Ub, free (0-based int32 | []), freeLb, freeUb, maxIter, tol)
      *      the fmincon solve of functions/single_shooting.m:114 for every column of x0, on the device */
     if (!strcmp(cmd, "single_shooting")) {

@@ -55,5 +55,17 @@ uInf = control.compute_u(v);
 v0 = control.compute_initial_v(.5);
 ss = integrator.single_shooting(prob, X0, v0, Lb, Ub, 'MaxIter', 300, 'TolX', 1e-6);
 
+% equilibrium as tests/solve_test_problem.m:21-29 computes it, on the device (one set, then a sweep over r)
+lb = [0; -Inf; prob.ControlBounds(1)];
+ub = [Inf; Inf; prob.ControlBounds(2)];
+[xEq, lamEq, uEq, resnormEq, residualEq, flagEq] = compute_equilibrium_cuda(prob, 2.7, 2.2, .7, lb, ub, p.r);
+rSweep = [.04, .05, .06];
+[xEqS, lamEqS, uEqS] = integrator.compute_equilibrium(prob, 2.7, 2.2, .7, lb, ub, rSweep, ...
+                                                       [p.c p.c p.c; p.m p.m p.m; rSweep]);
+
+% fb_sweep on the grid, discrete adjoint and the v1 continuous costate
+fbD = integrator.fb_sweep(prob, X0, .5*ones(1, length(integrator.t)), 'nSWEEPS', 60);
+fbC = integrator.fb_sweep(prob, X0, .5*ones(1, length(integrator.t)), 'nSWEEPS', 60, 'costate', 'continuous');
+
 delete(integrator);
 delete(integratorInf);

@@ -125,6 +125,19 @@ def make_mex(ocs):
             check(lib.ocs_b200_fb_sweep(h, L.dp(x0), Bt, L.dp(u0f), nbu, L.dp(bounds), sc(a[4]), sc(a[5]), int(sc(a[6])),
                                         sc(a[7]), L.dp(J), L.ip(sw), L.ip(cv), L.dp(mc)), h)
             return (J, sw.astype(float).reshape(1, -1), cv.astype(float).reshape(1, -1), mc)[:max(nargout, 1)]
+        if cmd == "compute_equilibrium":
+            P, guess = arr(a[1]), arr(a[2])
+            lb = arr(np.asarray(a[3]).ravel()) if np.asarray(a[3]).size else None
+            ub = arr(np.asarray(a[4]).ravel()) if np.asarray(a[4]).size else None
+            r = arr(np.asarray(a[5], dtype=float).ravel())
+            nsets = max(P.shape[1], guess.shape[1], r.size)
+            ny = guess.shape[0]
+            y, rn, rs = np.empty((ny, nsets), order="F"), np.empty((1, nsets)), np.empty((ny, nsets), order="F")
+            fl = np.empty(nsets, dtype=np.int32)
+            check(lib.ocs_b200_compute_equilibrium(h, L.dp(P), P.shape[0], P.shape[1], nsets, L.dp(guess), guess.shape[1], L.dp(lb),
+                                                   L.dp(ub), L.dp(r), r.size, int(sc(a[6])), sc(a[7]), L.dp(y), L.dp(rn),
+                                                   L.dp(rs), L.ip(fl), None), h)
+            return (y, rn, rs, fl.astype(float).reshape(1, -1))[:max(nargout, 1)]
         if cmd == "single_shooting":
             x0, v0, Lb, Ub = arr(a[1]), arr(a[2]), arr(np.asarray(a[3]).ravel()), arr(np.asarray(a[4]).ravel())
             free = np.asarray(a[5]).ravel().astype(np.int32)

@@ -54,3 +54,16 @@ def test_reference_backprop_test_with_the_drop_in_integrator(ocs, oracle):
     ss = w["ss"]
     assert ss["v"].shape == (21, 3) and np.all(ss["converged"] > 0)
     assert np.all(ss["v"] >= 0) and np.all(ss["v"] <= 1) and np.all(ss["J"] < out["J"] + 1e-9)
+    # compute_equilibrium_cuda.m / CudaRK4Integrator.compute_equilibrium (tests/solve_test_problem.m:21-29)
+    sc = lambda z: float(np.asarray(z).ravel()[0])
+    assert abs(sc(w["uEq"]) - 0.723368780097983) < 1e-12 and abs(sc(w["xEq"]) - 2.73556918863414) < 1e-12
+    assert sc(w["flagEq"]) == 1 and sc(w["resnormEq"]) < 1e-24
+    assert np.asarray(w["uEqS"]).shape == (1, 3) and abs(np.asarray(w["uEqS"])[0, 1] - sc(w["uEq"])) < 1e-12
+    for k, r in enumerate((.04, .05, .06)):
+        oxs, ols, ous = oracle.solve_equilibrium(oracle.TestOCProblem(1.5, 3.0, r), [2.7], [2.2], [.7], r)
+        assert abs(np.asarray(w["xEqS"])[0, k] - oxs[0]) < 1e-11 and abs(np.asarray(w["lamEqS"])[0, k] - ols[0]) < 1e-11
+    # fb_sweep through the .m class, both costates
+    fbD, fbC = w["fbD"], w["fbC"]
+    assert np.all(np.asarray(fbD["converged"]) > 0) and np.all(np.asarray(fbC["converged"]) > 0)
+    assert np.asarray(fbC["u"]).shape == (1, 1001, 3)
+    assert np.max(np.abs(np.asarray(fbD["J"]) - np.asarray(fbC["J"])) / np.abs(np.asarray(fbD["J"]))) < 1e-4
