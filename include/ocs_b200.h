@@ -207,6 +207,30 @@ OCS_B200_API int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, 
                                           const double *free_ub, int max_iter, double tol,
                                           double *v_opt, double *J, int32_t *iters, int32_t *converged);
 
+/* The `soln` struct of the reference, evaluated on the device for trajectories [b0, b0+nb) at the query
+ * times tq[nq]:
+ *   x   [n  x nq x nb] = vectorInterpolant(tspan, xOpt(1:end-1,:), 'pchip')(tq)     functions/single_shooting.m:129
+ *   lam [n  x nq x nb] = vectorInterpolant(tspan, lamOpt(1:end-1,:), 'pchip')(tq)   functions/single_shooting.m:130
+ *   u   [nc x nq x nb] = control.compute_uFunc(vOpt)(tq)                            functions/single_shooting.m:128
+ *                        (with a per-trajectory control grid, i.e. after fb_sweep: the pchip interpolant of the grid
+ *                         values, functions/fb_sweep.m:123)
+ * 'pchip' is MATLAB's shape-preserving cubic (functions/vectorInterpolant.m:1-12 -> griddedInterpolant).  x reads the
+ * resident node states; lam re-runs the costate sweep of the range (same terminal costate as the last
+ * compute_adjoints); u needs ocs_b200_set_control_ufunc.  Any output may be NULL.  segment as in fetch_*. */
+OCS_B200_API int ocs_b200_eval_solution(ocs_b200_handle *h, int segment, long b0, long nb, int nq, const double *tq,
+                                        double *x, double *lam, double *u);
+
+/* How control.compute_uFunc interpolates the coefficients v of the attached basis:
+ *   PREVIOUS  vectorInterpolant(intervalStarts, v, 'previous')  Control/PWConstantControl.m:58-61, knots = intervalStarts [K]
+ *   LINEAR    vectorInterpolant(controlPts, v, 'linear')        Control/PWLinearControl.m:74-77,   knots = controlPts [K]
+ *   CHEBYSHEV sum_k v_k T_k(tau(t)) with the recurrence of Control/ChebyshevControl.m:23-30,       knots = [t(1), t(end)]
+ * Queries outside the knots take the nearest end value (PREVIOUS, LINEAR). */
+#define OCS_B200_UFUNC_NONE 0
+#define OCS_B200_UFUNC_PREVIOUS 1
+#define OCS_B200_UFUNC_LINEAR 2
+#define OCS_B200_UFUNC_CHEBYSHEV 3
+OCS_B200_API int ocs_b200_set_control_ufunc(ocs_b200_handle *h, int kind, int nknots, const double *knots);
+
 /* Batched compute_equilibrium (functions/compute_equilibrium.m:1-33): for every parameter set, the steady state
  * [xStar; lamStar; uStar] of the infinite-horizon problem, i.e. the solution within [lb, ub] of (:10-21)
  *     F(0,x,u)(1:n) = 0;   r*lam - dFdx_times_vec(0,x,u,[lam;1])(1:n) = 0;   dFdu_times_vec(0,x,u,[lam;1]) = 0.

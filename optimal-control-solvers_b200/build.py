@@ -32,7 +32,7 @@ UNITS = [
     ("nvrtc_problem.o", "nvrtc_problem.cu", []),
     ("microbench.o", "microbench.cu", []),
 ]
-HEADERS = ["rk4_kernels.cuh", "problem_test.cuh", "kernel_table.h", os.path.join("..", "..", "include", "ocs_b200.h")]
+HEADERS = ["rk4_kernels.cuh", "solution_interp.cuh", "problem_test.cuh", "kernel_table.h", os.path.join("..", "..", "include", "ocs_b200.h")]
 
 
 def _newest_input() -> float:

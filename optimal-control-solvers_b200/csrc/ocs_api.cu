@@ -22,6 +22,7 @@
 
 #include "../../include/ocs_b200.h"
 #include "kernel_table.h"
+#include "solution_interp.cuh"
 
 #define OCS_NS ocs_host
 #include "rk4_kernels.cuh"
@@ -106,6 +107,11 @@ struct ocs_b200_handle {
     DevBuf d_v, d_ug;
     const double *v_ext = nullptr;     // caller-owned device v (set_control_v_dev)
     const int *fb_frozen = nullptr;    // trajectories the sweeps must leave untouched (single_shooting / fb_sweep)
+    double *lams_req = nullptr;        // set while ocs_b200_eval_solution wants the node costates of a segment (SoA)
+    long lams_ld = 0;
+    int lams_segment = 0;
+    int ufunc_kind = 0;                // compute_uFunc of the attached control (ocs_b200_set_control_ufunc)
+    std::vector<double> ufunc_knots;
     int fb_costate = 0;                // OCS_B200_COSTATE_* used by ocs_b200_fb_sweep
     bool user_lamT = false;            // last compute_adjoints carried an explicit lamT (kept in d_lamT_user)
     long user_lamT_ld = 0;
@@ -802,6 +808,10 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             if (only_segment == 1) {
                 a.lamgrid = d_lamgrid;
                 a.dJdugrid = d_dJdugrid;
+                if (h->lams_req && h->lams_segment == 1) {
+                    a.lams = h->lams_req;
+                    a.ldlams = h->lams_ld;
+                }
             }
         } else {
             if (h->has_tail) {
@@ -815,8 +825,12 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             a.lam0 = d_lam0;
             a.lamgrid = d_lamgrid;
             a.dJdugrid = d_dJdugrid;
+            if (h->lams_req && h->lams_segment == 0) {
+                a.lams = h->lams_req;
+                a.ldlams = h->lams_ld;
+            }
             um = main_umode(h);
-            const bool grids_req = d_lamgrid || d_dJdugrid;
+            const bool grids_req = d_lamgrid || d_dJdugrid || a.lams;
             if (d_dJdv && h->basis_kind == BASIS_NONE)
                 return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
             if (um == 2 && d_dJdv)
@@ -843,7 +857,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
                 bm = h->basis_kind;
             }
         }
-        const bool grids = a.lamgrid || a.dJdugrid;
+        const bool grids = a.lamgrid || a.dJdugrid || a.lams;
         if (grids && um != 1) bm = 0;   // the fetch variants write dJdu itself; only UMODE_COEF needs the basis
         const void *kern = nullptr;
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
@@ -1204,6 +1218,8 @@ int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
             h->kt.kd = K;
         }
         h->ctrl_mode = CTRL_NONE;   // coefficients belong to the previous basis
+        h->ufunc_kind = 0;          // ... and so does its uFunc
+        h->ufunc_knots.clear();
         mark_dirty(h);
         return 0;
     } catch (const std::exception &ex) {
@@ -1627,6 +1643,134 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_set_control_ufunc(ocs_b200_handle *h, int kind, int nknots, const double *knots)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (kind == OCS_B200_UFUNC_NONE) {
+        h->ufunc_kind = kind;
+        h->ufunc_knots.clear();
+        return 0;
+    }
+    if (kind < OCS_B200_UFUNC_PREVIOUS || kind > OCS_B200_UFUNC_CHEBYSHEV || !knots)
+        return h->fail(OCS_B200_ERR_ARG, "bad uFunc description");
+    if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "attach the control basis first (ocs_b200_set_control_basis)");
+    if ((kind == OCS_B200_UFUNC_CHEBYSHEV && nknots != 2) || (kind != OCS_B200_UFUNC_CHEBYSHEV && nknots != h->K))
+        return h->fail(OCS_B200_ERR_ARG, "uFunc needs K = %d knots (Chebyshev: the two end times)", h->K);
+    for (int k = 0; k < nknots; ++k)
+        if (!std::isfinite(knots[k]) || (k > 0 && !(knots[k] > knots[k - 1])))
+            return h->fail(OCS_B200_ERR_ARG, "uFunc knots must be finite and strictly increasing");
+    h->ufunc_kind = kind;
+    h->ufunc_knots.assign(knots, knots + nknots);
+    return 0;
+}
+
+int ocs_b200_eval_solution(ocs_b200_handle *h, int segment, long b0, long nb, int nq, const double *tq, double *x,
+                           double *lam, double *u)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "eval_solution needs a preceding compute_states");
+    if (segment < 0 || segment > 1 || (segment == 1 && !h->has_tail)) return h->fail(OCS_B200_ERR_ARG, "no such segment");
+    if (b0 < 0 || nb < 1 || b0 + nb > h->Bt) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
+    if (nq < 1 || !tq) return h->fail(OCS_B200_ERR_ARG, "no query times");
+    for (int q = 0; q < nq; ++q)
+        if (!std::isfinite(tq[q])) return h->fail(OCS_B200_ERR_ARG, "query times must be finite");
+    try {
+        CK(cudaSetDevice(h->device));
+        using namespace ocs_interp;
+        const int n = h->kt.n, nc = h->kt.nc;
+        Segment &s = h->seg[segment];
+        const int N = s.N, NP = N + 1, G = 2 * N + 1;
+        const long Bt = h->Bt;
+        const int maxrows = std::max(n, nc);
+        // scratch: abscissae (G) | tq | query records | knots | SoA result | MATLAB-layout result | lam node store
+        const size_t n_out = (size_t)maxrows * nq * nb;
+        const size_t n_lams = lam ? (size_t)n * NP * nb : 0;
+        const size_t n_knots = std::max<size_t>(h->ufunc_knots.size(), 2);
+        const size_t total = (size_t)G + nq + (size_t)QREC * nq + n_knots + 2 * n_out + n_lams + (size_t)nc * h->K + 8;
+        TRY(ensure(h, h->d_stage2, total));
+        double *d_abs = h->d_stage2.p, *d_tq = d_abs + G, *d_qrec = d_tq + nq, *d_knots = d_qrec + (size_t)QREC * nq,
+               *d_soa = d_knots + n_knots, *d_out = d_soa + n_out, *d_lams = d_out + n_out, *d_vsh = d_lams + n_lams;
+        CK(cudaMemcpyAsync(d_tq, tq, sizeof(double) * nq, cudaMemcpyHostToDevice, h->stream));
+        const int qchunk = 32;
+        const dim3 grid((unsigned)((nb + 127) / 128), (unsigned)((nq + qchunk - 1) / qchunk));
+        auto prepare = [&](const std::vector<double> &xs) -> int {
+            CK(cudaMemcpyAsync(d_abs, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, h->stream));
+            interp_prepare_kernel<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_abs, (int)xs.size(), d_tq, nq, d_qrec);
+            CK(cudaGetLastError());
+            h->launches++;
+            return 0;
+        };
+        auto deliver = [&](double *host, int rows) -> int {
+            TRY(from_soa(h, d_soa, d_out, (long)rows * nq, nb, nb, rows));
+            CK(cudaMemcpyAsync(host, d_out, sizeof(double) * rows * nq * nb, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));   // the scratch is reused by the next output
+            return 0;
+        };
+        if (x || lam) TRY(prepare(s.tspan));
+        if (x) {      // soln.x: pchip through the resident node states   single_shooting.m:129
+            pchip_eval_kernel<<<grid, 128, 0, h->stream>>>(s.d_xs + b0, Bt, NP, n, d_qrec, nq, qchunk, d_soa, nb, nb);
+            CK(cudaGetLastError());
+            h->launches++;
+            TRY(deliver(x, n));
+        }
+        if (lam) {    // soln.lam: the costate sweep is re-run for the range with its node values kept   :130
+            if (segment == 0 && h->has_tail) TRY(run_reverse(h, b0, nb, 1, nullptr, 0, nullptr, nullptr, nullptr, nullptr));
+            const double *d_lamT = (segment == 0 && !h->has_tail && h->user_lamT) ? h->d_lamT_user.p : nullptr;
+            h->lams_req = d_lams;
+            h->lams_ld = nb;
+            h->lams_segment = segment;
+            int rc = run_reverse(h, b0, nb, segment, d_lamT, h->user_lamT_ld, nullptr, nullptr, nullptr, nullptr);
+            h->lams_req = nullptr;
+            if (rc != 0) return rc;
+            pchip_eval_kernel<<<grid, 128, 0, h->stream>>>(d_lams, nb, NP, n, d_qrec, nq, qchunk, d_soa, nb, nb);
+            CK(cudaGetLastError());
+            h->launches++;
+            TRY(deliver(lam, n));
+        }
+        if (u) {      // soln.u   single_shooting.m:128 / fb_sweep.m:123
+            const int um = seg_umode(h, segment);
+            if (um == 2) {
+                // control on the grid (fb_sweep): pchip through the G grid values, as fb_sweep.m:123 does
+                // through its interpPts
+                TRY(prepare(s.t));
+                pchip_eval_kernel<<<grid, 128, 0, h->stream>>>(h->d_ug.p + b0, Bt, G, nc, d_qrec, nq, qchunk, d_soa, nb, nb);
+            } else if (um == 1 || (segment == 0 && h->ctrl_mode == CTRL_V_SHARED)) {
+                if (h->ufunc_kind == OCS_B200_UFUNC_NONE)
+                    return h->fail(OCS_B200_ERR_STATE, "soln.u needs the control's uFunc (ocs_b200_set_control_ufunc)");
+                CK(cudaMemcpyAsync(d_knots, h->ufunc_knots.data(), sizeof(double) * h->ufunc_knots.size(),
+                                   cudaMemcpyHostToDevice, h->stream));
+                const double *vp;
+                long ldv;
+                int vb;
+                if (h->ctrl_mode == CTRL_V_SHARED) {
+                    CK(cudaMemcpyAsync(d_vsh, h->ctrl_shared.data(), sizeof(double) * nc * h->K, cudaMemcpyHostToDevice,
+                                       h->stream));
+                    vp = d_vsh;
+                    ldv = 1;
+                    vb = 0;
+                } else {
+                    vp = (h->v_ext ? h->v_ext : h->d_v.p) + b0;
+                    ldv = Bt;
+                    vb = 1;
+                }
+                ufunc_eval_kernel<<<grid, 128, 0, h->stream>>>(h->ufunc_kind, vp, ldv, vb, h->K, nc, d_knots, d_tq, nq, qchunk,
+                                                               d_soa, nb, nb);
+            } else {
+                return h->fail(OCS_B200_ERR_STATE, "soln.u needs control coefficients v or a per-trajectory control grid");
+            }
+            CK(cudaGetLastError());
+            h->launches++;
+            TRY(deliver(u, nc));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        h->lams_req = nullptr;
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
 }

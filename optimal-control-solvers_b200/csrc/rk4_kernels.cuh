@@ -122,6 +122,8 @@ struct SweepArgs {
     double *lam0;           // [m][ldb] or null
     double *lamgrid;        // MATLAB layout m x (N+1) x nb, or null
     double *dJdugrid;       // MATLAB layout nc x (2N+1) x nb, or null
+    double *lams;           // fetch variant: node costates (state rows) in SoA layout [n][N+1][ldlams], or null
+    long ldlams;
     // fb_sweep (reverse sweep with control update)
     const double *bounds;   // [nc][2]
     double uRelTol, uAbsTol, relax;
@@ -670,10 +672,15 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     for (int c = 0; c < m; ++c)
         lam[c] = a.lamT ? (a.ldl ? a.lamT[soa(c, a.ldl, bb)] : a.lamT[c]) : (c == n ? 1.0 : 0.0);   // :63-66
     const bool lamout = GRIDS && a.lamgrid != nullptr, duout = GRIDS && a.dJdugrid != nullptr;
+    const bool lamsout = GRIDS && a.lams != nullptr;
     const bool want_du = GACC || duout;
     if (lamout && active) {
 #pragma unroll
         for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (N + (size_t)(N + 1) * b)] = lam[c];
+    }
+    if (lamsout && active) {
+#pragma unroll
+        for (int c = 0; c < n; ++c) a.lams[soa((long)c * (N + 1) + N, a.ldlams, b)] = lam[c];
     }
 
     ControlEval<nc, UMODE, BMODE, KD> ctl;
@@ -840,6 +847,10 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
             if (lamout && active) {
 #pragma unroll
                 for (int c = 0; c < m; ++c) a.lamgrid[c + (size_t)m * (i + (size_t)(N + 1) * b)] = lam[c];
+            }
+            if (lamsout && active) {
+#pragma unroll
+                for (int c = 0; c < n; ++c) a.lams[soa((long)c * (N + 1) + i, a.ldlams, b)] = lam[c];
             }
 
             if constexpr (FB != 0) {

@@ -82,6 +82,10 @@ class PWConstantControl(Control):
     def compute_initial_v(self, u0):                                           # :53-55
         return np.tile(np.atleast_1d(np.asarray(u0, dtype=np.float64)), self.nControlIntervals)
 
+    def ufunc_spec(self):
+        """(kind, knots) of compute_uFunc for the device (ocs_b200_set_control_ufunc)."""
+        return "previous", self.intervalStarts
+
     def compute_uFunc(self, v):                                                # :58-61 ('previous' interpolant)
         v = np.asarray(v, dtype=np.float64).reshape(self.nControls, -1, order="F")
         s = self.intervalStarts
@@ -135,6 +139,9 @@ class PWLinearControl(Control):
             return u0.reshape(-1, order="F")
         raise ValueError("compute_initial_v: u0 must have length 1 or nControlPts")
 
+    def ufunc_spec(self):
+        return "linear", self.controlPts
+
     def compute_uFunc(self, v):                                                # :74-77 ('linear' interpolant)
         v = np.asarray(v, dtype=np.float64).reshape(self.nControls, -1, order="F")
         p = self.controlPts
@@ -168,6 +175,9 @@ class ChebyshevControl(Control):
     def compute_initial_v(self, u0):                                           # :46-48
         u0 = np.atleast_1d(np.asarray(u0, dtype=np.float64))
         return np.concatenate([u0, np.zeros((self.nControlBasis - 1) * self.nControls)])
+
+    def ufunc_spec(self):
+        return "chebyshev", np.array([self._t0, self._t1])
 
     def compute_uFunc(self, v):
         v = np.asarray(v, dtype=np.float64).reshape(self.nControls, -1, order="F")

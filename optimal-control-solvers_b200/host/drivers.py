@@ -157,5 +157,8 @@ def single_shooting(prob, x0, tspan, nCONTROL_PTS, Control=None, Integrator=None
     J = out["J"]
     if getattr(prob, "MinMax", "Min") == "Max":
         J = -J
+    # soln.u / soln.x / soln.lam (single_shooting.m:128-130) are function handles in the reference; here
+    # soln["eval"](tq[, b0, nb]) evaluates all three on the device for a range of the batch
     return dict(J=J, v=out["v"], u=integ.get_control_u(0, J.size), converged=out["converged"], iters=out["iters"],
-                integrator=integ, control=control)
+                integrator=integ, control=control,
+                eval=lambda tq, b0=0, nb=None, want=("x", "lam", "u"): integ.eval_solution(tq, b0, nb, 0, want))

@@ -104,6 +104,11 @@ class CudaRK4Integrator:
         if B.shape[1] != self.t.size:
             raise ValueError("control basis was not built on this integrator's grid t")
         self._ck(self._lib.ocs_b200_set_control_basis(self._h, B.shape[0], _lib.dp(B)))
+        if hasattr(control, "ufunc_spec"):      # compute_uFunc on the device (eval_solution)
+            kind, knots = control.ufunc_spec()
+            kf = _lib.f64(np.asarray(knots, dtype=np.float64).ravel())
+            self._ck(self._lib.ocs_b200_set_control_ufunc(self._h, {"previous": 1, "linear": 2, "chebyshev": 3}[kind],
+                                                          kf.size, _lib.dp(kf)))
 
     def control_index(self):
         """(k_index, nnz) per grid point as the device stores them (0-based)."""
@@ -273,6 +278,22 @@ class CudaRK4Integrator:
         dJdu = np.empty((self._nc, 2 * N + 1, nb), order="F") if want_dJdu else None
         self._ck(self._lib.ocs_b200_fetch_adjoints(self._h, segment, b0, nb, _lib.dp(lam), _lib.dp(dJdu)))
         return lam, dJdu
+
+    def eval_solution(self, tq, b0=0, nb=None, segment=0, want=("x", "lam", "u")):
+        """soln.x(tq), soln.lam(tq), soln.u(tq) of functions/single_shooting.m:128-130 (fb_sweep.m:120-124) for
+        trajectories [b0, b0+nb), interpolated on the device: pchip through the node states / costates
+        (vectorInterpolant.m), the control's uFunc (or pchip through a per-trajectory control grid).
+        Returns a dict of arrays rows x nq x nb (x nq for a single-trajectory call)."""
+        nb = (self._Bt - b0) if nb is None else nb
+        tqf = _lib.f64(np.asarray(tq, dtype=np.float64).ravel())
+        nq = tqf.size
+        rows = dict(x=self._n, lam=self._n, u=self._nc)
+        out = {k: np.empty((rows[k], nq, nb), order="F") for k in want}
+        self._ck(self._lib.ocs_b200_eval_solution(self._h, int(segment), int(b0), int(nb), nq, _lib.dp(tqf),
+                                                  _lib.dp(out.get("x")), _lib.dp(out.get("lam")), _lib.dp(out.get("u"))))
+        if self._single and nb == 1:
+            out = {k: a[:, :, 0] for k, a in out.items()}
+        return out
 
     def get_control_u(self, b0=0, nb=1):
         u = np.empty((self._nc, self.t.size, nb), order="F")

@@ -64,7 +64,26 @@ classdef CudaRK4Integrator < Integrator
             ocs_b200_mex('set_control_basis', obj.handle, []);
          else
             ocs_b200_mex('set_control_basis', obj.handle, control.B);
+            % compute_uFunc on the device (eval_solution): the interpolant each reference class builds
+            if isa(control, 'PWConstantControl')          % PWConstantControl.m:58-61 'previous'
+               ocs_b200_mex('set_control_ufunc', obj.handle, 1, control.intervalStarts);
+            elseif isa(control, 'PWLinearControl')        % PWLinearControl.m:74-77 'linear'
+               ocs_b200_mex('set_control_ufunc', obj.handle, 2, control.controlPts);
+            elseif isa(control, 'ChebyshevControl')       % basis recurrence ChebyshevControl.m:23-30
+               ocs_b200_mex('set_control_ufunc', obj.handle, 3, [obj.t(1), obj.t(end)]);
+            end
          end
+      end
+
+      function soln = eval_solution(obj, tq, first, count, segment)
+         % soln.x(tq), soln.lam(tq), soln.u(tq) of functions/single_shooting.m:128-130 (pchip interpolants of the
+         % node states / costates, the control's uFunc) for trajectories first .. first+count-1 (1-based),
+         % evaluated on the device.  Arrays are rows x numel(tq) x count.
+         if nargin < 3 || isempty(first), first = 1; end
+         if nargin < 4 || isempty(count), count = obj.Bt - first + 1; end
+         if nargin < 5, segment = 0; end
+         [soln.x, soln.lam, soln.u] = ocs_b200_mex('eval_solution', obj.handle, segment, first - 1, count, tq(:)', ...
+                                                   obj.nStates, obj.nControls);
       end
 
       function [x, J] = compute_states(obj, prob, x0, u)

@@ -228,6 +228,34 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         check(rc, h);
         return;
     }
+    /* ---- mex('set_control_ufunc', h, kind, knots): how control.compute_uFunc interpolates v
+     *      (1 'previous' over intervalStarts, 2 'linear' over controlPts, 3 Chebyshev over [t(1) t(end)]) */
+    if (!strcmp(cmd, "set_control_ufunc")) {
+        FAIL_IF(nrhs < 4, "ocs_b200:nargin", "set_control_ufunc(h, kind, knots)");
+        check(ocs_b200_set_control_ufunc(h, (int)scalar(prhs[2]), (int)mxGetNumberOfElements(prhs[3]), dbl(prhs[3], "knots")), h);
+        return;
+    }
+    /* ---- [x, lam, u] = mex('eval_solution', h, segment, b0, nb, tq, n, nc): soln.x(tq), soln.lam(tq), soln.u(tq) of
+     *      functions/single_shooting.m:128-130 for trajectories b0 .. b0+nb-1; only the requested outputs are computed */
+    if (!strcmp(cmd, "eval_solution")) {
+        FAIL_IF(nrhs < 8, "ocs_b200:nargin", "eval_solution(h, segment, b0, nb, tq, n, nc)");
+        long nb = (long)scalar(prhs[4]);
+        int nq = (int)mxGetNumberOfElements(prhs[5]);
+        mwSize d[3];
+        d[1] = (mwSize)nq;
+        d[2] = (mwSize)nb;
+        d[0] = (mwSize)scalar(prhs[6]);
+        plhs[0] = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL);
+        mxArray *lam = nlhs > 1 ? mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL) : NULL;
+        d[0] = (mwSize)scalar(prhs[7]);
+        mxArray *uu = nlhs > 2 ? mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL) : NULL;
+        int rc = ocs_b200_eval_solution(h, (int)scalar(prhs[2]), (long)scalar(prhs[3]), nb, nq, dbl(prhs[5], "tq"),
+                                        mxGetPr(plhs[0]), lam ? mxGetPr(lam) : NULL, uu ? mxGetPr(uu) : NULL);
+        if (lam) plhs[1] = lam;
+        if (uu) plhs[2] = uu;
+        check(rc, h);
+        return;
+    }
     /* ---- [y, resnorm, residual, exitflag] = mex('compute_equilibrium', h, params, guess, lb, ub, r, maxIter, tol)
      *      functions/compute_equilibrium.m:1-33, one steady state per column of params */
     if (!strcmp(cmd, "compute_equilibrium")) {

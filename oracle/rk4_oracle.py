@@ -342,6 +342,7 @@ class ChebyshevControl(_BasisControl):
         self.nControlBasis, self.nControls = int(nControlBasis), int(nControls)
         t = np.asarray(t, dtype=np.float64)
         self.controlPts = matlab_linspace(t[0], t[-1], self.nControlBasis)   # :16
+        self.t0, self.t1 = t[0], t[-1]
         self.B = self.compute_basis_matrix(t)
 
     def compute_basis_matrix(self, t):
@@ -462,6 +463,102 @@ def _nodes_to_grid(a):
     g[:, 0::2] = a
     g[:, 1::2] = (a[:, :-1] + a[:, 1:]) / 2
     return g
+
+
+def pchip_slopes(x, y):
+    """Derivative values of MATLAB's shape-preserving cubic (pchip.m, local function pchipslopes;
+    Fritsch & Carlson 1980): interior points where the neighbouring secants agree in sign get their
+    weighted harmonic mean, all others zero; the ends use the non-centred three-point formula with
+    the shape-preserving clamps.  `griddedInterpolant(x, v, 'pchip')` (functions/vectorInterpolant.m:4,9)
+    documents itself as this interpolant."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    n = x.size
+    h = np.diff(x)
+    delta = np.diff(y) / h
+    d = np.zeros(n)
+    if n == 2:
+        d[:] = delta[0]
+        return d
+    for k in range(n - 2):                       # interior point k+1, secants delta[k], delta[k+1]
+        if np.sign(delta[k]) * np.sign(delta[k + 1]) > 0:
+            hs = h[k] + h[k + 1]
+            w1, w2 = (h[k] + hs) / (3 * hs), (hs + h[k + 1]) / (3 * hs)
+            dmax, dmin = max(abs(delta[k]), abs(delta[k + 1])), min(abs(delta[k]), abs(delta[k + 1]))
+            d[k + 1] = dmin / (w1 * (delta[k] / dmax) + w2 * (delta[k + 1] / dmax))
+
+    def end(h0, h1, d0, d1):
+        v = ((2 * h0 + h1) * d0 - h0 * d1) / (h0 + h1)
+        if np.sign(v) != np.sign(d0):
+            return 0.0
+        if np.sign(d0) != np.sign(d1) and abs(v) > abs(3 * d0):
+            return 3 * d0
+        return v
+    d[0] = end(h[0], h[1], delta[0], delta[1])
+    d[-1] = end(h[-1], h[-2], delta[-1], delta[-2])
+    return d
+
+
+def pchip_eval(x, y, tq):
+    """griddedInterpolant(x, y, 'pchip')(tq) for one row: cubic Hermite on the interval holding each
+    query (end polynomials outside the grid), local form  y_k + s (d_k + s (c + s b))."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    tq = np.atleast_1d(np.asarray(tq, dtype=np.float64))
+    d = pchip_slopes(x, y)
+    h = np.diff(x)
+    delta = np.diff(y) / h
+    k = np.clip(np.searchsorted(x, tq, side="right") - 1, 0, x.size - 2)
+    s = tq - x[k]
+    c = (3 * delta[k] - 2 * d[k] - d[k + 1]) / h[k]
+    b = (d[k] - 2 * delta[k] + d[k + 1]) / (h[k] * h[k])
+    return y[k] + s * (d[k] + s * (c + s * b))
+
+
+def vector_interpolant(x, v, interpType):
+    """functions/vectorInterpolant.m:1-12: one griddedInterpolant per row of v.  interpType 'pchip',
+    'linear' (end values outside the knots) or 'previous'."""
+    v = np.atleast_2d(np.asarray(v, dtype=np.float64))
+    x = np.asarray(x, dtype=np.float64)
+
+    def f(t):
+        t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        if interpType == "pchip":
+            return np.stack([pchip_eval(x, row, t) for row in v])
+        if interpType == "linear":
+            if x.size == 1:
+                return np.repeat(v[:, :1], t.size, axis=1)
+            k = np.clip(np.searchsorted(x, t, side="right") - 1, 0, x.size - 2)
+            tc = np.clip(t, x[0], x[-1])
+            w = (tc - x[k]) / (x[k + 1] - x[k])
+            return v[:, k] + w * (v[:, k + 1] - v[:, k])
+        if interpType == "previous":
+            k = np.clip(np.searchsorted(x, t, side="right") - 1, 0, x.size - 1)
+            return v[:, k]
+        raise ValueError(interpType)
+    return f
+
+
+def compute_uFunc(control, v):
+    """control.compute_uFunc(v): PWConstantControl.m:58-61 ('previous' over intervalStarts),
+    PWLinearControl.m:74-77 ('linear' over controlPts); ChebyshevControl has none in the reference --
+    the basis recurrence (:23-30) evaluated at the query time."""
+    v = np.asarray(v, dtype=np.float64).reshape(control.nControls, -1, order="F")
+    if isinstance(control, PWConstantControl):
+        return vector_interpolant(control.intervalStarts, v, "previous")
+    if isinstance(control, PWLinearControl):
+        return vector_interpolant(control.controlPts, v, "linear")
+
+    def f(t):
+        t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        tau = 2 * (t - control.t0) / (control.t1 - control.t0) - 1
+        K = v.shape[1]
+        Bq = np.zeros((K, t.size))
+        Bq[0] = 1
+        if K > 1:
+            Bq[1] = tau
+        for i in range(2, K):
+            Bq[i] = 2 * tau * Bq[i - 1] - Bq[i - 2]
+        return v @ Bq
+    return f
 
 
 def compute_states_and_objective_legacy(prob, x0, t, u):

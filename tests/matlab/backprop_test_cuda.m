@@ -55,6 +55,10 @@ uInf = control.compute_u(v);
 v0 = control.compute_initial_v(.5);
 ss = integrator.single_shooting(prob, X0, v0, Lb, Ub, 'MaxIter', 300, 'TolX', 1e-6);
 
+% soln.x / soln.lam / soln.u (single_shooting.m:128-130) of the three minimisers, interpolated on the device
+tQuery = linspace(0, T, 41);
+solnSS = integrator.eval_solution(tQuery);
+
 % equilibrium as tests/solve_test_problem.m:21-29 computes it, on the device (one set, then a sweep over r)
 lb = [0; -Inf; prob.ControlBounds(1)];
 ub = [Inf; Inf; prob.ControlBounds(2)];

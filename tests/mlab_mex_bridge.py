@@ -125,6 +125,19 @@ def make_mex(ocs):
             check(lib.ocs_b200_fb_sweep(h, L.dp(x0), Bt, L.dp(u0f), nbu, L.dp(bounds), sc(a[4]), sc(a[5]), int(sc(a[6])),
                                         sc(a[7]), L.dp(J), L.ip(sw), L.ip(cv), L.dp(mc)), h)
             return (J, sw.astype(float).reshape(1, -1), cv.astype(float).reshape(1, -1), mc)[:max(nargout, 1)]
+        if cmd == "set_control_ufunc":
+            kn = arr(np.asarray(a[2]).ravel())
+            check(lib.ocs_b200_set_control_ufunc(h, int(sc(a[1])), kn.size, L.dp(kn)), h)
+            return ()
+        if cmd == "eval_solution":
+            seg, b0, nb = int(sc(a[1])), int(sc(a[2])), int(sc(a[3]))
+            tq = arr(np.asarray(a[4]).ravel())
+            n, nc = int(sc(a[5])), int(sc(a[6]))
+            x = np.empty((n, tq.size, nb), order="F")
+            lam = np.empty((n, tq.size, nb), order="F") if nargout > 1 else None
+            u = np.empty((nc, tq.size, nb), order="F") if nargout > 2 else None
+            check(lib.ocs_b200_eval_solution(h, seg, b0, nb, tq.size, L.dp(tq), L.dp(x), L.dp(lam), L.dp(u)), h)
+            return (x, lam, u)[:max(nargout, 1)]
         if cmd == "compute_equilibrium":
             P, guess = arr(a[1]), arr(a[2])
             lb = arr(np.asarray(a[3]).ravel()) if np.asarray(a[3]).size else None

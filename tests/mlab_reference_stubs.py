@@ -52,7 +52,19 @@ class _ControlObject:
         raise ValueError(name)
 
 
+def _wrap_isa(it):
+    """isa(control, 'PWLinearControl') for the host-mirror stand-ins."""
+    base = it.builtins["isa"]
+
+    def isa(a, cls):
+        if isinstance(a, _ControlObject):
+            return np.array([[float(type(a.ctl).__name__ == cls or cls == "Control")]])
+        return base(a, cls)
+    it.builtins["isa"] = isa
+
+
 def install(it, ocs):
+    _wrap_isa(it)
     for name in ("Integrator", "OCProblem", "Control"):
         it.cache[name] = ("classdef", dict(name=name, supers=["handle"], props=[], methods={}), None)
     kind, node = Parser(tokenize(_HOLDER), "<TestOCProblem holder>").parse_file()

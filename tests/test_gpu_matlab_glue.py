@@ -54,6 +54,14 @@ def test_reference_backprop_test_with_the_drop_in_integrator(ocs, oracle):
     ss = w["ss"]
     assert ss["v"].shape == (21, 3) and np.all(ss["converged"] > 0)
     assert np.all(ss["v"] >= 0) and np.all(ss["v"] <= 1) and np.all(ss["J"] < out["J"] + 1e-9)
+    # eval_solution through the .m class: soln.u of PWLinearControl is the linear interpolant of v over controlPts
+    sol = w["solnSS"]
+    assert sol["x"].shape == (1, 41, 3) and sol["lam"].shape == (1, 41, 3) and sol["u"].shape == (1, 41, 3)
+    tq = np.linspace(0, 10, 41)
+    cp = ocs.matlab_linspace(0, 10, 21)
+    for b in range(3):
+        assert relerr(sol["u"][0, :, b], np.interp(tq, cp, ss["v"][:, b])) < TOL
+    assert np.allclose(sol["x"][0, 0, :], [1, 1.5, 2]) and np.all(np.abs(sol["lam"][0, -1, :]) < 1e-12)
     # compute_equilibrium_cuda.m / CudaRK4Integrator.compute_equilibrium (tests/solve_test_problem.m:21-29)
     sc = lambda z: float(np.asarray(z).ravel()[0])
     assert abs(sc(w["uEq"]) - 0.723368780097983) < 1e-12 and abs(sc(w["xEq"]) - 2.73556918863414) < 1e-12

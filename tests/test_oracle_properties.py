@@ -136,3 +136,24 @@ def test_continuous_costate_matches_an_adaptive_solve(oracle):
         sol = solve_ivp(rhs, [4.0, 0.0], [0.0], rtol=1e-11, atol=1e-13, dense_output=True)
         errs.append(np.max(np.abs(sol.sol(integ.t[0::2])[0] - lam[0])))
     assert errs[0] < 1e-3 and errs[1] < errs[0] / 3.5 and errs[2] < errs[1] / 3.5
+
+
+def test_pchip_restatement_against_scipy(oracle):
+    """oracle.pchip_eval (MATLAB pchip.m's algorithm, used for soln.x / soln.lam) against SciPy's
+    PchipInterpolator -- an independent implementation of the same Fritsch-Carlson interpolant --
+    on monotone, oscillating, flat and non-uniformly spaced data, including the 2- and 3-point grids."""
+    from scipy.interpolate import PchipInterpolator
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 4, 7, 50, 501):
+        for kind in ("uniform", "random"):
+            x = np.linspace(0, 10, n) if kind == "uniform" else np.cumsum(rng.uniform(.1, 1.0, n))
+            for y in (rng.standard_normal(n), np.cumsum(rng.uniform(0, 1, n)), np.sin(x), np.where(x > x.mean(), 1.0, 0.0)):
+                tq = np.concatenate([x, rng.uniform(x[0], x[-1], 200)])
+                ref = PchipInterpolator(x, y)(tq) if n > 2 else np.interp(tq, x, y)
+                got = oracle.pchip_eval(x, y, tq)
+                assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(y)))
+                assert np.array_equal(got[:n - 1], y[:-1])     # nodes (s = 0) are reproduced exactly
+    vi = oracle.vector_interpolant(np.array([0., 1., 2.]), np.array([[1., 3., 2.], [0., 0., 4.]]), "previous")
+    assert np.array_equal(vi([0.0, 0.99, 1.0, 5.0]), [[1, 1, 3, 2], [0, 0, 0, 4]])
+    vl = oracle.vector_interpolant(np.array([0., 1., 2.]), np.array([[1., 3., 2.]]), "linear")
+    assert np.allclose(vl([0.5, 1.5, 2.0, 3.0]), [[2.0, 2.5, 2.0, 2.0]])
