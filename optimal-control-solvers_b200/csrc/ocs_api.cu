@@ -100,6 +100,8 @@ struct ocs_b200_handle {
     int basis_kind = BASIS_NONE;
     int K = 0;
     std::vector<int32_t> bk, bnnz;
+    bool bk_monotone = false;          // knot index non-decreasing along the grid: dJdv columns are stored once
+    bool bk_covered = false;           // ... and every knot is reached by the window, so dJdv needs no zero-fill
     std::vector<double> bw0, bw1, bdense;
     int ctrl_mode = CTRL_NONE;
     std::vector<double> ctrl_shared;   // v (nc*K) or u (nc*G)
@@ -822,6 +824,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
                 a.ldl = ldl;
             }
             a.dJdv = d_dJdv;
+            a.dJdv_store = h->bk_monotone ? 1 : 0;
             a.lam0 = d_lam0;
             a.lamgrid = d_lamgrid;
             a.dJdugrid = d_dJdugrid;
@@ -1200,6 +1203,16 @@ int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
         h->bnnz = nnz;
         if (sparse) {
             h->basis_kind = BASIS_SPARSE;
+            h->bk_monotone = true;      // the sliding knot window never returns to a knot it has left
+            for (int j = 1; j < G; ++j)
+                if (bk[j] < bk[j - 1]) h->bk_monotone = false;
+            {
+                std::vector<char> seen((size_t)K + 1, 0);
+                for (int j = 0; j < G; ++j) seen[bk[j]] = seen[bk[j] + 1] = 1;
+                h->bk_covered = h->bk_monotone;
+                for (int k = 0; k < K; ++k)
+                    if (!seen[k]) h->bk_covered = false;
+            }
             h->bk = bk;
             h->bw0 = w0;
             h->bw1 = w1;
@@ -1395,10 +1408,17 @@ int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, long Bt, doubl
     }
 }
 
+// The sparse-basis sweep stores every dJdv column exactly once when the knot window is monotone and reaches
+// every knot; otherwise (dense bases, exotic sparse ones, frozen trajectories) the buffer starts from zero.
+static bool needs_zero_fill(const ocs_b200_handle *h)
+{
+    return !(h->basis_kind == BASIS_SPARSE && h->bk_monotone && h->bk_covered && !h->fb_frozen);
+}
+
 static int adjoints_common(ocs_b200_handle *h, const double *d_lamT, long ldl, double *d_dJdv, double *d_lam0)
 {
     const int nc = h->kt.nc;
-    if (d_dJdv) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * nc * h->K * h->Bt, h->stream));
+    if (d_dJdv && needs_zero_fill(h)) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * nc * h->K * h->Bt, h->stream));
     return run_reverse(h, 0, h->Bt, -1, d_lamT, ldl, d_dJdv, d_lam0, nullptr, nullptr);
 }
 
@@ -1457,7 +1477,7 @@ int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_
                 if (!h->chunk_done[k]) CK(cudaEventCreateWithFlags(&h->chunk_done[k], cudaEventDisableTiming));
             const long chunk = (((Bt + 7) / 8) + 127) / 128 * 128;
             for (int k = 0; k < 2; ++k) TRY(ensure(h, h->d_pipe[k], (size_t)(rows + m) * chunk));
-            CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * rows * Bt, h->stream));
+            if (needs_zero_fill(h)) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * rows * Bt, h->stream));
             int k = 0;
             for (long b0 = 0; b0 < Bt; b0 += chunk, ++k) {
                 const long nb = std::min(chunk, Bt - b0);

@@ -119,6 +119,8 @@ struct SweepArgs {
     const double *lamT;     // [m][ldl] or null (= e_m, RK4Integrator.m:63-66)
     long ldl;               // batch stride of lamT; 0 = shared column
     double *dJdv;           // [(k*nc+c)][ldb], zero-initialised, or null
+    int dJdv_store;         // 1: every knot is flushed exactly once (knot index monotone along the grid), so a
+                            // finished accumulator is stored; 0: added to what the buffer holds
     double *lam0;           // [m][ldb] or null
     double *lamgrid;        // MATLAB layout m x (N+1) x nb, or null
     double *dJdugrid;       // MATLAB layout nc x (2N+1) x nb, or null
@@ -247,7 +249,9 @@ struct GradAcc {
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     const size_t idx = soa((long)k * nc + c, a.ldb, b);
-                    a.dJdv[idx] = a.dJdv[idx] + aO[c];   // buffer is zero-initialised; one owner thread per column
+                    // one owner thread per column.  A plain store when the knot cannot come back: the load of the
+                    // read-modify-write form stalled every warp of the block at the same step (long scoreboard)
+                    a.dJdv[idx] = a.dJdv_store ? aO[c] : a.dJdv[idx] + aO[c];
                 }
             }
 #pragma unroll
@@ -257,7 +261,7 @@ struct GradAcc {
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     const size_t idx = soa((long)k * nc + c, a.ldb, b);
-                    a.dJdv[idx] = a.dJdv[idx] + aE[c];
+                    a.dJdv[idx] = a.dJdv_store ? aE[c] : a.dJdv[idx] + aE[c];
                 }
             }
 #pragma unroll
