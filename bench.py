@@ -466,9 +466,8 @@ def main():
 
         def e2e_step():
             lib.check(L.ocs_b200_set_control_v(hnd, lib.dp(vf), 1), hnd)
-            lib.check(L.ocs_b200_compute_states(hnd, lib.dp(x0_h.numpy()), Bt, lib.dp(J_h.numpy()), lib.dp(xT_h.numpy()),
-                                                lib.ip(st_h.numpy())), hnd)
-            lib.check(L.ocs_b200_compute_adjoints(hnd, None, 0, lib.dp(dJdv_h.numpy()), lib.dp(lam0_h.numpy())), hnd)
+            lib.check(L.ocs_b200_evaluate(hnd, lib.dp(x0_h.numpy()), Bt, None, 0, lib.dp(J_h.numpy()), lib.dp(xT_h.numpy()),
+                                          lib.ip(st_h.numpy()), lib.dp(dJdv_h.numpy()), lib.dp(lam0_h.numpy())), hnd)
         ne = max(2, min(args.steps, 5))
         e2e_step()
         sync_all()
@@ -485,7 +484,7 @@ def main():
                "h2d_bytes_per_step": 8 * Bt + 8 * K_PWL,
                "d2h_bytes_per_step": 8 * Bt * (1 + 1 + K_PWL + 2) + 4 * Bt,
                "steps": ne, "ms_per_step": 1e3 * dt / ne,
-               "api": "ocs_b200_compute_states + ocs_b200_compute_adjoints on pinned host buffers (J, xT, status, dJdv, lam0 returned)"}
+               "api": "ocs_b200_evaluate (nlpObjective: compute_states + compute_adjoints) on pinned host buffers; J, xT, status, dJdv, lam0 returned"}
 
     if rank == 0:
         out["e2e"] = e2e

@@ -156,6 +156,14 @@ OCS_B200_API int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, l
 OCS_B200_API int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_nbatch,
                                            double *dJdv, double *lam0);
 
+/* nlpObjective of functions/single_shooting.m:137-150 in ONE call on host buffers: compute_states followed by
+ * compute_adjoints (same arguments, same results as the two calls in sequence).  For large batches the batch is
+ * swept in trajectory chunks -- forward and reverse sweep of a chunk back to back -- while the gradient of the
+ * previous chunk is transposed and downloaded on a second stream, so the PCIe transfer of dJdv ((nc*K) x Bt
+ * doubles) overlaps all of the arithmetic.  Any output may be NULL. */
+OCS_B200_API int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const double *lamT, long lamT_nbatch,
+                                   double *J, double *xT, int32_t *status, double *dJdv, double *lam0);
+
 /* Full grids for trajectories [b0, b0+nb), exactly the arrays the MATLAB methods return:
  *   x    [m x (N+1) x nb]   (RK4Integrator.m:54)     lam  [m x (N+1) x nb]  (RK4Integrator.m:68-89)
  *   dJdu [nc x G x nb]      (RK4Integrator.m:97-121)

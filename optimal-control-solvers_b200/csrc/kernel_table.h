@@ -11,6 +11,8 @@ struct ocs_kernel_table {
     int tile;      // RK4 steps per shared-memory tile
     int tpt_rev;   // trajectories per thread of the reverse (gradient) kernels
     int tpt_fwd;   // ... and of the forward kernels
+    int fb_ring;   // ... and of the fb_sweep costate kernels (ring*(n + 2 nc)*threads doubles)
+    int rev_ring;  // depth of the gradient kernels' cp.async node-state ring (shared memory: ring*tpt*n*threads doubles)
     const void *fwd[3][3][2];   // [UMODE][BMODE][params batched]
     const void *rev[3][3][2];
     const void *fwdg[3][3][2];  // fetch variants: also write the full grids (x with the J row; lam, dJdu)

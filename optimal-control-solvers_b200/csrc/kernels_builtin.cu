@@ -63,6 +63,8 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->tile = OCS_TILE;
     t->tpt_rev = OCS_TPT_REV;
     t->tpt_fwd = OCS_TPT_FWD;
+    t->rev_ring = OCS_RING;
+    t->fb_ring = OCS_FB_RING;
     for (int pb = 0; pb < 2; ++pb)
         for (int um = 0; um < 3; ++um)
             for (int bm = 0; bm < 3; ++bm)

@@ -127,6 +127,7 @@ struct ocs_b200_handle {
     DevBuf d_pipe[2];                 // double-buffered transpose staging of the chunked dJdv download
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};   // the download out of staging buffer k has finished
     int *d_status = nullptr;
     size_t status_cap = 0;
     int *d_frozen = nullptr, *d_sweeps = nullptr;
@@ -865,7 +866,12 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         const void *kern = nullptr;
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
         // dense-basis kernels keep K coefficients and K accumulators per trajectory in registers: one per thread
-        TRY(launch(h, kern, a, false, (grids || bm == 2) ? 1 : std::max(h->kt.tpt_rev, 1)));
+        {
+            const int tpt = (grids || bm == 2) ? 1 : std::max(h->kt.tpt_rev, 1);
+            // the gradient kernels (not the fetch variants) keep a cp.async ring of node states in shared memory
+            const size_t ring = grids ? 0 : (size_t)h->kt.rev_ring * tpt * h->kt.n * h->kt.threads;
+            TRY(launch(h, kern, a, false, tpt, ring));
+        }
         if (project) {
             const int G = 2 * s.N + 1;
             if (h->profiling) CK(cudaEventRecord(h->ev[2], h->stream));
@@ -1051,8 +1057,10 @@ int ocs_b200_destroy(ocs_b200_handle *h)
                       &h->d_pipe[0], &h->d_pipe[1], &h->d_z, &h->d_g, &h->d_zt, &h->d_gt, &h->d_Jacc, &h->d_Jhist,
                       &h->d_alpha, &h->d_lbub, &h->d_dug};
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 2; ++k) {
         if (h->chunk_done[k]) cudaEventDestroy(h->chunk_done[k]);
+        if (h->stage_free[k]) cudaEventDestroy(h->stage_free[k]);
+    }
     for (DevBuf *b : bufs) cudaFree(b->p);
     cudaFree(h->d_status);
     cudaFree(h->d_frozen);
@@ -1415,6 +1423,84 @@ static bool needs_zero_fill(const ocs_b200_handle *h)
     return !(h->basis_kind == BASIS_SPARSE && h->bk_monotone && h->bk_covered && !h->fb_frozen);
 }
 
+// Trajectory chunks of a host-buffer evaluation whose gradient download (rows*Bt doubles over PCIe) dominates:
+// the first chunk is small so that the transfer starts almost at once, later chunks double (the sweeps run
+// about three times faster than PCIe drains them) up to a quarter of the batch.
+static std::vector<std::pair<long, long>> chunk_schedule(long Bt)
+{
+    std::vector<std::pair<long, long>> out;
+    const long gran = 128 * 6;                       // whole blocks of both kernels (3 and 2 trajectories per thread)
+    long c = std::max<long>(gran, (Bt / 32 + gran - 1) / gran * gran);
+    const long cmax = std::max<long>(gran, (Bt / 4 + gran - 1) / gran * gran);
+    for (long b0 = 0; b0 < Bt;) {
+        const long nb = std::min(c, Bt - b0);
+        out.emplace_back(b0, nb);
+        b0 += nb;
+        c = std::min(2 * c, cmax);
+    }
+    return out;
+}
+
+// Sweeps trajectories chunk by chunk on the compute stream (forward too when `with_forward`) and transposes the
+// chunk's gradient into one of two staging buffers, while a second stream downloads the previous chunk.
+// OCS_B200_TRACE=1 prints the timeline (sweeps done / transposed / downloaded, per chunk) to stderr.
+static int pipelined_gradient(ocs_b200_handle *h, bool with_forward, const double *d_lamT, long ldl, double *d_dJdv,
+                              double *d_lam0, double *dJdv, double *lam0)
+{
+    const int m = h->kt.n + 1, nc = h->kt.nc;
+    const long Bt = h->Bt, rows = (long)nc * h->K;
+    if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        if (!h->chunk_done[k]) CK(cudaEventCreateWithFlags(&h->chunk_done[k], cudaEventDisableTiming));
+        if (!h->stage_free[k]) CK(cudaEventCreateWithFlags(&h->stage_free[k], cudaEventDisableTiming));
+    }
+    const auto sched = chunk_schedule(Bt);
+    long cmax = 0;
+    for (auto &c : sched) cmax = std::max(cmax, c.second);
+    for (int k = 0; k < 2; ++k) TRY(ensure(h, h->d_pipe[k], (size_t)(rows + m) * cmax));
+    if (needs_zero_fill(h)) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * rows * Bt, h->stream));
+    int k = 0;
+    const bool trace = getenv("OCS_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    mark(h->stream);
+    for (auto &c : sched) {
+        const long b0 = c.first, nb = c.second;
+        if (with_forward) TRY(run_forward(h, b0, nb, -1, nullptr, true));
+        TRY(run_reverse(h, b0, nb, -1, d_lamT, ldl, d_dJdv + b0, d_lam0 + b0, nullptr, nullptr));
+        // transpose on the compute stream (it has slack: the sweeps run ~3x faster than PCIe drains them) into the
+        // staging buffer whose previous download has finished, so that the copy stream only ever holds downloads
+        // and the transfer never pauses
+        mark(h->stream);
+        double *stg = h->d_pipe[k & 1].p;
+        if (k >= 2) CK(cudaStreamWaitEvent(h->stream, h->stage_free[k & 1], 0));
+        TRY(from_soa(h, d_dJdv + b0, stg, rows, nb, Bt, 1, h->stream));
+        if (lam0) TRY(from_soa(h, d_lam0 + b0, stg + (size_t)rows * cmax, m, nb, Bt, 1, h->stream));
+        CK(cudaEventRecord(h->chunk_done[k & 1], h->stream));
+        mark(h->stream);
+        CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[k & 1], 0));
+        CK(cudaMemcpyAsync(dJdv + (size_t)rows * b0, stg, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost,
+                           h->copy_stream));
+        if (lam0)
+            CK(cudaMemcpyAsync(lam0 + (size_t)m * b0, stg + (size_t)rows * cmax, sizeof(double) * m * nb,
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaEventRecord(h->stage_free[k & 1], h->copy_stream));
+        mark(h->copy_stream);
+        ++k;
+    }
+    if (trace) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            fprintf(stderr, "trace %zu (%s) %.3f ms\n", i, (i - 1) % 3 == 0 ? "sweeps done" : (i - 1) % 3 == 1 ? "transposed" : "downloaded", ms);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    return 0;
+}
+
 static int adjoints_common(ocs_b200_handle *h, const double *d_lamT, long ldl, double *d_dJdv, double *d_lam0)
 {
     const int nc = h->kt.nc;
@@ -1469,33 +1555,57 @@ int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_
             if (dJdv) TRY(download_soa(h, d_dJdv, Bt, 0, dJdv, rows, Bt));
             if (lam0) TRY(download_soa(h, d_lam0, Bt, 0, lam0, m, Bt));   // d_stage reuse is ordered by the stream
         } else {
-            // Large batch: the gradient download (rows*Bt doubles over PCIe) dominates the call.  Sweep the batch
-            // in trajectory chunks on the compute stream while a second stream transposes and downloads the
-            // previous chunk, so the transfer overlaps the arithmetic.
-            if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-            for (int k = 0; k < 2; ++k)
-                if (!h->chunk_done[k]) CK(cudaEventCreateWithFlags(&h->chunk_done[k], cudaEventDisableTiming));
-            const long chunk = (((Bt + 7) / 8) + 127) / 128 * 128;
-            for (int k = 0; k < 2; ++k) TRY(ensure(h, h->d_pipe[k], (size_t)(rows + m) * chunk));
-            if (needs_zero_fill(h)) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * rows * Bt, h->stream));
-            int k = 0;
-            for (long b0 = 0; b0 < Bt; b0 += chunk, ++k) {
-                const long nb = std::min(chunk, Bt - b0);
-                TRY(run_reverse(h, b0, nb, -1, d_lamT, ldl, d_dJdv + b0, d_lam0 + b0, nullptr, nullptr));
-                CK(cudaEventRecord(h->chunk_done[k & 1], h->stream));
-                CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[k & 1], 0));
-                double *stg = h->d_pipe[k & 1].p;     // its previous download precedes this one on copy_stream
-                TRY(from_soa(h, d_dJdv + b0, stg, rows, nb, Bt, 1, h->copy_stream));
-                CK(cudaMemcpyAsync(dJdv + (size_t)rows * b0, stg, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost,
-                                   h->copy_stream));
-                if (lam0) {
-                    TRY(from_soa(h, d_lam0 + b0, stg + (size_t)rows * chunk, m, nb, Bt, 1, h->copy_stream));
-                    CK(cudaMemcpyAsync(lam0 + (size_t)m * b0, stg + (size_t)rows * chunk, sizeof(double) * m * nb,
-                                       cudaMemcpyDeviceToHost, h->copy_stream));
-                }
-            }
+            // Large batch: the gradient download (rows*Bt doubles over PCIe) dominates the call; it overlaps
+            // the sweeps chunk by chunk.
+            TRY(pipelined_gradient(h, false, d_lamT, ldl, d_dJdv, d_lam0, dJdv, lam0));
             CK(cudaStreamSynchronize(h->copy_stream));
         }
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const double *lamT, long lamT_nbatch, double *J,
+                      double *xT, int32_t *status, double *dJdv, double *lam0)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    TRY(check_ready(h));
+    if (!x0 || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
+    if (lamT && lamT_nbatch != 1 && lamT_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
+    // small batches, no gradient, or a tail horizon (whose main sweep starts from the tail's result for the whole
+    // batch): the two calls in sequence
+    if (!dJdv || Bt < 262144 || h->has_tail) {
+        TRY(ocs_b200_compute_states(h, x0, Bt, J, xT, status));
+        if (!dJdv && !lam0) return 0;
+        return ocs_b200_compute_adjoints(h, lamT, lamT_nbatch, dJdv, lam0);
+    }
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+        TRY(alloc_batch(h, Bt));
+        TRY(upload_soa(h, x0, h->d_x0, n, Bt));
+        TRY(validate_control(h, Bt));
+        if (h->params_nbatch > 1 && h->params_nbatch != Bt)
+            return h->fail(OCS_B200_ERR_ARG, "params have %ld columns but the batch has %ld trajectories", h->params_nbatch, Bt);
+        if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
+        h->Bt = Bt;
+        const double *d_lamT = nullptr;
+        h->user_lamT = lamT != nullptr;
+        h->user_lamT_ld = lamT && lamT_nbatch > 1 ? Bt : 0;
+        if (lamT) {
+            TRY(upload_soa(h, lamT, h->d_lamT_user, m, lamT_nbatch));
+            d_lamT = h->d_lamT_user.p;
+        }
+        TRY(ensure(h, h->d_dJdv, (size_t)nc * h->K * Bt));
+        TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
+        TRY(pipelined_gradient(h, true, d_lamT, h->user_lamT_ld, h->d_dJdv.p, h->d_lam0.p, dJdv, lam0));
+        h->have_states = true;
+        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (xT) TRY(download_soa(h, h->d_xT.p, Bt, 0, xT, n, Bt));
+        if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->copy_stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     } catch (const std::exception &ex) {
@@ -1645,7 +1755,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             r.relax = relax;
             r.max_change = h->d_maxchg.p;
             r.frozen = h->d_frozen;
-            TRY(launch(h, kr, r, false));
+            TRY(launch(h, kr, r, false, 1, (size_t)h->kt.fb_ring * (n + 2 * nc) * h->kt.threads));
             CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
             fb_update_kernel<<<(unsigned)((Bt + 255) / 256), 256, 0, h->stream>>>(h->d_maxchg.p, h->d_frozen, h->d_sweeps,
                                                                                 sweep, Bt, d_nopen);

@@ -58,6 +58,16 @@
 #ifndef OCS_UPREFETCH
 #define OCS_UPREFETCH 1     // steps of per-trajectory grid control loaded ahead by reverse_body (UMODE_GRID)
 #endif
+#ifndef OCS_FB_RING
+#define OCS_FB_RING 0       // fb_sweep costate kernels: node state and the two grid controls of a step are fetched this
+                            // many steps ahead by cp.async into a per-thread shared-memory ring; 0 = register prefetch
+#endif
+#ifndef OCS_RING
+#define OCS_RING 0          // reverse_multi_body: node states are fetched this many steps ahead by cp.async into a
+                            // per-thread shared-memory ring (power of two, <= OCS_XS_SLACK); 0 = register prefetch.
+                            // Measured on B200 (profiles/r1_notes.md): 0: 3.71 ms, 2: 3.90, 4: 3.75, 8: 3.76 -- the
+                            // FP64-bound gradient kernel does not gain from it, the HBM-bound fb_sweep kernel does.
+#endif
 #ifndef OCS_KDENSE_MAX
 #define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
 #endif
@@ -321,6 +331,20 @@ struct MaxRatio {
     }
     __device__ __forceinline__ double value() const { return num / den; }
 };
+
+// ------------------------------------------------------------------ asynchronous per-thread prefetch (cp.async)
+// The reverse sweep consumes one node state per trajectory and step.  Prefetching it into registers ties the
+// prefetch distance to the register rotation of the unrolled loop (the rotation moves wait on the load);
+// cp.async (LDGSTS) writes it into a shared-memory slot owned by the thread instead, any number of steps ahead,
+// and the thread only waits (cp.async.wait_group) for the slot it is about to read.
+__device__ __forceinline__ void cp_async_8(double *smem_dst, const double *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 // ------------------------------------------------------------------ tile staging
 template <int RB>
@@ -701,6 +725,27 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
     for (int c = 0; c < nc; ++c) dcar[c] = 0.0;
     const double *xsp = a.xs + (size_t)(N - 1) * a.ldb + bb;   // node N-1
+    // fb_sweep variant: cp.async ring [DP][n + 2 nc][threads] of (x_i, u_{2i+1}, u_{2i}) per step
+    constexpr int DP = (FB != 0 && UMODE == UMODE_GRID) ? OCS_FB_RING : 0;
+    static_assert(DP == 0 || ((DP & (DP - 1)) == 0 && DP <= OCS_XS_SLACK), "OCS_FB_RING must be a power of two <= OCS_XS_SLACK");
+    constexpr int RW = n + 2 * nc;
+    double *ring = bs + (size_t)(2 * TL::S + 1) * BW + threadIdx.x;
+    auto ring_fill = [&](double *slot, int node) {     // node < 0: x from the slack (never used), u clamped
+        const int jm = 2 * node + 1 > 0 ? 2 * node + 1 : 0, jl = node > 0 ? 2 * node : 0;
+#pragma unroll
+        for (int c = 0; c < n; ++c)
+            cp_async_8(slot + (size_t)c * OCS_THREADS, a.xs + ((size_t)c * (N + 1) * a.ldb + bb) + (long)node * a.ldb);
+#pragma unroll
+        for (int c = 0; c < nc; ++c) {
+            cp_async_8(slot + (size_t)(n + c) * OCS_THREADS, a.ug + soa((long)c * G + jm, a.ldb, bb));
+            cp_async_8(slot + (size_t)(n + nc + c) * OCS_THREADS, a.ug + soa((long)c * G + jl, a.ldb, bb));
+        }
+        cp_async_commit();
+    };
+    if constexpr (DP > 0) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) ring_fill(ring + (size_t)(d * RW) * OCS_THREADS, N - 1 - d);
+    }
 #pragma unroll
     for (int c = 0; c < n; ++c) {
         yn1[c] = xsp[(size_t)c * (N + 1) * a.ldb];
@@ -718,7 +763,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
         if (i0 == i0_last) {
             ctl.eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb, uR);
-            if constexpr (UMODE == UMODE_GRID) {
+            if constexpr (UMODE == UMODE_GRID && DP == 0) {
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
                     const int jm = 2 * (N - 1 - d) + 1 > 0 ? 2 * (N - 1 - d) + 1 : 0;
@@ -734,6 +779,20 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
             const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
+            if constexpr (DP > 0) {
+                // step i sits in slot (N-1-i) mod DP; all but the DP-1 youngest groups have landed.  fb_sweep only
+                // overwrites grid points of steps >= i, the ring only reads steps <= i - 1: no hazard.
+                double *slot = ring + (size_t)(((N - 1 - i) & (DP - 1)) * RW) * OCS_THREADS;
+                cp_async_wait<DP - 1>();
+#pragma unroll
+                for (int c = 0; c < n; ++c) y1[c] = slot[(size_t)c * OCS_THREADS];
+#pragma unroll
+                for (int c = 0; c < nc; ++c) {
+                    uM[c] = slot[(size_t)(n + c) * OCS_THREADS];
+                    uL[c] = slot[(size_t)(n + nc + c) * OCS_THREADS];
+                }
+                ring_fill(slot, i - DP);
+            } else {
 #pragma unroll
             for (int c = 0; c < n; ++c) { y1[c] = yn1[c]; yn1[c] = yn2[c]; }
             xsp -= a.ldb;
@@ -741,8 +800,11 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
             // Unconditional: for i < 2 it reads the slack in front of the store and is never used.
 #pragma unroll
             for (int c = 0; c < n; ++c) yn2[c] = xsp[(size_t)c * (N + 1) * a.ldb];
+            }
             if constexpr (UMODE == UMODE_UNIFORM) ctl.eval(a, rR, bR, 2 * i + 2, bb, uR);   // shared-memory reads
-            if constexpr (UMODE == UMODE_GRID) {
+            if constexpr (DP > 0) {
+                // controls came out of the ring
+            } else if constexpr (UMODE == UMODE_GRID) {
                 // per-trajectory grid control: loaded one step ahead (fb_sweep only overwrites grid points of the
                 // current step after they were read, so the early loads never see an updated value)
 #pragma unroll
@@ -951,8 +1013,11 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     double uMn[T][nc], uLn[T][nc];      // UMODE_GRID: control of the next step, loaded one step ahead
     constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
     constexpr int UNR = OCS_REV_UNROLL;
-    double y1[T][n], yn[D][T][n];
+    constexpr int DP = OCS_RING;             // > 0: cp.async ring in shared memory [DP][T][n][threads] instead of yn
+    static_assert(DP == 0 || ((DP & (DP - 1)) == 0 && DP <= OCS_XS_SLACK), "OCS_RING must be a power of two <= OCS_XS_SLACK");
+    double y1[T][n], yn[DP > 0 ? 1 : D][T][n];
     const double *xsp[T];
+    double *ring = bs + (size_t)(2 * TL::S + 1) * BW + threadIdx.x;
 #pragma unroll
     for (int q = 0; q < T; ++q) {
         b[q] = ((long)blockIdx.x * T + q) * blockDim.x + threadIdx.x;
@@ -969,12 +1034,30 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
         for (int c = 0; c < nc; ++c) dcar[q][c] = 0.0;
         xsp[q] = a.xs + (size_t)(N - 1) * a.ldb + bb[q];     // node N-1; nodes below 0 fall into the slack
+        if constexpr (DP == 0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
+            for (int d = 0; d < D; ++d) {
 #pragma unroll
-            for (int c = 0; c < n; ++c) yn[d][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb - (size_t)d * a.ldb];
+                for (int c = 0; c < n; ++c) yn[d][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb - (size_t)d * a.ldb];
+            }
+            xsp[q] -= (size_t)(D - 1) * a.ldb;
         }
-        xsp[q] -= (size_t)(D - 1) * a.ldb;
+    }
+    if constexpr (DP > 0) {
+        // fill the ring: nodes N-1 ... N-DP, one commit group per node (slot = step count mod DP)
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+#pragma unroll
+                for (int c = 0; c < n; ++c)
+                    cp_async_8(ring + (size_t)((d * T + q) * n + c) * OCS_THREADS,
+                               xsp[q] + (size_t)c * (N + 1) * a.ldb - (size_t)d * a.ldb);
+            }
+            cp_async_commit();
+        }
+#pragma unroll
+        for (int q = 0; q < T; ++q) xsp[q] -= (size_t)(DP - 1) * a.ldb;      // node N-DP: the deepest prefetch so far
     }
 
     const int i0_last = ((N - 1) / TL::S) * TL::S;
@@ -1002,8 +1085,27 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
             const double tR = rR[0], tM = rM[0], tL = rL[0];
             const bool moves = BMODE == BMODE_SPARSE ? (rec_flags(bM) & 4) != 0 : true;
+            if constexpr (DP > 0) {
+                // node i sits in slot (N-1-i) mod DP; every group but the DP-1 youngest has landed
+                double *slot = ring + (size_t)(((N - 1 - i) & (DP - 1)) * T * n) * OCS_THREADS;
+                cp_async_wait<DP - 1>();
 #pragma unroll
-            for (int q = 0; q < T; ++q) {
+                for (int q = 0; q < T; ++q) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) y1[q][c] = slot[(size_t)(q * n + c) * OCS_THREADS];
+                }
+                // refill the slot with node i-DP (below node 0: the slack in front of the store, never used)
+#pragma unroll
+                for (int q = 0; q < T; ++q) {
+                    xsp[q] -= a.ldb;
+#pragma unroll
+                    for (int c = 0; c < n; ++c)
+                        cp_async_8(slot + (size_t)(q * n + c) * OCS_THREADS, xsp[q] + (size_t)c * (N + 1) * a.ldb);
+                }
+                cp_async_commit();
+            }
+#pragma unroll
+            for (int q = 0; q < T && DP == 0; ++q) {
                 // rotate the ring (register renaming under the unroll) and issue the load D nodes ahead;
                 // unconditional: below node 0 it reads the slack in front of the store and is never used
 #pragma unroll
@@ -1377,7 +1479,7 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
         o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2);                                          \
-        o[6] = OCS_TILE; o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24);               \
+        o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24); \
     }
 
 #define OCS_EQ_KERNEL(P, tag)                                                                         \

@@ -219,18 +219,17 @@ class CudaRK4Integrator:
         Bt = x0f.shape[1]
         m = self._n + 1
         out = dict(J=np.empty(Bt), xT=np.empty((self._n, Bt), order="F"), status=np.empty(Bt, dtype=np.int32))
-        self._ck(self._lib.ocs_b200_compute_states(self._h, _lib.dp(x0f), Bt, _lib.dp(out["J"]), _lib.dp(out["xT"]),
-                                                   _lib.ip(out["status"])))
-        self._Bt, self._single = Bt, single
+        lt, lnb = None, 0
         if gradient:
             out["dJdv"] = np.empty((self._nc * self._control.nBasis, Bt), order="F")
             out["lam0"] = np.empty((m, Bt), order="F")
-            lt, lnb = None, 0
             if lamT is not None:
                 lt = _lib.f64(np.asarray(lamT, dtype=np.float64).reshape(m, -1))
                 lnb = lt.shape[1]
-            self._ck(self._lib.ocs_b200_compute_adjoints(self._h, _lib.dp(lt), lnb, _lib.dp(out["dJdv"]),
-                                                         _lib.dp(out["lam0"])))
+        self._ck(self._lib.ocs_b200_evaluate(self._h, _lib.dp(x0f), Bt, _lib.dp(lt), lnb, _lib.dp(out["J"]),
+                                             _lib.dp(out["xT"]), _lib.ip(out["status"]), _lib.dp(out.get("dJdv")),
+                                             _lib.dp(out.get("lam0"))))
+        self._Bt, self._single = Bt, single
         return out
 
     # ------------------------------------------------------------------ device-resident variants

@@ -117,10 +117,9 @@ classdef CudaRK4Integrator < Integrator
          % column of x0: v is (nControls*K) x 1 (shared) or x Bt.
          obj.bind(prob);
          ocs_b200_mex('set_control_v', obj.handle, v);
-         [out.J, out.xT, out.status] = ocs_b200_mex('compute_states', obj.handle, x0);
+         [out.J, out.xT, out.status, out.lam0, out.dJdv] = ocs_b200_mex('evaluate', obj.handle, x0, [], ...
+                                                                        size(obj.control.B, 1)*obj.nControls);
          obj.Bt = size(x0, 2);
-         [out.lam0, out.dJdv] = ocs_b200_mex('compute_adjoints', obj.handle, [], obj.nStates + 1, obj.Bt, ...
-                                             size(obj.control.B, 1)*obj.nControls);
       end
 
       function out = single_shooting(obj, prob, x0, v0, Lb, Ub, varargin)

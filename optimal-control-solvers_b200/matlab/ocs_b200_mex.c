@@ -168,6 +168,24 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         check(rc, h);
         return;
     }
+    /* ---- [J, xT, status, lam0, dJdv] = mex('evaluate', h, x0, lamT | [], nv)   nlpObjective, single_shooting.m:137-150:
+     *      compute_states + compute_adjoints in one call (chunked, gradient download overlapped) */
+    if (!strcmp(cmd, "evaluate")) {
+        FAIL_IF(nrhs < 5, "ocs_b200:nargin", "evaluate(h, x0, lamT, nv)");
+        const double *lamT = dbl(prhs[3], "lamT");
+        long n = (long)mxGetM(prhs[2]), Bt = (long)mxGetN(prhs[2]), nv = (long)scalar(prhs[4]);
+        plhs[0] = mxCreateDoubleMatrix(1, Bt, mxREAL);
+        mxArray *xT = mxCreateDoubleMatrix(n, Bt, mxREAL), *st = int32_row(Bt);
+        mxArray *l0 = mxCreateDoubleMatrix(n + 1, Bt, mxREAL), *g = mxCreateDoubleMatrix(nv, Bt, mxREAL);
+        int rc = ocs_b200_evaluate(h, dbl(prhs[2], "x0"), Bt, lamT, lamT ? (long)mxGetN(prhs[3]) : 0, mxGetPr(plhs[0]),
+                                   mxGetPr(xT), (int32_t *)mxGetData(st), nv > 0 ? mxGetPr(g) : NULL, mxGetPr(l0));
+        if (nlhs > 1) plhs[1] = xT; else mxDestroyArray(xT);
+        if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
+        if (nlhs > 3) plhs[3] = l0; else mxDestroyArray(l0);
+        if (nlhs > 4) plhs[4] = g; else mxDestroyArray(g);
+        check(rc, h);
+        return;
+    }
     /* ---- x = mex('fetch_states', h, segment, b0, nb, m, N)                  x of RK4Integrator.m:54 */
     if (!strcmp(cmd, "fetch_states")) {
         FAIL_IF(nrhs < 7, "ocs_b200:nargin", "fetch_states(h, segment, b0, nb, m, N)");

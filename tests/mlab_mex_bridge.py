@@ -97,6 +97,16 @@ def make_mex(ocs):
             check(lib.ocs_b200_compute_adjoints(h, L.dp(lamT), lamT.shape[1] if lamT is not None else 0, L.dp(dJdv),
                                                 L.dp(lam0)), h)
             return (lam0, dJdv if dJdv is not None else np.zeros((0, 0)))[:max(nargout, 1)]
+        if cmd == "evaluate":
+            x0 = arr(a[1])
+            lamT = arr(a[2]) if np.asarray(a[2]).size else None
+            nv = int(sc(a[3]))
+            n, Bt = x0.shape
+            J, xT, st = np.empty((1, Bt)), np.empty((n, Bt), order="F"), np.empty(Bt, dtype=np.int32)
+            lam0, g = np.empty((n + 1, Bt), order="F"), np.empty((nv, Bt), order="F")
+            check(lib.ocs_b200_evaluate(h, L.dp(x0), Bt, L.dp(lamT), lamT.shape[1] if lamT is not None else 0, L.dp(J),
+                                        L.dp(xT), L.ip(st), L.dp(g) if nv > 0 else None, L.dp(lam0)), h)
+            return (J, xT, st.astype(np.float64).reshape(1, -1), lam0, g)[:max(nargout, 1)]
         if cmd == "fetch_states":
             seg, b0, nb, m, N = (int(sc(z)) for z in a[1:6])
             x = np.empty((m, N + 1, nb), order="F")
