@@ -898,6 +898,8 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
 
 int alloc_batch(H *h, long Bt)
 {
+    // the kernels address SoA rows with a 32-bit byte stride (soa_row in rk4_kernels.cuh)
+    if (Bt >= (1L << 29)) return h->fail(OCS_B200_ERR_ARG, "batches of 2^29 trajectories or more are not supported");
     const int n = h->kt.n, m = n + 1;
     TRY(ensure(h, h->d_x0, (size_t)n * Bt));
     TRY(ensure(h, h->d_J, (size_t)Bt));

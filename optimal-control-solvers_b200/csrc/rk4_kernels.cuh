@@ -145,6 +145,18 @@ struct SweepArgs {
 };
 
 __device__ __forceinline__ size_t soa(long row, long ld, long b) { return (size_t)row * (size_t)ld + (size_t)b; }
+// Row `row` of an SoA array whose batch offset is already folded into `base`.  Row index and byte stride are
+// 32-bit (the host refuses batches of 2^29 trajectories or more), so the address is ONE IMAD.WIDE.U32 instead of
+// a 64x64-bit multiply-add chain -- the per-step grid accesses of the fb_sweep kernels were spending more issue
+// slots on that chain than on arithmetic.
+__device__ __forceinline__ double *soa_row(double *base, unsigned row, unsigned ld8)
+{
+    return reinterpret_cast<double *>(reinterpret_cast<char *>(base) + (size_t)row * ld8);
+}
+__device__ __forceinline__ const double *soa_row(const double *base, unsigned row, unsigned ld8)
+{
+    return reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + (size_t)row * ld8);
+}
 
 // The first slot of a sparse basis record packs two ints (knot index k, flags) into one double; they are
 // taken apart with a bit cast of the loaded double, never through an int-typed pointer (no aliasing games).
@@ -158,6 +170,8 @@ template <int nc, int UMODE, int BMODE, int KD>
 struct ControlEval {
     static constexpr int KA = (KD > 0 ? KD : OCS_KDENSE_MAX);
     int kcur;
+    const double *ugb;      // UMODE_GRID: a.ug + trajectory
+    unsigned ld8;           // byte stride between grid rows
     // sparse basis: the window {k, k+1} of live coefficients, held by knot parity so that sliding the
     // window replaces one slot and never shuffles registers
     double vE[(UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1];
@@ -167,6 +181,8 @@ struct ControlEval {
     __device__ __forceinline__ void init(const SweepArgs &a, long bb)
     {
         kcur = -0x40000000;
+        ugb = UMODE == UMODE_GRID ? a.ug + bb : nullptr;
+        ld8 = (unsigned)a.ldb * 8u;
         if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
             const int K = KD > 0 ? KD : a.K;
 #pragma unroll
@@ -189,7 +205,7 @@ struct ControlEval {
         } else if constexpr (UMODE == UMODE_GRID) {
             const int G = 2 * a.N + 1;
 #pragma unroll
-            for (int c = 0; c < nc; ++c) u[c] = a.ug[soa((long)c * G + j, a.ldb, bb)];
+            for (int c = 0; c < nc; ++c) u[c] = *soa_row(ugb, (unsigned)(c * G + j), ld8);
         } else if constexpr (BMODE == BMODE_SPARSE) {
             const int k = rec_k(bas), kflags = rec_flags(bas);
             const double wE = bas[1], wO = bas[2];
@@ -600,8 +616,8 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                     if (a.ug_out && active[q]) {   // the reverse sweep reads the grid instead of re-evaluating v*B
 #pragma unroll
                         for (int c = 0; c < nc; ++c) {
-                            a.ug_out[soa((long)c * (2 * N + 1) + 2 * i + 1, a.ldb, b[q])] = uM[q][c];
-                            a.ug_out[soa((long)c * (2 * N + 1) + 2 * i + 2, a.ldb, b[q])] = uR[q][c];
+                            *soa_row(a.ug_out + b[q], (unsigned)(c * (2 * N + 1) + 2 * i + 1), (unsigned)a.ldb * 8u) = uM[q][c];
+                            *soa_row(a.ug_out + b[q], (unsigned)(c * (2 * N + 1) + 2 * i + 2), (unsigned)a.ldb * 8u) = uR[q][c];
                         }
                     }
                 }
@@ -722,6 +738,11 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     double y1[n], yn1[n], yn2[n];      // node states: current, and the next two (prefetched)
     double xR[n];                      // FB: node state to the right (for midpoint averages)
     MaxRatio chg;                      // FB: running max of |uNew-u| / (uRelTol |u| + uAbsTol)
+    double *ugw = (FB != 0) ? a.ug + bb : nullptr;     // FB: this trajectory's column of the control grid (bb == b when active)
+    double bnd[2 * nc];                // FB: ControlBounds, read once (ControlChar clamps with them twice per step)
+#pragma unroll
+    for (int c = 0; c < 2 * nc; ++c) bnd[c] = (FB != 0) ? a.bounds[c] : 0.0;
+    const unsigned ld8 = (unsigned)a.ldb * 8u;
 #pragma unroll
     for (int c = 0; c < nc; ++c) dcar[c] = 0.0;
     const double *xsp = a.xs + (size_t)(N - 1) * a.ldb + bb;   // node N-1
@@ -923,21 +944,21 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
                 // uNew at the right node and at the midpoint of step i (midpoint x, lam = mean of the
                 // neighbouring nodes, the same formula the grid uses for t, RK4Integrator.m:23)
                 double un[nc], xm[n], lm[n];
-                P::template ControlChar<HM>(ttR, tR, xR, lamR, p, a.bounds, un);
+                P::template ControlChar<HM>(ttR, tR, xR, lamR, p, bnd, un);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     chg.update(fabs(un[c] - uR[c]), a.uRelTol * fabs(uR[c]) + a.uAbsTol);          // fb_sweep.m:107-108
                     const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
-                    if (active) a.ug[soa((long)c * G + (2 * i + 2), a.ldb, b)] = uw;
+                    if (active) *soa_row(ugw, (unsigned)(c * G + 2 * i + 2), ld8) = uw;
                 }
 #pragma unroll
                 for (int c = 0; c < n; ++c) { xm[c] = (y1[c] + xR[c]) / 2; lm[c] = (lam[c] + lamR[c]) / 2; }
-                P::template ControlChar<HM>(ttM, tM, xm, lm, p, a.bounds, un);
+                P::template ControlChar<HM>(ttM, tM, xm, lm, p, bnd, un);
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     chg.update(fabs(un[c] - uM[c]), a.uRelTol * fabs(uM[c]) + a.uAbsTol);
                     const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uM[c] + a.relax * un[c];
-                    if (active) a.ug[soa((long)c * G + (2 * i + 1), a.ldb, b)] = uw;
+                    if (active) *soa_row(ugw, (unsigned)(c * G + 2 * i + 1), ld8) = uw;
                 }
 #pragma unroll
                 for (int c = 0; c < n; ++c) xR[c] = y1[c];
@@ -963,12 +984,12 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
         double lam0[n];
 #pragma unroll
         for (int c = 0; c < n; ++c) lam0[c] = lam[c];
-        P::template ControlChar<HM>(gp + 1 + nc, gp[0], xR, lam0, p, a.bounds, un);
+        P::template ControlChar<HM>(gp + 1 + nc, gp[0], xR, lam0, p, bnd, un);
 #pragma unroll
         for (int c = 0; c < nc; ++c) {
             chg.update(fabs(un[c] - uR[c]), a.uRelTol * fabs(uR[c]) + a.uAbsTol);
             const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
-            if (active) a.ug[soa((long)c * G, a.ldb, b)] = uw;
+            if (active) *soa_row(ugw, (unsigned)(c * G), ld8) = uw;
         }
         if (active && a.max_change) a.max_change[b] = chg.value();
     }
@@ -1015,7 +1036,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     constexpr int UNR = OCS_REV_UNROLL;
     constexpr int DP = OCS_RING;             // > 0: cp.async ring in shared memory [DP][T][n][threads] instead of yn
     static_assert(DP == 0 || ((DP & (DP - 1)) == 0 && DP <= OCS_XS_SLACK), "OCS_RING must be a power of two <= OCS_XS_SLACK");
-    double y1[T][n], yn[DP > 0 ? 1 : D][T][n];
+    double y1[T][n], yn[D][T][n];            // (yn is unused, and optimised away, with the shared-memory ring)
     const double *xsp[T];
     double *ring = bs + (size_t)(2 * TL::S + 1) * BW + threadIdx.x;
 #pragma unroll
@@ -1104,20 +1125,22 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 }
                 cp_async_commit();
             }
+            if constexpr (DP == 0) {
 #pragma unroll
-            for (int q = 0; q < T && DP == 0; ++q) {
-                // rotate the ring (register renaming under the unroll) and issue the load D nodes ahead;
-                // unconditional: below node 0 it reads the slack in front of the store and is never used
+                for (int q = 0; q < T; ++q) {
+                    // rotate the ring (register renaming under the unroll) and issue the load D nodes ahead;
+                    // unconditional: below node 0 it reads the slack in front of the store and is never used
 #pragma unroll
-                for (int c = 0; c < n; ++c) y1[q][c] = yn[0][q][c];
+                    for (int c = 0; c < n; ++c) y1[q][c] = yn[0][q][c];
 #pragma unroll
-                for (int d = 0; d + 1 < D; ++d) {
+                    for (int d = 0; d + 1 < D; ++d) {
 #pragma unroll
-                    for (int c = 0; c < n; ++c) yn[d][q][c] = yn[d + 1][q][c];
+                        for (int c = 0; c < n; ++c) yn[d][q][c] = yn[d + 1][q][c];
+                    }
+                    xsp[q] -= a.ldb;
+#pragma unroll
+                    for (int c = 0; c < n; ++c) yn[D - 1][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
                 }
-                xsp[q] -= a.ldb;
-#pragma unroll
-                for (int c = 0; c < n; ++c) yn[D - 1][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
             }
 #pragma unroll
             for (int q = 0; q < T; ++q) {
@@ -1182,8 +1205,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                         for (int c = 0; c < nc; ++c) {
                             if (active[q]) {
-                                a.dug[soa((long)c * G + 2 * i + 2, a.ldb, b[q])] = dcar[q][c] + dRq[c];
-                                a.dug[soa((long)c * G + 2 * i + 1, a.ldb, b[q])] = dM2[c] + dM3[c];
+                                *soa_row(a.dug + b[q], (unsigned)(c * G + 2 * i + 2), (unsigned)a.ldb * 8u) = dcar[q][c] + dRq[c];
+                                *soa_row(a.dug + b[q], (unsigned)(c * G + 2 * i + 1), (unsigned)a.ldb * 8u) = dM2[c] + dM3[c];
                             }
                         }
                         P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
