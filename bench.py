@@ -63,6 +63,18 @@ def make_workload(name, ocs, local_rank, bt_override=None):
                     flop_fwd=FLOP_FWD, flop_rev=FLOP_REV, bytes_fwd=BYTES_FWD, bytes_rev=BYTES_REV, label=WORKLOAD,
                     kernels=("ocs_fwd_test_fast_u0_b0_p0", "ocs_rev_test_fast_u0_b1_p0"),
                     x0_lo=0.5, x0_hi=2.5)
+    if name == "cfg2v":
+        # cfg2 with one coefficient vector per trajectory (what a batched single_shooting solve evaluates):
+        # control evaluated in the thread through the sliding two-knot window (c_u = 3 per grid point)
+        Bt = bt_override or BT
+        tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
+        integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+        ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+        return dict(integ=integ, prob=ocs.TestOCProblem(PARAMS, [[0.0, 1.0]]), ctl=ctl, n=1, rows=K_PWL, Bt=Bt,
+                    N_total=N_STEPS, v=None, v_batch=(K_PWL, Bt), v_kind="uniform",
+                    flop_fwd=FLOP_FWD + 2 * 3, flop_rev=FLOP_REV, bytes_fwd=BYTES_FWD, bytes_rev=BYTES_REV,
+                    label="cfg2v: cfg2 with per-trajectory PWLinearControl coefficients v (101 x 2^20), forward + adjoint",
+                    kernels=("ocs_fwd_test_fast_u1_b1_p0", "ocs_rev_test_fast_u1_b1_p0"), x0_lo=0.5, x0_hi=2.5)
     if name == "cfg3":
         # 6-state generated problem, one Chebyshev (degree 16) coefficient set per control candidate
         Bt = bt_override or 100_000
@@ -284,7 +296,7 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "fbsweep"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg3", "cfg4", "fbsweep"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
@@ -339,8 +351,11 @@ def main():
           torch.rand((n_st, Bt), dtype=torch.float64, device=dev, generator=gen)).contiguous()
     v_dev = None
     if wl["v_batch"] is not None:     # per-trajectory coefficients: constant term U[0.2,0.8], higher ones N(0, 0.05^2)
-        v_dev = 0.05 * torch.randn(wl["v_batch"], dtype=torch.float64, device=dev, generator=gen)
-        v_dev[:2] = 0.2 + 0.6 * torch.rand((2, Bt), dtype=torch.float64, device=dev, generator=gen)
+        if wl.get("v_kind") == "uniform":
+            v_dev = torch.rand(wl["v_batch"], dtype=torch.float64, device=dev, generator=gen)
+        else:
+            v_dev = 0.05 * torch.randn(wl["v_batch"], dtype=torch.float64, device=dev, generator=gen)
+            v_dev[:2] = 0.2 + 0.6 * torch.rand((2, Bt), dtype=torch.float64, device=dev, generator=gen)
         v_dev = v_dev.contiguous()
     # J and x(T) live in one packed (1+n) x Bt buffer so that one all-gather moves both; double-buffered and
     # gathered on a side stream so that the collective overlaps the next evaluation (host/dist.py)

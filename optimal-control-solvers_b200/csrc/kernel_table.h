@@ -10,7 +10,9 @@ struct ocs_kernel_table {
     int threads;   // block size the kernels were built for
     int tile;      // RK4 steps per shared-memory tile
     int tpt_rev;   // trajectories per thread of the reverse (gradient) kernels
+    int tpt_rev_coef;   // ... of the gradient kernels with per-trajectory coefficients (UMODE_COEF)
     int tpt_fwd;   // ... and of the forward kernels
+    int tpt_fwd_coef;
     int fb_ring;   // ... and of the fb_sweep costate kernels (ring*(n + 2 nc)*threads doubles)
     int rev_ring;  // depth of the gradient kernels' cp.async node-state ring (shared memory: ring*tpt*n*threads doubles)
     const void *fwd[3][3][2];   // [UMODE][BMODE][params batched]

@@ -30,6 +30,21 @@
 #ifndef OCS_TPT_FWD
 #define OCS_TPT_FWD 3
 #endif
+// Per-trajectory coefficients v (UMODE_COEF, what a batched single_shooting solve evaluates; bench.py --config cfg2v).
+// Same-box A/B of (trajectories per thread, min blocks/SM): forward (3,1: 134 regs) 3.88 ms / (3,4) 3.32 / (2,6) 3.29 /
+// (1,8: 64 regs) 2.91 / (1,12) 2.90; reverse (2,5: spills) 5.88 / (2,4: 126 regs) 5.70 / (1,8) 5.98 / (1,10) 5.97.
+#ifndef OCS_TPT_FWD_COEF
+#define OCS_TPT_FWD_COEF 1
+#endif
+#ifndef OCS_MINBLOCKS_FWD_COEF
+#define OCS_MINBLOCKS_FWD_COEF 8
+#endif
+#ifndef OCS_TPT_REV_COEF
+#define OCS_TPT_REV_COEF 2
+#endif
+#ifndef OCS_MINBLOCKS_REV_COEF
+#define OCS_MINBLOCKS_REV_COEF 4
+#endif
 #include "rk4_kernels.cuh"
 #include "problem_test.cuh"
 #include "kernel_table.h"
@@ -62,7 +77,9 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->threads = OCS_THREADS;
     t->tile = OCS_TILE;
     t->tpt_rev = OCS_TPT_REV;
+    t->tpt_rev_coef = OCS_TPT_REV_COEF;
     t->tpt_fwd = OCS_TPT_FWD;
+    t->tpt_fwd_coef = OCS_TPT_FWD_COEF;
     t->rev_ring = OCS_RING;
     t->fb_ring = OCS_FB_RING;
     for (int pb = 0; pb < 2; ++pb)

@@ -188,13 +188,15 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, c
     table->n = inf[0];
     table->nc = inf[1];
     table->np = inf[2];
-    for (int hm = 0; hm < 3; ++hm) table->ntt[hm] = inf[3 + hm];
+    for (int hm = 0; hm < 3; ++hm) table->ntt[hm] = inf[3 + hm] & 0xffff;
+    table->tpt_fwd_coef = (inf[5] >> 16) & 0xff;
     table->tile = inf[6] & 0xffff;
     table->rev_ring = (inf[6] >> 16) & 0xff;
     table->fb_ring = (inf[6] >> 24) & 0xff;
     table->threads = inf[7] & 0xffff;
     table->tpt_rev = (inf[7] >> 16) & 0xff;
-    table->tpt_fwd = (inf[7] >> 24) & 0xff;
+    table->tpt_fwd = (inf[7] >> 24) & 0xf;
+    table->tpt_rev_coef = (inf[7] >> 28) & 0xf;
     table->kd = 0;
     return 0;
 }

@@ -779,7 +779,7 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         }
         const void *kern = nullptr;
         TRY(resolve(h, d_xgrid ? KIND_FWDG : KIND_FWD, um, bm, pb_index(h), &kern));
-        TRY(launch(h, kern, a, true, (d_xgrid || bm == 2) ? 1 : std::max(h->kt.tpt_fwd, 1)));
+        TRY(launch(h, kern, a, true, (d_xgrid || bm == 2) ? 1 : std::max(um == 1 ? h->kt.tpt_fwd_coef : h->kt.tpt_fwd, 1)));
     }
     return 0;
 }
@@ -867,7 +867,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
         // dense-basis kernels keep K coefficients and K accumulators per trajectory in registers: one per thread
         {
-            const int tpt = (grids || bm == 2) ? 1 : std::max(h->kt.tpt_rev, 1);
+            const int tpt = (grids || bm == 2) ? 1 : std::max(um == 1 ? h->kt.tpt_rev_coef : h->kt.tpt_rev, 1);
             // the gradient kernels (not the fetch variants) keep a cp.async ring of node states in shared memory
             const size_t ring = grids ? 0 : (size_t)h->kt.rev_ring * tpt * h->kt.n * h->kt.threads;
             TRY(launch(h, kern, a, false, tpt, ring));

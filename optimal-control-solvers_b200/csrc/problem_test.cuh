@@ -5,8 +5,10 @@
 // Hoisted table (see HM_* in rk4_kernels.cuh).  Batch-uniform sub-expressions are
 // evaluated once per grid point with the very operations (and order) of the in-thread
 // form, so hoisting does not change a single bit of the result:
-//   HM_TIME          tt[0] = exp(-r t)        (F :25, dFdx_times_vec :31, dFdu_times_vec :37)
+//   HM_TIME          tt[0] = exp(-r t)        (F :25)
 //                    tt[1] = exp(r t)/(2c)    (ControlChar: u* = lam * (exp(r t) / (2c)))
+//                    tt[2] = 2*exp(-r t)      (dFdx_times_vec :31, left-to-right prefix)
+//                    tt[3] = 2*c*exp(-r t)    (dFdu_times_vec :37, left-to-right prefix of 2*c*exp(-r*t).*u)
 //   HM_TIME_CONTROL  tt[0] = exp(-r t)
 //                    tt[1] = c*u.^2           (F :25)
 //                    tt[2] = 2*exp(-r t)      (dFdx_times_vec :31, left-to-right prefix)
@@ -17,14 +19,17 @@ namespace OCS_NS {
 
 struct TestOCProblem {
     static constexpr int n = 1, nc = 1, np = 3;
-    __host__ __device__ static constexpr int ntt(int hm) { return hm == 1 ? 2 : (hm == 2 ? 4 : 0); }
+    __host__ __device__ static constexpr int ntt(int hm) { return hm == 0 ? 0 : 4; }
 
     template <int HM>
     __device__ __forceinline__ static void table(double t, const double *u, const double *p, double *tt)
     {
         if constexpr (HM == 1) {
-            tt[0] = exp(-p[2] * t);
+            const double E = exp(-p[2] * t);
+            tt[0] = E;
             tt[1] = exp(p[2] * t) / (2.0 * p[0]);
+            tt[2] = 2.0 * E;
+            tt[3] = 2.0 * p[0] * E;
         } else if constexpr (HM == 2) {
             const double E = exp(-p[2] * t);
             tt[0] = E;
@@ -53,7 +58,7 @@ struct TestOCProblem {
                                              const double *p, const double *v, double *o)
     {
         (void)u;
-        const double E2 = HM == 2 ? tt[2] : 2.0 * (HM ? tt[0] : exp(-p[2] * t));
+        const double E2 = HM ? tt[2] : 2.0 * exp(-p[2] * t);
         const double x = y[0];
         // m - 2*x: the product 2*x is exact, so the fused form rounds identically to MATLAB's two operations
         o[0] = fma(-2.0, x, p[1]) * v[0] + E2 * x * v[1];
@@ -65,7 +70,7 @@ struct TestOCProblem {
                                              const double *p, const double *v, double *o)
     {
         (void)y;
-        const double CEU = HM == 2 ? tt[3] : 2.0 * p[0] * (HM ? tt[0] : exp(-p[2] * t)) * u[0];
+        const double CEU = HM == 2 ? tt[3] : (HM == 1 ? tt[3] * u[0] : 2.0 * p[0] * exp(-p[2] * t) * u[0]);
         o[0] = -v[0] + CEU * v[1];
     }
 

@@ -52,6 +52,18 @@
 #ifndef OCS_MINBLOCKS_REV
 #define OCS_MINBLOCKS_REV 1 // __launch_bounds__ min blocks/SM of the reverse kernels (register cap)
 #endif
+#ifndef OCS_TPT_FWD_COEF
+#define OCS_TPT_FWD_COEF OCS_TPT_FWD              // trajectories per thread of the forward kernels with per-trajectory v
+#endif
+#ifndef OCS_MINBLOCKS_FWD_COEF
+#define OCS_MINBLOCKS_FWD_COEF OCS_MINBLOCKS_FWD
+#endif
+#ifndef OCS_TPT_REV_COEF
+#define OCS_TPT_REV_COEF OCS_TPT_REV              // ... of the gradient kernels with per-trajectory coefficients v
+#endif
+#ifndef OCS_MINBLOCKS_REV_COEF
+#define OCS_MINBLOCKS_REV_COEF OCS_MINBLOCKS_REV
+#endif
 #ifndef OCS_MINBLOCKS_FB
 #define OCS_MINBLOCKS_FB 1  // __launch_bounds__ min blocks/SM of the fb_sweep costate kernels
 #endif
@@ -194,6 +206,33 @@ struct ControlEval {
         }
     }
 
+    // Sparse basis, part 1: make {k, k+1} the live window of grid point j.  The branch is uniform across the
+    // batch (every trajectory shares the grid) and taken ~K times per sweep.
+    __device__ __forceinline__ void slide(const SweepArgs &a, const double *bas, long bb)
+    {
+        const int k = rec_k(bas);
+        if (k != kcur) {
+            const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+                vE[c] = (ke < a.K) ? a.v[soa((long)ke * nc + c, a.ldb, bb)] : 0.0;
+                vO[c] = (ko < a.K) ? a.v[soa((long)ko * nc + c, a.ldb, bb)] : 0.0;
+            }
+            kcur = k;
+        }
+    }
+    // Sparse basis, part 2: u = v_k B(k,j) + v_{k+1} B(k+1,j) with the two weights by knot parity, branch-free
+    // so that the chains of several trajectories share a basic block.  An absent entry has weight 0 and adds an
+    // exact zero -- MATLAB's v*B multiplies by those zeros as well -- so a PWConstantControl value stays an exact
+    // copy of its coefficient; with separately rounded products (strict mode) the sum is commutative, i.e. the
+    // reference's summation order.
+    __device__ __forceinline__ void value(const double *bas, double *u) const
+    {
+        const double wE = bas[1], wO = bas[2];
+#pragma unroll
+        for (int c = 0; c < nc; ++c) u[c] = vE[c] * wE + vO[c] * wO;
+    }
+
     // u(:,j) = reshape(v,nc,[]) * B(:,j)   (PWLinearControl.m:59-62 and twins)
     //   rec: grid-point record, bas: basis record of grid point j
     __device__ __forceinline__ void eval(const SweepArgs &a, const double *rec, const double *bas, int j, long bb,
@@ -207,28 +246,8 @@ struct ControlEval {
 #pragma unroll
             for (int c = 0; c < nc; ++c) u[c] = *soa_row(ugb, (unsigned)(c * G + j), ld8);
         } else if constexpr (BMODE == BMODE_SPARSE) {
-            const int k = rec_k(bas), kflags = rec_flags(bas);
-            const double wE = bas[1], wO = bas[2];
-            if (k != kcur) {   // uniform across the block: every trajectory shares the grid
-                const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
-#pragma unroll
-                for (int c = 0; c < nc; ++c) {
-                    vE[c] = (ke < a.K) ? a.v[soa((long)ke * nc + c, a.ldb, bb)] : 0.0;
-                    vO[c] = (ko < a.K) ? a.v[soa((long)ko * nc + c, a.ldb, bb)] : 0.0;
-                }
-                kcur = k;
-            }
-            // flags: bit0 = two non-zeros in the column; bit1 = (one non-zero) it sits on the odd slot
-            if (kflags & 1) {
-#pragma unroll
-                for (int c = 0; c < nc; ++c) u[c] = (k & 1) ? vO[c] * wO + vE[c] * wE : vE[c] * wE + vO[c] * wO;
-            } else if (kflags & 2) {
-#pragma unroll
-                for (int c = 0; c < nc; ++c) u[c] = vO[c] * wO;   // weight 1: exact copy of v (PWConstantControl)
-            } else {
-#pragma unroll
-                for (int c = 0; c < nc; ++c) u[c] = vE[c] * wE;
-            }
+            slide(a, bas, bb);
+            value(bas, u);
         } else {
             const int K = KD > 0 ? KD : a.K;
 #pragma unroll
@@ -592,6 +611,19 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
             const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bM = bs + (2 * s + 1) * BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h6 = st[4 * s + 3];
+            constexpr bool SPLIT = (UMODE == UMODE_COEF && BMODE == BMODE_SPARSE);
+            if constexpr (SPLIT) {
+                // controls of all T trajectories first: the (uniform, rare) window moves happen here, outside the
+                // arithmetic below, whose T dependency chains then share one basic block and interleave
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].slide(a, bM, bb[q]);
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].slide(a, bR, bb[q]);
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].value(bR, uR[q]);
+            }
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 if (active[q]) {
@@ -608,7 +640,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                     const int jm = 2 * i + 3 < 2 * N ? 2 * i + 3 : 2 * N, jr = 2 * i + 4 < 2 * N ? 2 * i + 4 : 2 * N;
                     ctl[q].eval(a, rM, bM, jm, bb[q], uMn[q]);
                     ctl[q].eval(a, rR, bR, jr, bb[q], uRn[q]);
-                } else {
+                } else if constexpr (!SPLIT) {
                     ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
                     ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
                 }
@@ -1142,6 +1174,17 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                     for (int c = 0; c < n; ++c) yn[D - 1][q][c] = xsp[q][(size_t)c * (N + 1) * a.ldb];
                 }
             }
+            constexpr bool SPLIT = (UMODE == UMODE_COEF && BMODE == BMODE_SPARSE);
+            if constexpr (SPLIT) {      // controls of all T trajectories first (see forward_multi_body)
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].slide(a, bM, bb[q]);
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].slide(a, bL, bb[q]);
+#pragma unroll
+                for (int q = 0; q < T; ++q) ctl[q].value(bL, uL[q]);
+            }
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
@@ -1151,7 +1194,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                     const int jm = 2 * i - 1 > 0 ? 2 * i - 1 : 0, jl = 2 * i - 2 > 0 ? 2 * i - 2 : 0;
                     ctl[q].eval(a, rM, bM, jm, bb[q], uMn[q]);
                     ctl[q].eval(a, rL, bL, jl, bb[q], uLn[q]);
-                } else {
+                } else if constexpr (!SPLIT) {
                     ctl[q].eval(a, rM, bM, 2 * i + 1, bb[q], uM[q]);
                     ctl[q].eval(a, rL, bL, 2 * i, bb[q], uL[q]);
                 }
@@ -1482,11 +1525,11 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     }
 #define OCS_COMMA ,
 #define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_FWD)>, tag, UM, BM, PB, ((UM) == 2 ? 4 : OCS_MINBLOCKS_FWD))
+    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : ((UM) == 1 ? OCS_TPT_FWD_COEF : OCS_TPT_FWD))>, tag, UM, BM, PB, ((UM) == 2 ? 4 : ((UM) == 1 && (BM) == 1 ? OCS_MINBLOCKS_FWD_COEF : OCS_MINBLOCKS_FWD)))
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : OCS_TPT_REV)>, tag, UM, BM, PB, ((BM) == 2 ? 1 : OCS_MINBLOCKS_REV))
+    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : ((UM) == 1 ? OCS_TPT_REV_COEF : OCS_TPT_REV))>, tag, UM, BM, PB, ((BM) == 2 ? 1 : ((UM) == 1 ? OCS_MINBLOCKS_REV_COEF : OCS_MINBLOCKS_REV)))
 #define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA 0 OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_FB_KERNEL(P, tag, PB) \
@@ -1501,8 +1544,8 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     extern "C" __global__ void ocs_info_##tag(int *o)                                                  \
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
-        o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2);                                          \
-        o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24); \
+        o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2) | (OCS_TPT_FWD_COEF << 16);               \
+        o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24) | (OCS_TPT_REV_COEF << 28); \
     }
 
 #define OCS_EQ_KERNEL(P, tag)                                                                         \
