@@ -119,6 +119,26 @@ def _measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _bind_to_gpu_numa_node(index):
+    """Restricts this process to the CPUs NVML reports as local to GPU `index`; returns a function that restores
+    the previous affinity.  No-op when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return lambda: None
+        os.sched_setaffinity(0, cpus)
+        return lambda: os.sched_setaffinity(0, old)
+    except Exception:
+        return lambda: None
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
 
@@ -467,6 +487,9 @@ def main():
     # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)
     e2e = None
     if not args.no_e2e and args.config == "cfg2":
+        # pinned host buffers on the NUMA node of this rank's GPU (first touch under the GPU's CPU affinity):
+        # with several ranks per box the downloads otherwise cross the socket interconnect
+        restore = _bind_to_gpu_numa_node(local_rank)
         x0_h = torch.empty((1, Bt), dtype=torch.float64).pin_memory()
         x0_h.copy_(x0.cpu())
         J_h = torch.empty(Bt, dtype=torch.float64).pin_memory()
@@ -474,6 +497,9 @@ def main():
         st_h = torch.empty(Bt, dtype=torch.int32).pin_memory()
         dJdv_h = torch.empty((Bt, K_PWL), dtype=torch.float64).pin_memory()   # MATLAB (nc*K) x Bt, column-major
         lam0_h = torch.empty((Bt, 2), dtype=torch.float64).pin_memory()
+        for buf in (x0_h, J_h, xT_h, dJdv_h, lam0_h):
+            buf.view(-1)[::512].add_(0)          # touch every page while the affinity is in place
+        restore()
         lib = ocs._lib
         vf = lib.f64(v)
         hnd = integ._h

@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -98,6 +99,20 @@ int ocs_compile_unit(const char *source, const char *unit, int strict, const cha
 
     std::string src;
     src += "#define OCS_NS ocs_gen\n";
+    // kernel tuning experiments: OCS_B200_NVRTC_DEFS="OCS_MINBLOCKS_REV=3;OCS_TPT_FWD=2" -> #define lines
+    if (const char *defs = getenv("OCS_B200_NVRTC_DEFS")) {
+        std::string d(defs);
+        size_t pos = 0;
+        while (pos < d.size()) {
+            size_t end = d.find(';', pos);
+            if (end == std::string::npos) end = d.size();
+            std::string item = d.substr(pos, end - pos);
+            const size_t eq = item.find('=');
+            if (!item.empty())
+                src += "#define " + (eq == std::string::npos ? item : item.substr(0, eq) + " " + item.substr(eq + 1)) + "\n";
+            pos = end + 1;
+        }
+    }
     src += "#include \"rk4_kernels.cuh\"\n";
     src += source;
     src += "\n";

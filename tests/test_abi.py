@@ -17,10 +17,12 @@ def declared_symbols():
 
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
-    assert len(syms) >= 28
+    assert len(syms) >= 34
     for must in ("ocs_b200_create", "ocs_b200_destroy", "ocs_b200_last_error", "ocs_b200_compute_states",
                  "ocs_b200_compute_adjoints", "ocs_b200_set_control_basis", "ocs_b200_set_problem_source",
-                 "ocs_b200_fb_sweep", "ocs_b200_fetch_states", "ocs_b200_fetch_adjoints"):
+                 "ocs_b200_fb_sweep", "ocs_b200_fetch_states", "ocs_b200_fetch_adjoints", "ocs_b200_evaluate",
+                 "ocs_b200_single_shooting", "ocs_b200_set_fb_costate", "ocs_b200_eval_solution",
+                 "ocs_b200_set_control_ufunc", "ocs_b200_compute_equilibrium"):
         assert must in syms
 
 
