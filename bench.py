@@ -238,6 +238,85 @@ def run_reference(args, rank, world):
 _REAL_STDOUT = None
 
 
+def run_rows(args, ocs, local_rank):
+    """--config rows: the rows either side of the path, each timed through the host API
+    (wall clock around the call, copies included) on one GPU.  Not a driver bench line; recorded in profiles/."""
+    import torch
+    out = {}
+    prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, r
+
+    # (4) batched compute_equilibrium: one steady state per parameter set
+    rng = np.random.default_rng(21)
+    ns = 1 << 20
+    c, m, r = rng.uniform(1.3, 1.7, ns), rng.uniform(2.8, 3.2, ns), rng.uniform(0.03, 0.07, ns)
+    sweep = ocs.TestOCProblem(dict(c=c, m=m, r=r), [[0.0, 1.0]])
+    integ0 = ocs.CudaRK4Integrator(np.array([0.0, 1.0]), device=local_rank)
+    dt, res = timed(lambda: ocs.compute_equilibrium(sweep, [2.7], [2.2], [.7], r=r, integrator=integ0))
+    integ0.close()
+    out["compute_equilibrium"] = {"parameter_sets": ns, "ms": 1e3 * dt, "solves_per_s": ns / dt,
+                                  "converged": int((res[5] == 1).sum()), "max_resnorm": float(res[3].max())}
+    from oracle import rk4_oracle
+    t0 = time.perf_counter()
+    nref = 50
+    for b in range(nref):
+        rk4_oracle.solve_equilibrium(rk4_oracle.TestOCProblem(c[b], m[b], r[b]), [2.7], [2.2], [.7], r[b])
+    out["compute_equilibrium"]["cpu_oracle_solves_per_s"] = nref / (time.perf_counter() - t0)
+
+    # (1) device-side batched single_shooting: tests/backprop_test.m's grid and control, 2^16 initial states
+    Bt = 1 << 16
+    tspan = ocs.matlab_linspace(0.0, 10.0, 501)
+    integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+    ctl = ocs.PWLinearControl(integ.t, 21, 1)
+    integ.attach_control(ctl)
+    x0 = np.random.default_rng(2).uniform(0.5, 2.5, (1, Bt))
+    Lb, Ub = ctl.compute_nlp_bounds(prob.ControlBounds)
+    dt, ss = timed(lambda: integ.single_shooting(prob, x0, ctl.compute_initial_v(0.5), Lb, Ub, max_iter=300, tol=1e-6), reps=1)
+    out["single_shooting"] = {"trajectories": Bt, "rk4_steps": 500, "K": 21, "ms": 1e3 * dt, "solves_per_s": Bt / dt,
+                              "converged": int(ss["converged"].sum()), "mean_iters": float(ss["iters"].mean()),
+                              "trajectory_steps_per_s": float(ss["iters"].max()) * Bt * 500 / dt}
+
+    # (3) soln.x / soln.lam / soln.u of those minimisers at nINTERP_PTS = 1001 query times (fb_sweep.m:22)
+    tq = np.linspace(0.0, 10.0, 1001)
+    nb = 1 << 14
+    L = ocs._lib
+    lib = L.load()
+    bufs = [torch.empty((nb, tq.size), dtype=torch.float64).pin_memory() for _ in range(3)]   # MATLAB 1 x nq x nb each
+    tqf = L.f64(tq)
+    dt, _ = timed(lambda: L.check(lib.ocs_b200_eval_solution(integ._h, 0, 0, nb, tq.size, L.dp(tqf), L.dp(bufs[0].numpy()),
+                                                             L.dp(bufs[1].numpy()), L.dp(bufs[2].numpy())), integ._h))
+    dtp, sol = timed(lambda: integ.eval_solution(tq, 0, nb))
+    assert np.array_equal(sol["x"][0].T, bufs[0].numpy()) and np.array_equal(sol["u"][0].T, bufs[2].numpy())
+    out["eval_solution"] = {"trajectories": nb, "queries": tq.size, "ms": 1e3 * dt,
+                            "interpolated_values_per_s": 3 * nb * tq.size / dt,
+                            "d2h_bytes": 3 * 8 * nb * tq.size, "ms_with_pageable_numpy_outputs": 1e3 * dtp}
+    integ.close()
+
+    # (2) fb_sweep with the continuous costate (v1 adjointRHS): one full solve of 2^16 trajectories
+    integ = ocs.CudaRK4Integrator(ocs.matlab_linspace(0.0, 10.0, 1001), device=local_rank)
+    u0 = np.full((1, 2001), 0.5)
+    for mode in ("discrete", "continuous"):
+        integ.set_profiling(True)
+        integ.kernel_stats(reset=True)
+        dt, fb = timed(lambda: integ.fb_sweep(prob, x0, u0, nSWEEPS=60, costate=mode), reps=1)
+        ks = integ.kernel_stats(reset=True)
+        integ.set_profiling(False)
+        out["fb_sweep_" + mode] = {"trajectories": Bt, "rk4_steps": 1000, "ms": 1e3 * dt, "solves_per_s": Bt / dt,
+                                   "converged": int(fb["converged"].sum()), "max_sweeps": int(fb["sweeps"].max()),
+                                   "kernel_ms_forward": ks["ms_forward"] / 2, "kernel_ms_costate": ks["ms_reverse"] / 2}
+    integ.close()
+    emit({"metric": "rows beside the RK4 path (SURVEY.md 8f), host API wall clock on one B200", "rows": out,
+          "n_gpus": 1, "data": "synthetic"})
+
+
 def run_fbsweep(args, ocs, local_rank, rank, world):
     """--config fbsweep: the forward-backward sweep iteration (functions/fb_sweep.m:79-115 on the RK4 grid) on
     cfg2's batch: per sweep one forward sweep and one costate sweep with the control of EVERY trajectory on the
@@ -316,7 +395,7 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg3", "cfg4", "fbsweep"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg3", "cfg4", "fbsweep", "rows"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
@@ -356,6 +435,10 @@ def main():
 
     if args.config == "fbsweep":
         run_fbsweep(args, ocs, local_rank, rank, world)
+        return
+    if args.config == "rows":
+        if rank == 0:
+            run_rows(args, ocs, local_rank)
         return
     wl = make_workload(args.config, ocs, local_rank, None if args.bt == BT else args.bt)
     integ, prob, ctl, Bt, n_st, rows, NT = wl["integ"], wl["prob"], wl["ctl"], wl["Bt"], wl["n"], wl["rows"], wl["N_total"]
