@@ -174,3 +174,35 @@ def test_non_monotone_sparse_basis_falls_back_to_accumulation(ocs, oracle):
     for key in ("J", "dJdv", "lam0"):
         assert relerr(out[key], ref[key]) < TOL, key
     integ.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 31, 33, 65])
+def test_grid_fetch_and_fb_sweep_for_odd_step_counts(ocs, oracle, N):
+    """The single-trajectory kernels (fetch variants writing lam / dJdu grids, fb_sweep costate kernels) at odd
+    and tiny step counts -- the unrolled gradient kernel once had a compiler problem exactly there."""
+    T = 0.5 + 0.05 * N
+    tspan = ocs.matlab_linspace(0.0, T, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ointeg = oracle.RK4Integrator(tspan)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    oprob = oracle.TestOCProblem(**TEST_PARAMS)
+    rng = np.random.default_rng(N)
+    Bt, G = 37, 2 * N + 1
+    x0 = rng.uniform(.5, 2.5, (1, Bt))
+    u = rng.uniform(0, 1, (1, G, Bt))
+    x, J = integ.compute_states(prob, x0, u, return_x=True)
+    lam, dJdu = integ.compute_adjoints(prob, u, grids=True)
+    for b in (0, 17, 36):
+        ox, oJ = ointeg.compute_states(oprob, x0[:, b], u[:, :, b])
+        olam, odu = ointeg.compute_adjoints(oprob, u[:, :, b])
+        assert relerr(x[:, :, b], ox) < TOL and relerr(J[b], oJ) < TOL
+        assert relerr(lam[:, :, b], olam) < TOL and relerr(dJdu[:, :, b], odu) < TOL
+    cc = lambda t, xx, ll: oracle.control_char_test_problem(oprob, t, xx, ll)
+    for mode in ("discrete", "continuous"):
+        one = integ.fb_sweep(prob, x0, u, nSWEEPS=1, costate=mode)
+        for b in (0, 36):
+            ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, b], u[:, :, b].copy(), cc, nSWEEPS=1, costate=mode)
+            un = integ.get_control_u(b, 1)[:, :, 0]
+            assert relerr(un, ref["u"]) < TOL, (mode, N)
+            assert relerr(one["maxChange"][b], ref["maxChange"]) < 1e-9
+    integ.close()
