@@ -325,21 +325,35 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
     One sweep of one RK4 step of one trajectory = one trajectory-step."""
     import ctypes
     import torch
-    Bt, S = args.bt, 4
+    gen = args.config == "cfg3fb"
+    Bt, S = (100_000 if gen and args.bt == BT else args.bt), 4
     tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
     integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
-    prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
-    x0 = np.random.default_rng(2 + rank).uniform(0.5, 2.5, (1, Bt))
-    u0 = np.full((1, 2 * N_STEPS + 1), 0.5)
+    kw = {}
+    if gen:
+        # BASELINE.json configs[2]: the generated 6-state problem, fb_sweep over 100k control candidates, each a
+        # ChebyshevControl (degree 16) coefficient set; u0 = v*B is evaluated on the device
+        prob = ocs.harvest_chain_problem()
+        ctl = ocs.ChebyshevControl(integ.t, 17, 2)
+        integ.attach_control(ctl)
+        rng = np.random.default_rng(3 + rank)
+        x0 = rng.uniform(1.0, 2.5, (6, Bt))
+        v0 = 0.05 * rng.standard_normal((34, Bt))
+        v0[:2] = rng.uniform(0.2, 0.8, (2, Bt))
+        u0, kw = None, dict(v0=v0)
+    else:
+        prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
+        x0 = np.random.default_rng(2 + rank).uniform(0.5, 2.5, (1, Bt))
+        u0 = np.full((1, 2 * N_STEPS + 1), 0.5)
     integ.set_profiling(True)
     for _ in range(max(1, min(args.warmup, 2))):
-        integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S)
+        integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S, **kw)
     integ.kernel_stats(reset=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     nrep = max(1, min(args.steps, 5))
     for _ in range(nrep):
-        out = integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S)
+        out = integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S, **kw)
     dt = time.perf_counter() - t0
     ks = integ.kernel_stats(reset=True)
     assert (out["sweeps"] == S).all()
@@ -353,8 +367,13 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
     # 16 B control read; costate sweep 4*C_X + 14*m + 2 ControlChar (4 flop each) + change measure (2 x 5) and
     # 8 B state read + 16 B control read + 16 B control write
     ff, fr, bf, br = 4 * 10 + 13 * 2, 4 * 8 + 14 * 2 + 2 * 4 + 10, 24, 40
-    kf = {"kernel": "ocs_fwd_test_fast_u2_b0_p0", "ms": ms_f, "tflops": units * ff / ms_f / 1e9, "gbs": units * bf / ms_f / 1e6}
-    kr = {"kernel": "ocs_fbrev_test_fast_u2_b0_p0", "ms": ms_r, "tflops": units * fr / ms_r / 1e9, "gbs": units * br / ms_r / 1e6}
+    tagk = "test_fast"
+    if gen:     # m = 7, nc = 2: states 48 B/step, controls 32 B/step each way; ControlChar of two controls
+        fl = prob.flops
+        ff, fr, bf, br = 4 * fl["C_F"] + 13 * 7, 4 * fl["C_X"] + 14 * 7 + 2 * 2 * 4 + 2 * 10, 48 + 32, 48 + 32 + 32
+        tagk = "gen"
+    kf = {"kernel": "ocs_fwd_%s_u2_b0_p0" % tagk, "ms": ms_f, "tflops": units * ff / ms_f / 1e9, "gbs": units * bf / ms_f / 1e6}
+    kr = {"kernel": "ocs_fbrev_%s_u2_b0_p0" % tagk, "ms": ms_r, "tflops": units * fr / ms_r / 1e9, "gbs": units * br / ms_r / 1e6}
     dom = kr if ms_r >= ms_f else kf
     fp_frac, hbm_frac = dom["tflops"] / tf.value, dom["gbs"] / hbm_peak
     bound = "hbm" if hbm_frac >= fp_frac else "fp64"
@@ -363,7 +382,10 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
         "value": units * 1e3 / (ms_f + ms_r), "unit": "trajectory-steps/s", "n_gpus": 1, "steps": nrep, "warmup": 1,
         "ms_per_step": (ms_f + ms_r) * S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "fbsweep: fb_sweep iteration of tests/TestOCProblem.m, 2^20 random x0 x 1000 RK4 steps, "
+        "config": {"workload": ("cfg3fb: fb_sweep iteration of the generated 6-state/6-costate harvest-chain problem over 100k "
+                                "control candidates (ChebyshevControl degree 16 each, evaluated on the device) x 1000 RK4 steps, "
+                                "%d sweeps per step" % S) if gen else
+                               "fbsweep: fb_sweep iteration of tests/TestOCProblem.m, 2^20 random x0 x 1000 RK4 steps, "
                                "per-trajectory control on the grid, %d sweeps per step" % S,
                    "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS, "l2": "inputs larger than L2 (8.4 GB states + 16.8 GB controls)"},
         "gpu_launches": int(ks["launches"]),
@@ -371,7 +393,7 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
                      "peak": hbm_peak if bound == "hbm" else tf.value, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                      "frac": max(hbm_frac, fp_frac), "kernel": dom["kernel"], "traffic": None, "peak_source": hbm_src,
                      "kernels": [kf, kr]},
-        "e2e": {"value": nrep * S * units / dt, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 * Bt + 8 * u0.size,
+        "e2e": {"value": nrep * S * units / dt, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 * x0.size + 8 * (kw["v0"].size if gen else u0.size),
                 "d2h_bytes_per_step": 8 * Bt * 2 + 4 * Bt * 2, "api": "ocs_b200_fb_sweep on host buffers"},
     })
     integ.close()
@@ -395,7 +417,7 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg3", "cfg4", "fbsweep", "rows"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
@@ -433,7 +455,7 @@ def main():
     from importlib import import_module
     distmod = import_module("optimal-control-solvers_b200.host.dist")
 
-    if args.config == "fbsweep":
+    if args.config in ("fbsweep", "cfg3fb"):
         run_fbsweep(args, ocs, local_rank, rank, world)
         return
     if args.config == "rows":

@@ -176,7 +176,9 @@ OCS_B200_API int ocs_b200_fetch_adjoints(ocs_b200_handle *h, int segment, long b
  * sweeps): u lives on the G grid points per trajectory; per sweep  x = forward(u), lam = adjoint(u),
  * uNew = ControlChar(t, x, lam) clamped to bounds (make_from_symbolic.m:102-112), convergence
  * max_j |uNew-u| / (uRelTol |u| + uAbsTol) <= 1 (fb_sweep.m:107-110) per trajectory.
- *   x0 [n x Bt]; u0 [nc x G x nbatch] initial control (nbatch in {1, Bt});
+ *   x0 [n x Bt]; u0 [nc x G x nbatch] initial control (nbatch in {1, Bt}), or NULL: start from the coefficients of
+ *   ocs_b200_set_control_v through the attached basis, u0 = reshape(v,nc,[])*B evaluated on the device (one
+ *   control candidate per trajectory without uploading nc x G x Bt values);
  *   bounds [nc x 2] ControlBounds; relax = 1 is the reference's pure replacement (fb_sweep.m:96).
  *   J [Bt], sweeps [Bt] (sweeps used), converged [Bt] (0/1), max_change [Bt]: any may be NULL.
  * The converged control stays on the device (ocs_b200_get_control_u), states/adjoints via fetch_*. */

@@ -486,6 +486,34 @@ __global__ void __launch_bounds__(128) dense_project_kernel(const double *__rest
         }
 }
 
+// ug[c][j][b] = sum_k v[(k*nc+c)][b] B(k,j): control.compute_u for every trajectory (Control/*Control.m compute_u),
+// from the basis records of build_records (sparse: the two weights by knot parity; dense: the column B(:,j)), in
+// the summation order of ControlEval.  Used once per fb_sweep solve that starts from coefficients.
+__global__ void __launch_bounds__(128) basis_eval_kernel(const double *__restrict__ v, const double *__restrict__ basrec,
+                                                         int BW, int sparse, int K, int nc, int G, long nb, long ldb,
+                                                         double *__restrict__ ug)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    for (int j = 0; j < G; ++j) {
+        const double *rec = basrec + (size_t)j * BW;
+        for (int c = 0; c < nc; ++c) {
+            double u;
+            if (sparse) {
+                const int k = ocs_host::rec_k(rec);
+                const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
+                const double vE = ke < K ? v[(size_t)(ke * nc + c) * ldb + b] : 0.0;
+                const double vO = ko < K ? v[(size_t)(ko * nc + c) * ldb + b] : 0.0;
+                u = vE * rec[1] + vO * rec[2];
+            } else {
+                u = v[(size_t)c * ldb + b] * rec[0];
+                for (int k = 1; k < K; ++k) u = u + v[(size_t)(k * nc + c) * ldb + b] * rec[k];
+            }
+            ug[((size_t)c * G + j) * ldb + b] = u;
+        }
+    }
+}
+
 __global__ void broadcast_rows_kernel(const double *__restrict__ col, double *dst, long rows, long nb)
 {
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1676,8 +1704,25 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
 {
     if (!h) return OCS_B200_ERR_ARG;
     TRY(check_ready(h));
-    if (!x0 || !u0 || !bounds || Bt < 1 || nSWEEPS < 1 || (u0_nbatch != 1 && u0_nbatch != Bt))
+    if (!x0 || !bounds || Bt < 1 || nSWEEPS < 1 || (u0 && u0_nbatch != 1 && u0_nbatch != Bt))
         return h->fail(OCS_B200_ERR_ARG, "bad fb_sweep arguments");
+    // u0 == NULL: start from the coefficients of ocs_b200_set_control_v, u0 = reshape(v,nc,[])*B
+    std::vector<double> u0_from_v;
+    bool u0_on_device = false;
+    if (!u0) {
+        if (h->basis_kind == BASIS_NONE || (h->ctrl_mode != CTRL_V_SHARED && h->ctrl_mode != CTRL_V_BATCH))
+            return h->fail(OCS_B200_ERR_STATE, "fb_sweep without u0 needs a basis and coefficients v (ocs_b200_set_control_v)");
+        TRY(validate_control(h, Bt));
+        if (h->ctrl_mode == CTRL_V_SHARED) {
+            const int G0 = 2 * h->seg[0].N + 1, nc0 = h->kt.nc;
+            u0_from_v.resize((size_t)nc0 * G0);
+            for (int j = 0; j < G0; ++j) shared_u_from_v(h, j, &u0_from_v[(size_t)nc0 * j]);
+            u0 = u0_from_v.data();
+            u0_nbatch = 1;
+        } else {
+            u0_on_device = true;
+        }
+    }
     if (h->has_tail) return h->fail(OCS_B200_ERR_ARG, "fb_sweep runs on a finite horizon");
     try {
         CK(cudaSetDevice(h->device));
@@ -1687,7 +1732,16 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
         TRY(alloc_batch(h, Bt));
         TRY(upload_soa(h, x0, h->d_x0, n, Bt));
         // control on the grid, one copy per trajectory
-        if (u0_nbatch == Bt) {
+        if (u0_on_device) {
+            h->seg[0].basis_dirty = h->seg[0].basis_dirty || h->seg[0].BW == 0;
+            TRY(build_records(h, 0));      // basis records of the attached control
+            TRY(ensure(h, h->d_ug, (size_t)nc * G * Bt));
+            const double *vp = h->v_ext ? h->v_ext : h->d_v.p;
+            basis_eval_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
+                vp, h->seg[0].d_basrec, h->seg[0].BW, h->basis_kind == BASIS_SPARSE, h->K, nc, G, Bt, Bt, h->d_ug.p);
+            CK(cudaGetLastError());
+            h->launches++;
+        } else if (u0_nbatch == Bt) {
             TRY(upload_soa(h, u0, h->d_ug, (long)nc * G, Bt, nc));
         } else {
             TRY(ensure(h, h->d_ug, (size_t)nc * G * Bt));

@@ -308,7 +308,7 @@ class CudaRK4Integrator:
         return val.value, idx.value
 
     # ------------------------------------------------------------------ fb_sweep on the RK4 grid
-    def fb_sweep(self, prob, x0, u0, uRelTol=1e-7, uAbsTol=1e-7, nSWEEPS=50, relax=1.0, costate="discrete"):
+    def fb_sweep(self, prob, x0, u0=None, uRelTol=1e-7, uAbsTol=1e-7, nSWEEPS=50, relax=1.0, costate="discrete", v0=None):
         """The sweep loop of functions/fb_sweep.m:79-115 with the RK4 forward / discrete-adjoint
         sweeps in place of odevr7, for every trajectory.  u0: nc x G shared or nc x G x Bt.
         costate="continuous" integrates the v1 API's adjointRHS (make_from_symbolic.m:11-14,
@@ -317,13 +317,20 @@ class CudaRK4Integrator:
         if costate not in ("discrete", "continuous"):
             raise ValueError("costate must be 'discrete' or 'continuous'")
         self._ck(self._lib.ocs_b200_set_fb_costate(self._h, 1 if costate == "continuous" else 0))
+        if u0 is None:          # start from coefficients: u0 = control.compute_u(v0), evaluated on the device
+            if v0 is None or self._control is None:
+                raise ValueError("fb_sweep needs u0, or v0 together with an attached control")
+            self._set_v(v0)
         x0f, single = self._x0(x0)
         Bt = x0f.shape[1]
-        u0 = np.asarray(u0, dtype=np.float64)
-        if u0.ndim == 1:
-            u0 = u0.reshape(1, -1)
-        nbu = 1 if u0.ndim == 2 else u0.shape[2]
-        u0f = _lib.f64(u0)
+        if u0 is None:
+            u0f, nbu = None, 0
+        else:
+            u0 = np.asarray(u0, dtype=np.float64)
+            if u0.ndim == 1:
+                u0 = u0.reshape(1, -1)
+            nbu = 1 if u0.ndim == 2 else u0.shape[2]
+            u0f = _lib.f64(u0)
         cb = _lib.f64(np.asarray(prob.ControlBounds, dtype=np.float64).reshape(-1, 2))
         out = dict(J=np.empty(Bt), sweeps=np.empty(Bt, dtype=np.int32), converged=np.empty(Bt, dtype=np.int32),
                    maxChange=np.empty(Bt))

@@ -227,3 +227,30 @@ def test_error_conventions(ocs):
     assert e.value.code == ocs._lib.ERR_STATE
     with pytest.raises(ValueError):
         integ.compute_states(prob, 1.0, np.zeros((1, 5)))
+
+
+@pytest.mark.parametrize("kind,K", [("pwl", 11), ("pwc", 8), ("cheb", 6)])
+def test_fb_sweep_started_from_coefficients(ocs, oracle, kind, K):
+    """fb_sweep over control CANDIDATES: u0 = control.compute_u(v) evaluated on the device for every trajectory
+    (ocs_b200_fb_sweep with u0 = NULL) equals handing the same grids over from the host, and the oracle."""
+    tspan, integ, prob, oprob, ointeg, ctl, octl = _setup(ocs, oracle, N=120, T=3.0, K=K, kind=kind)
+    integ.attach_control(ctl)
+    rng = np.random.default_rng(14)
+    Bt = 130
+    x0 = rng.uniform(.5, 2.5, (1, Bt))
+    v = rng.uniform(.1, .9, (K, Bt)) if kind != "cheb" else np.vstack([rng.uniform(.3, .7, (1, Bt)), .05 * rng.standard_normal((K - 1, Bt))])
+    u0 = np.stack([ctl.compute_u(v[:, b]) for b in range(Bt)], axis=2)           # nc x G x Bt on the host
+    a = integ.fb_sweep(prob, x0, v0=v, nSWEEPS=1)
+    ua = integ.get_control_u(0, Bt)
+    b_ = integ.fb_sweep(prob, x0, u0, nSWEEPS=1)
+    ub = integ.get_control_u(0, Bt)
+    assert relerr(ua, ub) < TOL and relerr(a["J"], b_["J"]) < TOL and relerr(a["maxChange"], b_["maxChange"]) < 1e-8
+    cc = lambda t, x, lam: oracle.control_char_test_problem(oprob, t, x, lam)
+    for b in (0, 129):
+        ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, b], octl.compute_u(v[:, b]), cc, nSWEEPS=1)
+        assert relerr(ua[:, :, b], ref["u"]) < TOL and relerr(a["J"][b], ref["J"]) < TOL
+    # a shared coefficient vector works too
+    s = integ.fb_sweep(prob, x0, v0=v[:, 0], nSWEEPS=1)
+    assert relerr(s["J"][0], a["J"][0]) < TOL
+    with pytest.raises(ValueError):
+        integ.fb_sweep(prob, x0)
