@@ -68,3 +68,83 @@ def test_cfg2_full_size_adjoint_equals_finite_difference(ocs):
     Jm = integ.evaluate(prob, x0, vm, gradient=False)["J"]
     cd = (Jp - Jm) / (2 * eps)
     assert np.max(np.abs(cd - g[k])) < 2e-8 * max(1.0, np.max(np.abs(g[k])))
+
+
+def test_cfg4_full_size_infinite_horizon_sample_vs_oracle(ocs, oracle):
+    """BASELINE.json configs[3]: RK4InfiniteIntegrator, 262144 trajectories x (10000 + 10000) steps, 42 GB of
+    node states in HBM; a sample against the C oracle's RK4InfiniteIntegrator."""
+    Bt, N, K = 1 << 18, 10_000, 101
+    uStar = 0.723368780097983
+    ts, te = ocs.matlab_linspace(0.0, 100.0, N + 1), ocs.matlab_linspace(100.0, 200.0, N + 1)
+    integ = ocs.CudaRK4InfiniteIntegrator(ts, te, uStar)
+    ctl = ocs.PWLinearControl(integ.t, K, 1)
+    integ.attach_control(ctl)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    v = np.full(K, uStar) + 0.05 * np.random.default_rng(1).standard_normal(K)
+    x0 = np.random.default_rng(4).uniform(.5, 2.5, (1, Bt))
+    out = integ.evaluate(prob, x0, v)
+    assert not out["status"].any()
+    idx = np.random.default_rng(3).choice(Bt, 48, replace=False)
+    idx[:2] = [0, Bt - 1]
+    ref = oracle.C.evaluate(list(TEST_PARAMS.values()), ts, ctl.B, x0[:, idx], v, tspan_extra=te, uStar=uStar)
+    assert relerr(out["J"][idx], ref["J"]) < TOL and relerr(out["xT"][:, idx], ref["xT"]) < TOL
+    assert relerr(out["dJdv"][:, idx], ref["dJdv"]) < TOL and relerr(out["lam0"][:, idx], ref["lam0"]) < TOL
+    integ.close()
+
+
+def test_fb_sweep_full_size_properties(ocs, oracle):
+    """The fb_sweep iteration on 2^20 trajectories x 1000 steps (16.8 GB of per-trajectory controls): every
+    trajectory converges, converged ones are frozen (a second call changes nothing), the fixed point satisfies
+    the control characterisation, and two sampled trajectories match the oracle's composition sweep for sweep."""
+    Bt, N = 1 << 20, 1000
+    tspan = ocs.matlab_linspace(0.0, 10.0, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    x0 = np.random.default_rng(2).uniform(.5, 2.5, (1, Bt))
+    u0 = np.full((1, 2 * N + 1), .5)
+    out = integ.fb_sweep(prob, x0, u0, nSWEEPS=50)
+    assert out["converged"].all() and out["maxChange"].max() <= 1.0 and out["sweeps"].max() <= 50
+    oprob, ointeg = oracle.TestOCProblem(**TEST_PARAMS), oracle.RK4Integrator(tspan)
+    cc = lambda t, x, lam: oracle.control_char_test_problem(oprob, t, x, lam)
+    for b in (0, Bt - 1):
+        ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, b], u0.copy(), cc, nSWEEPS=50)
+        assert ref["converged"] and out["sweeps"][b] == ref["sweeps"]
+        assert relerr(out["J"][b], ref["J"]) < 1e-9
+        un = integ.get_control_u(b, 1)[:, :, 0]
+        assert np.max(np.abs(un - ref["u"])) < 1e-6
+        # fixed point: u = ControlChar(t, x(u), lam(u)) up to the sweep tolerance
+        x, _ = ointeg.compute_states(oprob, x0[:, b], un)
+        lam = ointeg.compute_adjoints(oprob, un, want_dJdu=False)
+        fix = cc(ointeg.t, oracle._nodes_to_grid(x[:-1]), oracle._nodes_to_grid(lam[:-1]))
+        assert np.max(np.abs(fix - un)) < 1e-6
+    integ.close()
+
+
+def test_cfg3_full_size_sample_vs_oracle(ocs, oracle):
+    """BASELINE.json configs[2] at full size: the generated 6-state problem, 100k Chebyshev (degree 16) control
+    candidates x 1000 steps; sampled candidates against the NumPy oracle (lambdified twin of the same
+    expressions)."""
+    import importlib
+    from gen_util import oracle_problem
+    cg = importlib.import_module("optimal-control-solvers_b200.codegen")
+    prob = cg.harvest_chain_problem()
+    oprob = oracle_problem(oracle, prob)
+    Bt, N, K = 100_000, 1000, 17
+    tspan = ocs.matlab_linspace(0.0, 10.0, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ctl = ocs.ChebyshevControl(integ.t, K, 2)
+    integ.attach_control(ctl)
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    v = np.vstack([rng.uniform(.2, .8, (2, Bt)), 0.05 * rng.standard_normal((2 * (K - 1), Bt))])
+    out = integ.evaluate(prob, x0, v)
+    assert not out["status"].any()
+    ointeg = oracle.RK4Integrator(tspan)
+    octl = oracle.ChebyshevControl(ointeg.t, K, 2)
+    for b in (0, 54_321, Bt - 1):
+        u = octl.compute_u(v[:, b])
+        x, J = ointeg.compute_states(oprob, x0[:, b], u)
+        lam, dJdu = ointeg.compute_adjoints(oprob, u)
+        assert relerr(out["J"][b], J) < TOL and relerr(out["xT"][:, b], x[:-1, -1]) < TOL
+        assert relerr(out["dJdv"][:, b], octl.compute_dJdv(dJdu)) < TOL and relerr(out["lam0"][:, b], lam[:, 0]) < TOL
+    integ.close()
