@@ -399,6 +399,90 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
     integ.close()
 
 
+def run_solve(args, ocs, local_rank, rank, world):
+    """--config cfg2solve: BASELINE.json configs[1] as literally stated -- the batched single_shooting SOLVE
+    (functions/single_shooting.m:114) of 2^20 random initial conditions x 1000 RK4 steps, PWLinearControl K = 101,
+    box bounds from compute_nlp_bounds -- through the host-buffer C ABI (ocs_b200_single_shooting): x0 goes up,
+    vOpt, J, iters, converged come down, every objective/gradient evaluation stays on the device.  One bench "step"
+    is one whole solve; a trajectory-step is one RK4 step (forward + adjoint) of one trajectory that was still
+    open (converged trajectories are skipped by the sweeps and not counted)."""
+    import torch
+    import torch.distributed as dist
+    Bt = args.bt
+    dev = torch.device("cuda", local_rank)
+    prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
+    integ = ocs.CudaRK4Integrator(ocs.matlab_linspace(0.0, T_END, N_STEPS + 1), device=local_rank)
+    ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+    integ.attach_control(ctl)
+    x0 = np.random.default_rng(2 + rank).uniform(0.5, 2.5, (1, Bt))
+    Lb, Ub = ctl.compute_nlp_bounds(prob.ControlBounds)
+    v0 = ctl.compute_initial_v(0.5)
+    max_iter, tol = 200, 1e-6
+    # pinned host buffers for the results (vOpt is 848 MB)
+    restore = _bind_to_gpu_numa_node(local_rank)
+    v_h = torch.empty((Bt, K_PWL), dtype=torch.float64).pin_memory()       # MATLAB (nc*K) x Bt, column-major
+    J_h = torch.empty(Bt, dtype=torch.float64).pin_memory()
+    it_h, cv_h = torch.empty(Bt, dtype=torch.int32).pin_memory(), torch.empty(Bt, dtype=torch.int32).pin_memory()
+    v_h.view(-1)[::512].add_(0)
+    restore()
+    bufs = dict(v=v_h.numpy().T, J=J_h.numpy(), iters=it_h.numpy(), converged=cv_h.numpy())
+
+    def solve():
+        return integ.single_shooting(prob, x0, v0, Lb, Ub, max_iter=max_iter, tol=tol, out=bufs)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    for _ in range(max(1, min(args.warmup, 2))):
+        ss = solve()
+    reps = max(1, min(args.steps, 3))
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    integ.kernel_stats(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ss = solve()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = integ.kernel_stats(reset=True)["launches"]
+    evals = float(ss["iters"].astype(np.int64).sum())        # objective/gradient evaluations actually carried out
+    t = torch.tensor([dt, evals, float(ss["converged"].sum()), float(ss["iters"].max())], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, evals, nconv, itmax = float(tm[0]), float(t[1]), float(t[2]), float(tm[3])
+    else:
+        dt, evals, nconv, itmax = (float(z) for z in t)
+    integ.close()
+    if rank == 0:
+        per = dt / reps
+        val = evals * N_STEPS / per
+        nv = K_PWL
+        emit({"metric": "FP64 trajectory-steps/sec (batched single_shooting solve, fwd+adjoint RK4 sweeps)", "value": val,
+              "unit": "trajectory-steps/s", "n_gpus": world, "steps": reps, "warmup": max(1, min(args.warmup, 2)),
+              "ms_per_step": 1e3 * per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+              "data": "synthetic",
+              "config": {"workload": "cfg2solve: batched single_shooting solve of tests/TestOCProblem.m, 2^20 random x0 x 1000 "
+                                     "RK4 steps, PWLinearControl K=101 with box bounds, spectral projected gradient on the "
+                                     "device, tol 1e-6 on the projected gradient, host buffers in and out",
+                         "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS, "max_iter": max_iter,
+                         "timing": "wall clock around the C-ABI call (copies included), max over ranks",
+                         "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * N_STEPS * Bt)},
+              "clocks": clocks, "gpu_launches": int(launches),
+              "solve": {"solves_per_s": world * Bt / per, "converged": int(nconv), "trajectories": world * Bt,
+                        "mean_evaluations": evals / (world * Bt), "max_evaluations": int(itmax)},
+              "e2e": {"value": val, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 * Bt + 8 * 3 * nv,
+                      "d2h_bytes_per_step": 8 * Bt * (nv + 1) + 8 * Bt,
+                      "api": "ocs_b200_single_shooting on host buffers: x0 up; vOpt, J, iters, converged down"}})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def emit(obj):
     line = (json.dumps(obj) + "\n").encode()
     if _REAL_STDOUT is None:
@@ -417,7 +501,7 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg2solve", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
@@ -457,6 +541,9 @@ def main():
 
     if args.config in ("fbsweep", "cfg3fb"):
         run_fbsweep(args, ocs, local_rank, rank, world)
+        return
+    if args.config == "cfg2solve":
+        run_solve(args, ocs, local_rank, rank, world)
         return
     if args.config == "rows":
         if rank == 0:

@@ -343,10 +343,12 @@ class CudaRK4Integrator:
         return out
 
     # ------------------------------------------------------------------ batched single shooting on the device
-    def single_shooting(self, prob, x0, v0, Lb, Ub, FreeInitStates=(), FreeStateBounds=None, max_iter=200, tol=1e-6):
+    def single_shooting(self, prob, x0, v0, Lb, Ub, FreeInitStates=(), FreeStateBounds=None, max_iter=200, tol=1e-6,
+                        out=None):
         """The fmincon solve of functions/single_shooting.m:114 for every trajectory at once, on the device
         (spectral projected gradient; see ocs_b200_single_shooting).  v0: (nc*K,) shared or (nc*K, Bt).
-        Returns dict(v, J, iters, converged): v is (nc*K + nfree, Bt)."""
+        Returns dict(v, J, iters, converged): v is (nc*K + nfree, Bt).  `out` may supply those four arrays
+        (e.g. views of pinned host memory; v column-major)."""
         if self._control is None:
             raise RuntimeError("attach_control(control) first")
         self._bind(prob)
@@ -365,8 +367,13 @@ class CudaRK4Integrator:
         if nf:
             fb = np.asarray(FreeStateBounds, dtype=np.float64).reshape(nf, 2)
             flb, fub = _lib.f64(fb[:, 0].copy()), _lib.f64(fb[:, 1].copy())
-        out = dict(v=np.empty((nv + nf, Bt), order="F"), J=np.empty(Bt), iters=np.empty(Bt, dtype=np.int32),
-                   converged=np.empty(Bt, dtype=np.int32))
+        if out is None:
+            out = dict(v=np.empty((nv + nf, Bt), order="F"), J=np.empty(Bt), iters=np.empty(Bt, dtype=np.int32),
+                       converged=np.empty(Bt, dtype=np.int32))
+        elif (out["v"].shape != (nv + nf, Bt) or not out["v"].flags.f_contiguous or out["v"].dtype != np.float64
+              or out["J"].shape != (Bt,) or out["J"].dtype != np.float64
+              or any(out[k].shape != (Bt,) or out[k].dtype != np.int32 for k in ("iters", "converged"))):
+            raise ValueError("out: v (nc*K+nfree, Bt) float64 column-major, J (Bt,) float64, iters/converged (Bt,) int32")
         self._ck(self._lib.ocs_b200_single_shooting(
             self._h, _lib.dp(x0f), Bt, _lib.dp(v0f), nb0, _lib.dp(Lbf), _lib.dp(Ubf), nf,
             _lib.ip(free) if nf else None, _lib.dp(flb), _lib.dp(fub), int(max_iter), float(tol),
