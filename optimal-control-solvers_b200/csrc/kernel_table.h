@@ -22,5 +22,7 @@ struct ocs_kernel_table {
     const void *fbrev[2];
     const void *fbcont[2];      // fb_sweep with the continuous costate equation (v1 adjointRHS) instead of the discrete adjoint
     const void *tt;
+    int nfold[3];               // weight-folded table entries per hoisting mode (0: the problem / build does not fold)
+    const void *fold;           // fills the fold records [N][even(3*nfold)] from the grid-point and step records
     const void *eq;             // batched compute_equilibrium (one parameter set per thread)
 };

@@ -28,7 +28,7 @@
 #define OCS_MINBLOCKS_FB 8
 #endif
 #ifndef OCS_TPT_FWD
-#define OCS_TPT_FWD 3
+#define OCS_TPT_FWD 4
 #endif
 // Per-trajectory coefficients v (UMODE_COEF, what a batched single_shooting solve evaluates; bench.py --config cfg2v).
 // Same-box A/B of (trajectories per thread, min blocks/SM): forward (3,1: 134 regs) 3.88 ms / (3,4) 3.32 / (2,6) 3.29 /
@@ -105,5 +105,7 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->fbrev[0] = FBR(0); t->fbrev[1] = FBR(1);
     t->fbcont[0] = FBC(0); t->fbcont[1] = FBC(1);
     t->tt = (const void *)OCS_CAT2(ocs_tt_, OCS_TAGNAME);
+    for (int hm = 0; hm < 3; ++hm) t->nfold[hm] = OCS_NS::ocs_nfold<P>(hm);
+    t->fold = (const void *)OCS_CAT2(ocs_fold_, OCS_TAGNAME);
     t->eq = (const void *)OCS_CAT2(ocs_eq_, OCS_TAGNAME);
 }

@@ -126,7 +126,8 @@ int ocs_compile_unit(const char *source, const char *unit, int strict, const cha
         return OCS_B200_ERR_COMPILE;
     }
     const std::string inc = std::string("-I") + (include_dir ? std::string(include_dir) : default_include_dir());
-    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", inc.c_str(),
+    // -default-device: generic lambdas inside the sweep bodies carry no execution-space annotation
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device", inc.c_str(),
                                       strict ? "--fmad=false" : "--fmad=true"};
     r = rt.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t logsz = 0;

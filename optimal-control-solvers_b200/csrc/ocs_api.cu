@@ -40,6 +40,8 @@ void ocs_unload_problem(void *library);
 
 namespace {
 
+constexpr int OCS_FOLD_MAX = 15;     // most folded table entries per stage position a problem may declare
+
 std::string g_create_error = "";
 std::mutex g_mutex;
 
@@ -47,6 +49,8 @@ struct Segment {
     int N = 0;
     std::vector<double> tspan, t, h;
     double *d_gprec = nullptr, *d_steprec = nullptr, *d_basrec = nullptr;
+    double *d_foldrec = nullptr;            // weight-folded table entries [N][even(3*nfold)] (rk4_kernels.cuh), or null
+    int fold_nf = 0;                        // nfold the fold records were built for (0: none)
     size_t gprec_cap = 0, basrec_cap = 0;   // doubles
     double *h_rec = nullptr;  // pinned staging of the records (async upload)
     size_t h_rec_cap = 0;
@@ -658,6 +662,14 @@ int build_records(H *h, int si)
         void *args[] = {(void *)&s.d_gprec, (void *)&Gv, (void *)&hmv, (void *)&h->d_params.p};
         CK(cudaLaunchKernel(h->kt.tt, dim3((G + 127) / 128), dim3(128), args, 0, h->stream));
     }
+    s.fold_nf = h->kt.fold ? h->kt.nfold[hm] : 0;
+    if (s.fold_nf > 0) {        // stage weights folded into the table entries they multiply, once per step
+        if (!s.d_foldrec) CK(cudaMalloc(&s.d_foldrec, (size_t)N * 3 * (OCS_FOLD_MAX + 1) * sizeof(double)));
+        if (s.fold_nf > OCS_FOLD_MAX) return h->fail(OCS_B200_ERR_ARG, "too many folded table entries");
+        int hmv = hm, Nv = N;
+        void *args[] = {(void *)&s.d_gprec, (void *)&s.d_steprec, (void *)&s.d_foldrec, (void *)&Nv, (void *)&hmv};
+        CK(cudaLaunchKernel(h->kt.fold, dim3((N + 127) / 128), dim3(128), args, 0, h->stream));
+    }
     s.records_dirty = false;
     return 0;
 }
@@ -689,6 +701,7 @@ void base_args(H *h, int si, SweepArgs &a)
     a.BW = s.BW;
     a.gprec = s.d_gprec;
     a.steprec = s.d_steprec;
+    a.foldrec = s.fold_nf > 0 ? s.d_foldrec : nullptr;
     a.basrec = s.d_basrec;
     a.p = h->d_params.p;
     a.ldp = h->params_nbatch > 1 ? h->params_nbatch : 0;
@@ -699,7 +712,10 @@ void base_args(H *h, int si, SweepArgs &a)
 size_t smem_bytes(const H *h, const SweepArgs &a, size_t acc_doubles)
 {
     const int S = h->kt.tile;
-    return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW + acc_doubles) * sizeof(double);
+    int nf = 0;     // fold records of the tile (same width for every hoisting mode that folds)
+    for (int hm = 0; hm < 3; ++hm) nf = std::max(nf, h->kt.fold ? h->kt.nfold[hm] : 0);
+    const size_t fold = a.foldrec ? (size_t)S * ((3 * nf + 1) & ~1) : 0;
+    return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW + acc_doubles + fold) * sizeof(double);
 }
 
 // acc_doubles: shared-memory doubles per block beyond the record tiles (dense-basis gradient accumulators)
@@ -833,6 +849,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         a.xs = s.d_xs + b0;
         int um = 0, bm = 0;
         bool project = false;
+        a.lamJ_one = 1;      // lamT = e_m (RK4Integrator.m:63-66) unless the caller supplies one
         if (si == 1) {
             TRY(ensure(h, h->d_lamT_tail, (size_t)m * Bt));
             a.lam0 = h->d_lamT_tail.p + b0;
@@ -846,11 +863,14 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             }
         } else {
             if (h->has_tail) {
+                // lam2(:,1) of the tail sweep, which started from e_m: its last row is still exactly 1
+                // (the last row of dFdx_times_vec is zero, OCProblem.m:17-19)
                 a.lamT = h->d_lamT_tail.p + b0;
                 a.ldl = Bt;
             } else if (d_lamT) {
                 a.lamT = d_lamT + (ldl ? b0 : 0);
                 a.ldl = ldl;
+                a.lamJ_one = 0;      // arbitrary terminal costate: the unfolded adjoint chain
             }
             a.dJdv = d_dJdv;
             a.dJdv_store = h->bk_monotone ? 1 : 0;
@@ -1077,6 +1097,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     for (int si = 0; si < 2; ++si) {
         cudaFree(h->seg[si].d_gprec);
         cudaFree(h->seg[si].d_steprec);
+        cudaFree(h->seg[si].d_foldrec);
         cudaFree(h->seg[si].d_basrec);
         if (h->seg[si].h_rec) cudaFreeHost(h->seg[si].h_rec);
         if (h->seg[si].rec_uploaded) cudaEventDestroy(h->seg[si].rec_uploaded);

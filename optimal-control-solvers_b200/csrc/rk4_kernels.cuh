@@ -80,6 +80,23 @@
                             // Measured on B200 (profiles/r1_notes.md): 0: 3.71 ms, 2: 3.90, 4: 3.75, 8: 3.76 -- the
                             // FP64-bound gradient kernel does not gain from it, the HBM-bound fb_sweep kernel does.
 #endif
+// Sparse-basis window moves by predicated loads (1) or under a branch (0), per sweep direction; and whether the
+// forward sweep with per-trajectory coefficients folds the stage weights.  Same-box A/B on cfg2v (forward /
+// reverse ms): branch, no fold 2.91 / 5.59; branch + fold 3.16 / 6.01; predicated, no fold 3.69 / 6.06;
+// predicated + fold 3.74 / 5.24 -- so the forward sweep keeps the branch and does not fold, the reverse sweep
+// does both (profiles/r1_notes.md).
+#ifndef OCS_SLIDE_PRED_FWD
+#define OCS_SLIDE_PRED_FWD 0
+#endif
+#ifndef OCS_SLIDE_PRED_REV
+#define OCS_SLIDE_PRED_REV 1
+#endif
+#ifndef OCS_FOLD_FWD_COEF
+#define OCS_FOLD_FWD_COEF 0
+#endif
+#ifndef OCS_PRED_CLOBBER
+#define OCS_PRED_CLOBBER 1
+#endif
 #ifndef OCS_KDENSE_MAX
 #define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
 #endif
@@ -108,6 +125,32 @@ __host__ __device__ constexpr int ocs_hoist_mode(int umode, bool params_batched)
     return params_batched ? 0 : (umode == 0 ? 2 : 1);
 }
 
+// Weight folding (see problem_test.cuh): a problem may declare `nfold` table entries that meet the RK4 stage
+// weight of the objective row; they are multiplied by that weight once per step and stage position into the
+// fold records [N][ocs_fold_width] = [ L: fold(tt_L, h/6) | M: fold(tt_M, h/3) | R: fold(tt_R, h/6) | pad ] and
+// the sweeps call the problem's Ff / Xf / Uf.  Only in the FMA-contracted build (it re-associates products),
+// only when a table exists (uniform parameters), and in the adjoint sweep only while lam(end) == 1.
+template <bool B>
+struct ocs_bool { static constexpr bool value = B; };
+template <class P, class Tag>
+struct ocs_dep { typedef P type; };      // P, made dependent on Tag (calls in discarded if-constexpr branches of generic lambdas)
+template <class P>
+struct ocs_fold_traits {
+    template <class Q> __host__ __device__ static constexpr int get(decltype(Q::nfold) *) { return Q::nfold; }
+    template <class Q> __host__ __device__ static constexpr int get(...) { return 0; }
+    static constexpr int value = get<P>(nullptr);
+};
+template <class P>
+__host__ __device__ constexpr int ocs_nfold(int hm)
+{
+#if (defined(OCS_STRICT) && OCS_STRICT) || defined(OCS_NOFOLD)
+    return 0;
+#else
+    return hm == 0 ? 0 : ocs_fold_traits<P>::value;
+#endif
+}
+__host__ __device__ constexpr int ocs_fold_width(int nfold) { return ocs_even(3 * nfold); }
+
 // Argument block of one sweep over one RK4 segment (main horizon or tail).
 // SoA device arrays have leading dimension ldb (the batch stride); the kernel
 // handles trajectories [0, nb) of them, so a sub-range is a pointer offset.
@@ -121,6 +164,9 @@ struct SweepArgs {
     long ldp;               // batch stride of per-trajectory params
     const double *gprec;    // [2N+1][RB]
     const double *steprec;  // [N][4]     h, h/2, h/3, h/6
+    const double *foldrec;  // [N][ocs_fold_width(nfold)] weight-folded table entries, or null (problem without fold)
+    int lamJ_one;           // reverse sweep: lam(end) == 1 for every trajectory (lamT null, or chained from a tail
+                            // sweep that started from e_m), so the folded adjoint chain applies
     const double *basrec;   // [2N+1][BW]
     const double *x0;       // [n][ldb]
     const double *p;        // [np] or [np][ldp]
@@ -172,6 +218,17 @@ __device__ __forceinline__ const double *soa_row(const double *base, unsigned ro
 
 // The first slot of a sparse basis record packs two ints (knot index k, flags) into one double; they are
 // taken apart with a bit cast of the loaded double, never through an int-typed pointer (no aliasing games).
+// dst = *p if pred (a predicated load, never a branch)
+__device__ __forceinline__ void ld_global_if(double &dst, const double *p, bool pred)
+{
+#if OCS_PRED_CLOBBER
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.f64 %0, [%1];\n\t}"
+                 : "+d"(dst) : "l"(p), "r"((unsigned)pred) : "memory");
+#else
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.f64 %0, [%1];\n\t}"
+        : "+d"(dst) : "l"(p), "r"((unsigned)pred));
+#endif
+}
 __device__ __forceinline__ int rec_k(const double *bas) { return (int)(__double_as_longlong(bas[0]) & 0xffffffffLL); }
 __device__ __forceinline__ int rec_flags(const double *bas) { return (int)(__double_as_longlong(bas[0]) >> 32); }
 
@@ -193,6 +250,8 @@ struct ControlEval {
     __device__ __forceinline__ void init(const SweepArgs &a, long bb)
     {
         kcur = -0x40000000;
+#pragma unroll
+        for (int c = 0; c < ((UMODE == UMODE_COEF && BMODE == BMODE_SPARSE) ? nc : 1); ++c) vE[c] = vO[c] = 0.0;
         ugb = UMODE == UMODE_GRID ? a.ug + bb : nullptr;
         ld8 = (unsigned)a.ldb * 8u;
         if constexpr (UMODE == UMODE_COEF && BMODE == BMODE_DENSE) {
@@ -208,9 +267,26 @@ struct ControlEval {
 
     // Sparse basis, part 1: make {k, k+1} the live window of grid point j.  The branch is uniform across the
     // batch (every trajectory shares the grid) and taken ~K times per sweep.
+    template <bool PRED = false>
     __device__ __forceinline__ void slide(const SweepArgs &a, const double *bas, long bb)
     {
         const int k = rec_k(bas);
+        if constexpr (PRED) {
+        // Predicated loads instead of a branch: the move is uniform across the batch, but the compiler cannot
+        // know that and may wrap a branch in BSSY/BSYNC, splitting the arithmetic of the step into basic blocks
+        // (measured: +8 % on the forward sweep).  A slot whose knot lies outside the basis keeps its previous
+        // (finite; 0 at the start) value and meets weight 0 in value().
+        const bool mv = k != kcur;
+        const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
+        const unsigned ld8v = (unsigned)a.ldb * 8u;
+#pragma unroll
+        for (int c = 0; c < nc; ++c) {
+            ld_global_if(vE[c], soa_row(a.v + bb, (unsigned)(ke * nc + c), ld8v), mv && ke < a.K);
+            ld_global_if(vO[c], soa_row(a.v + bb, (unsigned)(ko * nc + c), ld8v), mv && ko < a.K);
+        }
+        kcur = k;
+        return;
+        }
         if (k != kcur) {
             const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
 #pragma unroll
@@ -401,12 +477,14 @@ __device__ __forceinline__ void copy_to_smem(double *dst, const double *src, int
 // Copies the grid-point records [2*i0, 2*(i0+ns)], step records [i0, i0+ns) and (BW > 0) basis
 // records of one tile into shared memory.  All threads of the block take part.
 template <int RB>
-__device__ __forceinline__ void stage_tile(const SweepArgs &a, int i0, int ns, int BW, double *gp, double *st, double *bs)
+__device__ __forceinline__ void stage_tile(const SweepArgs &a, int i0, int ns, int BW, double *gp, double *st, double *bs,
+                                           double *fo = nullptr, int FW = 0)
 {
     __syncthreads();   // the previous tile has been consumed by every warp
     copy_to_smem(gp, a.gprec + (size_t)2 * i0 * RB, (2 * ns + 1) * RB);
     copy_to_smem(st, a.steprec + (size_t)4 * i0, 4 * ns);
     if (BW > 0) copy_to_smem(bs, a.basrec + (size_t)2 * i0 * BW, (2 * ns + 1) * BW);
+    if (FW > 0) copy_to_smem(fo, a.foldrec + (size_t)FW * i0, FW * ns);
     __syncthreads();
 }
 
@@ -555,10 +633,12 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
     constexpr bool NEEDB = (UMODE == UMODE_COEF);
     constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
     typedef TileLayout<RB> TL;
+    constexpr int NF = (UMODE == UMODE_COEF && !OCS_FOLD_FWD_COEF) ? 0 : ocs_nfold<P>(HM), FW = ocs_fold_width(NF);
     const int BW = BWc >= 0 ? BWc : a.BW;
     const int N = a.N;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
-    if (a.RB != RB || (NEEDB && a.BW != BW)) {
+    double *fo = bs + (size_t)(2 * TL::S + 1) * (NEEDB ? BW : 0);       // fold records of the tile
+    if (a.RB != RB || (NEEDB && a.BW != BW) || (NF > 0 && !a.foldrec)) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
         return;
     }
@@ -588,7 +668,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
 
     for (int i0 = 0; i0 < N; i0 += TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
-        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
+        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, FW);
         if (i0 == 0) {
 #pragma unroll
             for (int q = 0; q < T; ++q) {
@@ -616,11 +696,11 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 // controls of all T trajectories first: the (uniform, rare) window moves happen here, outside the
                 // arithmetic below, whose T dependency chains then share one basic block and interleave
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].slide(a, bM, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD != 0>(a, bM, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].slide(a, bR, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD != 0>(a, bR, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bR, uR[q]);
             }
@@ -655,6 +735,28 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 }
 
                 double F[m], acc[m], ys[n];
+                if constexpr (NF > 0) {
+                    // weight-folded objective row: J += (w E)(..) per stage, state rows as below
+                    const double *fL = fo + s * FW, *fM = fL + NF, *fR = fM + NF;
+                    P::template Ff<HM>(rL + 1 + nc, fL, rL[0], y[q], uL[q], p[q], F, y[q][n]);   // F1   :39
+#pragma unroll
+                    for (int c = 0; c < n; ++c) acc[c] = F[c];
+#pragma unroll
+                    for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h2 * F[c];                     // xK2  :40
+                    P::template Ff<HM>(rM + 1 + nc, fM, rM[0], ys, uM[q], p[q], F, y[q][n]);     // F2   :42
+#pragma unroll
+                    for (int c = 0; c < n; ++c) acc[c] = acc[c] + 2.0 * F[c];
+#pragma unroll
+                    for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h2 * F[c];                     // xK3  :43
+                    P::template Ff<HM>(rM + 1 + nc, fM, rM[0], ys, uM[q], p[q], F, y[q][n]);     // F3   :45
+#pragma unroll
+                    for (int c = 0; c < n; ++c) acc[c] = acc[c] + 2.0 * F[c];
+#pragma unroll
+                    for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h * F[c];                      // xK4  :46
+                    P::template Ff<HM>(rR + 1 + nc, fR, rR[0], ys, uR[q], p[q], F, y[q][n]);     // F4   :48
+#pragma unroll
+                    for (int c = 0; c < n; ++c) y[q][c] = y[q][c] + h6 * (acc[c] + F[c]);        // :50-51
+                } else {
                 P::template F<HM>(rL + 1 + nc, rL[0], y[q], uL[q], p[q], F);         // F1   :39
 #pragma unroll
                 for (int c = 0; c < m; ++c) acc[c] = F[c];
@@ -673,6 +775,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 P::template F<HM>(rR + 1 + nc, rR[0], ys, uR[q], p[q], F);           // F4   :48
 #pragma unroll
                 for (int c = 0; c < m; ++c) y[q][c] = y[q][c] + h6 * (acc[c] + F[c]);   // :50-51
+                }
                 if constexpr (UMODE != UMODE_UNIFORM) {
 #pragma unroll
                     for (int c = 0; c < nc; ++c) uL[q][c] = uR[q][c];
@@ -1047,11 +1150,12 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     constexpr bool NEEDB = (BMODE != BMODE_NONE);
     constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
     typedef TileLayout<RB> TL;
+    constexpr int NF = ocs_nfold<P>(HM), FW = ocs_fold_width(NF);
     const int BW = BWc >= 0 ? BWc : a.BW;
     const int N = a.N, G = 2 * N + 1;
     const bool dugout = a.dug != nullptr;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
-    if (a.RB != RB || (NEEDB && a.BW != BW)) {
+    if (a.RB != RB || (NEEDB && a.BW != BW) || (NF > 0 && !a.foldrec)) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
         return;
     }
@@ -1071,6 +1175,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     double y1[T][n], yn[D][T][n];            // (yn is unused, and optimised away, with the shared-memory ring)
     const double *xsp[T];
     double *ring = bs + (size_t)(2 * TL::S + 1) * BW + threadIdx.x;
+    double *fo = bs + (size_t)(2 * TL::S + 1) * BW + (size_t)DP * T * n * OCS_THREADS;   // fold records of the tile
+    const bool folded = NF > 0 && a.lamJ_one != 0;     // uniform: the whole grid takes one of the two chains
 #pragma unroll
     for (int q = 0; q < T; ++q) {
         b[q] = ((long)blockIdx.x * T + q) * blockDim.x + threadIdx.x;
@@ -1116,7 +1222,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     const int i0_last = ((N - 1) / TL::S) * TL::S;
     for (int i0 = i0_last; i0 >= 0; i0 -= TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
-        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs);
+        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, folded ? FW : 0);
         if (i0 == i0_last) {
 #pragma unroll
             for (int q = 0; q < T; ++q) {
@@ -1130,7 +1236,9 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
         // one RK4 step (all T trajectories) as a lambda, so that the step loop below can be unrolled by hand:
         // `#pragma unroll 2` on this loop miscompiled the peeled remainder iteration for odd step counts
         // (nvcc 12.9, caught by tests/test_gpu_edges.py); pairs + one explicit odd step are equivalent and safe.
-        auto rk4_reverse_step = [&](const int s) {
+        auto rk4_reverse_step = [&](auto fold_tag, const int s) {
+            constexpr bool FO = decltype(fold_tag)::value;
+            typedef typename ocs_dep<P, decltype(fold_tag)>::type PF;
             const int i = i0 + s;
             const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
@@ -1177,11 +1285,11 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             constexpr bool SPLIT = (UMODE == UMODE_COEF && BMODE == BMODE_SPARSE);
             if constexpr (SPLIT) {      // controls of all T trajectories first (see forward_multi_body)
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].slide(a, bM, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV != 0>(a, bM, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].slide(a, bL, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV != 0>(a, bL, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bL, uL[q]);
             }
@@ -1217,6 +1325,25 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 const bool du = GA || dugout;
                 double k4[m], k3[m], k2[m], k1[m], g3[n], g2[n], g1[n], g0[n];
                 double dRq[nc], dM3[nc], dM2[nc];
+                const double *fL = fo + s * FW, *fM = fL + NF, *fR = fM + NF;      // (FO only)
+                if constexpr (FO) {
+                    // lam(end) == 1: the objective row of every dJdk is the stage weight, already folded into fL/fM/fR
+#pragma unroll
+                    for (int c = 0; c < n; ++c) k4[c] = h6 * lam[q][c];                          // :73
+                    if (du) PF::template Uf<HM>(ttR, fR, tR, y4, uR[q], p[q], k4, dRq);          // :119-120 / :116
+                    PF::template Xf<HM>(ttR, fR, tR, y4, uR[q], p[q], k4, g3);                   // :74-75
+#pragma unroll
+                    for (int c = 0; c < n; ++c) k3[c] = h3 * lam[q][c] + h * g3[c];              // :77
+                    if (du) PF::template Uf<HM>(ttM, fM, tM, y3, uM[q], p[q], k3, dM3);          // :108-109
+                    PF::template Xf<HM>(ttM, fM, tM, y3, uM[q], p[q], k3, g2);                   // :78-79
+#pragma unroll
+                    for (int c = 0; c < n; ++c) k2[c] = h3 * lam[q][c] + h2 * g2[c];             // :81
+                    if (du) PF::template Uf<HM>(ttM, fM, tM, y2, uM[q], p[q], k2, dM2);          // :106-107
+                    PF::template Xf<HM>(ttM, fM, tM, y2, uM[q], p[q], k2, g1);                   // :82-83
+#pragma unroll
+                    for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
+                    PF::template Xf<HM>(ttL, fL, tL, y1[q], uL[q], p[q], k1, g0);                // :86-88
+                } else {
 #pragma unroll
                 for (int c = 0; c < m; ++c) k4[c] = h6 * lam[q][c];                          // :73
                 if (du) P::template U<HM>(ttR, tR, y4, uR[q], p[q], k4, dRq);               // :119-120 / :116
@@ -1235,6 +1362,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
                 k1[n] = h6 * lam[q][n];
                 P::template X<HM>(ttL, tL, y1[q], uL[q], p[q], k1, g0);                     // :86-88
+                }
 
                 if constexpr (GA) {
 #pragma unroll
@@ -1242,7 +1370,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                         dR[q][c] = dcar[q][c] + dRq[c];        // stage 1 of step i+1 (carried) + stage 4 of step i
                         dM[q][c] = dM2[c] + dM3[c];            // stages 2 + 3
                     }
-                    P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);            // :101-102 / :112-116
+                    if constexpr (FO) PF::template Uf<HM>(ttL, fL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
+                    else P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);       // :101-102 / :112-116
                 } else {
                     if (dugout) {            // dJdu itself, SoA [nc][G][batch], coalesced (dense bases project it later)
 #pragma unroll
@@ -1252,7 +1381,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                                 *soa_row(a.dug + b[q], (unsigned)(c * G + 2 * i + 1), (unsigned)a.ldb * 8u) = dM2[c] + dM3[c];
                             }
                         }
-                        P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
+                        if constexpr (FO) PF::template Uf<HM>(ttL, fL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
+                        else P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
                     }
                 }
 #pragma unroll
@@ -1280,16 +1410,24 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 }
             }
         };
-        int s = ns - 1;
-        if constexpr (UNR >= 2) {
+        auto run_tile = [&](auto fold_tag) {
+            int s = ns - 1;
+            if constexpr (UNR >= 2) {
 #pragma unroll 1
-            for (; s >= 1; s -= 2) {
-                rk4_reverse_step(s);
-                rk4_reverse_step(s - 1);
+                for (; s >= 1; s -= 2) {
+                    rk4_reverse_step(fold_tag, s);
+                    rk4_reverse_step(fold_tag, s - 1);
+                }
             }
-        }
 #pragma unroll 1
-        for (; s >= 0; --s) rk4_reverse_step(s);
+            for (; s >= 0; --s) rk4_reverse_step(fold_tag, s);
+        };
+        if constexpr (NF > 0) {
+            if (folded) run_tile(ocs_bool<true>{});
+            else run_tile(ocs_bool<false>{});
+        } else {
+            run_tile(ocs_bool<false>{});
+        }
     }
 #pragma unroll
     for (int q = 0; q < T; ++q) {
@@ -1340,6 +1478,26 @@ __device__ __forceinline__ void table_body(double *gprec, int G, int hm, const d
         P::template table<HM_TIME_CONTROL>(r[0], u, pr, tt);
 #pragma unroll
         for (int k = 0; k < NT; ++k) r[1 + nc + k] = tt[k];
+    }
+}
+
+// Fills the fold records of one segment (after the table kernel): for every step the problem's fold entries at
+// the left node (weight h/6), the midpoint (h/3) and the right node (h/6).
+template <class P, int HM>
+__device__ __forceinline__ void fold_rows(const double *gprec, const double *steprec, double *foldrec, int N)
+{
+    constexpr int NF = ocs_nfold<P>(HM);
+    if constexpr (NF > 0) {
+        constexpr int RB = ocs_rec_width(P::nc, P::ntt(HM)), FW = ocs_fold_width(NF);
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= N) return;
+        const double h3 = steprec[4 * i + 2], h6 = steprec[4 * i + 3];
+        const double *ttL = gprec + (size_t)(2 * i) * RB + 1 + P::nc;
+        double *f = foldrec + (size_t)i * FW;
+        P::template fold<HM>(ttL, h6, f);
+        P::template fold<HM>(ttL + RB, h3, f + NF);
+        P::template fold<HM>(ttL + 2 * RB, h6, f + 2 * NF);
+        for (int k = 3 * NF; k < FW; ++k) f[k] = 0.0;
     }
 }
 
@@ -1540,6 +1698,12 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int hm, const double *p)             \
     {                                                                                                  \
         OCS_NS::table_body<P>(gprec, G, hm, p);                                                        \
+    }                                                                                                  \
+    extern "C" __global__ void ocs_fold_##tag(const double *gprec, const double *steprec, double *foldrec, \
+                                              int N, int hm)                                           \
+    {                                                                                                  \
+        if (hm == 1) OCS_NS::fold_rows<P, 1>(gprec, steprec, foldrec, N);                              \
+        else if (hm == 2) OCS_NS::fold_rows<P, 2>(gprec, steprec, foldrec, N);                         \
     }                                                                                                  \
     extern "C" __global__ void ocs_info_##tag(int *o)                                                  \
     {                                                                                                  \
