@@ -127,7 +127,7 @@ struct ocs_b200_handle {
     bool have_states = false;
     DevBuf d_x0, d_J, d_xT, d_lamT_tail, d_lamT_user, d_dJdv, d_lam0, d_stage, d_stage2, d_maxchg;
     DevBuf d_dug;                     // dJdu grid [nc][G][Bt] of the dense-basis gradient path
-    DevBuf d_z, d_g, d_zt, d_gt, d_Jacc, d_Jhist, d_alpha, d_lbub;   // single_shooting (SPG) state
+    DevBuf d_z, d_g, d_zt, d_gt, d_Jacc, d_Jhist, d_alpha, d_lbub, d_pred;   // single_shooting (SPG) state
     DevBuf d_pipe[2];                 // double-buffered transpose staging of the chunked dJdv download
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
@@ -423,6 +423,121 @@ __global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double
     }
     const unsigned bal = __ballot_sync(0xffffffffu, open);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_open, __popc(bal));
+}
+
+// The same update with the rows of a trajectory split over G thread groups (block = 32 trajectories x G groups,
+// group kg owns rows kg, kg + G, ...): every row of zt, gt, z, g is read once and z, g, zt are written once
+// (7 passes over the (nc K) x Bt arrays instead of the 12 of the kernel above) -- the trial rows wait in
+// registers while the Barzilai-Borwein sums are reduced across the groups through shared memory.  The Armijo
+// term g.(z - zt) of the NEXT acceptance test is formed while zt is written and kept in pred[b].  Sums run in a
+// different (fixed) order than in spg_update_kernel, so the two differ by rounding only.
+template <int VPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
+    long nz, long nb, double *z, double *g, double *zt, const double *gt, double *J, const double *Jt, double *Jhist,
+    double *alpha, double *pred, const double *lb, const double *ub, int *frozen, int *iters, int iter, double tol,
+    int first, int *n_open)
+{
+    extern __shared__ double spg_sm[];                   // [5][G][32]
+    const int lane = threadIdx.x, kg = threadIdx.y, G = blockDim.y;
+    const long b = (long)blockIdx.x * 32 + lane;
+    const bool live = b < nb && !frozen[b];
+    bool accept = first != 0;
+    double a = 0.0, Jtb = 0.0;
+    if (live) {
+        a = alpha[b];
+        Jtb = Jt[b];
+        if (!first) {
+            double Jref = -INFINITY;
+            for (int j = 0; j < SPG_M; ++j) Jref = fmax(Jref, Jhist[(size_t)j * nb + b]);
+            accept = isfinite(Jtb) && Jtb <= Jref - 1e-4 * pred[b];
+        }
+    }
+    double zn[VPT], gn[VPT];
+    double sts = 0.0, sty = 0.0, pg = 0.0, gmax = 0.0;
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const long k = kg + (long)G * j;
+            zn[j] = gn[j] = 0.0;
+            if (k < nz) {
+                const size_t i = (size_t)k * nb + b;
+                if (accept) {
+                    zn[j] = zt[i];
+                    gn[j] = gt[i];
+                    const double sk = zn[j] - z[i], yk = gn[j] - g[i];
+                    sts += sk * sk;
+                    sty += sk * yk;
+                    z[i] = zn[j];
+                    g[i] = gn[j];
+                    const double proj = fmin(ub[k], fmax(lb[k], zn[j] - gn[j]));
+                    pg = fmax(pg, fabs(zn[j] - proj));
+                    gmax = fmax(gmax, fabs(gn[j]));
+                } else {                     // rejected: a shorter step from the accepted point
+                    zn[j] = z[i];
+                    gn[j] = g[i];
+                }
+            }
+        }
+    }
+    double *r0 = spg_sm, *r1 = r0 + G * 32, *r2 = r1 + G * 32, *r3 = r2 + G * 32, *r4 = r3 + G * 32;
+    r0[kg * 32 + lane] = sts;
+    r1[kg * 32 + lane] = sty;
+    r2[kg * 32 + lane] = pg;
+    r3[kg * 32 + lane] = gmax;
+    __syncthreads();
+    sts = sty = pg = gmax = 0.0;
+    for (int q = 0; q < G; ++q) {
+        sts += r0[q * 32 + lane];
+        sty += r1[q * 32 + lane];
+        pg = fmax(pg, r2[q * 32 + lane]);
+        gmax = fmax(gmax, r3[q * 32 + lane]);
+    }
+    int fz = 0;
+    if (live) {
+        if (accept) {
+            if (first) a = 1.0 / fmax(gmax, 1e-8);
+            else a = sty > 0.0 ? fmin(1e10, fmax(1e-10, sts / sty)) : fmin(1e10, 10.0 * a);
+            if (pg <= tol) fz = 1;
+        } else {
+            a *= 0.25;
+            if (a < 1e-14) fz = 2;                               // stalled
+        }
+    }
+    double pr = 0.0;
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const long k = kg + (long)G * j;
+            if (k < nz) {
+                const size_t i = (size_t)k * nb + b;
+                const double zn_new = fz ? zn[j] : fmin(ub[k], fmax(lb[k], zn[j] - a * gn[j]));   // frozen: the minimiser stays
+                zt[i] = zn_new;
+                pr += gn[j] * (zn[j] - zn_new);
+            }
+        }
+    }
+    r4[kg * 32 + lane] = pr;
+    __syncthreads();
+    if (kg == 0) {
+        int open = 0;
+        if (live) {
+            pr = 0.0;
+            for (int q = 0; q < G; ++q) pr += r4[q * 32 + lane];
+            pred[b] = pr;
+            alpha[b] = a;
+            iters[b] = iter;
+            if (accept) {
+                J[b] = Jtb;
+                Jhist[(size_t)(iter % SPG_M) * nb + b] = Jtb;
+                if (first)
+                    for (int j = 0; j < SPG_M; ++j) Jhist[(size_t)j * nb + b] = Jtb;
+            }
+            if (fz) frozen[b] = fz;
+            else open = 1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, open);
+        if (lane == 0 && bal) atomicAdd(n_open, __popc(bal));
+    }
 }
 
 // dJdv = dJdu * B' for a dense basis (ChebyshevControl.m:34-37):
@@ -1106,7 +1221,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
                       &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg,
                       &h->d_pipe[0], &h->d_pipe[1], &h->d_z, &h->d_g, &h->d_zt, &h->d_gt, &h->d_Jacc, &h->d_Jhist,
-                      &h->d_alpha, &h->d_lbub, &h->d_dug};
+                      &h->d_alpha, &h->d_lbub, &h->d_dug, &h->d_pred};
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int k = 0; k < 2; ++k) {
         if (h->chunk_done[k]) cudaEventDestroy(h->chunk_done[k]);
@@ -2093,6 +2208,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         TRY(ensure(h, h->d_Jacc, Bt));
         TRY(ensure(h, h->d_Jhist, (size_t)SPG_M * Bt));
         TRY(ensure(h, h->d_alpha, Bt));
+        TRY(ensure(h, h->d_pred, Bt));
         TRY(ensure(h, h->d_lbub, 2 * (size_t)nz));
         TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
         // starting point: zt = [v0; x0(free)] projected onto the box
@@ -2149,7 +2265,10 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
             h->fb_frozen = h->d_frozen;
             int rc = run_forward(h, 0, Bt, -1, nullptr, true);
             if (rc == 0) {
-                CK(cudaMemsetAsync(h->d_gt.p, 0, sizeof(double) * nv * Bt, h->stream));
+                // store-once gradient columns (sparse basis, monotone knot index reaching every knot) need no
+                // zero-fill; frozen trajectories are skipped by the sweeps and their gt is never read again
+                if (!(h->basis_kind == BASIS_SPARSE && h->bk_monotone && h->bk_covered))
+                    CK(cudaMemsetAsync(h->d_gt.p, 0, sizeof(double) * nv * Bt, h->stream));
                 rc = run_reverse(h, 0, Bt, -1, nullptr, 0, h->d_gt.p, h->d_lam0.p, nullptr, nullptr);
             }
             h->fb_frozen = nullptr;
@@ -2158,9 +2277,26 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                 CK(cudaMemcpyAsync(h->d_gt.p + (size_t)(nv + f) * Bt, h->d_lam0.p + (size_t)free_states[f] * Bt,
                                    sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
             CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
-            spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
-                nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
-                h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+            {
+                // rows of a trajectory over G thread groups of up to 16 rows each (nz <= 512); beyond that the
+                // one-thread-per-trajectory kernel
+                const int Gk = (int)((nz + 15) / 16);
+                const dim3 blk(32, Gk), grd((unsigned)((Bt + 31) / 32));
+                const size_t sm = sizeof(double) * 5 * Gk * 32;
+                if (nz > 512 || getenv("OCS_B200_SPG_SERIAL")) {
+                    spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
+                        nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
+                        h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+                } else if (Gk <= 16) {
+                    spg_update_split_kernel<16, 512><<<grd, blk, sm, h->stream>>>(
+                        nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
+                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+                } else {
+                    spg_update_split_kernel<16, 1024><<<grd, blk, sm, h->stream>>>(
+                        nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
+                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+                }
+            }
             CK(cudaGetLastError());
             int nopen = 0;
             CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
