@@ -33,6 +33,9 @@
 #ifndef OCS_TILE
 #define OCS_TILE 32         // RK4 steps per shared-memory tile
 #endif
+#ifndef OCS_TILE_SINGLE
+#define OCS_TILE_SINGLE (OCS_TILE < 32 ? OCS_TILE : 32)   // ... of the one-trajectory bodies (fetch and fb_sweep kernels); never
+#endif                                                    // larger than OCS_TILE, which sizes the host's allocation
 #define OCS_XS_SLACK 8      // nodes of slack in front of the node-state store (>= any OCS_PREFETCH)
 #ifndef OCS_PREFETCH
 #define OCS_PREFETCH 2      // node states prefetched ahead by the reverse sweep (slack in front of the store)
@@ -458,9 +461,9 @@ template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 // ------------------------------------------------------------------ tile staging
-template <int RB>
+template <int RB, int TS = OCS_TILE>
 struct TileLayout {
-    static constexpr int S = OCS_TILE;
+    static constexpr int S = TS;
     static constexpr int GP = (2 * S + 1) * RB;   // grid-point records
     static constexpr int ST = 4 * S;              // step records
 };
@@ -498,7 +501,7 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
     constexpr int RB = ocs_rec_width(nc, P::ntt(HM));
     constexpr bool NEEDB = (UMODE == UMODE_COEF);
     constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
-    typedef TileLayout<RB> TL;
+    typedef TileLayout<RB, OCS_TILE_SINGLE> TL;
     const int BW = BWc >= 0 ? BWc : a.BW;
     const int N = a.N;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
@@ -828,7 +831,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     constexpr bool NEEDB = (BMODE != BMODE_NONE);
     constexpr bool GACC = NEEDB && !GRIDS && FB == 0;   // fold dJdu into dJdv (the fetch variant writes dJdu itself)
     constexpr int BWc = NEEDB ? (BMODE == BMODE_SPARSE ? 4 : (KD > 0 ? ocs_even(KD) : -1)) : 0;
-    typedef TileLayout<RB> TL;
+    typedef TileLayout<RB, OCS_TILE_SINGLE> TL;
     const int BW = BWc >= 0 ? BWc : a.BW;
     const int N = a.N, G = 2 * N + 1;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
