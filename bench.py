@@ -200,6 +200,13 @@ def cpu_oracle_run(ntraj, nthreads=0, mode=1):
     ctl = rk4_oracle.PWLinearControl(rk4_oracle.RK4Integrator(tspan).t, K_PWL, 1)
     v = np.random.default_rng(1).random(K_PWL)
     x0 = np.random.default_rng(2).uniform(0.5, 2.5, (1, ntraj))
+    if nthreads <= 0:
+        # every host thread this process may run on -- set explicitly: torchrun exports OMP_NUM_THREADS=1, which
+        # would silently time the reference on one core
+        try:
+            nthreads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            nthreads = os.cpu_count() or 1
     t0 = time.perf_counter()
     oracle_c.evaluate(list(PARAMS.values()), tspan, ctl.B, x0, v, mode=mode, nthreads=nthreads)
     dt = time.perf_counter() - t0
