@@ -40,6 +40,9 @@ PARAMS = dict(c=1.5, m=3.0, r=0.05)          # tests/backprop_test.m:9-11
 WORKLOAD = ("cfg2: batched single_shooting evaluation of tests/TestOCProblem.m, 2^20 random x0 x 1000 RK4 steps, "
             "shared PWLinearControl K=101, forward + discrete adjoint (J, dJdv)")
 
+METRIC = "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)"     # BASELINE.json's metric on configs[1]: one trajectory-step =
+                                                                # one RK4 step of one trajectory, forward AND adjoint
+
 # ---- algorithmic work per trajectory-step (add/mul/div/exp = 1, FMA = 2)
 # TestOCProblem: C_F = 10, C_X = 8, C_U = 7, m = 2, nc = 1.  The control is shared by the batch, so
 # its evaluation is per grid point, not per trajectory: c_u = 0.  c_v = 4 (PWLinear dJdv scatter).
@@ -231,7 +234,7 @@ def run_reference(args, rank, world):
     value = args.steps * ntraj * N_STEPS / dt
     sample = f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps per step (fwd + adjoint)"
     emit({
-        "impl": "reference", "metric": "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
@@ -674,7 +677,7 @@ def main():
         # whole-evaluation view: (fwd + rev) algorithmic flops over the measured step time
         roof["step_fp64_frac"] = value / world * (wl["flop_fwd"] + wl["flop_rev"]) / 1e12 / tf.value
         out = {
-            "metric": "FP64 trajectory-steps/sec (fwd+adjoint RK4 sweep)", "value": value,
+            "metric": METRIC, "value": value,
             "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -682,6 +685,11 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * n_st * NT * Bt),
                        "collective": "all_gather of J and x(T) (NCCL)" if world > 1 else "none"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
+            # the two modes side by side, per GPU, from the per-kernel CUDA-event times
+            "modes": {"fwd_only": {"value": units / (ms_fwd * 1e-3), "unit": "trajectory-steps/s", "ms": ms_fwd,
+                                   "what": "compute_states alone (J, x(T))"},
+                      "fwd_bwd": {"value": units / ((ms_fwd + ms_rev) * 1e-3), "unit": "trajectory-steps/s",
+                                  "ms": ms_fwd + ms_rev, "what": "compute_states + compute_adjoints (J, dJdv)"}},
         }
 
     # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)

@@ -2251,6 +2251,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         h->ctrl_mode = CTRL_V_BATCH;
         h->ctrl_nbatch = Bt;
         h->seg[0].records_dirty = true;
+        const bool spg_serial = nz > 512 || getenv("OCS_B200_SPG_SERIAL") != nullptr;   // (the env switch is for the A/B test)
         for (int iter = 0; iter < max_iter; ++iter) {
             for (int f = 0; f < nfree; ++f)      // x0(FreeInitStates) = v(end-nFREE_STATES+1:end)   single_shooting.m:145
                 CK(cudaMemcpyAsync(h->d_x0.p + (size_t)free_states[f] * Bt, h->d_zt.p + (size_t)(nv + f) * Bt,
@@ -2283,7 +2284,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                 const int Gk = (int)((nz + 15) / 16);
                 const dim3 blk(32, Gk), grd((unsigned)((Bt + 31) / 32));
                 const size_t sm = sizeof(double) * 5 * Gk * 32;
-                if (nz > 512 || getenv("OCS_B200_SPG_SERIAL")) {
+                if (spg_serial) {
                     spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
                         h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);

@@ -270,11 +270,23 @@ struct ControlEval {
 
     // Sparse basis, part 1: make {k, k+1} the live window of grid point j.  The branch is uniform across the
     // batch (every trajectory shares the grid) and taken ~K times per sweep.
-    template <bool PRED = false>
+    template <int PRED = 0>     // 0: branch, 1: predicated loads, 2: branch on a warp vote (provably uniform)
     __device__ __forceinline__ void slide(const SweepArgs &a, const double *bas, long bb)
     {
         const int k = rec_k(bas);
-        if constexpr (PRED) {
+        if constexpr (PRED == 2) {
+            if (__any_sync(0xffffffffu, k != kcur)) {
+                const int ke = (k & 1) ? k + 1 : k, ko = (k & 1) ? k : k + 1;
+#pragma unroll
+                for (int c = 0; c < nc; ++c) {
+                    vE[c] = (ke < a.K) ? a.v[soa((long)ke * nc + c, a.ldb, bb)] : 0.0;
+                    vO[c] = (ko < a.K) ? a.v[soa((long)ko * nc + c, a.ldb, bb)] : 0.0;
+                }
+                kcur = k;
+            }
+            return;
+        }
+        if constexpr (PRED == 1) {
         // Predicated loads instead of a branch: the move is uniform across the batch, but the compiler cannot
         // know that and may wrap a branch in BSSY/BSYNC, splitting the arithmetic of the step into basic blocks
         // (measured: +8 % on the forward sweep).  A slot whose knot lies outside the basis keeps its previous
@@ -699,11 +711,11 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 // controls of all T trajectories first: the (uniform, rare) window moves happen here, outside the
                 // arithmetic below, whose T dependency chains then share one basic block and interleave
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD != 0>(a, bM, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD>(a, bM, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD != 0>(a, bR, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD>(a, bR, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bR, uR[q]);
             }
@@ -1288,11 +1300,11 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             constexpr bool SPLIT = (UMODE == UMODE_COEF && BMODE == BMODE_SPARSE);
             if constexpr (SPLIT) {      // controls of all T trajectories first (see forward_multi_body)
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV != 0>(a, bM, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV>(a, bM, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
 #pragma unroll
-                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV != 0>(a, bL, bb[q]);
+                for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV>(a, bL, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bL, uL[q]);
             }
