@@ -621,7 +621,7 @@ def main():
     sync_all()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    launches = integ.kernel_stats(reset=True)["launches"] + args.steps   # + the dJdv memset per step
+    launches = integ.kernel_stats(reset=True)["launches"]    # sweeps + the table / fold kernels of every evaluation
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

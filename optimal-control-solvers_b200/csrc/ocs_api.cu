@@ -776,6 +776,7 @@ int build_records(H *h, int si)
         int hmv = hm, Gv = G;
         void *args[] = {(void *)&s.d_gprec, (void *)&Gv, (void *)&hmv, (void *)&h->d_params.p};
         CK(cudaLaunchKernel(h->kt.tt, dim3((G + 127) / 128), dim3(128), args, 0, h->stream));
+        h->launches++;
     }
     s.fold_nf = h->kt.fold ? h->kt.nfold[hm] : 0;
     if (s.fold_nf > 0) {        // stage weights folded into the table entries they multiply, once per step
@@ -784,6 +785,7 @@ int build_records(H *h, int si)
         int hmv = hm, Nv = N;
         void *args[] = {(void *)&s.d_gprec, (void *)&s.d_steprec, (void *)&s.d_foldrec, (void *)&Nv, (void *)&hmv};
         CK(cudaLaunchKernel(h->kt.fold, dim3((N + 127) / 128), dim3(128), args, 0, h->stream));
+        h->launches++;
     }
     s.records_dirty = false;
     return 0;
@@ -2298,6 +2300,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                         h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
                 }
             }
+            h->launches++;
             CK(cudaGetLastError());
             int nopen = 0;
             CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
