@@ -701,7 +701,18 @@ int build_records(H *h, int si)
                         const int kprev = (j + 2 < G) ? h->bk[j + 2] : -0x40000000;   // handled before point j+1
                         moves = (h->bk[j + 1] != kprev) || (h->bk[j] != h->bk[j + 1]);
                     }
-                    int32_t kk[2] = {k, (two ? 1 : 0) | ((!two && odd) ? 2 : 0) | (moves ? 4 : 0)};
+                    // bit3 / bit4 (on midpoint records): the CONTROL window of a per-trajectory-coefficient sweep moves
+                    // while the reverse / forward sweep evaluates this step's controls (reverse: midpoint after the
+                    // right node, left node after the midpoint; forward: midpoint after the left node, right node
+                    // after the midpoint), so that the sweeps test one flag per step instead of comparing knots at
+                    // every grid point
+                    int cmoves_rev = 0, cmoves_fwd = 0;
+                    if (j & 1) {
+                        cmoves_rev = (h->bk[j] != h->bk[j + 1]) || (h->bk[j - 1] != h->bk[j]);
+                        cmoves_fwd = (h->bk[j] != h->bk[j - 1]) || (h->bk[j + 1] != h->bk[j]);
+                    }
+                    int32_t kk[2] = {k, (two ? 1 : 0) | ((!two && odd) ? 2 : 0) | (moves ? 4 : 0) | (cmoves_rev ? 8 : 0) |
+                                            (cmoves_fwd ? 16 : 0)};
                     memcpy(r, kk, sizeof kk);
                     r[1] = odd ? h->bw1[j] : h->bw0[j];
                     r[2] = odd ? h->bw0[j] : h->bw1[j];

@@ -710,6 +710,24 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
             if constexpr (SPLIT) {
                 // controls of all T trajectories first: the (uniform, rare) window moves happen here, outside the
                 // arithmetic below, whose T dependency chains then share one basic block and interleave
+                if constexpr (OCS_SLIDE_PRED_FWD == 3) {
+                    // one host-computed flag per step (bit4 of the midpoint's basis record): does the window move here?
+                    if (rec_flags(bM) & 16) {
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].template slide<0>(a, bM, bb[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].template slide<0>(a, bR, bb[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bR, uR[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bR, uR[q]);
+                    }
+                } else {
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD>(a, bM, bb[q]);
 #pragma unroll
@@ -718,6 +736,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_FWD>(a, bR, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bR, uR[q]);
+                }
             }
 #pragma unroll
             for (int q = 0; q < T; ++q) {
@@ -1299,6 +1318,23 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             }
             constexpr bool SPLIT = (UMODE == UMODE_COEF && BMODE == BMODE_SPARSE);
             if constexpr (SPLIT) {      // controls of all T trajectories first (see forward_multi_body)
+                if constexpr (OCS_SLIDE_PRED_REV == 3) {
+                    if (rec_flags(bM) & 8) {        // host-computed: the control window moves within this step
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].template slide<0>(a, bM, bb[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].template slide<0>(a, bL, bb[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bL, uL[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bM, uM[q]);
+#pragma unroll
+                        for (int q = 0; q < T; ++q) ctl[q].value(bL, uL[q]);
+                    }
+                } else {
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV>(a, bM, bb[q]);
 #pragma unroll
@@ -1307,6 +1343,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 for (int q = 0; q < T; ++q) ctl[q].template slide<OCS_SLIDE_PRED_REV>(a, bL, bb[q]);
 #pragma unroll
                 for (int q = 0; q < T; ++q) ctl[q].value(bL, uL[q]);
+                }
             }
 #pragma unroll
             for (int q = 0; q < T; ++q) {
