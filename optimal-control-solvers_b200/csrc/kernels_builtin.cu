@@ -33,11 +33,12 @@
 // Per-trajectory coefficients v (UMODE_COEF, what a batched single_shooting solve evaluates; bench.py --config cfg2v).
 // Same-box A/B of (trajectories per thread, min blocks/SM): forward (3,1: 134 regs) 3.88 ms / (3,4) 3.32 / (2,6) 3.29 /
 // (1,8: 64 regs) 2.91 / (1,12) 2.90; reverse (2,5: spills) 5.88 / (2,4: 126 regs) 5.70 / (1,8) 5.98 / (1,10) 5.97.
+// (with the per-step window flag and folded weights, session 4: forward (1,8) 2.80 / (2,5: 94 regs) 2.69 ms)
 #ifndef OCS_TPT_FWD_COEF
-#define OCS_TPT_FWD_COEF 1
+#define OCS_TPT_FWD_COEF 2
 #endif
 #ifndef OCS_MINBLOCKS_FWD_COEF
-#define OCS_MINBLOCKS_FWD_COEF 8
+#define OCS_MINBLOCKS_FWD_COEF 5
 #endif
 #ifndef OCS_TPT_REV_COEF
 #define OCS_TPT_REV_COEF 2

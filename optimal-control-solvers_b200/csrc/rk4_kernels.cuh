@@ -83,19 +83,24 @@
                             // Measured on B200 (profiles/r1_notes.md): 0: 3.71 ms, 2: 3.90, 4: 3.75, 8: 3.76 -- the
                             // FP64-bound gradient kernel does not gain from it, the HBM-bound fb_sweep kernel does.
 #endif
-// Sparse-basis window moves by predicated loads (1) or under a branch (0), per sweep direction; and whether the
-// forward sweep with per-trajectory coefficients folds the stage weights.  Same-box A/B on cfg2v (forward /
-// reverse ms): branch, no fold 2.91 / 5.59; branch + fold 3.16 / 6.01; predicated, no fold 3.69 / 6.06;
-// predicated + fold 3.74 / 5.24 -- so the forward sweep keeps the branch and does not fold, the reverse sweep
-// does both (profiles/r1_notes.md).
+// How the sweeps with per-trajectory coefficients move the sparse-basis control window, per sweep direction:
+//   0  compare the knot index at every grid point, reload under a branch
+//   1  ... reload by predicated loads (ld_global_if)
+//   2  ... branch on a warp vote
+//   3  test ONE host-computed flag per step (bits 3 / 4 of the midpoint's basis record: the window moves within this
+//      step) and only then run the compares and reloads -- the common step carries no window instructions at all
+// and whether the forward sweep with per-trajectory coefficients folds the stage weights.  Same-box A/B on cfg2v
+// (forward / reverse ms): mode 0 without folding 2.91 / 5.59; 0 + fold 3.16 / 6.01; 1 + fold 3.74 / 5.24 (4.97 with
+// 64-step tiles); 2: 2.89 / 6.02; 3 + fold: 2.80 / 4.29, and 2.69 with two trajectories per thread in the forward
+// sweep (profiles/r1_notes.md).
 #ifndef OCS_SLIDE_PRED_FWD
-#define OCS_SLIDE_PRED_FWD 0
+#define OCS_SLIDE_PRED_FWD 3
 #endif
 #ifndef OCS_SLIDE_PRED_REV
-#define OCS_SLIDE_PRED_REV 1
+#define OCS_SLIDE_PRED_REV 3
 #endif
 #ifndef OCS_FOLD_FWD_COEF
-#define OCS_FOLD_FWD_COEF 0
+#define OCS_FOLD_FWD_COEF 1
 #endif
 #ifndef OCS_PRED_CLOBBER
 #define OCS_PRED_CLOBBER 1
