@@ -433,9 +433,9 @@ __global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double
 // different (fixed) order than in spg_update_kernel, so the two differ by rounding only.
 template <int VPT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
-    long nz, long nb, double *z, double *g, double *zt, const double *gt, double *J, const double *Jt, double *Jhist,
-    double *alpha, double *pred, const double *lb, const double *ub, int *frozen, int *iters, int iter, double tol,
-    int first, int *n_open)
+    long nz, long nb, double *__restrict__ z, double *__restrict__ g, double *__restrict__ zt, const double *__restrict__ gt,
+    double *J, const double *Jt, double *Jhist, double *alpha, double *pred, const double *__restrict__ lb,
+    const double *__restrict__ ub, int *frozen, int *iters, int iter, double tol, int first, int *n_open)
 {
     extern __shared__ double spg_sm[];                   // [5][G][32]
     const int lane = threadIdx.x, kg = threadIdx.y, G = blockDim.y;
@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
                     const double sk = zn[j] - z[i], yk = gn[j] - g[i];
                     sts += sk * sk;
                     sty += sk * yk;
-                    z[i] = zn[j];
-                    g[i] = gn[j];
+                    // (z and g are overwritten in the second phase: with no store in this loop the compiler is free to
+                    //  issue all 4 x VPT loads of the thread up front)
                     const double proj = fmin(ub[k], fmax(lb[k], zn[j] - gn[j]));
                     pg = fmax(pg, fabs(zn[j] - proj));
                     gmax = fmax(gmax, fabs(gn[j]));
@@ -511,6 +511,10 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
             if (k < nz) {
                 const size_t i = (size_t)k * nb + b;
                 const double zn_new = fz ? zn[j] : fmin(ub[k], fmax(lb[k], zn[j] - a * gn[j]));   // frozen: the minimiser stays
+                if (accept) {
+                    z[i] = zn[j];
+                    g[i] = gn[j];
+                }
                 zt[i] = zn_new;
                 pr += gn[j] * (zn[j] - zn_new);
             }
