@@ -60,6 +60,43 @@ def test_six_state_problem_source_compiles_for_sm100a(cg):
         assert r.returncode == 0, r.stderr
 
 
+# the options of csrc/nvrtc_problem.cu (ocs_compile_unit); JIT mode is stricter than nvcc: e.g. generic lambdas in
+# the sweep bodies need -default-device, which the nvcc test above cannot notice
+NVRTC_OPTS = ["--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_every_kernel_unit_of_a_generated_problem_compiles_under_nvrtc(cg, strict):
+    """What the GPU box does on demand (NVRTC, one unit per kernel variant), done here without a device: the
+    table/info kernels and every sweep variant a generated problem can be asked for."""
+    nvrtc = pytest.importorskip("cuda.bindings.nvrtc")
+    src_api = open(os.path.join(ROOT, "optimal-control-solvers_b200", "csrc", "nvrtc_problem.cu")).read()
+    for opt in NVRTC_OPTS:
+        assert '"%s"' % opt in src_api, opt          # this test and the library use the same options
+    p = cg.harvest_chain_problem()
+    units = ["OCS_TT_KERNEL(ocs_gen::Problem, gen)",
+             "OCS_EQ_KERNEL(ocs_gen::Problem, gen)",
+             "OCS_FWD_KERNEL(ocs_gen::Problem, gen, 0, 0, 0, 0)", "OCS_FWD_KERNEL(ocs_gen::Problem, gen, 1, 1, 1, 0)",
+             "OCS_FWD_KERNEL(ocs_gen::Problem, gen, 1, 2, 0, 17)", "OCS_FWD_KERNEL(ocs_gen::Problem, gen, 2, 0, 0, 0)",
+             "OCS_FWDG_KERNEL(ocs_gen::Problem, gen, 1, 1, 0, 0)",
+             "OCS_REV_KERNEL(ocs_gen::Problem, gen, 0, 1, 0, 0)", "OCS_REV_KERNEL(ocs_gen::Problem, gen, 1, 1, 0, 0)",
+             "OCS_REV_KERNEL(ocs_gen::Problem, gen, 2, 0, 1, 0)", "OCS_REVG_KERNEL(ocs_gen::Problem, gen, 1, 2, 0, 17)",
+             "OCS_FB_KERNEL(ocs_gen::Problem, gen, 0)", "OCS_FBC_KERNEL(ocs_gen::Problem, gen, 1)"]
+    inc = "-I" + os.path.join(ROOT, "optimal-control-solvers_b200", "csrc")
+    opts = [o.encode() for o in NVRTC_OPTS + [inc, "--fmad=false" if strict else "--fmad=true"]]
+    for unit in units:
+        src = '#define OCS_NS ocs_gen\n#include "rk4_kernels.cuh"\n' + p.source + "\n" + unit + "\n"
+        err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"ocs_generated_problem.cu", 0, [], [])
+        assert int(err) == 0
+        (rc,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+        if int(rc) != 0:
+            _, n = nvrtc.nvrtcGetProgramLogSize(prog)
+            log = b" " * n
+            nvrtc.nvrtcGetProgramLog(prog, log)
+            pytest.fail("%s did not compile under NVRTC:\n%s" % (unit, log.decode(errors="replace")[:3000]))
+        nvrtc.nvrtcDestroyProgram(prog)
+
+
 def test_oracle_twin_of_generated_problem(cg, oracle):
     """The lambdified SymPy twin agrees with the oracle's hand-written TestOCProblem."""
     p = cg.test_problem_symbolic()

@@ -81,3 +81,24 @@ def test_gather_over_gloo_world_size_2():
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("gather ok" in o for o in outs), outs
+
+
+def test_reference_arm_uses_every_host_thread_and_prints_one_line():
+    """bench.py --impl reference: ONE JSON line on stdout, same metric/unit as the GPU arm, and the C oracle on every
+    host thread even when the launcher exports OMP_NUM_THREADS=1 (torchrun does)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "trajectory-steps/s" and j["higher_is_better"] is True
+    assert j["metric"].startswith("FP64 trajectory-steps/sec") and j["config"]["workload"].startswith("cfg2")
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["value"] > 0 and j["gpu_launches"] == 0
