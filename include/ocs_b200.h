@@ -13,7 +13,9 @@
  *     available from ocs_b200_last_error(handle) (or with handle == NULL for
  *     create-time failures).  Nothing throws or longjmps across this boundary.
  *   - all host arrays are FP64, MATLAB (column-major) layout, read-only inputs
- *     are never retained past the call.
+ *     are never retained past the call.  Host arrays may be pageable (every mxArray is): large transfers
+ *     then go through a pinned ring and copy threads inside the handle instead of the driver's slow
+ *     pageable path; pinned / registered arrays are handed to the copy engine as they are.
  *   - n = number of true states, m = n+1 (augmented with the running objective,
  *     last row), nc = controls, N = RK4 steps, G = 2N+1 grid points (nodes and
  *     interval midpoints), K = control basis size, Bt = trajectories in a batch.
@@ -79,6 +81,28 @@ typedef struct ocs_b200_handle ocs_b200_handle;
  * single IEEE operations as RK4Integrator.m:17-24 and can be read back with ocs_b200_get_grid. */
 OCS_B200_API int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extra,
                                  int device, int math_mode, ocs_b200_handle **out);
+
+/* The same integrator spread over several GPUs of one node behind ONE handle: the reference's host is a single
+ * MATLAB process that constructs one integrator object (functions/single_shooting.m:41-45), so multi-GPU lives inside
+ * the handle, not in extra processes.  devices [ndev]: distinct CUDA ordinals; devices[0] is the root.  A batch of Bt
+ * trajectories is cut into contiguous shards (the first Bt mod ndev take one trajectory more); every host-buffer
+ * entry point below forwards shard k to device k on its own host thread and stream, reading and writing the
+ * caller's arrays directly (column-major with the trajectory index last: a shard is one contiguous block), so there is
+ * no collective on that path.  Entry points that take DEVICE pointers or a stream of one device
+ * (ocs_b200_set_stream, *_dev) are refused on such a handle; use ocs_b200_evaluate_resident,
+ * ocs_b200_gather_results_dev and ocs_b200_get_results instead. */
+OCS_B200_API int ocs_b200_create_multi(int N, const double *tspan, int N2, const double *tspan_extra, int ndev,
+                                       const int *devices, int math_mode, ocs_b200_handle **out);
+
+/* Devices behind a handle and the shard offsets of its resident batch: devices [<= cap], offsets [<= cap] with
+ * offsets[k] .. offsets[k+1] the trajectories of device k (ndev + 1 entries when cap allows).  Any pointer may be NULL. */
+OCS_B200_API int ocs_b200_get_devices(const ocs_b200_handle *h, int *ndev, int *devices, long *offsets, int cap);
+
+/* Sizes the handle was built / bound with: dims = { n, nc, np, K, N, N2, 0, 0 } (n, nc, np are 0 before a problem is
+ * bound, K is 0 without a basis).  A binding (the MEX gateway) sizes its outputs from these, not from caller-supplied
+ * scalars.  ocs_b200_get_batch: trajectories of the resident batch (0: none). */
+OCS_B200_API int ocs_b200_get_dims(const ocs_b200_handle *h, int32_t dims[8]);
+OCS_B200_API long ocs_b200_get_batch(const ocs_b200_handle *h);
 
 /* delete(obj): frees the device-resident trajectory store (the xK cache of RK4Integrator.m:8-10). */
 OCS_B200_API int ocs_b200_destroy(ocs_b200_handle *h);
@@ -265,7 +289,7 @@ OCS_B200_API int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, lo
 
 /* ------------------------------------------------------------------ device-resident variants
  * Same sweeps with caller-owned DEVICE buffers in structure-of-arrays layout [row][Bt]
- * (batch fastest) -- for pipelines that keep the batch in HBM and for multi-GPU gathers.
+ * (batch fastest) -- for pipelines that keep the batch in HBM on ONE device.
  * stream: a cudaStream_t (NULL = the handle's own stream). */
 OCS_B200_API int ocs_b200_set_stream(ocs_b200_handle *h, void *cuda_stream);
 OCS_B200_API int ocs_b200_set_control_v_dev(ocs_b200_handle *h, const double *v_soa, long nbatch);
@@ -275,10 +299,29 @@ OCS_B200_API int ocs_b200_compute_adjoints_dev(ocs_b200_handle *h, const double 
                                                double *dJdv_soa, double *lam0_soa);
 OCS_B200_API int ocs_b200_synchronize(ocs_b200_handle *h);
 
+/* Device-resident evaluation for solver loops and multi-GPU pipelines (works on single- and multi-device handles):
+ *   ocs_b200_evaluate_resident  nlpObjective (functions/single_shooting.m:137-150) of the batch whose initial states are
+ *                               x0 [n x Bt] (host; uploaded and kept), or of the resident initial states when x0 == NULL
+ *                               (Bt ignored) -- e.g. after ocs_b200_set_control_v with a new candidate.  want_gradient
+ *                               != 0 also runs the adjoint sweep.  All results stay on the device(s); asynchronous.
+ *   ocs_b200_gather_results_dev J [Bt] and x(T) [n][Bt] (SoA) into DEVICE buffers on the root device -- the one
+ *                               exchange of the multi-GPU path (north star: "NCCL ... only to gather the small
+ *                               per-trajectory J and final-state results"): a gather to root with grouped NCCL
+ *                               ncclSend/ncclRecv (ncclCommInitAll inside this process), or peer copies on the copy
+ *                               engines when libnccl is not loadable or OCS_B200_GATHER=p2p.  Asynchronous; ordered on
+ *                               the root device's stream.  Either pointer may be NULL.
+ *   ocs_b200_get_results        the resident results into host arrays (any may be NULL). */
+OCS_B200_API int ocs_b200_evaluate_resident(ocs_b200_handle *h, const double *x0, long Bt, int want_gradient);
+OCS_B200_API int ocs_b200_gather_results_dev(ocs_b200_handle *h, double *J_root, double *xT_root_soa);
+OCS_B200_API int ocs_b200_get_results(ocs_b200_handle *h, double *J, double *xT, int32_t *status, double *dJdv, double *lam0);
+
 /* Device time (ms, CUDA events on the launch stream) and launch count of the sweep kernels since
  * the last call with reset != 0. */
 OCS_B200_API int ocs_b200_kernel_stats(ocs_b200_handle *h, int reset, double *ms_forward, double *ms_reverse,
                                        long *launches);
+/* The same split further: ms[0] forward sweeps, ms[1] reverse sweeps, ms[2] dense-basis projection dJdu*B',
+ * ms[3] solver update (single_shooting); entries beyond nms are not written.  Multi-device: the slowest device. */
+OCS_B200_API int ocs_b200_kernel_stats_ex(ocs_b200_handle *h, int reset, double *ms, int nms, long *launches);
 /* enable/disable the CUDA-event bracketing used by ocs_b200_kernel_stats (off by default) */
 OCS_B200_API int ocs_b200_set_profiling(ocs_b200_handle *h, int on);
 

@@ -27,6 +27,15 @@ REDUCE_SUM, REDUCE_MIN, REDUCE_MAX = 0, 1, 2
 SIGNATURES = {
     "ocs_b200_create": (ctypes.c_int, [ctypes.c_int, c_dp, ctypes.c_int, c_dp, ctypes.c_int, ctypes.c_int,
                                        ctypes.POINTER(c_h)]),
+    "ocs_b200_create_multi": (ctypes.c_int, [ctypes.c_int, c_dp, ctypes.c_int, c_dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                             ctypes.c_int, ctypes.POINTER(c_h)]),
+    "ocs_b200_get_devices": (ctypes.c_int, [c_h, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), c_lp, ctypes.c_int]),
+    "ocs_b200_get_dims": (ctypes.c_int, [c_h, c_ip]),
+    "ocs_b200_get_batch": (ctypes.c_long, [c_h]),
+    "ocs_b200_evaluate_resident": (ctypes.c_int, [c_h, c_dp, ctypes.c_long, ctypes.c_int]),
+    "ocs_b200_gather_results_dev": (ctypes.c_int, [c_h, ctypes.c_void_p, ctypes.c_void_p]),
+    "ocs_b200_get_results": (ctypes.c_int, [c_h, c_dp, c_dp, c_ip, c_dp, c_dp]),
+    "ocs_b200_kernel_stats_ex": (ctypes.c_int, [c_h, ctypes.c_int, c_dp, ctypes.c_int, c_lp]),
     "ocs_b200_destroy": (ctypes.c_int, [c_h]),
     "ocs_b200_last_error": (ctypes.c_char_p, [c_h]),
     "ocs_b200_abi_version": (ctypes.c_int, []),

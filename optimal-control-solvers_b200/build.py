@@ -29,10 +29,11 @@ UNITS = [
     ("kernels_fast.o", "kernels_builtin.cu", ["-DOCS_STRICT=0", "-fmad=true"]),
     ("kernels_strict.o", "kernels_builtin.cu", ["-DOCS_STRICT=1", "-fmad=false"]),
     ("ocs_api.o", "ocs_api.cu", []),
+    ("ocs_multi.o", "ocs_multi.cu", []),
     ("nvrtc_problem.o", "nvrtc_problem.cu", []),
     ("microbench.o", "microbench.cu", []),
 ]
-HEADERS = ["rk4_kernels.cuh", "solution_interp.cuh", "problem_test.cuh", "kernel_table.h", os.path.join("..", "..", "include", "ocs_b200.h")]
+HEADERS = ["rk4_kernels.cuh", "solution_interp.cuh", "problem_test.cuh", "kernel_table.h", "ocs_internal.h", "host_stager.h", os.path.join("..", "..", "include", "ocs_b200.h")]
 
 
 def _newest_input() -> float:
@@ -64,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(_compile, UNITS))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + [os.path.join(OBJ, o) for o in objs] + ["-ldl"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + [os.path.join(OBJ, o) for o in objs] + ["-ldl", "-lpthread"]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
@@ -88,7 +89,7 @@ def build_variant(name: str, flags: list[str]) -> str:
         raise RuntimeError(p.stdout + p.stderr)
     lib = os.path.join(vdir, f"libocs_{name}.so")
     others = [os.path.join(OBJ, u[0]) for u in UNITS if u[0] != "kernels_fast.o"]
-    p = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib, obj] + others + ["-ldl"], capture_output=True, text=True)
+    p = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib, obj] + others + ["-ldl", "-lpthread"], capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(p.stdout + p.stderr)
     return lib

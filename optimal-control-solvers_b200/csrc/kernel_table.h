@@ -14,13 +14,15 @@ struct ocs_kernel_table {
     int tpt_fwd;   // ... and of the forward kernels
     int tpt_fwd_coef;
     int fb_ring;   // ... and of the fb_sweep costate kernels (ring*(n + 2 nc)*threads doubles)
-    int rev_ring;  // depth of the gradient kernels' cp.async node-state ring (shared memory: ring*tpt*n*threads doubles)
+    int rev_ring;  // depth of the gradient kernels' cp.async node-state ring (shared memory: ring*tpt*(n [+ 2 nc])*threads doubles)
+    int async_stage;   // multi-trajectory bodies keep two record tiles in shared memory (the next one is fetched with cp.async)
     const void *fwd[3][3][2];   // [UMODE][BMODE][params batched]
     const void *rev[3][3][2];
     const void *fwdg[3][3][2];  // fetch variants: also write the full grids (x with the J row; lam, dJdu)
     const void *revg[3][3][2];
     const void *fbrev[2];
     const void *fbcont[2];      // fb_sweep with the continuous costate equation (v1 adjointRHS) instead of the discrete adjoint
+    const void *fbcontg[2];     // ... its fetch variant: writes the costate grid, leaves the control alone
     const void *tt;
     int nfold[3];               // weight-folded table entries per hoisting mode (0: the problem / build does not fold)
     const void *fold;           // fills the fold records [N][even(3*nfold)] from the grid-point and step records

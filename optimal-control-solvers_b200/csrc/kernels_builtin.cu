@@ -71,6 +71,7 @@ OCS_DEFINE_KERNELS(ocs_fast::TestOCProblem, test_fast, 0)
 #define REVG(UM, BM, PB) (const void *)OCS_CAT5(ocs_revg_, OCS_TAGNAME, _u##UM, _b##BM, _p##PB)
 #define FBR(PB) (const void *)OCS_CAT3(ocs_fbrev_, OCS_TAGNAME, _u2_b0_p##PB)
 #define FBC(PB) (const void *)OCS_CAT3(ocs_fbcont_, OCS_TAGNAME, _u2_b0_p##PB)
+#define FBCG(PB) (const void *)OCS_CAT3(ocs_fbcontg_, OCS_TAGNAME, _u2_b0_p##PB)
 
 extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
 {
@@ -85,6 +86,7 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->tpt_fwd = OCS_TPT_FWD;
     t->tpt_fwd_coef = OCS_TPT_FWD_COEF;
     t->rev_ring = OCS_RING;
+    t->async_stage = OCS_ASYNC_STAGE;
     t->fb_ring = OCS_FB_RING;
     for (int pb = 0; pb < 2; ++pb)
         for (int um = 0; um < 3; ++um)
@@ -108,6 +110,7 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->revg[2][0][0] = REVG(2, 0, 0); t->revg[2][0][1] = REVG(2, 0, 1);
     t->fbrev[0] = FBR(0); t->fbrev[1] = FBR(1);
     t->fbcont[0] = FBC(0); t->fbcont[1] = FBC(1);
+    t->fbcontg[0] = FBCG(0); t->fbcontg[1] = FBCG(1);
     t->tt = (const void *)OCS_CAT2(ocs_tt_, OCS_TAGNAME);
     for (int hm = 0; hm < 3; ++hm) t->nfold[hm] = OCS_NS::ocs_nfold<P>(hm);
     t->fold = (const void *)OCS_CAT2(ocs_fold_, OCS_TAGNAME);

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,8 @@ struct Nvrtc {
 bool load_nvrtc(Nvrtc &n, std::string *log)
 {
     static Nvrtc cached;
+    static std::mutex mu;                       // a multi-device handle compiles on one thread per device
+    std::lock_guard<std::mutex> lock(mu);
     if (cached.lib) {
         n = cached;
         return true;
@@ -92,13 +95,22 @@ std::string default_include_dir()
 // resulting library.  Sweep variants are compiled one at a time, on first use: a 6-state problem
 // takes a second or two per variant instead of a minute for all of them.
 int ocs_compile_unit(const char *source, const char *unit, int strict, const char *include_dir,
-                     const char *const *names, int nnames, const void **kernels, void **library, std::string *log)
+                     const char *const *names, int nnames, const void **kernels, void **library, std::string *log,
+                     int n_states)
 {
     Nvrtc rt;
     if (!load_nvrtc(rt, log)) return OCS_B200_ERR_COMPILE;
 
     std::string src;
     src += "#define OCS_NS ocs_gen\n";
+    // Sweep-kernel tuning by problem size (B200, profiles/r2_notes.md).  A problem with several states carries
+    // 150+ live registers per trajectory, so only 8-12 warps are resident per SM: nothing hides a global-load
+    // latency.  Its per-step loads therefore go through a cp.async ring 4 steps ahead, the reverse step loop is not
+    // unrolled (fewer live values) and the kernels are capped at 168 registers (3 blocks of 128 threads per SM).
+    if (n_states >= 4) {
+        src += "#define OCS_REV_UNROLL 1\n#define OCS_RING 4\n#define OCS_FB_RING 4\n"
+               "#define OCS_MINBLOCKS_REV 3\n#define OCS_MINBLOCKS_FWD 3\n#define OCS_MINBLOCKS_FB 3\n";
+    }
     // kernel tuning experiments: OCS_B200_NVRTC_DEFS="OCS_MINBLOCKS_REV=3;OCS_TPT_FWD=2" -> #define lines
     if (const char *defs = getenv("OCS_B200_NVRTC_DEFS")) {
         std::string d(defs);
@@ -108,8 +120,10 @@ int ocs_compile_unit(const char *source, const char *unit, int strict, const cha
             if (end == std::string::npos) end = d.size();
             std::string item = d.substr(pos, end - pos);
             const size_t eq = item.find('=');
-            if (!item.empty())
+            if (!item.empty()) {
+                src += "#undef " + (eq == std::string::npos ? item : item.substr(0, eq)) + "\n";
                 src += "#define " + (eq == std::string::npos ? item : item.substr(0, eq) + " " + item.substr(eq + 1)) + "\n";
+            }
             pos = end + 1;
         }
     }
@@ -183,7 +197,7 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, c
     unit += "OCS_TT_KERNEL(ocs_gen::Problem, gen)\n";
     const char *names[2] = {"ocs_tt_gen", "ocs_info_gen"};
     const void *kern[2] = {nullptr, nullptr};
-    int rc = ocs_compile_unit(source, unit.c_str(), strict, include_dir, names, 2, kern, library, log);
+    int rc = ocs_compile_unit(source, unit.c_str(), strict, include_dir, names, 2, kern, library, log, n);
     if (rc != 0) return rc;
     memset(table, 0, sizeof *table);
     table->tt = kern[0];
@@ -208,7 +222,8 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, c
     table->tpt_fwd_coef = (inf[5] >> 16) & 0xff;
     table->tile = inf[6] & 0xffff;
     table->rev_ring = (inf[6] >> 16) & 0xff;
-    table->fb_ring = (inf[6] >> 24) & 0xff;
+    table->fb_ring = (inf[6] >> 24) & 0xf;
+    table->async_stage = (inf[6] >> 28) & 1;
     table->threads = inf[7] & 0xffff;
     table->tpt_rev = (inf[7] >> 16) & 0xff;
     table->tpt_fwd = (inf[7] >> 24) & 0xf;

@@ -7,21 +7,7 @@
 // grid (diff / midpoints, RK4Integrator.m:17-24), h/2, h/3, h/6 and -- for a control
 // shared by the whole batch -- the product u = v*B for the G grid points.
 // There is no CPU fallback: without a CUDA device every compute call fails.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <vector>
-
-#include "../../include/ocs_b200.h"
-#include "kernel_table.h"
+#include "ocs_internal.h"
 #include "solution_interp.cuh"
 
 #define OCS_NS ocs_host
@@ -35,146 +21,19 @@ extern "C" void ocs_builtin_table_test_strict(ocs_kernel_table *t);
 int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, const char *include_dir,
                         ocs_kernel_table *table, void **library, std::string *log);
 int ocs_compile_unit(const char *source, const char *unit, int strict, const char *include_dir,
-                     const char *const *names, int nnames, const void **kernels, void **library, std::string *log);
+                     const char *const *names, int nnames, const void **kernels, void **library, std::string *log,
+                     int n_states);
 void ocs_unload_problem(void *library);
 
 namespace {
 
-constexpr int OCS_FOLD_MAX = 15;     // most folded table entries per stage position a problem may declare
+using ocs_detail::Segment;
+using ocs_detail::DevBuf;
+using ocs_detail::OCS_FOLD_MAX;
+using namespace ocs_detail;
 
 std::string g_create_error = "";
 std::mutex g_mutex;
-
-struct Segment {
-    int N = 0;
-    std::vector<double> tspan, t, h;
-    double *d_gprec = nullptr, *d_steprec = nullptr, *d_basrec = nullptr;
-    double *d_foldrec = nullptr;            // weight-folded table entries [N][even(3*nfold)] (rk4_kernels.cuh), or null
-    int fold_nf = 0;                        // nfold the fold records were built for (0: none)
-    size_t gprec_cap = 0, basrec_cap = 0;   // doubles
-    double *h_rec = nullptr;  // pinned staging of the records (async upload)
-    size_t h_rec_cap = 0;
-    int BW = 0;               // doubles per basis record
-    int hm = 0;               // hoisting mode the records were built for
-    bool basis_dirty = true;
-    cudaEvent_t rec_uploaded = nullptr;
-    bool steps_uploaded = false;
-    double *d_xs_base = nullptr;   // allocation: OCS_XS_SLACK*Bt doubles of slack, then node states [n][N+1][Bt]
-    double *d_xs = nullptr;        // = d_xs_base + OCS_XS_SLACK*Bt
-    size_t xs_cap = 0;             // doubles (whole allocation)
-    int R = 0;
-    bool records_dirty = true;
-};
-
-enum { CTRL_NONE = 0, CTRL_V_SHARED, CTRL_V_BATCH, CTRL_U_SHARED, CTRL_U_BATCH };
-enum { BASIS_NONE = 0, BASIS_SPARSE = 1, BASIS_DENSE = 2 };
-
-struct DevBuf {
-    double *p = nullptr;
-    size_t cap = 0;   // doubles
-};
-
-}  // namespace
-
-struct ocs_b200_handle {
-    int device = 0;
-    int math_mode = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    std::string err;
-    int sticky = 0;
-
-    Segment seg[2];
-    bool has_tail = false;
-
-    // problem
-    bool have_problem = false;
-    ocs_kernel_table kt{};
-    std::vector<void *> gen_libraries;
-    std::string gen_source, gen_include;
-    int gen_n = 0, gen_nc = 0, gen_np = 0;
-    bool is_generated = false;
-
-    // params
-    std::vector<double> params_shared;
-    long params_nbatch = 0;
-    DevBuf d_params;
-    std::vector<double> uStar;
-
-    // control
-    int basis_kind = BASIS_NONE;
-    int K = 0;
-    std::vector<int32_t> bk, bnnz;
-    bool bk_monotone = false;          // knot index non-decreasing along the grid: dJdv columns are stored once
-    bool bk_covered = false;           // ... and every knot is reached by the window, so dJdv needs no zero-fill
-    std::vector<double> bw0, bw1, bdense;
-    int ctrl_mode = CTRL_NONE;
-    std::vector<double> ctrl_shared;   // v (nc*K) or u (nc*G)
-    long ctrl_nbatch = 0;
-    DevBuf d_v, d_ug;
-    const double *v_ext = nullptr;     // caller-owned device v (set_control_v_dev)
-    const int *fb_frozen = nullptr;    // trajectories the sweeps must leave untouched (single_shooting / fb_sweep)
-    double *lams_req = nullptr;        // set while ocs_b200_eval_solution wants the node costates of a segment (SoA)
-    long lams_ld = 0;
-    int lams_segment = 0;
-    int ufunc_kind = 0;                // compute_uFunc of the attached control (ocs_b200_set_control_ufunc)
-    std::vector<double> ufunc_knots;
-    int fb_costate = 0;                // OCS_B200_COSTATE_* used by ocs_b200_fb_sweep
-    bool user_lamT = false;            // last compute_adjoints carried an explicit lamT (kept in d_lamT_user)
-    long user_lamT_ld = 0;
-
-    // batch state
-    long Bt = 0;
-    bool have_states = false;
-    DevBuf d_x0, d_J, d_xT, d_lamT_tail, d_lamT_user, d_dJdv, d_lam0, d_stage, d_stage2, d_maxchg;
-    DevBuf d_dug;                     // dJdu grid [nc][G][Bt] of the dense-basis gradient path
-    DevBuf d_z, d_g, d_zt, d_gt, d_Jacc, d_Jhist, d_alpha, d_lbub, d_pred;   // single_shooting (SPG) state
-    DevBuf d_pipe[2];                 // double-buffered transpose staging of the chunked dJdv download
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t chunk_done[2] = {nullptr, nullptr};
-    cudaEvent_t stage_free[2] = {nullptr, nullptr};   // the download out of staging buffer k has finished
-    int *d_status = nullptr;
-    size_t status_cap = 0;
-    int *d_frozen = nullptr, *d_sweeps = nullptr;
-    size_t frozen_cap = 0;
-    double *d_bounds = nullptr;
-    double *d_red = nullptr;   // reduction scratch
-    int *d_errflag = nullptr;  // set by a kernel whose compiled record layout disagrees with the host's
-
-    // profiling
-    bool profiling = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double ms_fwd = 0, ms_rev = 0;
-    long launches = 0;
-
-    int fail(int code, const char *fmt, ...)
-    {
-        char buf[1024];
-        va_list ap;
-        va_start(ap, fmt);
-        vsnprintf(buf, sizeof buf, fmt, ap);
-        va_end(ap);
-        err = buf;
-        if (code == OCS_B200_ERR_CUDA) sticky = code;
-        return code;
-    }
-};
-
-namespace {
-
-typedef ocs_b200_handle H;
-
-#define CK(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return h->fail(OCS_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
-                           __FILE__, __LINE__);                                                         \
-    } while (0)
-#define TRY(expr)                  \
-    do {                           \
-        int rc_ = (expr);          \
-        if (rc_ != 0) return rc_;  \
-    } while (0)
 
 int ensure(H *h, DevBuf &b, size_t n)
 {
@@ -202,6 +61,54 @@ int ensure_raw(H *h, double **p, size_t *cap, size_t n)
     *p = b.p;
     *cap = b.cap;
     return rc;
+}
+
+// ---------------------------------------------------------------- caller buffers
+// Host <-> device copies of caller-owned host arrays.  Pinned / registered memory goes straight to the copy
+// engine; large pageable arrays (every MATLAB mxArray, every NumPy array) go through the handle's pinned ring and
+// copy threads (host_stager.h).  Everything is ordered on `st`; the data is in place after finish_host().
+int h2d(H *h, void *dst, const void *src, size_t bytes, cudaStream_t st = nullptr)
+{
+    if (bytes == 0) return 0;
+    if (!st) st = h->stream;
+    if (bytes >= HostStager::kMinBytes && HostStager::enabled() && !HostStager::is_pinned(src)) {
+        CK(h->stager.h2d(h->device, dst, src, bytes, st));
+        h->staged = true;
+        return 0;
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+int d2h(H *h, void *dst, const void *src, size_t bytes, cudaStream_t st = nullptr)
+{
+    if (bytes == 0) return 0;
+    if (!st) st = h->stream;
+    if (bytes >= HostStager::kMinBytes && HostStager::enabled() && !HostStager::is_pinned(dst)) {
+        CK(h->stager.d2h(h->device, dst, src, bytes, st));
+        h->staged = true;
+        return 0;
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+// The end of every host-buffer call: streams drained, staged copies delivered, and the flag a kernel raises when it
+// was compiled for another record layout than the host packed (it then returns without writing anything) turned
+// into an error instead of stale results.
+int finish_host(H *h)
+{
+    if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->staged) {
+        h->staged = false;
+        CK(h->stager.finish());
+    }
+    if (h->h_errflag && *h->h_errflag) {
+        *h->h_errflag = 0;
+        h->have_states = false;
+        return h->fail(OCS_B200_ERR_STATE, "a sweep kernel was compiled for another record layout than the host packed "
+                                           "(stale kernel variant or OCS_B200_NVRTC_DEFS mismatch); no results were written");
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------- layout kernels
@@ -267,25 +174,18 @@ int from_soa(H *h, const double *d_src, double *d_dst, long rows, long nb, long 
 int upload_soa(H *h, const double *host, DevBuf &dst, long rows, long nb, int nc = 1)
 {
     TRY(ensure(h, dst, (size_t)rows * nb));
-    if (rows == 1) {
-        CK(cudaMemcpyAsync(dst.p, host, sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
-        return 0;
-    }
+    if (rows == 1) return h2d(h, dst.p, host, sizeof(double) * nb);
     TRY(ensure(h, h->d_stage, (size_t)rows * nb));
-    CK(cudaMemcpyAsync(h->d_stage.p, host, sizeof(double) * rows * nb, cudaMemcpyHostToDevice, h->stream));
+    TRY(h2d(h, h->d_stage.p, host, sizeof(double) * rows * nb));
     return to_soa(h, h->d_stage.p, dst.p, rows, nb, nb, nc);
 }
 // device SoA [rows][ld] (first nb columns from b0) -> host [rows x nb]
 int download_soa(H *h, const double *d_src, long ld, long b0, double *host, long rows, long nb, int nc = 1)
 {
-    if (rows == 1) {
-        CK(cudaMemcpyAsync(host, d_src + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, h->stream));
-        return 0;
-    }
+    if (rows == 1) return d2h(h, host, d_src + b0, sizeof(double) * nb);
     TRY(ensure(h, h->d_stage, (size_t)rows * nb));
     TRY(from_soa(h, d_src + b0, h->d_stage.p, rows, nb, ld, nc));
-    CK(cudaMemcpyAsync(host, h->d_stage.p, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost, h->stream));
-    return 0;
+    return d2h(h, host, h->d_stage.p, sizeof(double) * rows * nb);
 }
 
 // ---------------------------------------------------------------- batch reductions (warp shuffles)
@@ -546,67 +446,69 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
 
 // dJdv = dJdu * B' for a dense basis (ChebyshevControl.m:34-37):
 // dug [nc][G][ldb] (SoA, written by the reverse sweep), basrec [G][BW] = B(:,j), dJdv [(k*nc+c)][ldb].
-// The block stages B for a tile of grid points in shared memory.  A thread owns PROJ_T trajectories and keeps
-// KC accumulators for each in registers (K is walked in chunks of KC): one row B(:,j) read from shared memory
-// feeds PROJ_T*KC FMAs, and the dJdu loads of 4 grid points are issued ahead of their use.  Summation runs
-// over ascending j.
-#define PROJ_JT 64
-#define PROJ_T 4
+// HBM-bound (every dJdu value is read once, 17 FMAs each at K = 17), so what matters is bytes in flight: a block is
+// 32 trajectories (lanes) x PROJ_W warps; warp w sums the grid points of segment w of [0, G) for ONE control
+// (blockIdx.y) with KC accumulators per thread and 8 loads in flight per thread; B(:,j) of the warp's current run of
+// PROJ_JT grid points sits in a warp-private shared-memory tile (every lane reads the same entry: a broadcast).  The
+// PROJ_W partial sums of a trajectory are added in ascending segment order through shared memory (fixed order:
+// deterministic).  48 registers -> all 1024+ threads of an SM resident, ~64 KB of loads in flight per SM; the first
+// version (4 trajectories x 18 accumulators per thread, 254 registers, 196 blocks) reached 2.0 TB/s.
+#define PROJ_JT 32
+#define PROJ_W 8
 template <int KC>
-__global__ void __launch_bounds__(128) dense_project_kernel(const double *__restrict__ dug, const double *__restrict__ basrec,
-                                                            int BW, int K, int nc, int G, long nb, long ldb, double *dJdv)
+__global__ void __launch_bounds__(32 * PROJ_W, 3) dense_project_kernel(const double *__restrict__ dug, const double *__restrict__ basrec,
+                                                                   int BW, int K, int nc, int G, long nb, long ldb, double *dJdv)
 {
     extern __shared__ double2 proj_smem2[];
-    double *Bs = reinterpret_cast<double *>(proj_smem2);      // [PROJ_JT][BW]
-    long b[PROJ_T], bb[PROJ_T];
+    double *sm = reinterpret_cast<double *>(proj_smem2);
+    const int lane = threadIdx.x, w = threadIdx.y, c = blockIdx.y;
+    double *Bs = sm + (size_t)w * PROJ_JT * BW;                 // [PROJ_JT][BW], private to the warp
+    const long b = (long)blockIdx.x * 32 + lane;
+    const long bb = b < nb ? b : nb - 1;
+    const int seg = (G + PROJ_W - 1) / PROJ_W;
+    const int ja = w * seg, jb = ja + seg < G ? ja + seg : G;
+    const double *dp = dug + (size_t)c * G * ldb + bb;
+    const unsigned ld8 = (unsigned)ldb * 8u;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        double acc[KC];
 #pragma unroll
-    for (int q = 0; q < PROJ_T; ++q) {
-        b[q] = ((long)blockIdx.x * PROJ_T + q) * blockDim.x + threadIdx.x;
-        bb[q] = b[q] < nb ? b[q] : nb - 1;
-    }
-    for (int c = 0; c < nc; ++c)
-        for (int k0 = 0; k0 < K; k0 += KC) {
-            double acc[PROJ_T][KC];
+        for (int kk = 0; kk < KC; ++kk) acc[kk] = 0.0;
+        for (int j0 = ja; j0 < jb; j0 += PROJ_JT) {
+            const int nj = jb - j0 < PROJ_JT ? jb - j0 : PROJ_JT;
+            __syncwarp();
+            for (int k = lane; k < PROJ_JT * BW; k += 32) Bs[k] = k < nj * BW ? basrec[(size_t)j0 * BW + k] : 0.0;
+            __syncwarp();
+#pragma unroll 1
+            for (int jj = 0; jj < PROJ_JT; jj += 8) {
+                if (jj >= nj) break;
+                double d[8];
 #pragma unroll
-            for (int q = 0; q < PROJ_T; ++q)
-#pragma unroll
-                for (int kk = 0; kk < KC; ++kk) acc[q][kk] = 0.0;
-            const double *dp = dug + (size_t)c * G * ldb;
-            for (int j0 = 0; j0 < G; j0 += PROJ_JT) {
-                const int nj = G - j0 < PROJ_JT ? G - j0 : PROJ_JT;
-                __syncthreads();
-                for (int k = threadIdx.x; k < PROJ_JT * BW; k += blockDim.x)
-                    Bs[k] = k < nj * BW ? basrec[(size_t)j0 * BW + k] : 0.0;   // rows past the grid multiply by zero
-                __syncthreads();
-                for (int jj = 0; jj < PROJ_JT; jj += 4) {
-                    if (jj >= nj) break;
-                    double d[4][PROJ_T];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int j = j0 + jj + r < G ? j0 + jj + r : G - 1;   // clamped rows meet a zero B row
-#pragma unroll
-                        for (int q = 0; q < PROJ_T; ++q) d[r][q] = dp[(size_t)j * ldb + bb[q]];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        double Bj[KC];
-#pragma unroll
-                        for (int kk = 0; kk < KC; ++kk) Bj[kk] = (k0 + kk < BW) ? Bs[(jj + r) * BW + k0 + kk] : 0.0;
-#pragma unroll
-                        for (int q = 0; q < PROJ_T; ++q)
-#pragma unroll
-                            for (int kk = 0; kk < KC; ++kk) acc[q][kk] = acc[q][kk] + d[r][q] * Bj[kk];
-                    }
+                for (int r = 0; r < 8; ++r) {
+                    const int j = j0 + jj + r < G ? j0 + jj + r : G - 1;      // clamped rows meet a zero B row
+                    d[r] = *ocs_host::soa_row(dp, (unsigned)j, ld8);
                 }
-            }
 #pragma unroll
-            for (int q = 0; q < PROJ_T; ++q)
-                if (b[q] < nb) {
+                for (int r = 0; r < 8; ++r) {
+                    const double *Bj = Bs + (jj + r) * BW + k0;
 #pragma unroll
                     for (int kk = 0; kk < KC; ++kk)
-                        if (k0 + kk < K) dJdv[(size_t)((k0 + kk) * nc + c) * ldb + b[q]] = acc[q][kk];
+                        if (k0 + kk < BW) acc[kk] = acc[kk] + d[r] * Bj[kk];
                 }
+            }
         }
+        // partial sums of the PROJ_W segments, added in ascending segment order
+        __syncthreads();
+        double *red = sm;                                        // [PROJ_W][KC][32]
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) red[((size_t)w * KC + kk) * 32 + lane] = acc[kk];
+        __syncthreads();
+        for (int kk = w; kk < KC; kk += PROJ_W) {
+            double sum = red[(size_t)kk * 32 + lane];
+            for (int q = 1; q < PROJ_W; ++q) sum = sum + red[((size_t)q * KC + kk) * 32 + lane];
+            if (b < nb && k0 + kk < K) dJdv[(size_t)((k0 + kk) * nc + c) * ldb + b] = sum;
+        }
+        __syncthreads();
+    }
 }
 
 // ug[c][j][b] = sum_k v[(k*nc+c)][b] B(k,j): control.compute_u for every trajectory (Control/*Control.m compute_u),
@@ -634,6 +536,21 @@ __global__ void __launch_bounds__(128) basis_eval_kernel(const double *__restric
             }
             ug[((size_t)c * G + j) * ldb + b] = u;
         }
+    }
+}
+
+// x grid (MATLAB layout m x NP x nb) read back from the resident node store [n][NP][ld]; the running-objective row is
+// not kept there: NaN, except its last entry = J
+__global__ void store_to_grid_kernel(const double *__restrict__ xs, long ld, int n, int NP, long nb, const double *__restrict__ J,
+                                     double *__restrict__ xgrid)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const int m = n + 1;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < NP; ++i) {
+        for (int c = 0; c < n; ++c) xgrid[c + (size_t)m * (i + (size_t)NP * b)] = xs[((size_t)c * NP + i) * ld + b];
+        xgrid[n + (size_t)m * (i + (size_t)NP * b)] = i == NP - 1 ? J[b] : qnan;
     }
 }
 
@@ -837,17 +754,22 @@ void base_args(H *h, int si, SweepArgs &a)
     a.basrec = s.d_basrec;
     a.p = h->d_params.p;
     a.ldp = h->params_nbatch > 1 ? h->params_nbatch : 0;
+    if (h->params_nbatch == 1)      // batch-uniform parameters also travel by value (constant-bank operands in the kernels)
+        for (int k = 0; k < h->kt.np && k < OCS_NPC; ++k) a.pc[k] = h->params_shared[k];
     a.error_flag = h->d_errflag;
     a.frozen = h->fb_frozen;
 }
 
+// Upper bound of what any kernel variant lays out: the record tile (twice when the next tile is fetched asynchronously
+// into a second buffer) followed by `acc_doubles` of per-thread rings.
 size_t smem_bytes(const H *h, const SweepArgs &a, size_t acc_doubles)
 {
     const int S = h->kt.tile;
     int nf = 0;     // fold records of the tile (same width for every hoisting mode that folds)
     for (int hm = 0; hm < 3; ++hm) nf = std::max(nf, h->kt.fold ? h->kt.nfold[hm] : 0);
     const size_t fold = a.foldrec ? (size_t)S * ((3 * nf + 1) & ~1) : 0;
-    return ((size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW + acc_doubles + fold) * sizeof(double);
+    const size_t tile = (size_t)(2 * S + 1) * a.RB + 4 * S + (size_t)(2 * S + 1) * a.BW + fold;
+    return ((h->kt.async_stage ? 2 : 1) * tile + acc_doubles) * sizeof(double);
 }
 
 // acc_doubles: shared-memory doubles per block beyond the record tiles (dense-basis gradient accumulators)
@@ -878,7 +800,7 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1,
 
 int pb_index(const H *h) { return h->params_nbatch > 1 ? 1 : 0; }
 
-enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB, KIND_FBC };
+enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB, KIND_FBC, KIND_FBCG };
 
 // The kernel of one sweep variant.  Built-in problems have every variant compiled in; generated
 // problems compile the variant with NVRTC the first time it is needed.
@@ -888,14 +810,14 @@ int resolve(H *h, int kind, int um, int bm, int pb, const void **out)
                       : kind == KIND_FWDG ? &h->kt.fwdg[um][bm][pb]
                       : kind == KIND_REV ? &h->kt.rev[um][bm][pb]
                       : kind == KIND_REVG ? &h->kt.revg[um][bm][pb]
-                      : kind == KIND_FB ? &h->kt.fbrev[pb] : &h->kt.fbcont[pb];
+                      : kind == KIND_FB ? &h->kt.fbrev[pb] : kind == KIND_FBC ? &h->kt.fbcont[pb] : &h->kt.fbcontg[pb];
     if (!*slot && h->is_generated) {
         static const char *macro[] = {"OCS_FWD_KERNEL", "OCS_FWDG_KERNEL", "OCS_REV_KERNEL", "OCS_REVG_KERNEL", "OCS_FB_KERNEL",
-                                      "OCS_FBC_KERNEL"};
-        static const char *prefix[] = {"ocs_fwd_", "ocs_fwdg_", "ocs_rev_", "ocs_revg_", "ocs_fbrev_", "ocs_fbcont_"};
+                                      "OCS_FBC_KERNEL", "OCS_FBCG_KERNEL"};
+        static const char *prefix[] = {"ocs_fwd_", "ocs_fwdg_", "ocs_rev_", "ocs_revg_", "ocs_fbrev_", "ocs_fbcont_", "ocs_fbcontg_"};
         char unit[256], name[96];
         const int kd = bm == 2 ? h->K : 0;
-        if (kind == KIND_FB || kind == KIND_FBC) {
+        if (kind == KIND_FB || kind == KIND_FBC || kind == KIND_FBCG) {
             snprintf(unit, sizeof unit, "%s(ocs_gen::Problem, gen, %d)", macro[kind], pb);
             snprintf(name, sizeof name, "%sgen_u2_b0_p%d", prefix[kind], pb);
         } else {
@@ -907,7 +829,8 @@ int resolve(H *h, int kind, int um, int bm, int pb, const void **out)
         void *lib = nullptr;
         std::string log;
         int rc = ocs_compile_unit(h->gen_source.c_str(), unit, h->math_mode == OCS_B200_MATH_STRICT,
-                                  h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log);
+                                  h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log,
+                                  h->gen_n);
         if (rc != 0) return h->fail(rc, "kernel %s of the generated problem did not compile:\n%s", name, log.c_str());
         h->gen_libraries.push_back(lib);
         *slot = kern[0];
@@ -1043,25 +966,49 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         }
         const bool grids = a.lamgrid || a.dJdugrid || a.lams;
         if (grids && um != 1) bm = 0;   // the fetch variants write dJdu itself; only UMODE_COEF needs the basis
+        if (grids && si == 0 && h->fb_resident && h->fb_costate == OCS_B200_COSTATE_CONTINUOUS) {
+            // soln.lam of a continuous-costate fb_sweep solve is that costate (compute_x_lam.m:11-14), not the discrete
+            // adjoint: the fb_sweep kernel's fetch variant re-integrates it and leaves the control grid alone
+            if (a.dJdugrid) return h->fail(OCS_B200_ERR_ARG, "dJdu belongs to the discrete adjoint; the continuous costate has none");
+            a.ug = h->d_ug.p + b0;
+            a.bounds = h->d_bounds;
+            a.relax = 1.0;
+            a.fb_readonly = 1;
+            a.lamT = nullptr;
+            a.dJdv = nullptr;
+            a.lam0 = nullptr;
+            const void *kc = nullptr;
+            TRY(resolve(h, KIND_FBCG, 2, 0, pb_index(h), &kc));
+            TRY(launch(h, kc, a, false, 1, (size_t)h->kt.fb_ring * (h->kt.n + 2 * h->kt.nc) * h->kt.threads));
+            continue;
+        }
         const void *kern = nullptr;
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
         // dense-basis kernels keep K coefficients and K accumulators per trajectory in registers: one per thread
         {
             const int tpt = (grids || bm == 2) ? 1 : std::max(um == 1 ? h->kt.tpt_rev_coef : h->kt.tpt_rev, 1);
             // the gradient kernels (not the fetch variants) keep a cp.async ring of node states in shared memory
-            const size_t ring = grids ? 0 : (size_t)h->kt.rev_ring * tpt * h->kt.n * h->kt.threads;
+            // (with a per-trajectory control grid a ring slot also carries the step's two controls)
+            const size_t ring = grids ? 0 : (size_t)h->kt.rev_ring * tpt * (h->kt.n + (um == 2 ? 2 * h->kt.nc : 0)) * h->kt.threads;
             TRY(launch(h, kern, a, false, tpt, ring));
         }
         if (project) {
             const int G = 2 * s.N + 1;
             if (h->profiling) CK(cudaEventRecord(h->ev[2], h->stream));
-            const size_t psm = (size_t)PROJ_JT * s.BW * sizeof(double);
-            const unsigned pblocks = (unsigned)((nb + 128 * PROJ_T - 1) / (128 * PROJ_T));
-            // K <= 18: one pass with 18 accumulators per trajectory; larger K in chunks of 16
-            if (h->K <= 18)
-                dense_project_kernel<18><<<pblocks, 128, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
-            else
-                dense_project_kernel<16><<<pblocks, 128, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
+            // K <= 18: one pass with 18 accumulators per thread; larger K in chunks of 16
+            const int KC = h->K <= 18 ? 18 : 16;
+            const size_t psm = std::max((size_t)PROJ_W * PROJ_JT * s.BW, (size_t)PROJ_W * KC * 32) * sizeof(double);
+            const dim3 pgrid((unsigned)((nb + 31) / 32), (unsigned)h->kt.nc), pblock(32, PROJ_W);
+            if (psm > 200 * 1024) return h->fail(OCS_B200_ERR_ARG, "control basis too wide for the projection kernel");
+            if (KC == 18) {
+                if (psm > 48 * 1024)
+                    CK(cudaFuncSetAttribute(dense_project_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+                dense_project_kernel<18><<<pgrid, pblock, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
+            } else {
+                if (psm > 48 * 1024)
+                    CK(cudaFuncSetAttribute(dense_project_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+                dense_project_kernel<16><<<pgrid, pblock, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
+            }
             CK(cudaGetLastError());
             if (h->profiling) {
                 CK(cudaEventRecord(h->ev[3], h->stream));
@@ -1069,6 +1016,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
                 h->ms_rev += ms;
+                h->ms_proj += ms;
             }
             h->launches++;
         }
@@ -1123,15 +1071,31 @@ int validate_control(H *h, long Bt)
     }
 }
 
-int states_common(H *h, long Bt)
+// Control and parameters fit a batch of Bt trajectories.  Checked BEFORE anything is (re)allocated for a new batch and
+// again by every call that sweeps the resident one (a setter may have changed them in between: the kernels index
+// d_v / d_ug / d_params with the batch stride Bt).
+int validate_batch(H *h, long Bt)
 {
     TRY(validate_control(h, Bt));
     if (h->params_nbatch > 1 && h->params_nbatch != Bt)
         return h->fail(OCS_B200_ERR_ARG, "params have %ld columns but the batch has %ld trajectories", h->params_nbatch, Bt);
+    return 0;
+}
+
+int states_common(H *h, long Bt)
+{
     h->Bt = Bt;
+    h->fb_resident = false;
     TRY(run_forward(h, 0, Bt, -1, nullptr, true));
     h->have_states = true;
     return 0;
+}
+
+// Calls that use the resident sweep: it exists and still matches the control / parameters that are set now.
+int check_resident(H *h, const char *who)
+{
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "%s needs a preceding compute_states on this handle", who);
+    return validate_batch(h, h->Bt);
 }
 
 }  // namespace
@@ -1195,8 +1159,13 @@ int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extr
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->ev[k]);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_errflag, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(h->d_errflag, 0, sizeof(int));
+    // the kernels' "wrong record layout" flag lives in mapped pinned host memory: raised by the device (only on an
+    // error), read by the host at every synchronisation point without a copy
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_errflag, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *h->h_errflag = 0;
+        e = cudaHostGetDevicePointer((void **)&h->d_errflag, h->h_errflag, 0);
+    }
     if (e != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
         delete h;
@@ -1224,6 +1193,7 @@ int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extr
 int ocs_b200_destroy(ocs_b200_handle *h)
 {
     if (!h) return 0;
+    if (h->multi) return ocs_multi_destroy(h);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (int si = 0; si < 2; ++si) {
@@ -1250,7 +1220,8 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     cudaFree(h->d_sweeps);
     cudaFree(h->d_bounds);
     cudaFree(h->d_red);
-    cudaFree(h->d_errflag);
+    if (h->h_errflag) cudaFreeHost(h->h_errflag);
+    h->stager.shutdown();
     for (int k = 0; k < 4; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     for (void *lib : h->gen_libraries) ocs_unload_problem(lib);
@@ -1262,6 +1233,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
 
 int ocs_b200_get_grid(const ocs_b200_handle *h, int segment, double *t, double *hstep)
 {
+    if (h && h->multi) return ocs_multi_get_grid(h, segment, t, hstep);
     if (!h || segment < 0 || segment > 1 || h->seg[segment].N == 0) return OCS_B200_ERR_ARG;
     const Segment &s = h->seg[segment];
     if (t) memcpy(t, s.t.data(), sizeof(double) * s.t.size());
@@ -1272,6 +1244,7 @@ int ocs_b200_get_grid(const ocs_b200_handle *h, int segment, double *t, double *
 int ocs_b200_set_problem_builtin(ocs_b200_handle *h, int problem_id)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_problem_builtin(h, problem_id);
     if (problem_id != OCS_B200_PROBLEM_TEST) return h->fail(OCS_B200_ERR_ARG, "unknown built-in problem %d", problem_id);
     if (h->math_mode == OCS_B200_MATH_STRICT)
         ocs_builtin_table_test_strict(&h->kt);
@@ -1288,20 +1261,22 @@ int ocs_b200_set_problem_source(ocs_b200_handle *h, const char *cuda_source, int
                                 const char *kernel_include_dir)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_problem_source(h, cuda_source, n, nc, np, kernel_include_dir);
     if (!cuda_source || n < 1 || nc < 1 || np < 0) return h->fail(OCS_B200_ERR_ARG, "bad generated-problem description");
     try {
         CK(cudaSetDevice(h->device));
+        std::string log;
+        ocs_kernel_table kt{};
+        void *lib = nullptr;
+        int rc = ocs_compile_problem(cuda_source, n, nc, np, h->math_mode == OCS_B200_MATH_STRICT,
+                                     (kernel_include_dir && kernel_include_dir[0]) ? kernel_include_dir : nullptr, &kt, &lib, &log);
+        // a failed compilation leaves the handle as it was (problem, lazily compiled variants and their source)
+        if (rc != 0) return h->fail(rc, "generated problem did not compile:\n%s", log.c_str());
         h->gen_source = cuda_source;
         h->gen_include = kernel_include_dir ? kernel_include_dir : "";
         h->gen_n = n;
         h->gen_nc = nc;
         h->gen_np = np;
-        std::string log;
-        ocs_kernel_table kt{};
-        void *lib = nullptr;
-        int rc = ocs_compile_problem(cuda_source, n, nc, np, h->math_mode == OCS_B200_MATH_STRICT,
-                                     h->gen_include.empty() ? nullptr : h->gen_include.c_str(), &kt, &lib, &log);
-        if (rc != 0) return h->fail(rc, "generated problem did not compile:\n%s", log.c_str());
         for (void *old : h->gen_libraries) ocs_unload_problem(old);
         h->gen_libraries.clear();
         h->gen_libraries.push_back(lib);
@@ -1319,6 +1294,7 @@ int ocs_b200_set_problem_source(ocs_b200_handle *h, const char *cuda_source, int
 int ocs_b200_set_params(ocs_b200_handle *h, const double *params, int np, long nbatch)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_params(h, params, np, nbatch);
     if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting parameters");
     if (np != h->kt.np || nbatch < 1 || (!params && np > 0))
         return h->fail(OCS_B200_ERR_ARG, "the problem takes %d parameters (got %d, nbatch %ld)", h->kt.np, np, nbatch);
@@ -1327,7 +1303,7 @@ int ocs_b200_set_params(ocs_b200_handle *h, const double *params, int np, long n
         if (nbatch == 1) {
             h->params_shared.assign(params, params + np);
             TRY(ensure(h, h->d_params, np));
-            CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+            TRY(h2d(h, h->d_params.p, params, sizeof(double) * np));
             CK(cudaStreamSynchronize(h->stream));
         } else {
             TRY(upload_soa(h, params, h->d_params, np, nbatch));
@@ -1344,6 +1320,7 @@ int ocs_b200_set_params(ocs_b200_handle *h, const double *params, int np, long n
 int ocs_b200_set_tail_control(ocs_b200_handle *h, const double *uStar, int nc)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_tail_control(h, uStar, nc);
     if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting uStar");
     if (!uStar || nc != h->kt.nc) return h->fail(OCS_B200_ERR_ARG, "uStar must have nc = %d entries", h->kt.nc);
     h->uStar.assign(uStar, uStar + nc);
@@ -1354,10 +1331,15 @@ int ocs_b200_set_tail_control(ocs_b200_handle *h, const double *uStar, int nc)
 int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_control_basis(h, K, B);
     try {
         if (K == 0) {
             h->basis_kind = BASIS_NONE;
             h->K = 0;
+            if (h->ctrl_mode == CTRL_V_SHARED || h->ctrl_mode == CTRL_V_BATCH) {
+                h->ctrl_mode = CTRL_NONE;     // coefficients without a basis mean nothing
+                h->have_states = false;
+            }
             mark_dirty(h);
             return 0;
         }
@@ -1422,6 +1404,7 @@ int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
             h->kt.kd = K;
         }
         h->ctrl_mode = CTRL_NONE;   // coefficients belong to the previous basis
+        h->have_states = false;     // ... and the resident sweep to the previous control
         h->ufunc_kind = 0;          // ... and so does its uFunc
         h->ufunc_knots.clear();
         mark_dirty(h);
@@ -1433,6 +1416,7 @@ int ocs_b200_set_control_basis(ocs_b200_handle *h, int K, const double *B)
 
 int ocs_b200_get_control_index(const ocs_b200_handle *h, int32_t *k_index, int32_t *nnz)
 {
+    if (h && h->multi) return ocs_multi_get_control_index(h, k_index, nnz);
     if (!h || h->basis_kind == BASIS_NONE) return OCS_B200_ERR_STATE;
     const int G = 2 * h->seg[0].N + 1;
     if (k_index) memcpy(k_index, h->bk.data(), sizeof(int32_t) * G);
@@ -1443,6 +1427,7 @@ int ocs_b200_get_control_index(const ocs_b200_handle *h, int32_t *k_index, int32
 int ocs_b200_set_control_v(ocs_b200_handle *h, const double *v, long nbatch)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_control_v(h, v, nbatch);
     if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting the control");
     if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "attach a control basis before setting v");
     if (!v || nbatch < 1) return h->fail(OCS_B200_ERR_ARG, "bad v");
@@ -1469,6 +1454,9 @@ int ocs_b200_set_control_v(ocs_b200_handle *h, const double *v, long nbatch)
 int ocs_b200_set_control_v_dev(ocs_b200_handle *h, const double *v_soa, long nbatch)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi)
+        return h->fail(OCS_B200_ERR_ARG, "ocs_b200_set_control_v_dev takes pointers / a stream of ONE device; on a multi-device handle use "
+                                          "ocs_b200_evaluate_resident, ocs_b200_gather_results_dev and ocs_b200_get_results");
     if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "attach a control basis before setting v");
     if (!v_soa || nbatch < 2) return h->fail(OCS_B200_ERR_ARG, "device v needs one column per trajectory");
     h->v_ext = v_soa;
@@ -1481,6 +1469,7 @@ int ocs_b200_set_control_v_dev(ocs_b200_handle *h, const double *v_soa, long nba
 int ocs_b200_set_control_u(ocs_b200_handle *h, const double *u, long nbatch)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_control_u(h, u, nbatch);
     if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "bind a problem before setting the control");
     if (!u || nbatch < 1) return h->fail(OCS_B200_ERR_ARG, "bad u");
     try {
@@ -1506,6 +1495,7 @@ int ocs_b200_set_control_u(ocs_b200_handle *h, const double *u, long nbatch)
 int ocs_b200_get_control_u(ocs_b200_handle *h, long b0, long nb, double *u)
 {
     if (!h || !u) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_get_control_u(h, b0, nb, u);
     if (!h->have_problem || h->ctrl_mode == CTRL_NONE) return h->fail(OCS_B200_ERR_STATE, "no control set");
     try {
         CK(cudaSetDevice(h->device));
@@ -1521,15 +1511,14 @@ int ocs_b200_get_control_u(ocs_b200_handle *h, long b0, long nb, double *u)
         if (h->ctrl_mode == CTRL_U_BATCH) {
             if (b0 < 0 || nb < 1 || b0 + nb > h->ctrl_nbatch) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
             TRY(download_soa(h, h->d_ug.p, h->ctrl_nbatch, b0, u, (long)nc * G, nb, nc));
-            CK(cudaStreamSynchronize(h->stream));
-            return 0;
+            return finish_host(h);
         }
         // per-trajectory coefficients: evaluate v*B on the host for the requested columns
         if (b0 < 0 || nb < 1 || b0 + nb > h->ctrl_nbatch) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
         const long rows = (long)nc * h->K;
         std::vector<double> vcols((size_t)rows * nb);
         TRY(download_soa(h, h->v_ext ? h->v_ext : h->d_v.p, h->ctrl_nbatch, b0, vcols.data(), rows, nb));
-        CK(cudaStreamSynchronize(h->stream));
+        TRY(finish_host(h));
         std::vector<double> keep = h->ctrl_shared;
         for (long b = 0; b < nb; ++b) {
             h->ctrl_shared.assign(vcols.begin() + b * rows, vcols.begin() + (b + 1) * rows);
@@ -1545,6 +1534,9 @@ int ocs_b200_get_control_u(ocs_b200_handle *h, long b0, long nb, double *u)
 int ocs_b200_set_stream(ocs_b200_handle *h, void *cuda_stream)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi)
+        return h->fail(OCS_B200_ERR_ARG, "ocs_b200_set_stream takes pointers / a stream of ONE device; on a multi-device handle use "
+                                          "ocs_b200_evaluate_resident, ocs_b200_gather_results_dev and ocs_b200_get_results");
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return 0;
 }
@@ -1552,20 +1544,25 @@ int ocs_b200_set_stream(ocs_b200_handle *h, void *cuda_stream)
 int ocs_b200_synchronize(ocs_b200_handle *h)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_synchronize(h);
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return finish_host(h);
 }
 
 int ocs_b200_compute_states_dev(ocs_b200_handle *h, const double *x0_soa, long Bt, double *J, double *xT_soa,
                                 int32_t *status)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi)
+        return h->fail(OCS_B200_ERR_ARG, "ocs_b200_compute_states_dev takes pointers / a stream of ONE device; on a multi-device handle use "
+                                          "ocs_b200_evaluate_resident, ocs_b200_gather_results_dev and ocs_b200_get_results");
     TRY(check_ready(h));
     if (!x0_soa || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
     try {
         CK(cudaSetDevice(h->device));
         const int n = h->kt.n;
+        h->have_states = false;         // a failure below must not leave a half-replaced batch looking valid
+        TRY(validate_batch(h, Bt));
         TRY(alloc_batch(h, Bt));
         CK(cudaMemcpyAsync(h->d_x0.p, x0_soa, sizeof(double) * n * Bt, cudaMemcpyDeviceToDevice, h->stream));
         TRY(states_common(h, Bt));
@@ -1581,19 +1578,21 @@ int ocs_b200_compute_states_dev(ocs_b200_handle *h, const double *x0_soa, long B
 int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, long Bt, double *J, double *xT, int32_t *status)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_compute_states(h, x0, Bt, J, xT, status);
     TRY(check_ready(h));
     if (!x0 || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
     try {
         CK(cudaSetDevice(h->device));
         const int n = h->kt.n;
+        h->have_states = false;         // a failure below must not leave a half-replaced batch looking valid
+        TRY(validate_batch(h, Bt));
         TRY(alloc_batch(h, Bt));
         TRY(upload_soa(h, x0, h->d_x0, n, Bt));
         TRY(states_common(h, Bt));
-        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
         if (xT) TRY(download_soa(h, h->d_xT.p, Bt, 0, xT, n, Bt));
-        if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        if (status) TRY(d2h(h, status, h->d_status, sizeof(int) * Bt));
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -1642,42 +1641,48 @@ static int pipelined_gradient(ocs_b200_handle *h, bool with_forward, const doubl
     for (auto &c : sched) cmax = std::max(cmax, c.second);
     for (int k = 0; k < 2; ++k) TRY(ensure(h, h->d_pipe[k], (size_t)(rows + m) * cmax));
     if (needs_zero_fill(h)) CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * rows * Bt, h->stream));
-    int k = 0;
     const bool trace = getenv("OCS_B200_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     mark(h->stream);
-    for (auto &c : sched) {
-        const long b0 = c.first, nb = c.second;
+    // Software pipeline: the sweeps and the transposition of chunk c are launched first, THEN the download of chunk
+    // c-1 is issued.  Issuing a download may block this thread (a pageable destination drains through the pinned
+    // ring at host-memcpy speed); the device is busy with chunk c meanwhile.
+    auto download = [&](int c) -> int {
+        const long b0 = sched[c].first, nb = sched[c].second;
+        double *stg = h->d_pipe[c & 1].p;
+        CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c & 1], 0));
+        TRY(d2h(h, dJdv + (size_t)rows * b0, stg, sizeof(double) * rows * nb, h->copy_stream));
+        if (lam0) TRY(d2h(h, lam0 + (size_t)m * b0, stg + (size_t)rows * cmax, sizeof(double) * m * nb, h->copy_stream));
+        CK(cudaEventRecord(h->stage_free[c & 1], h->copy_stream));
+        mark(h->copy_stream);
+        return 0;
+    };
+    const int nchunks = (int)sched.size();
+    for (int c = 0; c < nchunks; ++c) {
+        const long b0 = sched[c].first, nb = sched[c].second;
         if (with_forward) TRY(run_forward(h, b0, nb, -1, nullptr, true));
         TRY(run_reverse(h, b0, nb, -1, d_lamT, ldl, d_dJdv + b0, d_lam0 + b0, nullptr, nullptr));
         // transpose on the compute stream (it has slack: the sweeps run ~3x faster than PCIe drains them) into the
         // staging buffer whose previous download has finished, so that the copy stream only ever holds downloads
         // and the transfer never pauses
         mark(h->stream);
-        double *stg = h->d_pipe[k & 1].p;
-        if (k >= 2) CK(cudaStreamWaitEvent(h->stream, h->stage_free[k & 1], 0));
+        double *stg = h->d_pipe[c & 1].p;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->stage_free[c & 1], 0));
         TRY(from_soa(h, d_dJdv + b0, stg, rows, nb, Bt, 1, h->stream));
         if (lam0) TRY(from_soa(h, d_lam0 + b0, stg + (size_t)rows * cmax, m, nb, Bt, 1, h->stream));
-        CK(cudaEventRecord(h->chunk_done[k & 1], h->stream));
+        CK(cudaEventRecord(h->chunk_done[c & 1], h->stream));
         mark(h->stream);
-        CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[k & 1], 0));
-        CK(cudaMemcpyAsync(dJdv + (size_t)rows * b0, stg, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost,
-                           h->copy_stream));
-        if (lam0)
-            CK(cudaMemcpyAsync(lam0 + (size_t)m * b0, stg + (size_t)rows * cmax, sizeof(double) * m * nb,
-                               cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaEventRecord(h->stage_free[k & 1], h->copy_stream));
-        mark(h->copy_stream);
-        ++k;
+        if (c >= 1) TRY(download(c - 1));
     }
+    TRY(download(nchunks - 1));
     if (trace) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamSynchronize(h->stream);
         for (size_t i = 1; i < tev.size(); ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, tev[0], tev[i]);
-            fprintf(stderr, "trace %zu (%s) %.3f ms\n", i, (i - 1) % 3 == 0 ? "sweeps done" : (i - 1) % 3 == 1 ? "transposed" : "downloaded", ms);
+            fprintf(stderr, "trace event %zu: %.3f ms\n", i, ms);
         }
         for (auto e : tev) cudaEventDestroy(e);
     }
@@ -1695,8 +1700,11 @@ int ocs_b200_compute_adjoints_dev(ocs_b200_handle *h, const double *lamT_soa, lo
                                   double *lam0_soa)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi)
+        return h->fail(OCS_B200_ERR_ARG, "ocs_b200_compute_adjoints_dev takes pointers / a stream of ONE device; on a multi-device handle use "
+                                          "ocs_b200_evaluate_resident, ocs_b200_gather_results_dev and ocs_b200_get_results");
     TRY(check_ready(h));
-    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "compute_adjoints needs a preceding compute_states on this handle");
+    TRY(check_resident(h, "compute_adjoints"));
     if (lamT_soa && lamT_nbatch != 1 && lamT_nbatch != h->Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
     try {
         CK(cudaSetDevice(h->device));
@@ -1710,8 +1718,9 @@ int ocs_b200_compute_adjoints_dev(ocs_b200_handle *h, const double *lamT_soa, lo
 int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_nbatch, double *dJdv, double *lam0)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_compute_adjoints(h, lamT, lamT_nbatch, dJdv, lam0);
     TRY(check_ready(h));
-    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "compute_adjoints needs a preceding compute_states on this handle");
+    TRY(check_resident(h, "compute_adjoints"));
     if (lamT && lamT_nbatch != 1 && lamT_nbatch != h->Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
     try {
         CK(cudaSetDevice(h->device));
@@ -1741,10 +1750,8 @@ int ocs_b200_compute_adjoints(ocs_b200_handle *h, const double *lamT, long lamT_
             // Large batch: the gradient download (rows*Bt doubles over PCIe) dominates the call; it overlaps
             // the sweeps chunk by chunk.
             TRY(pipelined_gradient(h, false, d_lamT, ldl, d_dJdv, d_lam0, dJdv, lam0));
-            CK(cudaStreamSynchronize(h->copy_stream));
         }
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -1754,6 +1761,7 @@ int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const doubl
                       double *xT, int32_t *status, double *dJdv, double *lam0)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_evaluate(h, x0, Bt, lamT, lamT_nbatch, J, xT, status, dJdv, lam0);
     TRY(check_ready(h));
     if (!x0 || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
     if (lamT && lamT_nbatch != 1 && lamT_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
@@ -1767,13 +1775,13 @@ int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const doubl
     try {
         CK(cudaSetDevice(h->device));
         const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+        h->have_states = false;
+        TRY(validate_batch(h, Bt));
+        if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
         TRY(alloc_batch(h, Bt));
         TRY(upload_soa(h, x0, h->d_x0, n, Bt));
-        TRY(validate_control(h, Bt));
-        if (h->params_nbatch > 1 && h->params_nbatch != Bt)
-            return h->fail(OCS_B200_ERR_ARG, "params have %ld columns but the batch has %ld trajectories", h->params_nbatch, Bt);
-        if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
         h->Bt = Bt;
+        h->fb_resident = false;
         const double *d_lamT = nullptr;
         h->user_lamT = lamT != nullptr;
         h->user_lamT_ld = lamT && lamT_nbatch > 1 ? Bt : 0;
@@ -1785,22 +1793,114 @@ int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const doubl
         TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
         TRY(pipelined_gradient(h, true, d_lamT, h->user_lamT_ld, h->d_dJdv.p, h->d_lam0.p, dJdv, lam0));
         h->have_states = true;
-        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
+        if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
         if (xT) TRY(download_soa(h, h->d_xT.p, Bt, 0, xT, n, Bt));
-        if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->copy_stream));
-        CK(cudaStreamSynchronize(h->stream));
+        if (status) TRY(d2h(h, status, h->d_status, sizeof(int) * Bt));
+        return finish_host(h);
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+// Evaluate on resident data, keep every result on the device: forward sweep (and, with want_gradient, the adjoint
+// sweep with dJdv, lam0 into the handle's own buffers) of the batch whose initial states are x0 [n x Bt] (host), or
+// of the resident initial states when x0 == NULL.  Asynchronous: returns once the work is queued.
+int ocs_b200_evaluate_resident(ocs_b200_handle *h, const double *x0, long Bt, int want_gradient)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_evaluate_resident(h, x0, Bt, want_gradient);
+    TRY(check_ready(h));
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+        if (x0) {
+            if (Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad batch size");
+            h->have_states = false;
+            TRY(validate_batch(h, Bt));
+            TRY(alloc_batch(h, Bt));
+            TRY(upload_soa(h, x0, h->d_x0, n, Bt));
+        } else {
+            if (h->Bt < 1 || h->d_x0.cap < (size_t)n * h->Bt) return h->fail(OCS_B200_ERR_STATE, "no resident initial states: pass x0 once");
+            Bt = h->Bt;
+            h->have_states = false;
+            TRY(validate_batch(h, Bt));
+        }
+        TRY(states_common(h, Bt));
+        if (want_gradient) {
+            if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "a gradient needs an attached control basis");
+            TRY(ensure(h, h->d_dJdv, (size_t)nc * h->K * Bt));
+            TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
+            h->user_lamT = false;
+            TRY(adjoints_common(h, nullptr, 0, h->d_dJdv.p, h->d_lam0.p));
+        }
         return 0;
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
 }
 
+// Results of the resident batch into host arrays (any may be NULL): J [Bt], xT [n x Bt], status [Bt], and after a
+// gradient evaluation dJdv [(nc*K) x Bt], lam0 [m x Bt].
+int ocs_b200_get_results(ocs_b200_handle *h, double *J, double *xT, int32_t *status, double *dJdv, double *lam0)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_get_results(h, J, xT, status, dJdv, lam0);
+    TRY(check_ready(h));
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "no resident results");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+        const long Bt = h->Bt;
+        if ((dJdv && h->d_dJdv.cap < (size_t)nc * h->K * Bt) || (lam0 && h->d_lam0.cap < (size_t)m * Bt))
+            return h->fail(OCS_B200_ERR_STATE, "no resident gradient: evaluate with want_gradient first");
+        if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
+        if (xT) TRY(download_soa(h, h->d_xT.p, Bt, 0, xT, n, Bt));
+        if (status) TRY(d2h(h, status, h->d_status, sizeof(int) * Bt));
+        if (dJdv) {
+            TRY(finish_host(h));      // download_soa reuses one staging buffer
+            TRY(download_soa(h, h->d_dJdv.p, Bt, 0, dJdv, (long)nc * h->K, Bt));
+        }
+        if (lam0) {
+            TRY(finish_host(h));
+            TRY(download_soa(h, h->d_lam0.p, Bt, 0, lam0, m, Bt));
+        }
+        return finish_host(h);
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
+// J [Bt] and x(T) [n][Bt] of the resident batch into DEVICE buffers on the root device (the handle's device, or
+// devices[0] of a multi-device handle, which gathers the shards over NVLink).  Asynchronous on the root's stream.
+int ocs_b200_gather_results_dev(ocs_b200_handle *h, double *J_root, double *xT_root)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_gather_results_dev(h, J_root, xT_root);
+    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "no resident results to gather");
+    CK(cudaSetDevice(h->device));
+    if (J_root) CK(cudaMemcpyAsync(J_root, h->d_J.p, sizeof(double) * h->Bt, cudaMemcpyDeviceToDevice, h->stream));
+    if (xT_root) CK(cudaMemcpyAsync(xT_root, h->d_xT.p, sizeof(double) * h->kt.n * h->Bt, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+// Devices behind the handle and the shard offsets of the resident batch (offsets has ndev + 1 entries).
+int ocs_b200_get_devices(const ocs_b200_handle *h, int *ndev, int *devices, long *offsets, int cap)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_device_info(h, ndev, devices, offsets, cap);
+    if (ndev) *ndev = 1;
+    if (devices && cap > 0) devices[0] = h->device;
+    if (offsets && cap > 0) offsets[0] = 0;
+    if (offsets && cap > 1) offsets[1] = h->have_states ? h->Bt : 0;
+    return 0;
+}
+
 int ocs_b200_fetch_states(ocs_b200_handle *h, int segment, long b0, long nb, double *x)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_fetch_states(h, segment, b0, nb, x);
     TRY(check_ready(h));
-    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "fetch_states needs a preceding compute_states");
+    TRY(check_resident(h, "fetch_states"));
     if (segment < 0 || segment > 1 || (segment == 1 && !h->has_tail)) return h->fail(OCS_B200_ERR_ARG, "no such segment");
     if (b0 < 0 || nb < 1 || b0 + nb > h->Bt) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
     if (!x) return 0;
@@ -1809,12 +1909,22 @@ int ocs_b200_fetch_states(ocs_b200_handle *h, int segment, long b0, long nb, dou
         const int m = h->kt.n + 1;
         const size_t cnt = (size_t)m * (h->seg[segment].N + 1) * nb;
         TRY(ensure(h, h->d_stage2, cnt));
-        // re-run the (deterministic) forward sweep of the requested trajectories with the full grid
-        // written out, J row included; the resident store is rewritten with identical values
-        TRY(run_forward(h, b0, nb, segment, h->d_stage2.p, false));
-        CK(cudaMemcpyAsync(x, h->d_stage2.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        if (h->fb_resident) {
+            // after fb_sweep the control grid already holds uNew while the resident states belong to the control the
+            // last sweep started from (final_sweep(u), fb_sweep.m:82,117-122): they are read, not re-swept.  The
+            // running-objective row is not part of the store: NaN except x(end,end) = J.
+            const int NP = h->seg[segment].N + 1;
+            store_to_grid_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, h->stream>>>(h->seg[segment].d_xs + b0, h->Bt, h->kt.n, NP, nb,
+                                                                                      h->d_J.p + b0, h->d_stage2.p);
+            CK(cudaGetLastError());
+            h->launches++;
+        } else {
+            // re-run the (deterministic) forward sweep of the requested trajectories with the full grid
+            // written out, J row included; the resident store is rewritten with identical values
+            TRY(run_forward(h, b0, nb, segment, h->d_stage2.p, false));
+        }
+        TRY(d2h(h, x, h->d_stage2.p, sizeof(double) * cnt));
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -1823,8 +1933,9 @@ int ocs_b200_fetch_states(ocs_b200_handle *h, int segment, long b0, long nb, dou
 int ocs_b200_fetch_adjoints(ocs_b200_handle *h, int segment, long b0, long nb, double *lam, double *dJdu)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_fetch_adjoints(h, segment, b0, nb, lam, dJdu);
     TRY(check_ready(h));
-    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "fetch_adjoints needs a preceding compute_states");
+    TRY(check_resident(h, "fetch_adjoints"));
     if (segment < 0 || segment > 1 || (segment == 1 && !h->has_tail)) return h->fail(OCS_B200_ERR_ARG, "no such segment");
     if (b0 < 0 || nb < 1 || b0 + nb > h->Bt) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
     try {
@@ -1842,10 +1953,9 @@ int ocs_b200_fetch_adjoints(ocs_b200_handle *h, int segment, long b0, long nb, d
         const double *d_lamT = (segment == 0 && !h->has_tail && h->user_lamT) ? h->d_lamT_user.p : nullptr;
         TRY(run_reverse(h, b0, nb, segment, d_lamT, h->user_lamT_ld, nullptr, nullptr, lam ? d_lam : nullptr,
                         dJdu ? d_du : nullptr));
-        if (lam) CK(cudaMemcpyAsync(lam, d_lam, sizeof(double) * nl, cudaMemcpyDeviceToHost, h->stream));
-        if (dJdu) CK(cudaMemcpyAsync(dJdu, d_du, sizeof(double) * nu, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        if (lam) TRY(d2h(h, lam, d_lam, sizeof(double) * nl));
+        if (dJdu) TRY(d2h(h, dJdu, d_du, sizeof(double) * nu));
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -1856,6 +1966,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
                       int32_t *sweeps, int32_t *converged, double *max_change)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_fb_sweep(h, x0, Bt, u0, u0_nbatch, bounds, uRelTol, uAbsTol, nSWEEPS, relax, J, sweeps, converged, max_change);
     TRY(check_ready(h));
     if (!x0 || !bounds || Bt < 1 || nSWEEPS < 1 || (u0 && u0_nbatch != 1 && u0_nbatch != Bt))
         return h->fail(OCS_B200_ERR_ARG, "bad fb_sweep arguments");
@@ -1881,8 +1992,10 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
         CK(cudaSetDevice(h->device));
         const int n = h->kt.n, nc = h->kt.nc, G = 2 * h->seg[0].N + 1;
         if (h->params_nbatch > 1 && h->params_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "params batch mismatch");
-        h->Bt = Bt;
+        h->have_states = false;        // a failure below must not leave a half-replaced batch looking valid
         TRY(alloc_batch(h, Bt));
+        h->Bt = Bt;
+        h->fb_resident = false;
         TRY(upload_soa(h, x0, h->d_x0, n, Bt));
         // control on the grid, one copy per trajectory
         if (u0_on_device) {
@@ -1975,12 +2088,12 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             if (nopen == 0) break;
         }
         h->have_states = true;
-        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        if (sweeps) CK(cudaMemcpyAsync(sweeps, h->d_sweeps, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        if (converged) CK(cudaMemcpyAsync(converged, h->d_frozen, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        if (max_change) CK(cudaMemcpyAsync(max_change, h->d_maxchg.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        h->fb_resident = true;      // x, J: the sweep's input control (final_sweep(u), fb_sweep.m:82); d_ug: uNew = soln.u (:123)
+        if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
+        if (sweeps) TRY(d2h(h, sweeps, h->d_sweeps, sizeof(int) * Bt));
+        if (converged) TRY(d2h(h, converged, h->d_frozen, sizeof(int) * Bt));
+        if (max_change) TRY(d2h(h, max_change, h->d_maxchg.p, sizeof(double) * Bt));
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -1989,6 +2102,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
 int ocs_b200_set_control_ufunc(ocs_b200_handle *h, int kind, int nknots, const double *knots)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_control_ufunc(h, kind, nknots, knots);
     if (kind == OCS_B200_UFUNC_NONE) {
         h->ufunc_kind = kind;
         h->ufunc_knots.clear();
@@ -2011,8 +2125,9 @@ int ocs_b200_eval_solution(ocs_b200_handle *h, int segment, long b0, long nb, in
                            double *lam, double *u)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_eval_solution(h, segment, b0, nb, nq, tq, x, lam, u);
     TRY(check_ready(h));
-    if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "eval_solution needs a preceding compute_states");
+    TRY(check_resident(h, "eval_solution"));
     if (segment < 0 || segment > 1 || (segment == 1 && !h->has_tail)) return h->fail(OCS_B200_ERR_ARG, "no such segment");
     if (b0 < 0 || nb < 1 || b0 + nb > h->Bt) return h->fail(OCS_B200_ERR_ARG, "trajectory range out of bounds");
     if (nq < 1 || !tq) return h->fail(OCS_B200_ERR_ARG, "no query times");
@@ -2034,7 +2149,7 @@ int ocs_b200_eval_solution(ocs_b200_handle *h, int segment, long b0, long nb, in
         TRY(ensure(h, h->d_stage2, total));
         double *d_abs = h->d_stage2.p, *d_tq = d_abs + G, *d_qrec = d_tq + nq, *d_knots = d_qrec + (size_t)QREC * nq,
                *d_soa = d_knots + n_knots, *d_out = d_soa + n_out, *d_lams = d_out + n_out, *d_vsh = d_lams + n_lams;
-        CK(cudaMemcpyAsync(d_tq, tq, sizeof(double) * nq, cudaMemcpyHostToDevice, h->stream));
+        TRY(h2d(h, d_tq, tq, sizeof(double) * nq));
         const int qchunk = 32;
         const dim3 grid((unsigned)((nb + 127) / 128), (unsigned)((nq + qchunk - 1) / qchunk));
         auto prepare = [&](const std::vector<double> &xs) -> int {
@@ -2046,7 +2161,7 @@ int ocs_b200_eval_solution(ocs_b200_handle *h, int segment, long b0, long nb, in
         };
         auto deliver = [&](double *host, int rows) -> int {
             TRY(from_soa(h, d_soa, d_out, (long)rows * nq, nb, nb, rows));
-            CK(cudaMemcpyAsync(host, d_out, sizeof(double) * rows * nq * nb, cudaMemcpyDeviceToHost, h->stream));
+            TRY(d2h(h, host, d_out, sizeof(double) * rows * nq * nb));
             CK(cudaStreamSynchronize(h->stream));   // the scratch is reused by the next output
             return 0;
         };
@@ -2106,8 +2221,7 @@ int ocs_b200_eval_solution(ocs_b200_handle *h, int segment, long b0, long nb, in
             h->launches++;
             TRY(deliver(u, nc));
         }
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        return finish_host(h);
     } catch (const std::exception &ex) {
         h->lams_req = nullptr;
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
@@ -2119,6 +2233,7 @@ int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int n
                                  double tol, double *y, double *resnorm, double *residual, int32_t *exitflag, int32_t *iters)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_compute_equilibrium(h, params, np, nparams, nsets, guess, nguess, lb, ub, r, nr, max_iter, tol, y, resnorm, residual, exitflag, iters);
     if (h->sticky) return h->sticky;
     if (!h->have_problem) return h->fail(OCS_B200_ERR_STATE, "no problem bound (ocs_b200_set_problem_*)");
     if (np != h->kt.np) return h->fail(OCS_B200_ERR_ARG, "the problem has %d parameters, got %d", h->kt.np, np);
@@ -2135,7 +2250,8 @@ int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int n
             std::string log;
             int rc = ocs_compile_unit(h->gen_source.c_str(), "OCS_EQ_KERNEL(ocs_gen::Problem, gen)",
                                       h->math_mode == OCS_B200_MATH_STRICT,
-                                      h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log);
+                                      h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log,
+                                      h->gen_n);
             if (rc != 0) return h->fail(rc, "equilibrium kernel of the generated problem did not compile:\n%s", log.c_str());
             h->gen_libraries.push_back(lib);
             h->kt.eq = kern[0];
@@ -2149,11 +2265,11 @@ int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int n
         double *d_par = d, *d_gs = d_par + n_par, *d_lb = d_gs + n_gs, *d_ub = d_lb + NY, *d_r = d_ub + NY, *d_y = d_r + nr,
                *d_rn = d_y + n_y, *d_res = d_rn + nsets;
         int *d_flag = reinterpret_cast<int *>(d_res + n_y), *d_it = d_flag + nsets;
-        if (np > 0) CK(cudaMemcpyAsync(d_par, params, sizeof(double) * np * nparams, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(d_gs, guess, sizeof(double) * n_gs, cudaMemcpyHostToDevice, h->stream));
-        if (lb) CK(cudaMemcpyAsync(d_lb, lb, sizeof(double) * NY, cudaMemcpyHostToDevice, h->stream));
-        if (ub) CK(cudaMemcpyAsync(d_ub, ub, sizeof(double) * NY, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(d_r, r, sizeof(double) * nr, cudaMemcpyHostToDevice, h->stream));
+        if (np > 0) TRY(h2d(h, d_par, params, sizeof(double) * np * nparams));
+        TRY(h2d(h, d_gs, guess, sizeof(double) * n_gs));
+        if (lb) TRY(h2d(h, d_lb, lb, sizeof(double) * NY));
+        if (ub) TRY(h2d(h, d_ub, ub, sizeof(double) * NY));
+        TRY(h2d(h, d_r, r, sizeof(double) * nr));
         EqArgs a;
         memset(&a, 0, sizeof a);
         a.nsets = nsets;
@@ -2176,13 +2292,12 @@ int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int n
         void *args[] = {(void *)&a};
         CK(cudaLaunchKernel(h->kt.eq, dim3((unsigned)((nsets + 127) / 128)), dim3(128), args, 0, h->stream));
         h->launches++;
-        CK(cudaMemcpyAsync(y, d_y, sizeof(double) * n_y, cudaMemcpyDeviceToHost, h->stream));
-        if (resnorm) CK(cudaMemcpyAsync(resnorm, d_rn, sizeof(double) * nsets, cudaMemcpyDeviceToHost, h->stream));
-        if (residual) CK(cudaMemcpyAsync(residual, d_res, sizeof(double) * n_y, cudaMemcpyDeviceToHost, h->stream));
-        if (exitflag) CK(cudaMemcpyAsync(exitflag, d_flag, sizeof(int) * nsets, cudaMemcpyDeviceToHost, h->stream));
-        if (iters) CK(cudaMemcpyAsync(iters, d_it, sizeof(int) * nsets, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        TRY(d2h(h, y, d_y, sizeof(double) * n_y));
+        if (resnorm) TRY(d2h(h, resnorm, d_rn, sizeof(double) * nsets));
+        if (residual) TRY(d2h(h, residual, d_res, sizeof(double) * n_y));
+        if (exitflag) TRY(d2h(h, exitflag, d_flag, sizeof(int) * nsets));
+        if (iters) TRY(d2h(h, iters, d_it, sizeof(int) * nsets));
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -2191,6 +2306,7 @@ int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int n
 int ocs_b200_set_fb_costate(ocs_b200_handle *h, int mode)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_fb_costate(h, mode);
     if (mode != OCS_B200_COSTATE_DISCRETE && mode != OCS_B200_COSTATE_CONTINUOUS)
         return h->fail(OCS_B200_ERR_ARG, "costate mode must be OCS_B200_COSTATE_DISCRETE or _CONTINUOUS");
     h->fb_costate = mode;
@@ -2203,6 +2319,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                              double *J, int32_t *iters, int32_t *converged)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_single_shooting(h, x0, Bt, v0, v0_nbatch, Lb, Ub, nfree, free_states, free_lb, free_ub, max_iter, tol, v_opt, J, iters, converged);
     TRY(check_ready(h));
     if (!x0 || !v0 || !Lb || !Ub || Bt < 1 || max_iter < 1 || (v0_nbatch != 1 && v0_nbatch != Bt) || nfree < 0 ||
         (nfree > 0 && (!free_states || !free_lb || !free_ub)))
@@ -2215,8 +2332,10 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         for (int f = 0; f < nfree; ++f)
             if (free_states[f] < 0 || free_states[f] >= n) return h->fail(OCS_B200_ERR_ARG, "free state index out of range");
         if (h->params_nbatch > 1 && h->params_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "params batch mismatch");
-        h->Bt = Bt;
+        h->have_states = false;        // a failure below must not leave a half-replaced batch looking valid
         TRY(alloc_batch(h, Bt));
+        h->Bt = Bt;
+        h->fb_resident = false;
         TRY(upload_soa(h, x0, h->d_x0, n, Bt));
         TRY(ensure(h, h->d_z, (size_t)nz * Bt));
         TRY(ensure(h, h->d_g, (size_t)nz * Bt));
@@ -2236,7 +2355,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
             CK(cudaMemcpyAsync(h->d_lbub.p, lbub.data(), sizeof(double) * 2 * nz, cudaMemcpyHostToDevice, h->stream));
             if (v0_nbatch == Bt) {
                 TRY(ensure(h, h->d_stage, (size_t)nv * Bt));
-                CK(cudaMemcpyAsync(h->d_stage.p, v0, sizeof(double) * nv * Bt, cudaMemcpyHostToDevice, h->stream));
+                TRY(h2d(h, h->d_stage.p, v0, sizeof(double) * nv * Bt));
                 TRY(to_soa(h, h->d_stage.p, h->d_zt.p, nv, Bt, Bt));
             } else {
                 std::vector<double> v0p(v0, v0 + nv);
@@ -2331,11 +2450,10 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         TRY(run_forward(h, 0, Bt, -1, nullptr, true));
         h->have_states = true;
         if (v_opt) TRY(download_soa(h, h->d_z.p, Bt, 0, v_opt, nz, Bt));
-        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        if (iters) CK(cudaMemcpyAsync(iters, h->d_sweeps, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        if (converged) CK(cudaMemcpyAsync(converged, h->d_frozen, sizeof(int) * Bt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
+        if (iters) TRY(d2h(h, iters, h->d_sweeps, sizeof(int) * Bt));
+        if (converged) TRY(d2h(h, converged, h->d_frozen, sizeof(int) * Bt));
+        return finish_host(h);
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -2344,6 +2462,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
 int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, long *index)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_reduce_J(h, op, value, index);
     if (!h->have_states) return h->fail(OCS_B200_ERR_STATE, "reduce_J needs a preceding compute_states");
     if (!value || op < 0 || op > 2) return h->fail(OCS_B200_ERR_ARG, "bad reduction");
     try {
@@ -2374,6 +2493,7 @@ int ocs_b200_reduce_J(ocs_b200_handle *h, int op, double *value, long *index)
 int ocs_b200_set_profiling(ocs_b200_handle *h, int on)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_profiling(h, on);
     h->profiling = on != 0;
     return 0;
 }
@@ -2381,14 +2501,51 @@ int ocs_b200_set_profiling(ocs_b200_handle *h, int on)
 int ocs_b200_kernel_stats(ocs_b200_handle *h, int reset, double *ms_forward, double *ms_reverse, long *launches)
 {
     if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_kernel_stats(h, reset, ms_forward, ms_reverse, launches);
     if (ms_forward) *ms_forward = h->ms_fwd;
     if (ms_reverse) *ms_reverse = h->ms_rev;
     if (launches) *launches = h->launches;
     if (reset) {
-        h->ms_fwd = h->ms_rev = 0;
+        h->ms_fwd = h->ms_rev = h->ms_proj = h->ms_upd = 0;
         h->launches = 0;
     }
     return 0;
+}
+
+int ocs_b200_kernel_stats_ex(ocs_b200_handle *h, int reset, double *ms, int nms, long *launches)
+{
+    if (!h || (nms > 0 && !ms)) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_kernel_stats_ex(h, reset, ms, nms, launches);
+    const double v[4] = {h->ms_fwd, h->ms_rev - h->ms_proj, h->ms_proj, h->ms_upd};
+    for (int k = 0; k < nms; ++k) ms[k] = k < 4 ? v[k] : 0.0;
+    if (launches) *launches = h->launches;
+    if (reset) {
+        h->ms_fwd = h->ms_rev = h->ms_proj = h->ms_upd = 0;
+        h->launches = 0;
+    }
+    return 0;
+}
+
+int ocs_b200_get_dims(const ocs_b200_handle *h, int32_t dims[8])
+{
+    if (!h || !dims) return OCS_B200_ERR_ARG;
+    if (h->multi) h = ocs_multi_first(h);
+    dims[0] = h->have_problem ? h->kt.n : 0;
+    dims[1] = h->have_problem ? h->kt.nc : 0;
+    dims[2] = h->have_problem ? h->kt.np : 0;
+    dims[3] = h->K;
+    dims[4] = h->seg[0].N;
+    dims[5] = h->seg[1].N;
+    dims[6] = 0;
+    dims[7] = 0;
+    return 0;
+}
+
+long ocs_b200_get_batch(const ocs_b200_handle *h)
+{
+    if (!h) return -1;
+    if (h->multi) return ocs_multi_batch(h);
+    return h->have_states ? h->Bt : 0;
 }
 
 }  // extern "C"

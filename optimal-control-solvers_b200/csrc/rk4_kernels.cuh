@@ -108,6 +108,15 @@
 #ifndef OCS_KDENSE_MAX
 #define OCS_KDENSE_MAX 32   // run-time K limit of the dense-basis kernels (compile-time K has none)
 #endif
+#define OCS_NPC 16          // batch-uniform problem parameters travel inside SweepArgs (kernel-parameter constant bank) up
+                            // to this count: an FP64 instruction takes them as a constant operand, so they cost neither
+                            // registers nor loads (6 parameters of the generated 6-state problem were 12 registers)
+#ifndef OCS_ASYNC_STAGE
+#define OCS_ASYNC_STAGE 1   // multi-trajectory bodies: the record tile of the NEXT block of steps is fetched with cp.async
+                            // into a second shared-memory buffer while the current one is consumed (one block barrier per
+                            // tile instead of two, no exposed load latency at the tile switch -- with the 8 resident warps
+                            // per SM of a generated 6-state problem the synchronous staging was 12 % of the forward sweep)
+#endif
 
 namespace OCS_NS {
 
@@ -178,6 +187,7 @@ struct SweepArgs {
     const double *basrec;   // [2N+1][BW]
     const double *x0;       // [n][ldb]
     const double *p;        // [np] or [np][ldp]
+    double pc[OCS_NPC];     // batch-uniform parameters by value (np <= OCS_NPC), read as constant-bank operands
     const double *v;        // UMODE_COEF: [(k*nc+c)][ldb]
     double *ug;             // UMODE_GRID: [nc][2N+1][ldb]   (fb_sweep updates it in place)
     double *ug_out;         // dense UMODE_COEF forward sweep: the evaluated control grid is kept here for the
@@ -207,6 +217,7 @@ struct SweepArgs {
     double uRelTol, uAbsTol, relax;
     double *max_change;     // [nb]
     const int *frozen;      // [nb] trajectories already converged (skipped), or null
+    int fb_readonly;        // fb_sweep kernels used as a costate fetch: the control grid is read, never updated
     int *error_flag;        // set to 1 when the host's record layout disagrees with the kernel's
 };
 
@@ -473,6 +484,11 @@ __device__ __forceinline__ void cp_async_8(double *smem_dst, const double *gmem_
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(double *smem_dst, const double *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
@@ -508,6 +524,23 @@ __device__ __forceinline__ void stage_tile(const SweepArgs &a, int i0, int ns, i
     __syncthreads();
 }
 
+// The same copies issued with cp.async (16 bytes each; both sides are 16-byte aligned, ndoubles is even): no barrier,
+// no commit -- the caller commits the group and waits for it before the block barrier that publishes the tile.
+__device__ __forceinline__ void copy_to_smem_async(double *dst, const double *src, int ndoubles)
+{
+    const int cnt = ndoubles >> 1;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) cp_async_16(dst + 2 * k, src + 2 * k);
+}
+template <int RB>
+__device__ __forceinline__ void stage_tile_async(const SweepArgs &a, int i0, int ns, int BW, double *gp, double *st, double *bs,
+                                                 double *fo, int FW)
+{
+    copy_to_smem_async(gp, a.gprec + (size_t)2 * i0 * RB, (2 * ns + 1) * RB);
+    copy_to_smem_async(st, a.steprec + (size_t)4 * i0, 4 * ns);
+    if (BW > 0) copy_to_smem_async(bs, a.basrec + (size_t)2 * i0 * BW, (2 * ns + 1) * BW);
+    if (FW > 0) copy_to_smem_async(fo, a.foldrec + (size_t)FW * i0, FW * ns);
+}
+
 // ------------------------------------------------------------------ forward sweep
 // RK4Integrator.m:28-56 for one trajectory per thread.
 template <class P, int UMODE, int BMODE, bool PB, int KD, bool GRIDS>
@@ -534,7 +567,7 @@ __device__ __forceinline__ void forward_body(const SweepArgs &a, double *sm)
 
     double p[np > 0 ? np : 1];
 #pragma unroll
-    for (int k = 0; k < np; ++k) p[k] = PB ? a.p[soa(k, a.ldp, bb)] : a.p[k];
+    for (int k = 0; k < np; ++k) p[k] = PB ? a.p[soa(k, a.ldp, bb)] : (np <= OCS_NPC ? a.pc[k] : a.p[k]);
 
     double y[m];
 #pragma unroll
@@ -656,6 +689,9 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
     constexpr int NF = (UMODE == UMODE_COEF && !OCS_FOLD_FWD_COEF) ? 0 : ocs_nfold<P>(HM), FW = ocs_fold_width(NF);
     const int BW = BWc >= 0 ? BWc : a.BW;
     const int N = a.N;
+    // one tile = [grid-point records | step records | basis records | fold records]; two of them when the next tile is
+    // fetched asynchronously while this one is consumed
+    const int TD = TL::GP + TL::ST + (2 * TL::S + 1) * (NEEDB ? BW : 0) + TL::S * FW;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
     double *fo = bs + (size_t)(2 * TL::S + 1) * (NEEDB ? BW : 0);       // fold records of the tile
     if (a.RB != RB || (NEEDB && a.BW != BW) || (NF > 0 && !a.foldrec)) {
@@ -678,7 +714,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
         bb[q] = active[q] ? b[q] : a.nb - 1;
         if (a.frozen && a.frozen[bb[q]]) active[q] = false;
 #pragma unroll
-        for (int k = 0; k < np; ++k) p[q][k] = PB ? a.p[soa(k, a.ldp, bb[q])] : a.p[k];
+        for (int k = 0; k < np; ++k) p[q][k] = PB ? a.p[soa(k, a.ldp, bb[q])] : (np <= OCS_NPC ? a.pc[k] : a.p[k]);
 #pragma unroll
         for (int c = 0; c < n; ++c) y[q][c] = a.x0[soa(c, a.ldb, bb[q])];
         y[q][n] = 0.0;                                                // xK(:,1,1) = [x0; 0]   :33
@@ -686,9 +722,27 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
         xsp[q] = a.xs + b[q];
     }
 
+    if constexpr (OCS_ASYNC_STAGE) {
+        stage_tile_async<RB>(a, 0, N < TL::S ? N : TL::S, NEEDB ? BW : 0, gp, st, bs, fo, FW);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
     for (int i0 = 0; i0 < N; i0 += TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
-        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, FW);
+        if constexpr (OCS_ASYNC_STAGE) {
+            // this tile is complete and visible (barrier at the end of the previous iteration); fetch the next one
+            // into the other buffer while this one is consumed
+            if (i0 + TL::S < N) {
+                const int nn = (N - i0 - TL::S < TL::S) ? (N - i0 - TL::S) : TL::S;
+                double *ng = gp == sm ? sm + TD : sm;
+                stage_tile_async<RB>(a, i0 + TL::S, nn, NEEDB ? BW : 0, ng, ng + TL::GP, ng + TL::GP + TL::ST,
+                                     ng + TL::GP + TL::ST + (size_t)(2 * TL::S + 1) * (NEEDB ? BW : 0), FW);
+                cp_async_commit();
+            }
+        } else {
+            stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, FW);
+        }
         if (i0 == 0) {
 #pragma unroll
             for (int q = 0; q < T; ++q) {
@@ -821,6 +875,16 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
                 }
             }
         }
+        if constexpr (OCS_ASYNC_STAGE) {
+            if (i0 + TL::S < N) {
+                cp_async_wait<0>();     // this thread's copies of the next tile have landed ...
+                __syncthreads();        // ... and so have everybody else's; nobody reads the old tile any more
+                gp = gp == sm ? sm + TD : sm;
+                st = gp + TL::GP;
+                bs = st + TL::ST;
+                fo = bs + (size_t)(2 * TL::S + 1) * (NEEDB ? BW : 0);
+            }
+        }
     }
 
 #pragma unroll
@@ -883,7 +947,7 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 
     double p[np > 0 ? np : 1];
 #pragma unroll
-    for (int k = 0; k < np; ++k) p[k] = PB ? a.p[soa(k, a.ldp, bb)] : a.p[k];
+    for (int k = 0; k < np; ++k) p[k] = PB ? a.p[soa(k, a.ldp, bb)] : (np <= OCS_NPC ? a.pc[k] : a.p[k]);
 
     double lam[m];
 #pragma unroll
@@ -912,6 +976,9 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     double y1[n], yn1[n], yn2[n];      // node states: current, and the next two (prefetched)
     double xR[n];                      // FB: node state to the right (for midpoint averages)
     MaxRatio chg;                      // FB: running max of |uNew-u| / (uRelTol |u| + uAbsTol)
+    bool unfinite = true;              // FB: every uNew so far was finite (a NaN compares false everywhere and would
+                                       // otherwise leave the maximum at 0, i.e. "converged")
+    const bool fbwrite = (FB != 0) && !a.fb_readonly;
     double *ugw = (FB != 0) ? a.ug + bb : nullptr;     // FB: this trajectory's column of the control grid (bb == b when active)
     double bnd[2 * nc];                // FB: ControlBounds, read once (ControlChar clamps with them twice per step)
 #pragma unroll
@@ -927,13 +994,15 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
     double *ring = bs + (size_t)(2 * TL::S + 1) * BW + threadIdx.x;
     auto ring_fill = [&](double *slot, int node) {     // node < 0: x from the slack (never used), u clamped
         const int jm = 2 * node + 1 > 0 ? 2 * node + 1 : 0, jl = node > 0 ? 2 * node : 0;
+        // one IMAD.WIDE per address (row index relative to the start of the slack in front of the store)
+        const double *xbase = a.xs + bb - (size_t)OCS_XS_SLACK * a.ldb;
 #pragma unroll
         for (int c = 0; c < n; ++c)
-            cp_async_8(slot + (size_t)c * OCS_THREADS, a.xs + ((size_t)c * (N + 1) * a.ldb + bb) + (long)node * a.ldb);
+            cp_async_8(slot + (size_t)c * OCS_THREADS, soa_row(xbase, (unsigned)(c * (N + 1) + node + OCS_XS_SLACK), ld8));
 #pragma unroll
         for (int c = 0; c < nc; ++c) {
-            cp_async_8(slot + (size_t)(n + c) * OCS_THREADS, a.ug + soa((long)c * G + jm, a.ldb, bb));
-            cp_async_8(slot + (size_t)(n + nc + c) * OCS_THREADS, a.ug + soa((long)c * G + jl, a.ldb, bb));
+            cp_async_8(slot + (size_t)(n + c) * OCS_THREADS, soa_row(a.ug + bb, (unsigned)(c * G + jm), ld8));
+            cp_async_8(slot + (size_t)(n + nc + c) * OCS_THREADS, soa_row(a.ug + bb, (unsigned)(c * G + jl), ld8));
         }
         cp_async_commit();
     };
@@ -1122,8 +1191,9 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     chg.update(fabs(un[c] - uR[c]), a.uRelTol * fabs(uR[c]) + a.uAbsTol);          // fb_sweep.m:107-108
+                    unfinite = unfinite && isfinite(un[c]);
                     const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
-                    if (active) *soa_row(ugw, (unsigned)(c * G + 2 * i + 2), ld8) = uw;
+                    if (active && fbwrite) *soa_row(ugw, (unsigned)(c * G + 2 * i + 2), ld8) = uw;
                 }
 #pragma unroll
                 for (int c = 0; c < n; ++c) { xm[c] = (y1[c] + xR[c]) / 2; lm[c] = (lam[c] + lamR[c]) / 2; }
@@ -1131,8 +1201,9 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
                 for (int c = 0; c < nc; ++c) {
                     chg.update(fabs(un[c] - uM[c]), a.uRelTol * fabs(uM[c]) + a.uAbsTol);
+                    unfinite = unfinite && isfinite(un[c]);
                     const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uM[c] + a.relax * un[c];
-                    if (active) *soa_row(ugw, (unsigned)(c * G + 2 * i + 1), ld8) = uw;
+                    if (active && fbwrite) *soa_row(ugw, (unsigned)(c * G + 2 * i + 1), ld8) = uw;
                 }
 #pragma unroll
                 for (int c = 0; c < n; ++c) xR[c] = y1[c];
@@ -1162,10 +1233,12 @@ __device__ __forceinline__ void reverse_body(const SweepArgs &a, double *sm)
 #pragma unroll
         for (int c = 0; c < nc; ++c) {
             chg.update(fabs(un[c] - uR[c]), a.uRelTol * fabs(uR[c]) + a.uAbsTol);
+            unfinite = unfinite && isfinite(un[c]);
             const double uw = (a.relax == 1.0) ? un[c] : (1.0 - a.relax) * uR[c] + a.relax * un[c];
-            if (active) *soa_row(ugw, (unsigned)(c * G), ld8) = uw;
+            if (active && fbwrite) *soa_row(ugw, (unsigned)(c * G), ld8) = uw;
         }
-        if (active && a.max_change) a.max_change[b] = chg.value();
+        // a non-finite uNew never counts as converged (the reference's max() would propagate the NaN and fail `<= 1`)
+        if (active && a.max_change) a.max_change[b] = unfinite ? chg.value() : __longlong_as_double(0x7ff0000000000000LL);
     }
     if (a.lam0 && active) {
 #pragma unroll
@@ -1193,6 +1266,9 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     const int BW = BWc >= 0 ? BWc : a.BW;
     const int N = a.N, G = 2 * N + 1;
     const bool dugout = a.dug != nullptr;
+    // one tile = [grid-point records | step records | basis records | fold records]; two of them when the next tile is
+    // fetched asynchronously while this one is consumed (forward_multi_body has the details); the node-state ring follows
+    const int TD = TL::GP + TL::ST + (2 * TL::S + 1) * BW + TL::S * FW;
     double *gp = sm, *st = sm + TL::GP, *bs = st + TL::ST;
     if (a.RB != RB || (NEEDB && a.BW != BW) || (NF > 0 && !a.foldrec)) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && a.error_flag) *a.error_flag = 1;
@@ -1209,13 +1285,35 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     double uMn[T][nc], uLn[T][nc];      // UMODE_GRID: control of the next step, loaded one step ahead
     constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
     constexpr int UNR = OCS_REV_UNROLL;
-    constexpr int DP = OCS_RING;             // > 0: cp.async ring in shared memory [DP][T][n][threads] instead of yn
+    constexpr int DP = OCS_RING;             // > 0: cp.async ring in shared memory [DP][T][n (+ 2 nc)][threads] instead of yn
     static_assert(DP == 0 || ((DP & (DP - 1)) == 0 && DP <= OCS_XS_SLACK), "OCS_RING must be a power of two <= OCS_XS_SLACK");
+    // with a per-trajectory control grid the ring also carries the step's two controls (midpoint, left node): every
+    // per-step global load of the sweep then completes through cp.async groups, DP steps ahead, instead of the
+    // scoreboard -- with 8 resident warps per SM a quarter of the generated 6-state reverse sweep was ONE instruction
+    // waiting for a scoreboard shared with the loads issued just before it (profiles/r2_notes.md)
+    constexpr int RW = n + (UMODE == UMODE_GRID ? 2 * nc : 0);
     double y1[T][n], yn[D][T][n];            // (yn is unused, and optimised away, with the shared-memory ring)
     const double *xsp[T];
-    double *ring = bs + (size_t)(2 * TL::S + 1) * BW + threadIdx.x;
-    double *fo = bs + (size_t)(2 * TL::S + 1) * BW + (size_t)DP * T * n * OCS_THREADS;   // fold records of the tile
+    double *ring = sm + (size_t)(OCS_ASYNC_STAGE ? 2 : 1) * TD + threadIdx.x;
+    double *fo = bs + (size_t)(2 * TL::S + 1) * BW;    // fold records of the tile
     const bool folded = NF > 0 && a.lamJ_one != 0;     // uniform: the whole grid takes one of the two chains
+    // ring slot of one node (step): states x_node, then u at grid points 2 node + 1 and 2 node (clamped at 0)
+    auto ring_issue = [&](double *slot, int q, int node) {
+        // one IMAD.WIDE per address: row index relative to the start of the slack in front of the store (node >= -SLACK)
+        const double *xbase = a.xs + bb[q] - (size_t)OCS_XS_SLACK * a.ldb;
+#pragma unroll
+        for (int c = 0; c < n; ++c)
+            cp_async_8(slot + (size_t)(q * RW + c) * OCS_THREADS,
+                       soa_row(xbase, (unsigned)(c * (N + 1) + node + OCS_XS_SLACK), (unsigned)a.ldb * 8u));
+        if constexpr (UMODE == UMODE_GRID) {
+            const int jm = 2 * node + 1 > 0 ? 2 * node + 1 : 0, jl = node > 0 ? 2 * node : 0;
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+                cp_async_8(slot + (size_t)(q * RW + n + c) * OCS_THREADS, soa_row(a.ug + bb[q], (unsigned)(c * G + jm), (unsigned)a.ldb * 8u));
+                cp_async_8(slot + (size_t)(q * RW + n + nc + c) * OCS_THREADS, soa_row(a.ug + bb[q], (unsigned)(c * G + jl), (unsigned)a.ldb * 8u));
+            }
+        }
+    };
 #pragma unroll
     for (int q = 0; q < T; ++q) {
         b[q] = ((long)blockIdx.x * T + q) * blockDim.x + threadIdx.x;
@@ -1223,7 +1321,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
         bb[q] = active[q] ? b[q] : a.nb - 1;
         if (a.frozen && a.frozen[bb[q]]) active[q] = false;
 #pragma unroll
-        for (int k = 0; k < np; ++k) p[q][k] = PB ? a.p[soa(k, a.ldp, bb[q])] : a.p[k];
+        for (int k = 0; k < np; ++k) p[q][k] = PB ? a.p[soa(k, a.ldp, bb[q])] : (np <= OCS_NPC ? a.pc[k] : a.p[k]);
 #pragma unroll
         for (int c = 0; c < m; ++c)
             lam[q][c] = a.lamT ? (a.ldl ? a.lamT[soa(c, a.ldl, bb[q])] : a.lamT[c]) : (c == n ? 1.0 : 0.0);
@@ -1241,32 +1339,41 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             xsp[q] -= (size_t)(D - 1) * a.ldb;
         }
     }
+    const int i0_last = ((N - 1) / TL::S) * TL::S;
+    if constexpr (OCS_ASYNC_STAGE) {
+        stage_tile_async<RB>(a, i0_last, N - i0_last, NEEDB ? BW : 0, gp, st, bs, fo, folded ? FW : 0);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
     if constexpr (DP > 0) {
         // fill the ring: nodes N-1 ... N-DP, one commit group per node (slot = step count mod DP)
 #pragma unroll
         for (int d = 0; d < DP; ++d) {
 #pragma unroll
-            for (int q = 0; q < T; ++q) {
-#pragma unroll
-                for (int c = 0; c < n; ++c)
-                    cp_async_8(ring + (size_t)((d * T + q) * n + c) * OCS_THREADS,
-                               xsp[q] + (size_t)c * (N + 1) * a.ldb - (size_t)d * a.ldb);
-            }
+            for (int q = 0; q < T; ++q) ring_issue(ring + (size_t)(d * T * RW) * OCS_THREADS, q, N - 1 - d);
             cp_async_commit();
         }
-#pragma unroll
-        for (int q = 0; q < T; ++q) xsp[q] -= (size_t)(DP - 1) * a.ldb;      // node N-DP: the deepest prefetch so far
     }
 
-    const int i0_last = ((N - 1) / TL::S) * TL::S;
     for (int i0 = i0_last; i0 >= 0; i0 -= TL::S) {
         const int ns = (N - i0 < TL::S) ? (N - i0) : TL::S;
-        stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, folded ? FW : 0);
+        if constexpr (OCS_ASYNC_STAGE) {
+            // this tile is complete and visible; fetch the one below it (always a full tile) into the other buffer
+            if (i0 > 0) {
+                double *ng = gp == sm ? sm + TD : sm;
+                stage_tile_async<RB>(a, i0 - TL::S, TL::S, NEEDB ? BW : 0, ng, ng + TL::GP, ng + TL::GP + TL::ST,
+                                     ng + TL::GP + TL::ST + (size_t)(2 * TL::S + 1) * BW, folded ? FW : 0);
+                cp_async_commit();
+            }
+        } else {
+            stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, folded ? FW : 0);
+        }
         if (i0 == i0_last) {
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 ctl[q].eval(a, gp + (2 * ns) * RB, bs + (2 * ns) * BW, 2 * N, bb[q], uR[q]);
-                if constexpr (UMODE == UMODE_GRID) {
+                if constexpr (UMODE == UMODE_GRID && DP == 0) {
                     ctl[q].eval(a, gp, bs, 2 * N - 1, bb[q], uMn[q]);
                     ctl[q].eval(a, gp, bs, 2 * N - 2, bb[q], uLn[q]);
                 }
@@ -1286,22 +1393,25 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             const double tR = rR[0], tM = rM[0], tL = rL[0];
             const bool moves = BMODE == BMODE_SPARSE ? (rec_flags(bM) & 4) != 0 : true;
             if constexpr (DP > 0) {
-                // node i sits in slot (N-1-i) mod DP; every group but the DP-1 youngest has landed
-                double *slot = ring + (size_t)(((N - 1 - i) & (DP - 1)) * T * n) * OCS_THREADS;
+                // node i sits in slot (N-1-i) mod DP; every group but the DP-1 youngest has landed (a tile fetch
+                // committed in between only makes this wait for one ring group more than it needs)
+                double *slot = ring + (size_t)(((N - 1 - i) & (DP - 1)) * T * RW) * OCS_THREADS;
                 cp_async_wait<DP - 1>();
 #pragma unroll
                 for (int q = 0; q < T; ++q) {
 #pragma unroll
-                    for (int c = 0; c < n; ++c) y1[q][c] = slot[(size_t)(q * n + c) * OCS_THREADS];
+                    for (int c = 0; c < n; ++c) y1[q][c] = slot[(size_t)(q * RW + c) * OCS_THREADS];
+                    if constexpr (UMODE == UMODE_GRID) {
+#pragma unroll
+                        for (int c = 0; c < nc; ++c) {
+                            uM[q][c] = slot[(size_t)(q * RW + n + c) * OCS_THREADS];
+                            uL[q][c] = slot[(size_t)(q * RW + n + nc + c) * OCS_THREADS];
+                        }
+                    }
                 }
                 // refill the slot with node i-DP (below node 0: the slack in front of the store, never used)
 #pragma unroll
-                for (int q = 0; q < T; ++q) {
-                    xsp[q] -= a.ldb;
-#pragma unroll
-                    for (int c = 0; c < n; ++c)
-                        cp_async_8(slot + (size_t)(q * n + c) * OCS_THREADS, xsp[q] + (size_t)c * (N + 1) * a.ldb);
-                }
+                for (int q = 0; q < T; ++q) ring_issue(slot, q, i - DP);
                 cp_async_commit();
             }
             if constexpr (DP == 0) {
@@ -1353,7 +1463,9 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 if constexpr (UMODE == UMODE_UNIFORM) ctl[q].eval(a, rR, bR, 2 * i + 2, bb[q], uR[q]);
-                if constexpr (UMODE == UMODE_GRID) {     // loaded one step ahead, see reverse_body
+                if constexpr (UMODE == UMODE_GRID && DP > 0) {
+                    // controls came out of the ring
+                } else if constexpr (UMODE == UMODE_GRID) {     // loaded one step ahead, see reverse_body
 #pragma unroll
                     for (int c = 0; c < nc; ++c) { uM[q][c] = uMn[q][c]; uL[q][c] = uLn[q][c]; }
                     const int jm = 2 * i - 1 > 0 ? 2 * i - 1 : 0, jl = 2 * i - 2 > 0 ? 2 * i - 2 : 0;
@@ -1382,6 +1494,15 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 const bool du = GA || dugout;
                 double k4[m], k3[m], k2[m], k1[m], g3[n], g2[n], g1[n], g0[n];
                 double dRq[nc], dM3[nc], dM2[nc];
+                // Larger problems (FMA-contracted build only) add each g to a running sum as soon as it is known --
+                // lam + g3 + g2 + g1 + g0 instead of the reference's lam + g1 + g2 + g3 + g0 (:86): the same terms in
+                // another order (rounding only), and 2 n fewer live doubles across the step
+#if defined(OCS_STRICT) && OCS_STRICT
+                constexpr bool RUNSUM = false;
+#else
+                constexpr bool RUNSUM = n >= 3;
+#endif
+                double ls[n];
                 const double *fL = fo + s * FW, *fM = fL + NF, *fR = fM + NF;      // (FO only)
                 if constexpr (FO) {
                     // lam(end) == 1: the objective row of every dJdk is the stage weight, already folded into fL/fM/fR
@@ -1391,14 +1512,26 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                     PF::template Xf<HM>(ttR, fR, tR, y4, uR[q], p[q], k4, g3);                   // :74-75
 #pragma unroll
                     for (int c = 0; c < n; ++c) k3[c] = h3 * lam[q][c] + h * g3[c];              // :77
+                    if constexpr (RUNSUM) {
+#pragma unroll
+                        for (int c = 0; c < n; ++c) ls[c] = lam[q][c] + g3[c];
+                    }
                     if (du) PF::template Uf<HM>(ttM, fM, tM, y3, uM[q], p[q], k3, dM3);          // :108-109
                     PF::template Xf<HM>(ttM, fM, tM, y3, uM[q], p[q], k3, g2);                   // :78-79
 #pragma unroll
                     for (int c = 0; c < n; ++c) k2[c] = h3 * lam[q][c] + h2 * g2[c];             // :81
+                    if constexpr (RUNSUM) {
+#pragma unroll
+                        for (int c = 0; c < n; ++c) ls[c] = ls[c] + g2[c];
+                    }
                     if (du) PF::template Uf<HM>(ttM, fM, tM, y2, uM[q], p[q], k2, dM2);          // :106-107
                     PF::template Xf<HM>(ttM, fM, tM, y2, uM[q], p[q], k2, g1);                   // :82-83
 #pragma unroll
                     for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
+                    if constexpr (RUNSUM) {
+#pragma unroll
+                        for (int c = 0; c < n; ++c) ls[c] = ls[c] + g1[c];
+                    }
                     PF::template Xf<HM>(ttL, fL, tL, y1[q], uL[q], p[q], k1, g0);                // :86-88
                 } else {
 #pragma unroll
@@ -1408,16 +1541,28 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                 for (int c = 0; c < n; ++c) k3[c] = h3 * lam[q][c] + h * g3[c];              // :77
                 k3[n] = h3 * lam[q][n];
+                if constexpr (RUNSUM) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) ls[c] = lam[q][c] + g3[c];
+                }
                 if (du) P::template U<HM>(ttM, tM, y3, uM[q], p[q], k3, dM3);               // :108-109
                 P::template X<HM>(ttM, tM, y3, uM[q], p[q], k3, g2);                        // :78-79
 #pragma unroll
                 for (int c = 0; c < n; ++c) k2[c] = h3 * lam[q][c] + h2 * g2[c];             // :81
                 k2[n] = h3 * lam[q][n];
+                if constexpr (RUNSUM) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) ls[c] = ls[c] + g2[c];
+                }
                 if (du) P::template U<HM>(ttM, tM, y2, uM[q], p[q], k2, dM2);               // :106-107
                 P::template X<HM>(ttM, tM, y2, uM[q], p[q], k2, g1);                        // :82-83
 #pragma unroll
                 for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
                 k1[n] = h6 * lam[q][n];
+                if constexpr (RUNSUM) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) ls[c] = ls[c] + g1[c];
+                }
                 P::template X<HM>(ttL, tL, y1[q], uL[q], p[q], k1, g0);                     // :86-88
                 }
 
@@ -1443,7 +1588,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < n; ++c) lam[q][c] = lam[q][c] + g1[c] + g2[c] + g3[c] + g0[c];   // :86
+                for (int c = 0; c < n; ++c)
+                    lam[q][c] = RUNSUM ? ls[c] + g0[c] : lam[q][c] + g1[c] + g2[c] + g3[c] + g0[c];   // :86
                 if constexpr (UMODE != UMODE_UNIFORM) {
 #pragma unroll
                     for (int c = 0; c < nc; ++c) uR[q][c] = uL[q][c];
@@ -1484,6 +1630,19 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             else run_tile(ocs_bool<false>{});
         } else {
             run_tile(ocs_bool<false>{});
+        }
+        if constexpr (OCS_ASYNC_STAGE) {
+            if (i0 > 0) {
+                // the tile fetch is older than the last ns ring groups: waiting for all but DP-1 groups covers it
+                // whenever the tile had at least DP steps (only the first, partial tile can be shorter)
+                if (DP > 0 && ns >= DP) cp_async_wait<(DP > 0 ? DP - 1 : 0)>();
+                else cp_async_wait<0>();
+                __syncthreads();        // everybody's copies have landed; nobody reads the old tile any more
+                gp = gp == sm ? sm + TD : sm;
+                st = gp + TL::GP;
+                bs = st + TL::ST;
+                fo = bs + (size_t)(2 * TL::S + 1) * BW;
+            }
         }
     }
 #pragma unroll
@@ -1751,6 +1910,8 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 1 OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
 #define OCS_FBC_KERNEL(P, tag, PB) \
     OCS_KERNEL_(ocs_fbcont_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 2 OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
+#define OCS_FBCG_KERNEL(P, tag, PB) \
+    OCS_KERNEL_(ocs_fbcontg_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 2 OCS_COMMA true>, tag, 2, 0, PB, 1)
 #define OCS_TT_KERNEL(P, tag)                                                                         \
     extern "C" __global__ void ocs_tt_##tag(double *gprec, int G, int hm, const double *p)             \
     {                                                                                                  \
@@ -1766,7 +1927,7 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
         o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2) | (OCS_TPT_FWD_COEF << 16);               \
-        o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24) | (OCS_TPT_REV_COEF << 28); \
+        o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24) | (OCS_ASYNC_STAGE << 28); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24) | (OCS_TPT_REV_COEF << 28); \
     }
 
 #define OCS_EQ_KERNEL(P, tag)                                                                         \
@@ -1793,7 +1954,8 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     OCS_REVG_KERNEL(P, tag, 1, 2, PB, KD)       \
     OCS_REVG_KERNEL(P, tag, 2, 0, PB, KD)       \
     OCS_FB_KERNEL(P, tag, PB)                   \
-    OCS_FBC_KERNEL(P, tag, PB)
+    OCS_FBC_KERNEL(P, tag, PB)                  \
+    OCS_FBCG_KERNEL(P, tag, PB)
 
 #define OCS_DEFINE_KERNELS(P, tag, KD)   \
     OCS_DEFINE_KERNELS_PB(P, tag, 0, KD) \
