@@ -9,7 +9,7 @@ compute_u -> compute_states -> compute_adjoints -> compute_dJdv) over the whole 
 BASELINE.json configs[1]: 2^20 random initial conditions x 1000 RK4 steps of the bundled test
 problem with a shared PWLinearControl (K = 101).  One trajectory-step = one RK4 step of one
 trajectory, forward AND adjoint.  N > 1: every rank owns its own 2^20
-trajectories (weak scaling) and J, x(T) are all-gathered over NCCL inside the timed region.
+trajectories (weak scaling) and J, x(T) are gathered to rank 0 over NCCL inside the timed region.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
 host-buffer C ABI with the copies inside the timed region; `roofline` is for the dominant
@@ -78,6 +78,26 @@ def make_workload(name, ocs, local_rank, bt_override=None):
                     flop_fwd=FLOP_FWD + 2 * 3, flop_rev=FLOP_REV, bytes_fwd=BYTES_FWD, bytes_rev=BYTES_REV,
                     label="cfg2v: cfg2 with per-trajectory PWLinearControl coefficients v (101 x 2^20), forward + adjoint",
                     kernels=("ocs_fwd_test_fast_u1_b1_p0", "ocs_rev_test_fast_u1_b1_p0"), x0_lo=0.5, x0_hi=2.5)
+    if name in ("cfg2p", "cfg2pv"):
+        # parameter sweep: every trajectory its own (c, m, r) (tests/TestOCProblem.m:13-19) -- nothing is batch-uniform
+        # any more, so exp(-r t) runs in the thread (4 per forward step, 8 per reverse step) and no table / weight
+        # folding applies.  cfg2p: shared control coefficients; cfg2pv: per-trajectory coefficients as well.
+        Bt = bt_override or BT
+        tspan = ocs.matlab_linspace(0.0, T_END, N_STEPS + 1)
+        integ = ocs.CudaRK4Integrator(tspan, device=local_rank)
+        ctl = ocs.PWLinearControl(integ.t, K_PWL, 1)
+        rng = np.random.default_rng(31)
+        prob = ocs.TestOCProblem(dict(c=rng.uniform(1.3, 1.7, Bt), m=rng.uniform(2.8, 3.2, Bt), r=rng.uniform(0.03, 0.07, Bt)),
+                                 [[0.0, 1.0]])
+        pv = name == "cfg2pv"
+        return dict(integ=integ, prob=prob, ctl=ctl, n=1, rows=K_PWL, Bt=Bt, N_total=N_STEPS,
+                    v=None if pv else np.random.default_rng(1).random(K_PWL), v_batch=(K_PWL, Bt) if pv else None, v_kind="uniform",
+                    flop_fwd=FLOP_FWD + (2 * 3 if pv else 0), flop_rev=FLOP_REV, bytes_fwd=BYTES_FWD + 24 / N_STEPS,
+                    bytes_rev=BYTES_REV + 24 / N_STEPS,
+                    label=name + ": parameter sweep of tests/TestOCProblem.m, 2^20 trajectories each with its own (c, m, r) and x0 "
+                                 "x 1000 RK4 steps, " + ("per-trajectory" if pv else "shared") + " PWLinearControl K=101, forward + adjoint",
+                    kernels=("ocs_fwd_test_fast_u%d_b%d_p1" % ((1, 1) if pv else (0, 0)),
+                             "ocs_rev_test_fast_u%d_b1_p1" % (1 if pv else 0)), x0_lo=0.5, x0_hi=2.5)
     if name == "cfg3":
         # 6-state generated problem, one Chebyshev (degree 16) coefficient set per control candidate
         Bt = bt_override or 100_000
@@ -91,10 +111,12 @@ def make_workload(name, ocs, local_rank, bt_override=None):
         return dict(integ=integ, prob=prob, ctl=ctl, n=6, rows=2 * K, Bt=Bt, N_total=N_STEPS, v=None,
                     v_batch=(2 * K, Bt),
                     flop_fwd=4 * fl["C_F"] + 13 * 7 + 2 * cu, flop_rev=4 * fl["C_X"] + 14 * 7 + 4 * fl["C_U"] + 2 * 2 + 2 * cv,
-                    bytes_fwd=48, bytes_rev=48,
+                    # forward: node states (48 B) + the control grid kept for the reverse sweep (32 B) written; reverse sweep:
+                    # both read again + dJdu written (32 B); the projection reads dJdu once (32 B), 2 K nc flops per grid point
+                    bytes_fwd=48 + 32, bytes_rev=48 + 32 + 32, flop_proj=2 * cv, bytes_proj=32, default_bt=100_000,
                     label="cfg3: generated 6-state/6-costate harvest-chain problem (make_from_symbolic CUDA backend, NVRTC), "
                           "100k control candidates x 1000 RK4 steps, per-candidate ChebyshevControl degree 16, forward + adjoint",
-                    kernels=("ocs_fwd_gen_u1_b2_p0", "ocs_rev_gen_u1_b2_p0"), x0_lo=1.0, x0_hi=2.5)
+                    kernels=("ocs_fwd_gen_u1_b2_p0", "ocs_rev_gen_u2_b0_p0"), x0_lo=1.0, x0_hi=2.5)
     if name == "cfg4":
         # RK4InfiniteIntegrator: main horizon + tail under uStar, stored state grids of both in HBM
         Bt = bt_override or 262_144
@@ -194,50 +216,69 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_oracle_run(ntraj, nthreads=0, mode=1):
-    """Times the C restatement oracle on `ntraj` trajectories of the bench workload.
-    Returns (trajectory-steps/s, threads used)."""
-    from oracle import oracle_c, rk4_oracle
-    oracle_c.build()
-    tspan = rk4_oracle.matlab_linspace(0.0, T_END, N_STEPS + 1)
-    ctl = rk4_oracle.PWLinearControl(rk4_oracle.RK4Integrator(tspan).t, K_PWL, 1)
-    v = np.random.default_rng(1).random(K_PWL)
-    x0 = np.random.default_rng(2).uniform(0.5, 2.5, (1, ntraj))
-    if nthreads <= 0:
+class CpuOracle:
+    """The C restatement oracle on the bench workload with everything that is not the sweep (grid, basis matrix,
+    control coefficients, initial states) built ONCE, outside any timed region."""
+
+    def __init__(self, ntraj_max):
+        from oracle import oracle_c, rk4_oracle
+        oracle_c.build()
+        self.oc = oracle_c
+        self.tspan = rk4_oracle.matlab_linspace(0.0, T_END, N_STEPS + 1)
+        self.B = rk4_oracle.PWLinearControl(rk4_oracle.RK4Integrator(self.tspan).t, K_PWL, 1).B
+        self.v = np.random.default_rng(1).random(K_PWL)
+        self.x0 = np.random.default_rng(2).uniform(0.5, 2.5, (1, ntraj_max))
         # every host thread this process may run on -- set explicitly: torchrun exports OMP_NUM_THREADS=1, which
         # would silently time the reference on one core
         try:
-            nthreads = len(os.sched_getaffinity(0))
+            self.nthreads = len(os.sched_getaffinity(0))
         except AttributeError:
-            nthreads = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    oracle_c.evaluate(list(PARAMS.values()), tspan, ctl.B, x0, v, mode=mode, nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    return ntraj * N_STEPS / dt, oracle_c.num_threads()
+            self.nthreads = os.cpu_count() or 1
+
+    def run(self, ntraj, mode=1):
+        """One forward + adjoint evaluation of the first ntraj trajectories; returns seconds."""
+        x0 = np.ascontiguousarray(self.x0[:, :ntraj])
+        t0 = time.perf_counter()
+        self.oc.evaluate(list(PARAMS.values()), self.tspan, self.B, x0, self.v, mode=mode, nthreads=self.nthreads)
+        return time.perf_counter() - t0
+
+    def threads_used(self):
+        return self.oc.num_threads()
+
+
+def main_config(Bt, world):
+    """The `config` object of the bench line; the reference arm prints the same keys (plus `sample`)."""
+    return {"workload": WORKLOAD, "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS,
+            "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * N_STEPS * Bt),
+            "collective": "gather of J and x(T) to rank 0 (NCCL send/recv)" if world > 1 else "none"}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is MATLAB
-    only and neither MATLAB nor Octave is installed, so this times the oracle port (C restatement of
-    RK4Integrator.m / PWLinearControl.m / TestOCProblem.m, OpenMP across trajectories, every host
-    thread), each step a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation of the path.  The reference is MATLAB only and neither
+    MATLAB nor Octave is installed, so this times the oracle port (C restatement of RK4Integrator.m /
+    PWLinearControl.m / TestOCProblem.m, OpenMP across trajectories, every host thread).  Each step is a bounded
+    sample of the workload (2^17 of the 2^20 trajectories, all 1000 RK4 steps, forward + adjoint); one full 2^20
+    step is timed once on top of that and reported as `full_step`.  Grid, basis and inputs are built before the
+    timed region."""
     if rank != 0:
         return
-    ntraj = 16384
+    ntraj = 1 << 17
+    oracle = CpuOracle(BT)
     for _ in range(args.warmup):
-        cpu_oracle_run(2048)
-    t0 = time.perf_counter()
-    cores = 1
+        oracle.run(4096)
+    dt = 0.0
     for _ in range(args.steps):
-        _, cores = cpu_oracle_run(ntraj)
-    dt = time.perf_counter() - t0
+        dt += oracle.run(ntraj)
+    cores = oracle.threads_used()
     value = args.steps * ntraj * N_STEPS / dt
-    sample = f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps per step (fwd + adjoint)"
+    full = oracle.run(BT)
+    sample = f"{ntraj} of the 2^20 trajectories x {N_STEPS} RK4 steps per step (fwd + adjoint), inputs prebuilt"
     emit({
         "impl": "reference", "metric": METRIC, "value": value,
         "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "dtype": "f64", "data": "synthetic", "config": dict(main_config(BT, args.gpus), sample=sample),
+        "full_step": {"trajectories": BT, "seconds": full, "value": BT * N_STEPS / full, "unit": "trajectory-steps/s"},
         "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -503,6 +544,82 @@ def emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
+def measure_fp64_peak(ocs, local_rank):
+    """FP64 FMA peak by the DFMA micro-benchmark, with the SM clock sampled WHILE it runs and derived from the
+    kernel's own cycle counter (cycles / elapsed): 148 SMs x 64 FMA/clk x 2 x clock is the nominal figure the
+    measured one is compared with."""
+    import ctypes
+    L = ocs._lib.load()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    tf, mhz = ctypes.c_double(), ctypes.c_double()
+    if hasattr(L, "ocs_b200_measure_fp64_peak_ex"):
+        L.ocs_b200_measure_fp64_peak_ex(local_rank, ctypes.byref(tf), ctypes.byref(mhz))
+    else:
+        L.ocs_b200_measure_fp64_peak(local_rank, ctypes.byref(tf))
+    clocks = sampler.stop()
+    import torch
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    eff_mhz = mhz.value or (clocks["sm_mhz"] or 0)
+    nominal = sms * 64 * 2 * eff_mhz * 1e6 / 1e12 if eff_mhz else None
+    return tf.value, {"fp64_peak_tflops": tf.value, "fp64_peak_clock_mhz": mhz.value or None,
+                      "fp64_peak_clock_mhz_nvml": clocks["sm_mhz"], "fp64_peak_reasons": clocks["reasons"],
+                      "fp64_nominal_at_that_clock_tflops": nominal,
+                      "fp64_peak_over_nominal": (tf.value / nominal) if nominal else None}
+
+
+def pcie_ceiling(nbytes, dev, world):
+    """What the host link gives this rank while EVERY rank downloads at once and nothing computes: one pinned
+    device->host copy of `nbytes` per rank, started together.  The ceiling the end-to-end numbers are held against."""
+    import torch
+    import torch.distributed as dist
+    n = nbytes // 8
+    src = torch.empty(n, dtype=torch.float64, device=dev)
+    dst = torch.empty(n, dtype=torch.float64).pin_memory()
+    dst[::512] = 0
+    best = 0.0
+    for rep in range(3):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if rep > 0:
+            best = max(best, nbytes / dt / 1e9)
+    del src, dst
+    return best
+
+
+def run_sub_config(name, extra=()):
+    """One of the other BASELINE.json configurations in a subprocess of this script (its own CUDA context and
+    memory); returns a compact record for the `configs` block of the main line."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--config", name, "--steps", "5", "--warmup", "3", "--no-cpu",
+           "--no-e2e", "--no-configs", *extra]
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        j = json.loads(line)
+    except Exception as e:          # a failing side configuration must not take the bench line with it
+        return {"error": repr(e)[:200]}
+    rf = j.get("roofline", {})
+    out = {"workload": j["config"]["workload"], "value": j["value"], "unit": j["unit"], "ms_per_step": j["ms_per_step"],
+           "bound": rf.get("bound"), "frac": rf.get("frac"), "kernel": rf.get("kernel"),
+           "kernels": [{k: q[k] for k in ("kernel", "ms", "tflops", "gbs") if k in q} for q in rf.get("kernels", [])],
+           "wall_s": time.perf_counter() - t0}
+    for k in ("step_fp64_frac",):
+        if k in rf:
+            out[k] = rf[k]
+    if "solve" in j:
+        out["solve"] = j["solve"]
+    if "e2e" in j and j["e2e"]:
+        out["e2e"] = j["e2e"].get("value")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -512,7 +629,10 @@ def main():
     ap.add_argument("--bt", type=int, default=BT, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg2v", "cfg2solve", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
+    ap.add_argument("--no-configs", action="store_true", help="skip the bounded runs of the other BASELINE configs")
+    ap.add_argument("--gather", default="root", choices=["root", "all"], help="N > 1: gather J, x(T) to rank 0 (default) or all-gather")
+    ap.add_argument("--config", default="cfg2",
+                    choices=["cfg2", "cfg2v", "cfg2p", "cfg2pv", "cfg2solve", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
     args = ap.parse_args()
 
@@ -580,24 +700,27 @@ def main():
             v_dev = 0.05 * torch.randn(wl["v_batch"], dtype=torch.float64, device=dev, generator=gen)
             v_dev[:2] = 0.2 + 0.6 * torch.rand((2, Bt), dtype=torch.float64, device=dev, generator=gen)
         v_dev = v_dev.contiguous()
-    # J and x(T) live in one packed (1+n) x Bt buffer so that one all-gather moves both; double-buffered and
-    # gathered on a side stream so that the collective overlaps the next evaluation (host/dist.py)
-    pg = distmod.PipelinedGather(n_st, Bt, world, dev)
+    # J and x(T) live in one packed (1+n) x Bt buffer so that one gather moves both; double-buffered and gathered on
+    # a side stream so that the transfer overlaps the next evaluation (host/dist.py).  Gather to rank 0 by default.
+    pg = distmod.PipelinedGather(n_st, Bt, world, dev, rank=rank, mode=args.gather)
     status = torch.empty(Bt, dtype=torch.int32, device=dev)
     dJdv = torch.empty((rows, Bt), dtype=torch.float64, device=dev)
     lam0 = torch.empty((n_st + 1, Bt), dtype=torch.float64, device=dev)
+    bound = [False]
 
     def evaluate_dev():
         res = pg.next_buffer()
         integ.evaluate_dev(prob, x0.data_ptr(), Bt, v=v, v_ptr=(v_dev.data_ptr() if v_dev is not None else 0),
                            J_ptr=res[0].data_ptr(), xT_ptr=res[1:].data_ptr(), status_ptr=status.data_ptr(),
-                           dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+                           dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr(), bind=not bound[0])
+        bound[0] = True
         return res
 
     def step():
         res = evaluate_dev()
         if world > 1:
             pg.gather(res)
+        return res
 
     def sync_all():
         torch.cuda.synchronize()
@@ -615,17 +738,36 @@ def main():
     integ.kernel_stats(reset=True)
     ev0.record(stream)
     for _ in range(args.steps):
-        step()
+        res = step()
     pg.finish()                 # every gather of the timed steps has completed before the closing event
     ev1.record(stream)
     sync_all()
-    ms = ev0.elapsed_time(ev1)
+    ms_local = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     launches = integ.kernel_stats(reset=True)["launches"]    # sweeps + the table / fold kernels of every evaluation
+    ms, per_rank, gather_check = ms_local, None, None
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        t = torch.tensor([ms_local, float(clocks["sm_mhz"] or 0)], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per = [float(a[0]) for a in allt]
+        ms = max(per)
+        per_rank = {"ms_per_step_min": min(per) / args.steps, "ms_per_step_max": max(per) / args.steps,
+                    "ms_per_step": [p / args.steps for p in per], "sm_mhz": [float(a[1]) for a in allt]}
+        # what arrived at the root is what every rank computed: per-rank checksums of the last step's local J, x(T)
+        # against checksums of the root's gathered slices (exact: same doubles, same summation order on one device type)
+        loc = torch.stack([res[0].sum(), res[1:].sum(), res[0][Bt // 2], res[0].max()])
+        alls = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(alls, loc)
+        if rank == 0:
+            out_root = pg.out[pg.k]
+            ok = True
+            for r in range(world):
+                got = torch.stack([out_root[r, 0].sum(), out_root[r, 1:].sum(), out_root[r, 0][Bt // 2], out_root[r, 0].max()])
+                ok = ok and bool(torch.equal(got, alls[r]))
+            gather_check = {"gathered_equals_local": ok, "ranks": world, "bytes_per_rank_per_step": 8 * (1 + n_st) * Bt,
+                            "mode": args.gather}
+            assert ok, "the J / x(T) gathered on rank 0 differ from what the ranks computed"
     value = world * Bt * NT * args.steps / (ms * 1e-3)
 
     # ---- per-kernel device time (CUDA events around every launch, on the launch stream)
@@ -636,14 +778,12 @@ def main():
     torch.cuda.synchronize()
     ks = integ.kernel_stats(reset=True)
     integ.set_profiling(False)
-    ms_fwd, ms_rev = ks["ms_forward"] / nprof, ks["ms_reverse"] / nprof
+    ms_fwd, ms_rev = ks["ms_forward"] / nprof, ks["ms_reverse_sweep"] / nprof
+    ms_proj = ks["ms_project"] / nprof          # dense bases: dJdv = dJdu*B' is its own kernel after the reverse sweep
 
     out = None
     if rank == 0:
-        L = ocs._lib.load()
-        import ctypes
-        tf = ctypes.c_double()
-        L.ocs_b200_measure_fp64_peak(local_rank, ctypes.byref(tf))
+        tf_peak, peak_info = measure_fp64_peak(ocs, local_rank)
         hbm_peak, hbm_src = _measured_peaks()
         units = Bt * NT
 
@@ -651,12 +791,15 @@ def main():
             return {"kernel": name, "ms": ms_k, "tflops": units * flop / (ms_k * 1e-3) / 1e12,
                     "gbs": units * byt / (ms_k * 1e-3) / 1e9}
         kf = kern(wl["kernels"][0], ms_fwd, wl["flop_fwd"], wl["bytes_fwd"])
-        kr = kern(wl["kernels"][1], ms_rev, wl["flop_rev"], wl["bytes_rev"])
-        dom = kr if ms_rev >= ms_fwd else kf
-        fp_frac, hbm_frac = dom["tflops"] / tf.value, dom["gbs"] / hbm_peak
+        kr = kern(wl["kernels"][1], ms_rev, wl["flop_rev"] - wl.get("flop_proj", 0), wl["bytes_rev"])
+        kernels = [kf, kr]
+        if ms_proj > 0:
+            kernels.append(kern("dense_project_kernel", ms_proj, wl.get("flop_proj", 0), wl.get("bytes_proj", 0)))
+        dom = max(kernels, key=lambda k: k["ms"])
+        fp_frac, hbm_frac = dom["tflops"] / tf_peak, dom["gbs"] / hbm_peak
         if fp_frac >= hbm_frac:
-            roof = {"bound": "fp64", "achieved": dom["tflops"], "peak": tf.value, "unit": "TFLOP/s", "frac": fp_frac,
-                    "peak_source": "DFMA micro-benchmark in this run (ocs_b200_measure_fp64_peak); no FP64 entry in MEASURED_PEAKS.json"}
+            roof = {"bound": "fp64", "achieved": dom["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": fp_frac,
+                    "peak_source": "DFMA micro-benchmark in this run (ocs_b200_measure_fp64_peak_ex); no FP64 entry in MEASURED_PEAKS.json"}
         else:
             roof = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,
                     "peak_source": hbm_src}
@@ -664,33 +807,39 @@ def main():
         try:    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload only)
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
-            if Bt == BT:
+            if Bt == (wl.get("default_bt") or BT):
                 traffic = tj.get(args.config, {}).get(dom["kernel"], {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
         roof.update({"kernel": dom["kernel"], "traffic": traffic,
+                     "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload, committed; not re-measured per run)",
                      "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "peak_source": hbm_src},
-                     "fp64": {"achieved": dom["tflops"], "peak": tf.value, "unit": "TFLOP/s", "frac": fp_frac},
-                     "kernels": [kf, kr],
+                     "fp64": {"achieved": dom["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": fp_frac},
+                     "kernels": kernels, **peak_info,
                      "algorithmic": {"flop_per_step_fwd": wl["flop_fwd"], "flop_per_step_rev": wl["flop_rev"],
+                                     "flop_per_step_projection": wl.get("flop_proj", 0),
                                      "bytes_per_step_fwd": wl["bytes_fwd"], "bytes_per_step_rev": wl["bytes_rev"]}})
         # whole-evaluation view: (fwd + rev) algorithmic flops over the measured step time
-        roof["step_fp64_frac"] = value / world * (wl["flop_fwd"] + wl["flop_rev"]) / 1e12 / tf.value
+        roof["step_fp64_frac"] = value / world * (wl["flop_fwd"] + wl["flop_rev"]) / 1e12 / tf_peak
+        cfg = main_config(Bt, world) if args.config == "cfg2" else {
+            "workload": wl["label"], "trajectories_per_gpu": Bt, "rk4_steps": NT,
+            "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * n_st * NT * Bt),
+            "collective": "gather of J and x(T) to rank 0 (NCCL send/recv)" if world > 1 else "none"}
         out = {
             "metric": METRIC, "value": value,
             "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["label"], "trajectories_per_gpu": Bt, "rk4_steps": NT,
-                       "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * n_st * NT * Bt),
-                       "collective": "all_gather of J and x(T) (NCCL)" if world > 1 else "none"},
+            "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
             # the two modes side by side, per GPU, from the per-kernel CUDA-event times
             "modes": {"fwd_only": {"value": units / (ms_fwd * 1e-3), "unit": "trajectory-steps/s", "ms": ms_fwd,
                                    "what": "compute_states alone (J, x(T))"},
-                      "fwd_bwd": {"value": units / ((ms_fwd + ms_rev) * 1e-3), "unit": "trajectory-steps/s",
-                                  "ms": ms_fwd + ms_rev, "what": "compute_states + compute_adjoints (J, dJdv)"}},
+                      "fwd_bwd": {"value": units / ((ms_fwd + ms_rev + ms_proj) * 1e-3), "unit": "trajectory-steps/s",
+                                  "ms": ms_fwd + ms_rev + ms_proj, "what": "compute_states + compute_adjoints (J, dJdv)"}},
         }
+        if per_rank:
+            out["per_rank"] = per_rank
+            out["gather_check"] = gather_check
 
     # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)
     e2e = None
@@ -707,44 +856,167 @@ def main():
         lam0_h = torch.empty((Bt, 2), dtype=torch.float64).pin_memory()
         for buf in (x0_h, J_h, xT_h, dJdv_h, lam0_h):
             buf.view(-1)[::512].add_(0)          # touch every page while the affinity is in place
+        # the same arrays as a MATLAB caller holds them: ordinary pageable memory (every mxArray is)
+        pg_bufs = dict(x0=np.array(x0_h.numpy()), J=np.empty(Bt), xT=np.empty((1, Bt)), st=np.empty(Bt, dtype=np.int32),
+                       dJdv=np.zeros((Bt, K_PWL)), lam0=np.zeros((Bt, 2)))
         restore()
         lib = ocs._lib
         vf = lib.f64(v)
         hnd = integ._h
         L = lib.load()
+        pin_bufs = dict(x0=x0_h.numpy(), J=J_h.numpy(), xT=xT_h.numpy(), st=st_h.numpy(), dJdv=dJdv_h.numpy(), lam0=lam0_h.numpy())
 
-        def e2e_step():
+        def e2e_step(b):
             lib.check(L.ocs_b200_set_control_v(hnd, lib.dp(vf), 1), hnd)
-            lib.check(L.ocs_b200_evaluate(hnd, lib.dp(x0_h.numpy()), Bt, None, 0, lib.dp(J_h.numpy()), lib.dp(xT_h.numpy()),
-                                          lib.ip(st_h.numpy()), lib.dp(dJdv_h.numpy()), lib.dp(lam0_h.numpy())), hnd)
-        ne = max(2, min(args.steps, 5))
-        e2e_step()
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(ne):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+            lib.check(L.ocs_b200_evaluate(hnd, lib.dp(b["x0"]), Bt, None, 0, lib.dp(b["J"]), lib.dp(b["xT"]),
+                                          lib.ip(b["st"]), lib.dp(b["dJdv"]), lib.dp(b["lam0"])), hnd)
+
+        def timed_e2e(b):
+            ne = max(2, min(args.steps, 5))
+            e2e_step(b)
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(ne):
+                e2e_step(b)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return ne, dt
+        ne, dt = timed_e2e(pin_bufs)
+        nep, dtp = timed_e2e(pg_bufs)
+        same = bool(np.array_equal(pg_bufs["J"], pin_bufs["J"]) and np.array_equal(pg_bufs["dJdv"], pin_bufs["dJdv"]))
+        d2h_bytes = 8 * Bt * (1 + 1 + K_PWL + 2) + 4 * Bt
+        ceiling = pcie_ceiling(d2h_bytes, dev, world)           # GB/s per rank with every rank copying at once
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            t = torch.tensor([ceiling], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ceiling = float(t.item())
+        per_rank_gbs = d2h_bytes * ne / dt / 1e9
         e2e = {"value": world * Bt * N_STEPS * ne / dt, "unit": "trajectory-steps/s",
                "h2d_bytes_per_step": 8 * Bt + 8 * K_PWL,
-               "d2h_bytes_per_step": 8 * Bt * (1 + 1 + K_PWL + 2) + 4 * Bt,
+               "d2h_bytes_per_step": d2h_bytes,
                "steps": ne, "ms_per_step": 1e3 * dt / ne,
-               "api": "ocs_b200_evaluate (nlpObjective: compute_states + compute_adjoints) on pinned host buffers; J, xT, status, dJdv, lam0 returned"}
+               "api": "ocs_b200_evaluate (nlpObjective: compute_states + compute_adjoints) on pinned host buffers; J, xT, status, dJdv, lam0 returned",
+               # the D2H link with all ranks downloading and nothing computing, and how much of it the call reaches
+               "pcie_ceiling_gbs": ceiling, "d2h_gbs_per_rank": per_rank_gbs,
+               "frac_of_pcie_ceiling": per_rank_gbs / ceiling if ceiling else None,
+               "e2e_pageable": {"value": world * Bt * N_STEPS * nep / dtp, "unit": "trajectory-steps/s", "ms_per_step": 1e3 * dtp / nep,
+                                "vs_pinned": (dtp / nep) / (dt / ne), "results_identical_to_pinned": same,
+                                "what": "the same call on ordinary pageable NumPy arrays (what MATLAB mxArrays are): "
+                                        "transfers go through the handle's pinned ring and copy threads"}}
+
+    # ---- the whole batched single_shooting solve end to end (configs[1] as literally stated): x0 up, vOpt down once
+    solve = None
+    if not args.no_e2e and args.config == "cfg2":
+        ctl_s = ocs.PWLinearControl(integ.t, K_PWL, 1)
+        Lb, Ub = ctl_s.compute_nlp_bounds(prob.ControlBounds)
+        x0np = x0.cpu().numpy()
+        v_out = torch.empty((Bt, K_PWL), dtype=torch.float64).pin_memory()
+        sb = dict(v=v_out.numpy().T, J=np.empty(Bt), iters=np.empty(Bt, dtype=np.int32), converged=np.empty(Bt, dtype=np.int32))
+        integ.single_shooting(prob, x0np, ctl_s.compute_initial_v(0.5), Lb, Ub, max_iter=200, tol=1e-6, out=sb)
+        sync_all()
+        t0 = time.perf_counter()
+        ss = integ.single_shooting(prob, x0np, ctl_s.compute_initial_v(0.5), Lb, Ub, max_iter=200, tol=1e-6, out=sb)
+        torch.cuda.synchronize()
+        dts = time.perf_counter() - t0
+        ev_local = float(ss["iters"].astype(np.int64).sum())
+        t = torch.tensor([dts, ev_local, float(ss["converged"].sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dts, ev_all, nconv = float(tm[0]), float(t[1]), float(t[2])
+        else:
+            dts, ev_all, nconv = (float(z) for z in t)
+        solve = {"value": ev_all * N_STEPS / dts, "unit": "trajectory-steps/s", "ms_per_solve_batch": 1e3 * dts,
+                 "solves": world * Bt, "solves_per_s": world * Bt / dts, "converged": int(nconv),
+                 "mean_evaluations": ev_all / (world * Bt),
+                 "d2h_bytes": 8 * Bt * (K_PWL + 1) + 8 * Bt, "h2d_bytes": 8 * Bt,
+                 "api": "ocs_b200_single_shooting on host buffers: x0 up; vOpt, J, iters, converged down once per solve "
+                        "(every objective/gradient evaluation stays on the device); wall clock, max over ranks"}
+
+    # ---- the same workload through ONE multi-device handle of the C ABI (rank 0 drives every GPU of the job)
+    multi = None
+    if world > 1 and args.config == "cfg2" and not args.no_e2e:
+        integ.close()
+        del dJdv, lam0, x0, pg
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank == 0:
+            mi = ocs.CudaRK4Integrator(ocs.matlab_linspace(0.0, T_END, N_STEPS + 1), device=list(range(world)))
+            mi.attach_control(ocs.PWLinearControl(mi.t, K_PWL, 1))
+            x0m = np.random.default_rng(2).uniform(0.5, 2.5, (1, world * Bt))
+            Jr = torch.empty(world * Bt, dtype=torch.float64, device="cuda:0")
+            xTr = torch.empty((1, world * Bt), dtype=torch.float64, device="cuda:0")
+            mi.evaluate_resident(prob, x0m, v, gradient=True)
+            for _ in range(3):
+                mi.evaluate_resident(prob, None, None, gradient=True)
+                mi.gather_results_dev(Jr.data_ptr(), xTr.data_ptr())
+            mi.synchronize()
+            t0 = time.perf_counter()
+            nm = max(5, min(args.steps, 20))
+            for _ in range(nm):
+                mi.evaluate_resident(prob, None, None, gradient=True)
+                mi.gather_results_dev(Jr.data_ptr(), xTr.data_ptr())
+            mi.synchronize()
+            dtm = time.perf_counter() - t0
+            ref = mi.results(gradient=False)
+            okm = bool(np.array_equal(Jr.cpu().numpy(), ref["J"]) and np.array_equal(xTr.cpu().numpy(), ref["xT"]))
+            multi = {"value": world * Bt * N_STEPS * nm / dtm, "unit": "trajectory-steps/s", "ms_per_step": 1e3 * dtm / nm,
+                     "devices": world, "gathered_equals_host_results": okm,
+                     "gather": os.environ.get("OCS_B200_GATHER", "nccl"),
+                     "api": "ocs_b200_create_multi + ocs_b200_evaluate_resident + ocs_b200_gather_results_dev: one process, "
+                            "one handle, a worker thread per GPU, J and x(T) gathered to the root device every step; wall clock"}
+            mi.close()
+        # the other ranks wait on the HOST (a key of the rendezvous store): an NCCL barrier would be a kernel spinning on
+        # their GPU while rank 0's multi-device handle is sweeping on it
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("ocs_multi_done", "1")
+        else:
+            store.wait(["ocs_multi_done"])
+        dist.barrier()
 
     if rank == 0:
         out["e2e"] = e2e
+        if solve:
+            out["solve"] = solve
+        if multi:
+            out["c_abi_multi"] = multi
         if not args.no_cpu and args.config == "cfg2":
-            ntraj = 32768
-            val, cores = cpu_oracle_run(ntraj)
-            out["cpu_baseline"] = {"value": val, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
-                                   "sample": f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps, fwd + adjoint, "
+            ntraj = 1 << 17
+            oracle = CpuOracle(ntraj)
+            oracle.run(4096)
+            dtc = oracle.run(ntraj)
+            out["cpu_baseline"] = {"value": ntraj * N_STEPS / dtc, "unit": "trajectory-steps/s", "cores": oracle.threads_used(), "kind": "port",
+                                   "sample": f"{ntraj} of the 2^20 trajectories x {N_STEPS} steps, fwd + adjoint, inputs prebuilt, "
                                              "C restatement of the MATLAB reference (no MATLAB/Octave in the image), OpenMP"}
+        if args.config == "cfg2" and world == 1 and not args.no_configs:
+            # the other BASELINE.json configurations (and the solve), each a short run in its own process, so that the
+            # driver's bench record carries them too.  Bounded: ~10-20 s each.
+            try:
+                integ.close()
+            except Exception:
+                pass
+            torch.cuda.empty_cache()
+            t_cfg = time.perf_counter()
+            blocks = {}
+            for name in ("cfg3", "cfg3fb", "cfg4", "fbsweep", "cfg2v", "cfg2p", "cfg2solve"):
+                if time.perf_counter() - t_cfg > 200:
+                    blocks[name] = {"skipped": "time budget of the configs block used up"}
+                    continue
+                blocks[name] = run_sub_config(name)
+            out["configs"] = blocks
         emit(out)
-    integ.close()
+    try:
+        integ.close()
+    except Exception:
+        pass
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -329,6 +329,9 @@ OCS_B200_API int ocs_b200_set_profiling(ocs_b200_handle *h, int on);
 
 /* FP64 FMA peak of the device (dependent DFMA chains, all SMs): TFLOP/s. */
 OCS_B200_API int ocs_b200_measure_fp64_peak(int device, double *tflops);
+/* The same with longer runs and the SM clock the device ran at meanwhile (SM cycles of the kernel / its duration):
+ * nominal peak at that clock = SMs x 64 FMA/clk x 2 x sm_mhz. */
+OCS_B200_API int ocs_b200_measure_fp64_peak_ex(int device, double *tflops, double *sm_mhz);
 /* HBM streaming bandwidth with the sweeps' access pattern (FP64 coalesced write + read): GB/s each. */
 OCS_B200_API int ocs_b200_measure_hbm(int device, size_t bytes, double *write_gbs, double *read_gbs);
 

@@ -76,6 +76,7 @@ SIGNATURES = {
     "ocs_b200_kernel_stats": (ctypes.c_int, [c_h, ctypes.c_int, c_dp, c_dp, c_lp]),
     "ocs_b200_set_profiling": (ctypes.c_int, [c_h, ctypes.c_int]),
     "ocs_b200_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, c_dp]),
+    "ocs_b200_measure_fp64_peak_ex": (ctypes.c_int, [ctypes.c_int, c_dp, c_dp]),
     "ocs_b200_measure_hbm": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, c_dp, c_dp]),
 }
 

@@ -13,6 +13,7 @@ struct ocs_kernel_table {
     int tpt_rev_coef;   // ... of the gradient kernels with per-trajectory coefficients (UMODE_COEF)
     int tpt_fwd;   // ... and of the forward kernels
     int tpt_fwd_coef;
+    int tpt_fwd_pb, tpt_rev_pb;   // ... with per-trajectory parameters
     int fb_ring;   // ... and of the fb_sweep costate kernels (ring*(n + 2 nc)*threads doubles)
     int rev_ring;  // depth of the gradient kernels' cp.async node-state ring (shared memory: ring*tpt*(n [+ 2 nc])*threads doubles)
     int async_stage;   // multi-trajectory bodies keep two record tiles in shared memory (the next one is fetched with cp.async)

@@ -85,6 +85,8 @@ extern "C" void OCS_CAT2(ocs_builtin_table_, OCS_TAGNAME)(ocs_kernel_table *t)
     t->tpt_rev_coef = OCS_TPT_REV_COEF;
     t->tpt_fwd = OCS_TPT_FWD;
     t->tpt_fwd_coef = OCS_TPT_FWD_COEF;
+    t->tpt_fwd_pb = OCS_TPT_FWD_PB;
+    t->tpt_rev_pb = OCS_TPT_REV_PB;
     t->rev_ring = OCS_RING;
     t->async_stage = OCS_ASYNC_STAGE;
     t->fb_ring = OCS_FB_RING;

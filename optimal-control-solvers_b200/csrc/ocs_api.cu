@@ -446,69 +446,103 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
 
 // dJdv = dJdu * B' for a dense basis (ChebyshevControl.m:34-37):
 // dug [nc][G][ldb] (SoA, written by the reverse sweep), basrec [G][BW] = B(:,j), dJdv [(k*nc+c)][ldb].
-// HBM-bound (every dJdu value is read once, 17 FMAs each at K = 17), so what matters is bytes in flight: a block is
-// 32 trajectories (lanes) x PROJ_W warps; warp w sums the grid points of segment w of [0, G) for ONE control
-// (blockIdx.y) with KC accumulators per thread and 8 loads in flight per thread; B(:,j) of the warp's current run of
-// PROJ_JT grid points sits in a warp-private shared-memory tile (every lane reads the same entry: a broadcast).  The
-// PROJ_W partial sums of a trajectory are added in ascending segment order through shared memory (fixed order:
-// deterministic).  48 registers -> all 1024+ threads of an SM resident, ~64 KB of loads in flight per SM; the first
-// version (4 trajectories x 18 accumulators per thread, 254 registers, 196 blocks) reached 2.0 TB/s.
+// HBM-bound (every dJdu value is read once, K FMAs each), so what matters is bytes in flight and shared-memory
+// reads per FMA.  A block is 32 trajectories (lanes) x PROJ_W warps; warp w sums the grid points of segment w of
+// [0, G).  A thread owns one trajectory and NS controls (2 when the problem has at least two): the row B(:,j) it
+// reads from the warp-private shared-memory tile (LDS.128: every lane reads the same entries, a broadcast) feeds
+// NS*KC FMAs, and 8 grid points of dJdu are in flight per stream.  The PROJ_W partial sums of a trajectory are added
+// in ascending segment order through shared memory (fixed order: deterministic).  History (cfg3, 100k x 2001 x K=17,
+// 3.2 GB): 4 trajectories x 18 accumulators per thread, 254 registers, 196 blocks: 1.61 ms (latency-bound); one
+// trajectory and control per thread: 1.79 ms (one LDS per FMA); this form: see profiles/r2_notes.md.
 #define PROJ_JT 32
 #define PROJ_W 8
-template <int KC>
-__global__ void __launch_bounds__(32 * PROJ_W, 3) dense_project_kernel(const double *__restrict__ dug, const double *__restrict__ basrec,
-                                                                   int BW, int K, int nc, int G, long nb, long ldb, double *dJdv)
+template <int KC, int NS>
+__global__ void __launch_bounds__(32 * PROJ_W, 2) dense_project_kernel(const double *__restrict__ dug, const double *__restrict__ basrec,
+                                                                      int BW, int K, int nc, int G, long nb, long ldb, double *dJdv)
 {
     extern __shared__ double2 proj_smem2[];
     double *sm = reinterpret_cast<double *>(proj_smem2);
-    const int lane = threadIdx.x, w = threadIdx.y, c = blockIdx.y;
+    const int lane = threadIdx.x, w = threadIdx.y, c0 = blockIdx.y * NS;
     double *Bs = sm + (size_t)w * PROJ_JT * BW;                 // [PROJ_JT][BW], private to the warp
     const long b = (long)blockIdx.x * 32 + lane;
     const long bb = b < nb ? b : nb - 1;
     const int seg = (G + PROJ_W - 1) / PROJ_W;
     const int ja = w * seg, jb = ja + seg < G ? ja + seg : G;
-    const double *dp = dug + (size_t)c * G * ldb + bb;
-    const unsigned ld8 = (unsigned)ldb * 8u;
-    for (int k0 = 0; k0 < K; k0 += KC) {
-        double acc[KC];
+    const double *dp[NS];
 #pragma unroll
-        for (int kk = 0; kk < KC; ++kk) acc[kk] = 0.0;
+    for (int s = 0; s < NS; ++s) dp[s] = dug + (size_t)(c0 + s < nc ? c0 + s : nc - 1) * G * ldb + bb;
+    const unsigned ld8 = (unsigned)ldb * 8u;
+    static_assert(KC % 2 == 0, "KC accumulators are updated in double2 pairs");
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        double acc[NS][KC];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) acc[s][kk] = 0.0;
         for (int j0 = ja; j0 < jb; j0 += PROJ_JT) {
             const int nj = jb - j0 < PROJ_JT ? jb - j0 : PROJ_JT;
             __syncwarp();
             for (int k = lane; k < PROJ_JT * BW; k += 32) Bs[k] = k < nj * BW ? basrec[(size_t)j0 * BW + k] : 0.0;
             __syncwarp();
+            constexpr int R = 8 / NS;                 // grid points in flight per stream: 8 loads per thread either way
 #pragma unroll 1
-            for (int jj = 0; jj < PROJ_JT; jj += 8) {
+            for (int jj = 0; jj < PROJ_JT; jj += R) {
                 if (jj >= nj) break;
-                double d[8];
+                double d[NS][R];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < R; ++r) {
                     const int j = j0 + jj + r < G ? j0 + jj + r : G - 1;      // clamped rows meet a zero B row
-                    d[r] = *ocs_host::soa_row(dp, (unsigned)j, ld8);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) d[s][r] = *ocs_host::soa_row(dp[s], (unsigned)j, ld8);
                 }
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const double *Bj = Bs + (jj + r) * BW + k0;
+                for (int r = 0; r < R; ++r) {
+                    const double2 *Bj = reinterpret_cast<const double2 *>(Bs + (jj + r) * BW + k0);   // BW, k0 even: 16-byte aligned
 #pragma unroll
-                    for (int kk = 0; kk < KC; ++kk)
-                        if (k0 + kk < BW) acc[kk] = acc[kk] + d[r] * Bj[kk];
+                    for (int kk = 0; kk < KC; kk += 2) {
+                        if (k0 + kk < BW) {
+                            const double2 bq = Bj[kk >> 1];
+#pragma unroll
+                            for (int s = 0; s < NS; ++s) {
+                                acc[s][kk] = acc[s][kk] + d[s][r] * bq.x;
+                                acc[s][kk + 1] = acc[s][kk + 1] + d[s][r] * bq.y;
+                            }
+                        }
+                    }
                 }
             }
         }
         // partial sums of the PROJ_W segments, added in ascending segment order
         __syncthreads();
-        double *red = sm;                                        // [PROJ_W][KC][32]
+        double *red = sm;                                        // [PROJ_W][NS*KC][32]
 #pragma unroll
-        for (int kk = 0; kk < KC; ++kk) red[((size_t)w * KC + kk) * 32 + lane] = acc[kk];
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) red[((size_t)w * NS * KC + s * KC + kk) * 32 + lane] = acc[s][kk];
         __syncthreads();
-        for (int kk = w; kk < KC; kk += PROJ_W) {
-            double sum = red[(size_t)kk * 32 + lane];
-            for (int q = 1; q < PROJ_W; ++q) sum = sum + red[((size_t)q * KC + kk) * 32 + lane];
-            if (b < nb && k0 + kk < K) dJdv[(size_t)((k0 + kk) * nc + c) * ldb + b] = sum;
+        for (int e = w; e < NS * KC; e += PROJ_W) {
+            double sum = red[(size_t)e * 32 + lane];
+            for (int q = 1; q < PROJ_W; ++q) sum = sum + red[((size_t)q * NS * KC + e) * 32 + lane];
+            const int s = e / KC, kk = e % KC;
+            if (b < nb && k0 + kk < K && c0 + s < nc) dJdv[(size_t)((k0 + kk) * nc + c0 + s) * ldb + b] = sum;
         }
         __syncthreads();
     }
+}
+
+template <int KC, int NS>
+static cudaError_t launch_project(cudaStream_t st, const double *dug, const double *basrec, int BW, int K, int nc, int G, long nb,
+                                  long ldb, double *dJdv)
+{
+    const size_t psm = std::max((size_t)PROJ_W * PROJ_JT * BW, (size_t)PROJ_W * NS * KC * 32) * sizeof(double);
+    if (psm > 200 * 1024) return cudaErrorInvalidValue;
+    if (psm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dense_project_kernel<KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+        if (e != cudaSuccess) return e;
+    }
+    const dim3 grid((unsigned)((nb + 31) / 32), (unsigned)((nc + NS - 1) / NS)), block(32, PROJ_W);
+    dense_project_kernel<KC, NS><<<grid, block, psm, st>>>(dug, basrec, BW, K, nc, G, nb, ldb, dJdv);
+    return cudaGetLastError();
 }
 
 // ug[c][j][b] = sum_k v[(k*nc+c)][b] B(k,j): control.compute_u for every trajectory (Control/*Control.m compute_u),
@@ -800,6 +834,16 @@ int launch(H *h, const void *kernel, SweepArgs &a, bool is_forward, int tpt = 1,
 
 int pb_index(const H *h) { return h->params_nbatch > 1 ? 1 : 0; }
 
+// trajectories per thread of the multi-trajectory sweep variants (OCS_FWD_T / OCS_REV_T in rk4_kernels.cuh)
+int fwd_tpt(const H *h, int um)
+{
+    return std::max(h->params_nbatch > 1 ? h->kt.tpt_fwd_pb : (um == 1 ? h->kt.tpt_fwd_coef : h->kt.tpt_fwd), 1);
+}
+int rev_tpt(const H *h, int um)
+{
+    return std::max(h->params_nbatch > 1 ? h->kt.tpt_rev_pb : (um == 1 ? h->kt.tpt_rev_coef : h->kt.tpt_rev), 1);
+}
+
 enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB, KIND_FBC, KIND_FBCG };
 
 // The kernel of one sweep variant.  Built-in problems have every variant compiled in; generated
@@ -878,7 +922,7 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         }
         const void *kern = nullptr;
         TRY(resolve(h, d_xgrid ? KIND_FWDG : KIND_FWD, um, bm, pb_index(h), &kern));
-        TRY(launch(h, kern, a, true, (d_xgrid || bm == 2) ? 1 : std::max(um == 1 ? h->kt.tpt_fwd_coef : h->kt.tpt_fwd, 1)));
+        TRY(launch(h, kern, a, true, (d_xgrid || bm == 2) ? 1 : fwd_tpt(h, um)));
     }
     return 0;
 }
@@ -986,7 +1030,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         TRY(resolve(h, grids ? KIND_REVG : KIND_REV, um, bm, pb_index(h), &kern));
         // dense-basis kernels keep K coefficients and K accumulators per trajectory in registers: one per thread
         {
-            const int tpt = (grids || bm == 2) ? 1 : std::max(um == 1 ? h->kt.tpt_rev_coef : h->kt.tpt_rev, 1);
+            const int tpt = (grids || bm == 2) ? 1 : rev_tpt(h, um);
             // the gradient kernels (not the fetch variants) keep a cp.async ring of node states in shared memory
             // (with a per-trajectory control grid a ring slot also carries the step's two controls)
             const size_t ring = grids ? 0 : (size_t)h->kt.rev_ring * tpt * (h->kt.n + (um == 2 ? 2 * h->kt.nc : 0)) * h->kt.threads;
@@ -995,19 +1039,17 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         if (project) {
             const int G = 2 * s.N + 1;
             if (h->profiling) CK(cudaEventRecord(h->ev[2], h->stream));
-            // K <= 18: one pass with 18 accumulators per thread; larger K in chunks of 16
-            const int KC = h->K <= 18 ? 18 : 16;
-            const size_t psm = std::max((size_t)PROJ_W * PROJ_JT * s.BW, (size_t)PROJ_W * KC * 32) * sizeof(double);
-            const dim3 pgrid((unsigned)((nb + 31) / 32), (unsigned)h->kt.nc), pblock(32, PROJ_W);
-            if (psm > 200 * 1024) return h->fail(OCS_B200_ERR_ARG, "control basis too wide for the projection kernel");
-            if (KC == 18) {
-                if (psm > 48 * 1024)
-                    CK(cudaFuncSetAttribute(dense_project_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-                dense_project_kernel<18><<<pgrid, pblock, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
-            } else {
-                if (psm > 48 * 1024)
-                    CK(cudaFuncSetAttribute(dense_project_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-                dense_project_kernel<16><<<pgrid, pblock, psm, h->stream>>>(a.dug, s.d_basrec, s.BW, h->K, h->kt.nc, G, nb, Bt, d_dJdv);
+            // K <= 18: one pass with 18 accumulators per stream; larger K in chunks of 16.  Two controls per thread when
+            // the problem has them (the B row read from shared memory then feeds twice the FMAs)
+            {
+                const int ncv = h->kt.nc;
+                cudaError_t pe;
+                if (h->K <= 18) pe = ncv >= 2 ? launch_project<18, 2>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv)
+                                              : launch_project<18, 1>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv);
+                else pe = ncv >= 2 ? launch_project<16, 2>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv)
+                                   : launch_project<16, 1>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv);
+                if (pe == cudaErrorInvalidValue) return h->fail(OCS_B200_ERR_ARG, "control basis too wide for the projection kernel");
+                CK(pe);
             }
             CK(cudaGetLastError());
             if (h->profiling) {
@@ -2064,7 +2106,7 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             const void *kf = nullptr, *kr = nullptr;
             TRY(resolve(h, KIND_FWD, 2, 0, pb_index(h), &kf));
             TRY(resolve(h, h->fb_costate == OCS_B200_COSTATE_CONTINUOUS ? KIND_FBC : KIND_FB, 2, 0, pb_index(h), &kr));
-            TRY(launch(h, kf, a, true, std::max(h->kt.tpt_fwd, 1)));
+            TRY(launch(h, kf, a, true, fwd_tpt(h, 2)));
             SweepArgs r;
             base_args(h, 0, r);
             r.nb = Bt;
@@ -2414,6 +2456,7 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                 CK(cudaMemcpyAsync(h->d_gt.p + (size_t)(nv + f) * Bt, h->d_lam0.p + (size_t)free_states[f] * Bt,
                                    sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
             CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
+            if (h->profiling) CK(cudaEventRecord(h->ev[2], h->stream));
             {
                 // rows of a trajectory over G thread groups of up to 16 rows each (nz <= 512); beyond that the
                 // one-thread-per-trajectory kernel
@@ -2436,6 +2479,13 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
             }
             h->launches++;
             CK(cudaGetLastError());
+            if (h->profiling) {
+                CK(cudaEventRecord(h->ev[3], h->stream));
+                CK(cudaEventSynchronize(h->ev[3]));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+                h->ms_upd += ms;
+            }
             int nopen = 0;
             CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));

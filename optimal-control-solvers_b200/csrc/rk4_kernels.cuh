@@ -70,6 +70,24 @@
 #ifndef OCS_MINBLOCKS_FB
 #define OCS_MINBLOCKS_FB 1  // __launch_bounds__ min blocks/SM of the fb_sweep costate kernels
 #endif
+// Per-trajectory parameters (a parameter sweep: nothing is batch-uniform, exp() and the like run in the thread and
+// every trajectory carries its parameters in registers) want their own trajectories-per-thread / register cap:
+// the values tuned for uniform parameters spilled (808 B in the grid-control forward kernel).  Defaults: inherit.
+#ifndef OCS_TPT_FWD_PB
+#define OCS_TPT_FWD_PB OCS_TPT_FWD
+#endif
+#ifndef OCS_MINBLOCKS_FWD_PB
+#define OCS_MINBLOCKS_FWD_PB OCS_MINBLOCKS_FWD
+#endif
+#ifndef OCS_TPT_REV_PB
+#define OCS_TPT_REV_PB OCS_TPT_REV
+#endif
+#ifndef OCS_MINBLOCKS_REV_PB
+#define OCS_MINBLOCKS_REV_PB OCS_MINBLOCKS_REV
+#endif
+#ifndef OCS_MINBLOCKS_FB_PB
+#define OCS_MINBLOCKS_FB_PB OCS_MINBLOCKS_FB
+#endif
 #ifndef OCS_UPREFETCH
 #define OCS_UPREFETCH 1     // steps of per-trajectory grid control loaded ahead by reverse_body (UMODE_GRID)
 #endif
@@ -1898,18 +1916,23 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
         OCS_NS::body_call(a, reinterpret_cast<double *>(ocs_smem2));                                   \
     }
 #define OCS_COMMA ,
+// trajectories per thread / min blocks per SM of a sweep variant (the host mirrors these in kernel_tpt())
+#define OCS_FWD_T(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? OCS_TPT_FWD_PB : ((UM) == 1 ? OCS_TPT_FWD_COEF : OCS_TPT_FWD)))
+#define OCS_FWD_LB(UM, BM, PB) ((PB) != 0 ? OCS_MINBLOCKS_FWD_PB : ((UM) == 2 ? 4 : ((UM) == 1 && (BM) == 1 ? OCS_MINBLOCKS_FWD_COEF : OCS_MINBLOCKS_FWD)))
+#define OCS_REV_T(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? OCS_TPT_REV_PB : ((UM) == 1 ? OCS_TPT_REV_COEF : OCS_TPT_REV)))
+#define OCS_REV_LB(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? OCS_MINBLOCKS_REV_PB : ((UM) == 1 ? OCS_MINBLOCKS_REV_COEF : OCS_MINBLOCKS_REV)))
 #define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : ((UM) == 1 ? OCS_TPT_FWD_COEF : OCS_TPT_FWD))>, tag, UM, BM, PB, ((UM) == 2 ? 4 : ((UM) == 1 && (BM) == 1 ? OCS_MINBLOCKS_FWD_COEF : OCS_MINBLOCKS_FWD)))
+    OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA OCS_FWD_T(UM, BM, PB)>, tag, UM, BM, PB, OCS_FWD_LB(UM, BM, PB))
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwdg_, forward_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_REV_KERNEL(P, tag, UM, BM, PB, KD) \
-    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA((BM) == 2 ? 1 : ((UM) == 1 ? OCS_TPT_REV_COEF : OCS_TPT_REV))>, tag, UM, BM, PB, ((BM) == 2 ? 1 : ((UM) == 1 ? OCS_MINBLOCKS_REV_COEF : OCS_MINBLOCKS_REV)))
+    OCS_KERNEL_(ocs_rev_, reverse_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA OCS_REV_T(UM, BM, PB)>, tag, UM, BM, PB, OCS_REV_LB(UM, BM, PB))
 #define OCS_REVG_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_revg_, reverse_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA 0 OCS_COMMA true>, tag, UM, BM, PB, 1)
 #define OCS_FB_KERNEL(P, tag, PB) \
-    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 1 OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
+    OCS_KERNEL_(ocs_fbrev_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 1 OCS_COMMA false>, tag, 2, 0, PB, ((PB) != 0 ? OCS_MINBLOCKS_FB_PB : OCS_MINBLOCKS_FB))
 #define OCS_FBC_KERNEL(P, tag, PB) \
-    OCS_KERNEL_(ocs_fbcont_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 2 OCS_COMMA false>, tag, 2, 0, PB, OCS_MINBLOCKS_FB)
+    OCS_KERNEL_(ocs_fbcont_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 2 OCS_COMMA false>, tag, 2, 0, PB, ((PB) != 0 ? OCS_MINBLOCKS_FB_PB : OCS_MINBLOCKS_FB))
 #define OCS_FBCG_KERNEL(P, tag, PB) \
     OCS_KERNEL_(ocs_fbcontg_, reverse_body<P OCS_COMMA 2 OCS_COMMA 0 OCS_COMMA(PB != 0) OCS_COMMA 0 OCS_COMMA 2 OCS_COMMA true>, tag, 2, 0, PB, 1)
 #define OCS_TT_KERNEL(P, tag)                                                                         \
@@ -1926,7 +1949,8 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     extern "C" __global__ void ocs_info_##tag(int *o)                                                  \
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
-        o[3] = P::ntt(0); o[4] = P::ntt(1); o[5] = P::ntt(2) | (OCS_TPT_FWD_COEF << 16);               \
+        o[3] = P::ntt(0); o[4] = P::ntt(1) | (OCS_TPT_FWD_PB << 16) | (OCS_TPT_REV_PB << 20);          \
+        o[5] = P::ntt(2) | (OCS_TPT_FWD_COEF << 16);                                                   \
         o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24) | (OCS_ASYNC_STAGE << 28); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24) | (OCS_TPT_REV_COEF << 28); \
     }
 

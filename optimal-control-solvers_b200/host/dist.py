@@ -1,7 +1,10 @@
-"""Multi-GPU plumbing: the trajectory batch shards trivially (independent trajectories,
-SURVEY.md section 8e) -- one process per GPU, contiguous slices, no data-path collective.
-The only exchange is the gather of the small per-trajectory results J and x(T) with
-torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+"""Multi-GPU plumbing for the one-process-per-GPU launch (torchrun): the trajectory batch shards
+trivially (independent trajectories) -- contiguous slices, no data-path
+collective.  The only exchange is the gather of the small per-trajectory results J and x(T) TO
+RANK 0 with torch.distributed (NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests):
+non-root ranks send (1+n) x Bt doubles, the root receives world-1 of them -- an eighth of the
+bytes of the all-gather round 1 used, and no rank other than the root waits for anybody.
+(Inside ONE process the C ABI does the same with ocs_b200_create_multi / ocs_b200_gather_results_dev.)"""
 from __future__ import annotations
 
 
@@ -43,24 +46,38 @@ def gather_ragged(J, world: int, rank: int, Bt_total: int, group=None):
     return torch.cat([out[r * big: r * big + (b1 - b0)] for r, (b0, b1) in enumerate(sizes)])
 
 
-class PipelinedGather:
-    """All-gather of the packed per-trajectory results [J; x(T)] ((1+n) x Bt_local per rank) that overlaps
-    with the next evaluation: results are double-buffered, the collective runs on its own CUDA stream behind
-    an event of the compute stream, and a buffer is only handed out again once its gather has completed.
+def gather_to_root(res, out, world: int, rank: int, group=None, root: int = 0):
+    """Gathers the packed per-trajectory results res [(1+n) x Bt_local] of every rank into out
+    [world, 1+n, Bt_local] on `root` (out is ignored elsewhere).  NCCL implements it as grouped
+    point-to-point transfers; non-root ranks only send."""
+    import torch.distributed as dist
+    if world == 1:
+        out[0].copy_(res)
+        return
+    dist.gather(res, [out[r] for r in range(world)] if rank == root else None, dst=root, group=group)
 
-        pg = PipelinedGather(n, Bt, world, device)
+
+class PipelinedGather:
+    """Gather of the packed per-trajectory results [J; x(T)] ((1+n) x Bt_local per rank) that overlaps with the
+    next evaluation: results are double-buffered, the collective runs on its own CUDA stream behind an event of
+    the compute stream, and a buffer is only handed out again once its gather has completed.
+    mode "root" (default): gather to rank 0 (the north star's "gather the small per-trajectory J and final-state
+    results"); mode "all": all-gather (every rank gets everything; 8x the bytes at 8 ranks).
+
+        pg = PipelinedGather(n, Bt, world, device, rank=rank)
         for step in ...:
             res = pg.next_buffer()          # (1+n, Bt) tensor: row 0 = J, rows 1.. = x(T)
             ... sweeps write res ...
             pg.gather(res)                  # asynchronous
-        pg.finish()                         # pg.out[k] (world, 1+n, Bt) holds the gathered results of buffer k
+        pg.finish()                         # pg.out[k] (world, 1+n, Bt) holds the gathered results of buffer k (on the root)
     """
 
-    def __init__(self, n, Bt, world, device, group=None):
+    def __init__(self, n, Bt, world, device, group=None, rank=0, mode="root"):
         import torch
-        self.world, self.group = world, group
+        self.world, self.group, self.rank, self.mode = world, group, rank, mode
         self.bufs = [torch.empty((1 + n, Bt), dtype=torch.float64, device=device) for _ in range(2)]
-        self.out = [torch.empty((world, 1 + n, Bt), dtype=torch.float64, device=device) for _ in range(2)]
+        holds_all = mode == "all" or rank == 0
+        self.out = [torch.empty((world if holds_all else 1, 1 + n, Bt), dtype=torch.float64, device=device) for _ in range(2)]
         self.cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.done = [None, None]
@@ -81,14 +98,19 @@ class PipelinedGather:
         if self.world == 1:
             self.out[k][0].copy_(res)
             return
+        def collective():
+            if self.mode == "all":
+                dist.all_gather_into_tensor(self.out[k].view(-1), res.view(-1), group=self.group)
+            else:
+                gather_to_root(res, self.out[k], self.world, self.rank, group=self.group)
         if not self.cuda:
-            dist.all_gather_into_tensor(self.out[k].view(-1), res.view(-1), group=self.group)
+            collective()
             return
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            dist.all_gather_into_tensor(self.out[k].view(-1), res.view(-1), group=self.group)
+            collective()
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.done[k] = ev

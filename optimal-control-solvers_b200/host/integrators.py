@@ -32,14 +32,22 @@ class CudaRK4Integrator:
     """RK4Integrator(tspan) on the GPU (Integrator/RK4Integrator.m:16-25)."""
 
     def __init__(self, tspan, device=0, math="fast", _tspanExtra=None):
+        """device: a CUDA ordinal, or a sequence of distinct ordinals -- the batch is then sharded over those GPUs
+        inside the one handle (ocs_b200_create_multi; MATLAB: CudaRK4Integrator(tspan, 'Device', 0:7))."""
         self._lib = _lib.load()
         tspan = _lib.f64(np.asarray(tspan, dtype=np.float64).ravel())
         self.nSTEPS = tspan.size - 1
         self._h = ctypes.c_void_p()
         te = None if _tspanExtra is None else _lib.f64(np.asarray(_tspanExtra, dtype=np.float64).ravel())
         self._N2 = 0 if te is None else te.size - 1
-        rc = self._lib.ocs_b200_create(self.nSTEPS, _lib.dp(tspan), self._N2, _lib.dp(te), int(device),
-                                       _MATH[math], ctypes.byref(self._h))
+        self.devices = [int(d) for d in np.atleast_1d(device)]
+        if np.ndim(device) == 0:
+            rc = self._lib.ocs_b200_create(self.nSTEPS, _lib.dp(tspan), self._N2, _lib.dp(te), int(device),
+                                           _MATH[math], ctypes.byref(self._h))
+        else:
+            devs = (ctypes.c_int * len(self.devices))(*self.devices)
+            rc = self._lib.ocs_b200_create_multi(self.nSTEPS, _lib.dp(tspan), self._N2, _lib.dp(te), len(self.devices), devs,
+                                                 _MATH[math], ctypes.byref(self._h))
         if rc != 0:
             self._h = ctypes.c_void_p()
             _lib.check(rc, None)
@@ -241,13 +249,14 @@ class CudaRK4Integrator:
         self._ck(self._lib.ocs_b200_synchronize(self._h))
 
     def evaluate_dev(self, prob, x0_ptr, Bt, v=None, v_ptr=None, J_ptr=0, xT_ptr=0, status_ptr=0,
-                     dJdv_ptr=0, lam0_ptr=0, lamT_ptr=0, lamT_nbatch=0, gradient=True):
+                     dJdv_ptr=0, lam0_ptr=0, lamT_ptr=0, lamT_nbatch=0, gradient=True, bind=True):
         """evaluate() on caller-owned DEVICE buffers in SoA layout [row][Bt] (raw pointers as ints):
         nothing crosses PCIe.  v: shared host coefficients, or v_ptr: device [(nc*K)][Bt].
         Asynchronous on the handle's stream."""
         if self._control is None:
             raise RuntimeError("attach_control(control) first")
-        self._bind(prob)
+        if bind:        # (a loop over the same problem object may skip the re-comparison of its parameter arrays)
+            self._bind(prob)
         if v_ptr:
             self._ck(self._lib.ocs_b200_set_control_v_dev(self._h, ctypes.c_void_p(int(v_ptr)), int(Bt)))
         else:
@@ -259,6 +268,49 @@ class CudaRK4Integrator:
         if gradient:
             self._ck(self._lib.ocs_b200_compute_adjoints_dev(self._h, P(lamT_ptr), int(lamT_nbatch), P(dJdv_ptr),
                                                              P(lam0_ptr)))
+
+    def evaluate_resident(self, prob, x0=None, v=None, gradient=True):
+        """nlpObjective on data that stays on the device(s) (ocs_b200_evaluate_resident): x0 (n x Bt) is uploaded and
+        kept, or -- x0 None -- the resident initial states are swept again, e.g. with new coefficients v.
+        Asynchronous; read the results with results() or gather_results_dev()."""
+        if self._control is None:
+            raise RuntimeError("attach_control(control) first")
+        self._bind(prob)
+        if v is not None:
+            self._set_v(v)
+        self._last_u = None
+        if x0 is None:
+            self._ck(self._lib.ocs_b200_evaluate_resident(self._h, None, 0, int(gradient)))
+        else:
+            x0f, single = self._x0(x0)
+            self._ck(self._lib.ocs_b200_evaluate_resident(self._h, _lib.dp(x0f), x0f.shape[1], int(gradient)))
+            self._Bt, self._single = x0f.shape[1], single
+
+    def results(self, gradient=True):
+        """J, xT, status (and dJdv, lam0) of the resident batch as host arrays (ocs_b200_get_results)."""
+        Bt, m = self._Bt, self._n + 1
+        out = dict(J=np.empty(Bt), xT=np.empty((self._n, Bt), order="F"), status=np.empty(Bt, dtype=np.int32))
+        if gradient:
+            out["dJdv"] = np.empty((self._nc * self._control.nBasis, Bt), order="F")
+            out["lam0"] = np.empty((m, Bt), order="F")
+        self._ck(self._lib.ocs_b200_get_results(self._h, _lib.dp(out["J"]), _lib.dp(out["xT"]), _lib.ip(out["status"]),
+                                                _lib.dp(out.get("dJdv")), _lib.dp(out.get("lam0"))))
+        return out
+
+    def gather_results_dev(self, J_ptr=0, xT_ptr=0):
+        """J [Bt] and x(T) [n][Bt] into device buffers on the root device (raw pointers as ints): the gather-to-root of
+        a multi-device handle (NCCL send/recv or peer copies), a device copy on one device.  Asynchronous."""
+        P = lambda a: ctypes.c_void_p(int(a)) if a else None
+        self._ck(self._lib.ocs_b200_gather_results_dev(self._h, P(J_ptr), P(xT_ptr)))
+
+    def shard_offsets(self):
+        """Trajectory offsets of the resident batch per device (ndev + 1 entries)."""
+        nd = ctypes.c_int()
+        cap = len(self.devices) + 1
+        devs = (ctypes.c_int * cap)()
+        off = (ctypes.c_long * cap)()
+        self._ck(self._lib.ocs_b200_get_devices(self._h, ctypes.byref(nd), devs, off, cap))
+        return list(devs)[:nd.value], list(off)[:nd.value + 1]
 
     # ------------------------------------------------------------------ grids on request
     def fetch_states(self, b0=0, nb=None, segment=0):
@@ -387,9 +439,13 @@ class CudaRK4Integrator:
         self._ck(self._lib.ocs_b200_set_profiling(self._h, int(on)))
 
     def kernel_stats(self, reset=True):
-        a, b, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_long()
-        self._ck(self._lib.ocs_b200_kernel_stats(self._h, int(reset), ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
-        return dict(ms_forward=a.value, ms_reverse=b.value, launches=n.value)
+        """Device time per kernel family since the last reset (needs set_profiling(True)): ms_forward, ms_reverse
+        (= reverse sweep + projection), and the split ms_reverse_sweep / ms_project / ms_update."""
+        ms = (ctypes.c_double * 4)()
+        n = ctypes.c_long()
+        self._ck(self._lib.ocs_b200_kernel_stats_ex(self._h, int(reset), ms, 4, ctypes.byref(n)))
+        return dict(ms_forward=ms[0], ms_reverse=ms[1] + ms[2], ms_reverse_sweep=ms[1], ms_project=ms[2], ms_update=ms[3],
+                    launches=n.value)
 
 
 class CudaRK4InfiniteIntegrator(CudaRK4Integrator):

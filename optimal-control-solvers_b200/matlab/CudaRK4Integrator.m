@@ -4,6 +4,7 @@ classdef CudaRK4Integrator < Integrator
    % through libocs_b200.so (C ABI: include/ocs_b200.h, MEX gateway: ocs_b200_mex.c).
    %
    %   integrator = CudaRK4Integrator(tspan);                       % as RK4Integrator(tspan)
+   %   integrator = CudaRK4Integrator(tspan, 'Device', 0:7);        % the batch sharded over eight GPUs, one object
    %   soln = single_shooting(prob, x0, tspan, nCONTROL_PTS, 'Integrator', integrator);
    %
    % Same property (t) and methods as the reference class; every array may carry a trailing
@@ -38,7 +39,8 @@ classdef CudaRK4Integrator < Integrator
    methods
       function obj = CudaRK4Integrator(tspan, varargin)
          p = inputParser;
-         p.addParameter('Device', 0);
+         p.addParameter('Device', 0);          % a CUDA ordinal, or a vector of them: trajectories are then sharded
+                                               % over those GPUs inside the one handle (ocs_b200_create_multi)
          p.addParameter('Math', 'fast');       % 'fast' (FMA contraction) or 'strict' (MATLAB-like rounding)
          p.addParameter('tspanExtra', []);
          parse(p, varargin{:});

@@ -28,17 +28,21 @@ def main():
     assert J_all.shape == (world * Bt,) and xT_all.shape == (world, 2, Bt)
     for r in range(world):
         assert torch.all(J_all[r * Bt:(r + 1) * Bt] == r) and torch.all(xT_all[r] == r + 0.25)
-    # packed, double-buffered gather used by bench.py (synchronous on CPU)
-    pg = d.PipelinedGather(2, Bt, world, "cpu")
-    for step in range(3):
-        res = pg.next_buffer()
-        res[0] = rank + 10 * step
-        res[1:] = rank + 0.5
-        pg.gather(res)
-        out = pg.out[pg.k]
-        for r in range(world):
-            assert torch.all(out[r, 0] == r + 10 * step) and torch.all(out[r, 1:] == r + 0.5)
-    pg.finish()
+    # packed, double-buffered gather used by bench.py (synchronous on CPU): to rank 0 (default) and to everybody
+    for mode in ("root", "all"):
+        pg = d.PipelinedGather(2, Bt, world, "cpu", rank=rank, mode=mode)
+        for step in range(3):
+            res = pg.next_buffer()
+            res[0] = rank + 10 * step
+            res[1:] = rank + 0.5
+            pg.gather(res)
+            out = pg.out[pg.k]
+            if mode == "all" or rank == 0:
+                for r in range(world):
+                    assert torch.all(out[r, 0] == r + 10 * step) and torch.all(out[r, 1:] == r + 0.5)
+            else:
+                assert out.shape[0] == 1         # non-root ranks hold nothing
+        pg.finish()
     dist.barrier()
     dist.destroy_process_group()
     print("gather ok", rank)

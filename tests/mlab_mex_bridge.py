@@ -39,8 +39,13 @@ def make_mex(ocs):
         if cmd == "create":
             ts, te = arr(np.asarray(a[0]).ravel()), arr(np.asarray(a[1]).ravel())
             h = ctypes.c_void_p()
-            rc = lib.ocs_b200_create(ts.size - 1, L.dp(ts), (te.size - 1) if te is not None else 0, L.dp(te),
-                                     int(sc(a[2])), int(sc(a[3])), ctypes.byref(h))
+            devs = [int(d) for d in np.asarray(a[2]).reshape(-1)]
+            if len(devs) == 1:
+                rc = lib.ocs_b200_create(ts.size - 1, L.dp(ts), (te.size - 1) if te is not None else 0, L.dp(te),
+                                         devs[0], int(sc(a[3])), ctypes.byref(h))
+            else:       # CudaRK4Integrator(tspan, 'Device', 0:7), as the real gateway does
+                rc = lib.ocs_b200_create_multi(ts.size - 1, L.dp(ts), (te.size - 1) if te is not None else 0, L.dp(te),
+                                               len(devs), (ctypes.c_int * len(devs))(*devs), int(sc(a[3])), ctypes.byref(h))
             if rc != 0:
                 raise RuntimeError(f"ocs_b200 error {rc}: {lib.ocs_b200_last_error(None).decode()}")
             return np.array([[float(h.value)]])

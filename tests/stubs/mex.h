@@ -44,6 +44,10 @@ mxArray *mxCreateDoubleScalar(double v);
 mxArray *mxCreateString(const char *s);
 void mxDestroyArray(mxArray *a);
 void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...);
+void mexLock(void);
+void mexUnlock(void);
+int mexIsLocked(void);
+int mexAtExit(void (*fn)(void));
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);
 #ifdef __cplusplus
 }

@@ -93,6 +93,14 @@ void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...)
     longjmp(g_jmp, 1);
 }
 
+/* ---- MEX lifecycle: lock count and the at-exit hook MATLAB would run on `clear mex` / exit */
+static int g_lock = 0;
+static void (*g_atexit)(void) = NULL;
+void mexLock(void) { ++g_lock; }
+void mexUnlock(void) { if (g_lock > 0) --g_lock; }
+int mexIsLocked(void) { return g_lock > 0; }
+int mexAtExit(void (*fn)(void)) { g_atexit = fn; return 0; }
+
 /* ---- helpers */
 static mxArray *dmat(mwSize m, mwSize n, const double *src)
 {
@@ -114,8 +122,63 @@ static mxArray *call(const char *cmd, int nlhs, mxArray **out, int nargs, ...)
     return lhs[0];
 }
 
+/* expects the call to raise a MATLAB error whose text contains `needle`; returns 1 if it did */
+static int g_expect_active = 0;
+static jmp_buf g_expect_jmp;
+#define EXPECT_ERROR(needle, stmt)                                                            \
+    do {                                                                                      \
+        jmp_buf saved;                                                                        \
+        memcpy(saved, g_jmp, sizeof saved);                                                   \
+        int raised = 0;                                                                       \
+        if (setjmp(g_jmp) == 0) { stmt; } else raised = 1;                                    \
+        memcpy(g_jmp, saved, sizeof saved);                                                   \
+        if (!raised || !strstr(g_err, needle)) {                                              \
+            fprintf(stderr, "expected an error containing '%s', got '%s'\n", needle, raised ? g_err : "(none)"); \
+            return 4;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+/* mex_driver --lifecycle <in.bin>: locking, the at-exit hook with live handles, stale handles, shape checks */
+static int lifecycle(int N, const double *tspan, const double *params)
+{
+    (void)g_expect_active; (void)g_expect_jmp;
+    mxArray *empty = mxCreateDoubleMatrix(0, 0, mxREAL);
+    if (mexIsLocked()) return 5;
+    mxArray *h1 = call("create", 1, NULL, 4, dmat(1, N + 1, tspan), empty, mxCreateDoubleScalar(0), mxCreateDoubleScalar(0));
+    mxArray *h2 = call("create", 1, NULL, 4, dmat(1, N + 1, tspan), empty, mxCreateDoubleScalar(0), mxCreateDoubleScalar(0));
+    if (!mexIsLocked() || !g_atexit) return 6;              /* live integrators pin the MEX file */
+    call("set_problem_builtin", 0, NULL, 2, h1, mxCreateDoubleScalar(0));
+    call("set_params", 0, NULL, 2, h1, dmat(3, 1, params));
+    /* sizes are the library's, and wrong shapes are refused before the C ABI sees them */
+    mxArray *d = call("get_dims", 1, NULL, 1, h1);
+    if (mxGetPr(d)[0] != 1 || mxGetPr(d)[1] != 1 || mxGetPr(d)[2] != 3 || mxGetPr(d)[4] != N || mxGetPr(d)[6] != 0) return 7;
+    double two[2] = {1.0, 2.0};
+    EXPECT_ERROR("x0 must have 1 rows", call("compute_states", 1, NULL, 2, h1, dmat(2, 1, two)));
+    EXPECT_ERROR("params must have 3 rows", call("set_params", 0, NULL, 2, h1, dmat(2, 1, two)));
+    EXPECT_ERROR("no resident batch", call("fetch_states", 1, NULL, 4, h1, mxCreateDoubleScalar(0), mxCreateDoubleScalar(0), mxCreateDoubleScalar(1)));
+    EXPECT_ERROR("one column per point", call("set_control_u", 0, NULL, 2, h1, dmat(1, 5, NULL)));
+    call("destroy", 0, NULL, 1, h1);
+    if (!mexIsLocked()) return 8;                            /* h2 is still alive */
+    EXPECT_ERROR("not a live integrator handle", call("get_dims", 1, NULL, 1, h1));
+    /* `clear mex` / MATLAB exit with a live handle: the hook frees it, later use of the value is refused */
+    g_atexit();
+    EXPECT_ERROR("not a live integrator handle", call("get_dims", 1, NULL, 1, h2));
+    mxArray *bogus = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+    *(uint64_t *)mxGetData(bogus) = 0xdeadbeefULL;
+    EXPECT_ERROR("not a live integrator handle", call("get_dims", 1, NULL, 1, bogus));
+    /* a fresh integrator after the hook works and locks again */
+    mxArray *h3 = call("create", 1, NULL, 4, dmat(1, N + 1, tspan), empty, mxCreateDoubleScalar(0), mxCreateDoubleScalar(0));
+    if (!mexIsLocked()) return 9;
+    call("destroy", 0, NULL, 1, h3);
+    if (mexIsLocked()) return 10;
+    printf("lifecycle ok\n");
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    int life = argc >= 3 && !strcmp(argv[1], "--lifecycle");
+    if (life) { argv[1] = argv[2]; }
     if (argc < 3) return 2;
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 2;
@@ -130,6 +193,7 @@ int main(int argc, char **argv)
         fprintf(stderr, "MATLAB error: %s\n", g_err);
         return 3;
     }
+    if (life) return lifecycle(N, tspan, params);
     mxArray *empty = mxCreateDoubleMatrix(0, 0, mxREAL);
     mxArray *h = call("create", 1, NULL, 4, dmat(1, N + 1, tspan), empty, mxCreateDoubleScalar(0), mxCreateDoubleScalar(0));
     call("set_problem_builtin", 0, NULL, 2, h, mxCreateDoubleScalar(0));

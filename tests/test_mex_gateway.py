@@ -68,6 +68,17 @@ def test_gateway_matches_golden(driver):
     assert relerr(dJdu, g["dJdu"].reshape(-1)) < TOL
 
 
+@pytest.mark.gpu
+def test_gateway_lifecycle_and_shape_checks(driver):
+    """mexLock while an integrator lives, the mexAtExit hook frees live handles (`clear mex` with a live object),
+    stale / bogus handle values are refused, and wrong input shapes never reach the C ABI (sizes come from
+    ocs_b200_get_dims, not from caller scalars)."""
+    exe, d = driver
+    _write_input(str(d / "in.bin"))
+    r = subprocess.run([exe, "--lifecycle", str(d / "in.bin")], capture_output=True, text=True)
+    assert r.returncode == 0 and "lifecycle ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
 def test_matlab_classes_run_under_the_interpreter_up_to_the_device(ocs):
     """CPU: the MATLAB host classes parse and execute under oracle/mlab (constructor, inputParser, property
     access) until the first C-ABI call, which reports the missing device exactly like the MEX gateway would."""
