@@ -843,7 +843,7 @@ def main():
 
     # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)
     e2e = None
-    if not args.no_e2e and args.config == "cfg2":
+    if not args.no_e2e and args.config in ("cfg2", "cfg4"):
         # pinned host buffers on the NUMA node of this rank's GPU (first touch under the GPU's CPU affinity):
         # with several ranks per box the downloads otherwise cross the socket interconnect
         restore = _bind_to_gpu_numa_node(local_rank)
@@ -895,7 +895,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             ceiling = float(t.item())
         per_rank_gbs = d2h_bytes * ne / dt / 1e9
-        e2e = {"value": world * Bt * N_STEPS * ne / dt, "unit": "trajectory-steps/s",
+        e2e = {"value": world * Bt * NT * ne / dt, "unit": "trajectory-steps/s",
                "h2d_bytes_per_step": 8 * Bt + 8 * K_PWL,
                "d2h_bytes_per_step": d2h_bytes,
                "steps": ne, "ms_per_step": 1e3 * dt / ne,
@@ -903,7 +903,7 @@ def main():
                # the D2H link with all ranks downloading and nothing computing, and how much of it the call reaches
                "pcie_ceiling_gbs": ceiling, "d2h_gbs_per_rank": per_rank_gbs,
                "frac_of_pcie_ceiling": per_rank_gbs / ceiling if ceiling else None,
-               "e2e_pageable": {"value": world * Bt * N_STEPS * nep / dtp, "unit": "trajectory-steps/s", "ms_per_step": 1e3 * dtp / nep,
+               "e2e_pageable": {"value": world * Bt * NT * nep / dtp, "unit": "trajectory-steps/s", "ms_per_step": 1e3 * dtp / nep,
                                 "vs_pinned": (dtp / nep) / (dt / ne), "results_identical_to_pinned": same,
                                 "what": "the same call on ordinary pageable NumPy arrays (what MATLAB mxArrays are): "
                                         "transfers go through the handle's pinned ring and copy threads"}}

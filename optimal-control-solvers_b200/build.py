@@ -30,6 +30,7 @@ UNITS = [
     ("kernels_strict.o", "kernels_builtin.cu", ["-DOCS_STRICT=1", "-fmad=false"]),
     ("ocs_api.o", "ocs_api.cu", []),
     ("ocs_multi.o", "ocs_multi.cu", []),
+    ("host_copy.o", "host_copy.cpp", []),
     ("nvrtc_problem.o", "nvrtc_problem.cu", []),
     ("microbench.o", "microbench.cu", []),
 ]

@@ -27,6 +27,8 @@
 #include <thread>
 #include <vector>
 
+extern "C" void ocs_host_copy(void *dst, const void *src, size_t n);   // host_copy.cpp: non-temporal stores for large blocks
+
 namespace ocs_detail {
 
 class HostStager {
@@ -90,7 +92,7 @@ public:
             const size_t n = bytes - off < slot_bytes_ ? bytes - off : slot_bytes_;
             const int k = acquire();
             if (k < 0) return error_;
-            memcpy(slots_[k].p, s + off, n);
+            ocs_host_copy(slots_[k].p, s + off, n);
             e = cudaMemcpyAsync(d + off, slots_[k].p, n, cudaMemcpyHostToDevice, stream);
             if (e == cudaSuccess) e = cudaEventRecord(slots_[k].ev, stream);
             if (e != cudaSuccess) {
@@ -228,7 +230,7 @@ private:
                 jobs_.pop_front();
             }
             const cudaError_t e = cudaEventSynchronize(slots_[j.slot].ev);
-            if (e == cudaSuccess && j.dst) memcpy(j.dst, slots_[j.slot].p, j.n);
+            if (e == cudaSuccess && j.dst) ocs_host_copy(j.dst, slots_[j.slot].p, j.n);
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 if (e != cudaSuccess && error_ == cudaSuccess) error_ = e;

@@ -46,6 +46,27 @@
 #ifndef OCS_MINBLOCKS_REV_COEF
 #define OCS_MINBLOCKS_REV_COEF 4
 #endif
+// Per-trajectory parameters (a parameter sweep, bench.py --config cfg2p / cfg2pv): exp(-r t) runs in the thread and
+// (c, m, r) live in registers, so the uniform-parameter settings above spilled (808 B in the grid-control forward
+// kernel, 136-360 B in the reverse kernels).  Same-box A/B of (trajectories per thread, min blocks/SM) forward;reverse,
+// cfg2p / cfg2pv in 1e10 trajectory-steps/s: inherited (4,-;2,5: spills) 6.59 / 5.50, (1,6;1,6) 7.99 / 6.69,
+// (1,8;1,5) 8.00 / 7.06, (2,4;2,4) 7.72 / 6.57, (2,3;2,3) 7.70 / 6.47.  One trajectory per thread it is; (1,5;1,4) is
+// the fastest setting without a single spilled byte in any _p1 variant (profiles/r2_notes.md).
+#ifndef OCS_TPT_FWD_PB
+#define OCS_TPT_FWD_PB 1
+#endif
+#ifndef OCS_MINBLOCKS_FWD_PB
+#define OCS_MINBLOCKS_FWD_PB 5
+#endif
+#ifndef OCS_TPT_REV_PB
+#define OCS_TPT_REV_PB 1
+#endif
+#ifndef OCS_MINBLOCKS_REV_PB
+#define OCS_MINBLOCKS_REV_PB 4
+#endif
+#ifndef OCS_MINBLOCKS_FB_PB
+#define OCS_MINBLOCKS_FB_PB 3
+#endif
 #ifndef OCS_TILE
 #define OCS_TILE 64         // RK4 steps per shared-memory tile: 32 / 64 / 128 measured 5.13 / 5.06 / 5.02 ms per cfg2 evaluation (fewer block barriers)
 #endif

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(32 * PROJ_W, 2) dense_project_kernel(const dou
     extern __shared__ double2 proj_smem2[];
     double *sm = reinterpret_cast<double *>(proj_smem2);
     const int lane = threadIdx.x, w = threadIdx.y, c0 = blockIdx.y * NS;
-    double *Bs = sm + (size_t)w * PROJ_JT * BW;                 // [PROJ_JT][BW], private to the warp
+    double *Bs = sm + (size_t)w * 2 * PROJ_JT * BW;             // 2 x [PROJ_JT][BW], private to the warp
     const long b = (long)blockIdx.x * 32 + lane;
     const long bb = b < nb ? b : nb - 1;
     const int seg = (G + PROJ_W - 1) / PROJ_W;
@@ -473,43 +473,65 @@ __global__ void __launch_bounds__(32 * PROJ_W, 2) dense_project_kernel(const dou
     for (int s = 0; s < NS; ++s) dp[s] = dug + (size_t)(c0 + s < nc ? c0 + s : nc - 1) * G * ldb + bb;
     const unsigned ld8 = (unsigned)ldb * 8u;
     static_assert(KC % 2 == 0, "KC accumulators are updated in double2 pairs");
+    constexpr int R = 8 / NS;                 // grid points per batch and stream: 8 loads per thread and batch
+    const int tile = PROJ_JT * BW;            // doubles of one B tile; the warp owns two (the next one is fetched with
+    double *Bt0 = Bs, *Bt1 = Bs + tile;       // cp.async while the current one is consumed)
+    auto fetch_tile = [&](double *dst, int j0) {
+        const int nj = jb - j0 < PROJ_JT ? jb - j0 : PROJ_JT;
+        for (int k = 2 * lane; k < nj * BW; k += 64) ocs_host::cp_async_16(dst + k, basrec + (size_t)j0 * BW + k);
+        ocs_host::cp_async_commit();
+    };
+    auto load_batch = [&](double (&d)[NS][R], int j) {      // dJdu of grid points j .. j+R-1 (clamped: they meet zero B rows)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int jc = j + r < G ? j + r : G - 1;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) d[s][r] = *ocs_host::soa_row(dp[s], (unsigned)jc, ld8);
+        }
+    };
     for (int k0 = 0; k0 < K; k0 += KC) {
         double acc[NS][KC];
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int kk = 0; kk < KC; ++kk) acc[s][kk] = 0.0;
-        for (int j0 = ja; j0 < jb; j0 += PROJ_JT) {
-            const int nj = jb - j0 < PROJ_JT ? jb - j0 : PROJ_JT;
-            __syncwarp();
-            for (int k = lane; k < PROJ_JT * BW; k += 32) Bs[k] = k < nj * BW ? basrec[(size_t)j0 * BW + k] : 0.0;
-            __syncwarp();
-            constexpr int R = 8 / NS;                 // grid points in flight per stream: 8 loads per thread either way
-#pragma unroll 1
-            for (int jj = 0; jj < PROJ_JT; jj += R) {
-                if (jj >= nj) break;
-                double d[NS][R];
+        auto fma_batch = [&](const double (&d)[NS][R], const double *Bt, int jj) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int j = j0 + jj + r < G ? j0 + jj + r : G - 1;      // clamped rows meet a zero B row
+            for (int r = 0; r < R; ++r) {
+                const double2 *Bj = reinterpret_cast<const double2 *>(Bt + (jj + r) * BW + k0);   // BW, k0 even: 16-byte aligned
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) d[s][r] = *ocs_host::soa_row(dp[s], (unsigned)j, ld8);
-                }
+                for (int kk = 0; kk < KC; kk += 2) {
+                    if (k0 + kk < BW) {
+                        const double2 bq = Bj[kk >> 1];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const double2 *Bj = reinterpret_cast<const double2 *>(Bs + (jj + r) * BW + k0);   // BW, k0 even: 16-byte aligned
-#pragma unroll
-                    for (int kk = 0; kk < KC; kk += 2) {
-                        if (k0 + kk < BW) {
-                            const double2 bq = Bj[kk >> 1];
-#pragma unroll
-                            for (int s = 0; s < NS; ++s) {
-                                acc[s][kk] = acc[s][kk] + d[s][r] * bq.x;
-                                acc[s][kk + 1] = acc[s][kk + 1] + d[s][r] * bq.y;
-                            }
+                        for (int s = 0; s < NS; ++s) {
+                            acc[s][kk] = acc[s][kk] + d[s][r] * bq.x;
+                            acc[s][kk + 1] = acc[s][kk + 1] + d[s][r] * bq.y;
                         }
                     }
                 }
+            }
+        };
+        __syncwarp();
+        if (ja < jb) fetch_tile(Bt0, ja);
+        double dA[NS][R], dB[NS][R];
+        load_batch(dA, ja);
+        for (int j0 = ja; j0 < jb; j0 += PROJ_JT) {
+            const int nj = jb - j0 < PROJ_JT ? jb - j0 : PROJ_JT;
+            double *Bc = ((j0 - ja) / PROJ_JT) & 1 ? Bt1 : Bt0, *Bn = Bc == Bt0 ? Bt1 : Bt0;
+            ocs_host::cp_async_wait<0>();
+            __syncwarp();                                 // the current tile is complete for every lane; the other one is free
+            if (j0 + PROJ_JT < jb) fetch_tile(Bn, j0 + PROJ_JT);
+            // rows past the end of the segment inside the last batch multiply by zero
+            for (int k = nj * BW + lane; k < ((nj + 2 * R - 1) / (2 * R)) * (2 * R) * BW && k < tile; k += 32) Bc[k] = 0.0;
+            __syncwarp();
+            // two batches per iteration: the loads of one are in flight while the other is multiplied
+#pragma unroll 1
+            for (int jj = 0; jj < nj; jj += 2 * R) {
+                load_batch(dB, j0 + jj + R);
+                fma_batch(dA, Bc, jj);
+                load_batch(dA, j0 + jj + 2 * R);
+                if (jj + R < nj) fma_batch(dB, Bc, jj + R);
             }
         }
         // partial sums of the PROJ_W segments, added in ascending segment order
@@ -534,7 +556,7 @@ template <int KC, int NS>
 static cudaError_t launch_project(cudaStream_t st, const double *dug, const double *basrec, int BW, int K, int nc, int G, long nb,
                                   long ldb, double *dJdv)
 {
-    const size_t psm = std::max((size_t)PROJ_W * PROJ_JT * BW, (size_t)PROJ_W * NS * KC * 32) * sizeof(double);
+    const size_t psm = std::max((size_t)PROJ_W * 2 * PROJ_JT * BW, (size_t)PROJ_W * NS * KC * 32) * sizeof(double);
     if (psm > 200 * 1024) return cudaErrorInvalidValue;
     if (psm > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(dense_project_kernel<KC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
@@ -1653,7 +1675,7 @@ static bool needs_zero_fill(const ocs_b200_handle *h)
 static std::vector<std::pair<long, long>> chunk_schedule(long Bt)
 {
     std::vector<std::pair<long, long>> out;
-    const long gran = 128 * 6;                       // whole blocks of both kernels (3 and 2 trajectories per thread)
+    const long gran = 128 * 12;                      // whole blocks of every kernel variant (1, 2, 3 or 4 trajectories per thread)
     long c = std::max<long>(gran, (Bt / 32 + gran - 1) / gran * gran);
     const long cmax = std::max<long>(gran, (Bt / 4 + gran - 1) / gran * gran);
     for (long b0 = 0; b0 < Bt;) {
@@ -1807,9 +1829,10 @@ int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const doubl
     TRY(check_ready(h));
     if (!x0 || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
     if (lamT && lamT_nbatch != 1 && lamT_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
-    // small batches, no gradient, or a tail horizon (whose main sweep starts from the tail's result for the whole
-    // batch): the two calls in sequence
-    if (!dJdv || Bt < 262144 || h->has_tail) {
+    // small batches (one chunk would not fill the device) or no gradient: the two calls in sequence.  With a tail
+    // horizon a chunk runs main forward, tail forward, tail reverse, main reverse (RK4InfiniteIntegrator.m:20-30 for
+    // the chunk's trajectories): trajectories are independent, so the chunking is the same.
+    if (!dJdv || Bt < 262144) {
         TRY(ocs_b200_compute_states(h, x0, Bt, J, xT, status));
         if (!dJdv && !lam0) return 0;
         return ocs_b200_compute_adjoints(h, lamT, lamT_nbatch, dJdv, lam0);

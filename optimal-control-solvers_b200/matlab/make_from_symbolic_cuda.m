@@ -10,8 +10,9 @@ function prob = make_from_symbolic_cuda(symObjective, symStateRHS, nStates, nCon
 %
 % This MATLAB twin of optimal-control-solvers_b200/codegen/make_from_symbolic.py emits the un-hoisted form
 % (ntt = 0 for every hoisting mode); the Python backend additionally tabulates batch-uniform
-% sub-expressions.  Untested in this repository's image (no MATLAB); the Python backend is the
-% one covered by tests.
+% sub-expressions.  Two halves: the derivations below need the Symbolic Math Toolbox and cannot run in this
+% repository's image; the string emission lives in emit_cuda_problem.m, which the tests execute under the
+% MATLAB-subset interpreter on the strings `ccode` would return and compile with the sweep kernels.
 
 param_names = fieldnames(params);
 t = sym('t');
@@ -43,49 +44,28 @@ catch
    haveCC = false;
 end
 
-   function s = body(exprs, out)
-      s = '';
-      for k = 1:numel(exprs)
-         c = ccode(exprs(k));
-         c = regexprep(c, '^\s*\w+\s*=\s*', '');
-         c = regexprep(c, ';\s*$', '');
-         s = sprintf('%s        %s[%d] = %s;\n', s, out, k-1, rename(c));
-      end
-   end
-
-   function c = rename(c)
-      for k = nStates:-1:1
-         c = regexprep(c, sprintf('\\<lam%d\\>', k), sprintf('lam[%d]', k-1));
-         c = regexprep(c, sprintf('\\<x%d\\>', k), sprintf('y[%d]', k-1));
-         c = regexprep(c, sprintf('\\<v%d\\>', k), sprintf('v[%d]', k-1));
-      end
-      c = regexprep(c, '\<vJ\>', sprintf('v[%d]', nStates));
-      for k = nControls:-1:1
-         c = regexprep(c, sprintf('\\<u%d\\>', k), sprintf('u[%d]', k-1));
-      end
-      for k = 1:numel(param_names)
-         c = regexprep(c, sprintf('\\<%s\\>', param_names{k}), sprintf('p[%d]', k-1));
-      end
-   end
-
-sig = 'const double *tt, double t, const double *y, const double *u, const double *p';
-src = sprintf('namespace ocs_gen {\nstruct Problem {\n');
-src = [src sprintf('    static constexpr int n = %d, nc = %d, np = %d;\n', nStates, nControls, numel(param_names))];
-src = [src sprintf('    __host__ __device__ static constexpr int ntt(int) { return 0; }\n')];
-src = [src sprintf('    template <int HM> __device__ __forceinline__ static void table(double, const double *, const double *, double *) {}\n')];
-src = [src sprintf('    template <int HM> __device__ __forceinline__ static void F(%s, double *o)\n    {\n        (void)tt; (void)t; (void)y; (void)u; (void)p;\n%s    }\n', sig, body(F, 'o'))];
-src = [src sprintf('    template <int HM> __device__ __forceinline__ static void X(%s, const double *v, double *o)\n    {\n        (void)tt; (void)t; (void)y; (void)u; (void)p; (void)v;\n%s    }\n', sig, body(X, 'o'))];
-src = [src sprintf('    template <int HM> __device__ __forceinline__ static void U(%s, const double *v, double *o)\n    {\n        (void)tt; (void)t; (void)y; (void)u; (void)p; (void)v;\n%s    }\n', sig, body(U, 'o'))];
-src = [src sprintf('    template <int HM> __device__ __forceinline__ static void ControlChar(const double *tt, double t, const double *y, const double *lam, const double *p, const double *bounds, double *o)\n    {\n        (void)tt; (void)t; (void)y; (void)lam; (void)p;\n')];
-if haveCC
-   src = [src body(CC, 'o')];
-   for c = 1:nControls                                  % value = min(umax, max(umin, value))   :111
-      src = [src sprintf('        o[%d] = fmin(bounds[%d], fmax(bounds[%d], o[%d]));\n', c-1, 2*c-1, 2*c-2, c-1)]; %#ok<AGROW>
-   end
-else
-   src = [src sprintf('        for (int c = 0; c < nc; ++c) o[c] = nan("");\n')];
+% hand the expressions over as C strings, exactly as ccode prints them; emit_cuda_problem.m (no toolbox needed,
+% executed by this repository's tests on such strings) renames the variables and prints the device functions
+cF = cell(numel(F), 1);
+for k = 1:numel(F)
+   cF{k} = ccode(F(k));
 end
-src = [src sprintf('    }\n};\n}  // namespace ocs_gen\n')];
+cX = cell(numel(X), 1);
+for k = 1:numel(X)
+   cX{k} = ccode(X(k));
+end
+cU = cell(numel(U), 1);
+for k = 1:numel(U)
+   cU{k} = ccode(U(k));
+end
+cCC = {};
+if haveCC
+   cCC = cell(nControls, 1);
+   for k = 1:nControls
+      cCC{k} = ccode(CC(k));
+   end
+end
+src = emit_cuda_problem(cF, cX, cU, cCC, nStates, nControls, param_names);
 
 prob = CudaOCProblem(src, nStates, nControls, params, ControlBounds);
 end

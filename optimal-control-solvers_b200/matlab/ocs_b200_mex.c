@@ -47,6 +47,7 @@ static void ocs_at_exit(void)
             ocs_b200_destroy(g_handles[k]);
             g_handles[k] = NULL;
         }
+    if (g_nhandles > 0) mexUnlock();      /* the lock was held for the handles that are gone now */
     g_nhandles = 0;
 }
 

@@ -506,9 +506,48 @@ def make_builtins(interp):
         from .interp import MCell
         return MCell(list(s_.keys()))
 
+    def sprintf(fmt, *args):
+        """MATLAB sprintf for the conversions the code generators use (%d %i %s %g %f %e, flags/width/precision),
+        escapes \\n \\t \\\\ and %%; numeric array arguments are consumed element by element."""
+        import re
+        vals = []
+        for a in args:
+            if isinstance(a, str):
+                vals.append(a)
+            else:
+                vals.extend(float(x) for x in np.asarray(as_array(a)).reshape(-1, order="F"))
+        py = fmt.replace("\\n", "\n").replace("\\t", "\t").replace("\\\\", "\\")
+        it = iter(vals)
+
+        def one(m):
+            if m.group() == "%%":
+                return "%"
+            v = next(it)
+            conv = m.group()[-1]
+            if conv in "di":
+                return (m.group()[:-1] + "d") % int(round(v)) if not isinstance(v, str) else v
+            if conv == "s":
+                return (m.group() % v) if isinstance(v, str) else (m.group()[:-1] + "g") % v
+            return m.group() % v
+        return re.sub(r"%%|%[-+ 0#]*\d*(?:\.\d+)?[disgfe]", one, py)
+
+    def _mregex(pat):
+        # MATLAB word anchors \< \> -> Python \b
+        return pat.replace("\\<", "\\b").replace("\\>", "\\b")
+
+    def regexprep(s_, pat, rep):
+        import re
+        rep_py = re.sub(r"\$(\d)", r"\\\1", rep.replace("\\", "\\\\"))
+        return re.sub(_mregex(pat), rep_py, s_)
+
+    def strrep(s_, a, b):
+        return s_.replace(a, b)
+
     bi = {
         "inputParser": lambda: InputParser(),
         "isequal": isequal, "error": merror, "fieldnames": fieldnames,
+        "sprintf": sprintf, "regexprep": regexprep, "strrep": strrep,
+        "num2str": lambda a: ("%g" % scalar(a)),
         "uint64": lambda a: np.asarray(as_array(a), dtype=np.float64).copy(),
         "int32": lambda a: np.round(as_array(a)),
         "logical": lambda a: as_logical(as_array(a) != 0),

@@ -8,7 +8,7 @@ for v in $1; do
 import sys,json
 l=sys.stdin.read().strip()
 try:
-    j=json.loads(l); ks=j['roofline']['kernels']; print('$cfg','$v','%.3e'%j['value'],' '.join('%s=%.3f'%(k['kernel'][:22],k['ms']) for k in ks))
+    j=json.loads(l); ks=j['roofline']['kernels']; print('$cfg','$v','%.3e'%j['value'],' '.join('%s=%.3f'%(k['kernel'][4:22],k['ms']) for k in ks))
 except Exception as e: print('$cfg','$v','FAILED',l[:200])
 "
 done; done

@@ -7,7 +7,7 @@ for d in $1; do
 import sys,json
 l=sys.stdin.read().strip()
 try:
-    j=json.loads(l); ks=j['roofline']['kernels']; print('$cfg','$d','%.3e'%j['value'],' '.join('%s=%.3f'%(k['kernel'][:22],k['ms']) for k in ks))
+    j=json.loads(l); ks=j['roofline']['kernels']; print('$cfg','$d','%.3e'%j['value'],' '.join('%s=%.3f'%(k['kernel'][4:22],k['ms']) for k in ks))
 except Exception as e: print('$cfg','$d','FAILED',l[:200]); print(open('/tmp/ab_err.txt').read()[-600:])
 "
 done; done

@@ -171,3 +171,74 @@ def test_six_state_problem_vs_oracle(ocs, oracle, cg, kind, K):
     ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, 0], u0.copy(), oprob.control_char, nSWEEPS=40, relax=0.5)
     assert bool(fb["converged"][0]) == ref["converged"] and fb["sweeps"][0] == ref["sweeps"]
     assert relerr(fb["J"][0], ref["J"]) < 1e-8
+
+
+# ------------------------------------------------------------------------------ MATLAB twin, string-emission half
+def _matlab_ccode_strings(p):
+    """The strings MATLAB's ccode would hand to emit_cuda_problem.m for the SymPy problem p: "  t0 = <expr>;" in the
+    reference's variable names (x1.., lam1.., u1.., v1.., vJ, parameter names)."""
+    s = p.sym
+    one = lambda e: "  t0 = " + sp.ccode(e) + ";"
+    return ([one(e) for e in s["F"]], [one(e) for e in s["X"]], [one(e) for e in s["U"]],
+            [one(e) for e in s["CC"]] if s["CC"] is not None else [])
+
+
+def _emit_with_matlab_twin(ocs, p):
+    """Runs optimal-control-solvers_b200/matlab/emit_cuda_problem.m (unmodified) under the MATLAB-subset interpreter."""
+    from oracle.mlab.interp import Frame, Interpreter, MCell
+    it = Interpreter([os.path.join(ROOT, "optimal-control-solvers_b200", "matlab")])
+    cF, cX, cU, cCC = _matlab_ccode_strings(p)
+    out = it.call_named("emit_cuda_problem", [MCell(cF), MCell(cX), MCell(cU), MCell(cCC), float(p.nStates),
+                                              float(p.nControls), MCell(list(p.param_names))], 1, Frame())
+    return out[0]
+
+
+@pytest.mark.parametrize("which", ["test_problem_symbolic", "harvest_chain_problem"])
+def test_matlab_emission_half_runs_and_compiles(ocs, cg, which):
+    """functions/make_from_symbolic.m:27-31 replaced by CUDA emission, MATLAB side: emit_cuda_problem.m executed on
+    the expression strings a Symbolic Toolbox `ccode` returns; the source it prints compiles for sm_100a together
+    with the sweep kernels (forward, gradient, fb_sweep and equilibrium units)."""
+    p = getattr(cg, which)()
+    src = _emit_with_matlab_twin(ocs, p)
+    assert "static constexpr int n = %d, nc = %d, np = %d;" % (p.nStates, p.nControls, len(p.param_names)) in src
+    for name in list(map(str, p.sym["x"])) + list(map(str, p.sym["u"])) + p.param_names:
+        # every reference-side name was renamed: none survives as a whole word
+        import re
+        assert not re.search(r"\b%s\b" % re.escape(name), src.split("struct Problem", 1)[1]), name
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as d:
+        cu = os.path.join(d, "gen.cu")
+        with open(cu, "w") as f:
+            f.write('#define OCS_NS ocs_gen\n#include "rk4_kernels.cuh"\n' + src +
+                    "\nOCS_TT_KERNEL(ocs_gen::Problem, gen)\nOCS_FWD_KERNEL(ocs_gen::Problem, gen, 1, 1, 0, 0)\n"
+                    "OCS_REV_KERNEL(ocs_gen::Problem, gen, 0, 1, 0, 0)\nOCS_FB_KERNEL(ocs_gen::Problem, gen, 0)\n"
+                    "OCS_EQ_KERNEL(ocs_gen::Problem, gen)\n")
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1",
+                            "-I", os.path.join(ROOT, "optimal-control-solvers_b200", "csrc"), "-cubin", "-o",
+                            os.path.join(d, "gen.cubin"), cu], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_matlab_emitted_problem_matches_the_python_backend(ocs, cg):
+    """The source printed by the MATLAB twin, bound through ocs_b200_set_problem_source, gives the results of the
+    Python backend's source for the same expressions (different expression order: rounding only)."""
+    p = cg.harvest_chain_problem()
+    twin = cg.CodegenProblem(p.nStates, p.nControls, p.params, p.ControlBounds, _emit_with_matlab_twin(ocs, p), p.sym, p.flops)
+    N, Bt = 100, 64
+    tspan = ocs.matlab_linspace(0.0, 5.0, N + 1)
+    rng = np.random.default_rng(5)
+    x0, v = rng.uniform(1.0, 2.5, (6, Bt)), rng.uniform(.2, .8, (2 * 9, Bt))
+    res = []
+    for prob in (p, twin):
+        integ = ocs.CudaRK4Integrator(tspan)
+        integ.attach_control(ocs.PWLinearControl(integ.t, 9, 2))
+        out = integ.evaluate(prob, x0, v)
+        fb = integ.fb_sweep(prob, x0[:, :8], np.full((2, 2 * N + 1), .4), nSWEEPS=3, relax=0.5)
+        res.append((out, fb))
+        integ.close()
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(res[1][0][key], res[0][0][key]) < 1e-12, key
+    assert relerr(res[1][1]["J"], res[0][1]["J"]) < 1e-12 and relerr(res[1][1]["maxChange"], res[0][1]["maxChange"]) < 1e-9

@@ -148,3 +148,43 @@ def test_cfg3_full_size_sample_vs_oracle(ocs, oracle):
         assert relerr(out["J"][b], J) < TOL and relerr(out["xT"][:, b], x[:-1, -1]) < TOL
         assert relerr(out["dJdv"][:, b], octl.compute_dJdv(dJdu)) < TOL and relerr(out["lam0"][:, b], lam[:, 0]) < TOL
     integ.close()
+
+
+@pytest.mark.parametrize("per_traj_v", [False, True])
+def test_parameter_sweep_full_size_sample_vs_oracle(ocs, oracle, per_traj_v):
+    """bench.py --config cfg2p / cfg2pv at full size: 2^20 trajectories, each with its own (c, m, r)
+    (tests/TestOCProblem.m:13-19 -- exactly what a parameter sweep varies) x 1000 RK4 steps; nothing is
+    batch-uniform, exp(-r t) runs in the thread.  A random sample against the C oracle."""
+    Bt, N, K = 1 << 20, 1000, 101
+    tspan = ocs.matlab_linspace(0.0, 10.0, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ctl = ocs.PWLinearControl(integ.t, K, 1)
+    integ.attach_control(ctl)
+    rng = np.random.default_rng(31)
+    c, m, r = rng.uniform(1.3, 1.7, Bt), rng.uniform(2.8, 3.2, Bt), rng.uniform(0.03, 0.07, Bt)
+    prob = ocs.TestOCProblem(dict(c=c, m=m, r=r), [[0, 1]])
+    v = rng.random((K, Bt)) if per_traj_v else rng.random(K)
+    x0 = rng.uniform(.5, 2.5, (1, Bt))
+    out = integ.evaluate(prob, x0, v)
+    assert not out["status"].any()
+    idx = np.random.default_rng(3).choice(Bt, 192, replace=False)
+    idx[:2] = [0, Bt - 1]
+    ref = oracle.C.evaluate(np.stack([c[idx], m[idx], r[idx]]), tspan, ctl.B, x0[:, idx], v[:, idx] if per_traj_v else v)
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(out[key][..., idx], ref[key]) < TOL, key
+    # the infinite-horizon composition with per-trajectory parameters: chunked (pipelined) host path, tail included
+    integ.close()
+    Bs = 1 << 18
+    tsE = ocs.matlab_linspace(10.0, 20.0, 501)
+    inf = ocs.CudaRK4InfiniteIntegrator(ocs.matlab_linspace(0.0, 10.0, 501), tsE, 0.72)
+    ctl2 = ocs.PWLinearControl(inf.t, 21, 1)
+    inf.attach_control(ctl2)
+    prob2 = ocs.TestOCProblem(dict(c=c[:Bs], m=m[:Bs], r=r[:Bs]), [[0, 1]])
+    v2 = rng.random(21)
+    out2 = inf.evaluate(prob2, x0[:, :Bs], v2)
+    sel = idx[idx < Bs][:64]
+    ref2 = oracle.C.evaluate(np.stack([c[sel], m[sel], r[sel]]), ocs.matlab_linspace(0.0, 10.0, 501), ctl2.B, x0[:, sel], v2,
+                             tspan_extra=tsE, uStar=0.72)
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(out2[key][..., sel], ref2[key]) < TOL, key
+    inf.close()
