@@ -221,6 +221,50 @@ def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, Co
             parts.append(f"        {kw} constexpr (HM == {hm}) {{\n{body}\n        }}")
         return "\n".join(parts)
 
+    # Time exponentials by recurrence (per-trajectory parameters; rk4_kernels.cuh, ocs_ntexp): the HM_TIME table is a
+    # function of (t, p).  Every exp(a*t) in it, a free of t, becomes one per-trajectory value E_k that the sweeps
+    # advance by a multiplication per grid point; table_from_texp rebuilds the table entries from E (and t, p).
+    texp_src = ""
+    exps = []
+    for _, e in tables[1]:
+        for ex in sorted(e.atoms(sp.exp), key=str):
+            arg = sp.expand(ex.args[0])
+            rate = sp.diff(arg, t)
+            if rate != 0 and not rate.has(t) and sp.simplify(arg - rate * t) == 0 and all(sp.simplify(rate - r0) != 0 for r0, _ in exps):
+                exps.append((rate, ex))
+    if exps and tables[1]:
+        Esyms = [sp.Symbol(f"E[{k}]") for k in range(len(exps))]
+        sub_p = {s_: sp.Symbol(f"p[{k}]") for k, s_ in enumerate(psyms)}
+        rate_lines = "\n".join(f"        a[{k}] = {pr.doprint(r0.xreplace(sub_p))};" for k, (r0, _) in enumerate(exps))
+
+        def with_E(e):
+            def rep(ex):
+                arg = sp.expand(ex.args[0])
+                rate = sp.diff(arg, t)
+                for k, (r0, _) in enumerate(exps):
+                    if not rate.has(t) and sp.simplify(rate - r0) == 0 and sp.simplify(arg - rate * t) == 0:
+                        return Esyms[k]
+                return ex
+            return e.replace(lambda q: isinstance(q, sp.exp), rep)
+        tbl = [with_E(e) for _, e in tables[1]]
+        repl, red = sp.cse(tbl, symbols=sp.numbered_symbols("w"), optimizations="basic")
+        body = [f"        const double {s_} = {pr.doprint(e.xreplace(sub_p))};" for s_, e in repl]
+        body += [f"        tt[{k}] = {pr.doprint(e.xreplace(sub_p))};" for k, e in enumerate(red)]
+        texp_src = f"""
+    // exp(a_k t) of the HM_TIME table, advanced along the grid by recurrence when the parameters are per trajectory
+    static constexpr int ntexp = {len(exps)};
+    __device__ __forceinline__ static void texp_rates(const double *p, double *a)
+    {{
+        (void)p;
+{rate_lines}
+    }}
+    __device__ __forceinline__ static void table_from_texp(const double *E, double t, const double *p, double *tt)
+    {{
+        (void)E; (void)t; (void)p;
+{chr(10).join(body)}
+    }}
+"""
+
     sig = "const double *tt, double t, const double *y, const double *u, const double *p"
     unused = "(void)tt; (void)t; (void)y; (void)u; (void)p;"
     lo_hi = "\n".join(f"            o[{c}] = fmin(bounds[{2 * c + 1}], fmax(bounds[{2 * c}], o[{c}]));" for c in range(nc))
@@ -261,6 +305,7 @@ struct Problem {{
 {table_code()}
     }}
 
+{texp_src}
     // F = [g; f]   (OCProblem.m:9-11)
     template <int HM>
     __device__ __forceinline__ static void F({sig}, double *o)

@@ -807,6 +807,11 @@ void base_args(H *h, int si, SweepArgs &a)
     a.gprec = s.d_gprec;
     a.steprec = s.d_steprec;
     a.foldrec = s.fold_nf > 0 ? s.d_foldrec : nullptr;
+    {   // steps equal to rounding (linspace grids are): see ocs_ntexp in rk4_kernels.cuh
+        double dmax = 0.0;
+        for (double hi : s.h) dmax = std::max(dmax, std::fabs(hi - s.h[0]));
+        a.texp_uniform = dmax <= 1e-12 * std::fabs(s.h[0]) ? 1 : 0;
+    }
     a.basrec = s.d_basrec;
     a.p = h->d_params.p;
     a.ldp = h->params_nbatch > 1 ? h->params_nbatch : 0;
@@ -1669,13 +1674,30 @@ static bool needs_zero_fill(const ocs_b200_handle *h)
     return !(h->basis_kind == BASIS_SPARSE && h->bk_monotone && h->bk_covered && !h->fb_frozen);
 }
 
-// Trajectory chunks of a host-buffer evaluation whose gradient download (rows*Bt doubles over PCIe) dominates:
-// the first chunk is small so that the transfer starts almost at once, later chunks double (the sweeps run
-// about three times faster than PCIe drains them) up to a quarter of the batch.
-static std::vector<std::pair<long, long>> chunk_schedule(long Bt)
+// Trajectory chunks of a host-buffer evaluation whose gradient download (rows*Bt doubles over PCIe) overlaps the
+// sweeps.  Short horizons (the download dominates): the first chunk is small so that the transfer starts almost at
+// once, later chunks double (the sweeps run about three times faster than PCIe drains them) up to a quarter of the
+// batch.  Long horizons (the sweeps dominate: a block takes N steps whatever the chunk size, so a chunk below one
+// wave of resident blocks costs a whole wave's time -- cfg4, 20 000 steps, took 60 ms in 7 geometric chunks against
+// 27 ms of sweeps): equal chunks of at least one wave each, or a single chunk.
+static std::vector<std::pair<long, long>> chunk_schedule(const ocs_b200_handle *h, long Bt)
 {
     std::vector<std::pair<long, long>> out;
     const long gran = 128 * 12;                      // whole blocks of every kernel variant (1, 2, 3 or 4 trajectories per thread)
+    const long ntot = h->seg[0].N + (h->has_tail ? h->seg[1].N : 0);
+    if (ntot > 2500) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const long wave = (long)sms * 1280;          // trajectories resident at once in the widest sweep kernel
+        long nch = std::min<long>(8, Bt / wave);
+        if (nch < 2) {
+            out.emplace_back(0, Bt);
+            return out;
+        }
+        const long c = ((Bt + nch - 1) / nch + gran - 1) / gran * gran;
+        for (long b0 = 0; b0 < Bt; b0 += c) out.emplace_back(b0, std::min(c, Bt - b0));
+        return out;
+    }
     long c = std::max<long>(gran, (Bt / 32 + gran - 1) / gran * gran);
     const long cmax = std::max<long>(gran, (Bt / 4 + gran - 1) / gran * gran);
     for (long b0 = 0; b0 < Bt;) {
@@ -1700,7 +1722,7 @@ static int pipelined_gradient(ocs_b200_handle *h, bool with_forward, const doubl
         if (!h->chunk_done[k]) CK(cudaEventCreateWithFlags(&h->chunk_done[k], cudaEventDisableTiming));
         if (!h->stage_free[k]) CK(cudaEventCreateWithFlags(&h->stage_free[k], cudaEventDisableTiming));
     }
-    const auto sched = chunk_schedule(Bt);
+    const auto sched = chunk_schedule(h, Bt);
     long cmax = 0;
     for (auto &c : sched) cmax = std::max(cmax, c.second);
     for (int k = 0; k < 2; ++k) TRY(ensure(h, h->d_pipe[k], (size_t)(rows + m) * cmax));

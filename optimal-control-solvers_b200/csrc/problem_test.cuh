@@ -49,6 +49,20 @@ struct TestOCProblem {
         }
     }
 
+    // Per-trajectory parameters: exp(-r t) advances along the grid by recurrence (ocs_ntexp in rk4_kernels.cuh) and
+    // the right-hand sides run in their HM_TIME form on a per-trajectory table with the entries of table<1> (tt[1],
+    // the ControlChar factor, is not needed by F / dFdx_times_vec / dFdu_times_vec).
+    static constexpr int ntexp = 1;
+    __device__ __forceinline__ static void texp_rates(const double *p, double *a) { a[0] = -p[2]; }
+    __device__ __forceinline__ static void table_from_texp(const double *E, double t, const double *p, double *tt)
+    {
+        (void)t;
+        tt[0] = E[0];
+        tt[1] = 0.0;
+        tt[2] = 2.0 * E[0];
+        tt[3] = 2.0 * p[0] * E[0];
+    }
+
     static constexpr int nfold = 3;
     template <int HM>
     __device__ __forceinline__ static void fold(const double *tt, double w, double *fw)

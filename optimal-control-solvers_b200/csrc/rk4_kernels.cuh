@@ -186,6 +186,31 @@ __host__ __device__ constexpr int ocs_nfold(int hm)
 }
 __host__ __device__ constexpr int ocs_fold_width(int nfold) { return ocs_even(3 * nfold); }
 
+// Time exponentials by recurrence (per-trajectory parameters, FMA-contracted build only).  With one parameter set per
+// trajectory nothing can be tabulated per grid point, and a problem like the bundled one evaluates exp(-r t) in every
+// right-hand side: ~40 FP64 instructions each, 4 per forward and 8 per reverse step -- the parameter-sweep kernels
+// were spending 3/4 of their FP64 issue slots inside exp().  A problem may therefore declare `ntexp` exponentials
+// E_k(t) = exp(a_k t) (texp_rates) and how its HM_TIME table follows from them (table_from_texp).  The multi-trajectory
+// sweeps then keep E_k per trajectory and advance it by one multiplication per grid point, E(t + h/2) = E(t) exp(a h/2),
+// re-anchored with a real exp() at every tile of steps (<= 2*OCS_TILE products in a row: relative error below 3e-14, well
+// inside the 1e-10 parity bound; the strict build and the single-trajectory fetch / fb_sweep kernels keep exp()).
+// On a grid whose steps differ by more than rounding the factor is recomputed every step (one exp instead of four).
+template <class P>
+struct ocs_texp_traits {
+    template <class Q> __host__ __device__ static constexpr int get(decltype(Q::ntexp) *) { return Q::ntexp; }
+    template <class Q> __host__ __device__ static constexpr int get(...) { return 0; }
+    static constexpr int value = get<P>(nullptr);
+};
+template <class P>
+__host__ __device__ constexpr int ocs_ntexp(bool params_batched)
+{
+#if (defined(OCS_STRICT) && OCS_STRICT) || defined(OCS_NOTEXP)
+    return 0;
+#else
+    return params_batched ? ocs_texp_traits<P>::value : 0;
+#endif
+}
+
 // Argument block of one sweep over one RK4 segment (main horizon or tail).
 // SoA device arrays have leading dimension ldb (the batch stride); the kernel
 // handles trajectories [0, nb) of them, so a sub-range is a pointer offset.
@@ -200,6 +225,8 @@ struct SweepArgs {
     const double *gprec;    // [2N+1][RB]
     const double *steprec;  // [N][4]     h, h/2, h/3, h/6
     const double *foldrec;  // [N][ocs_fold_width(nfold)] weight-folded table entries, or null (problem without fold)
+    int texp_uniform;       // the segment's steps agree to rounding: the half-step factor of a time exponential is
+                            // computed once per tile instead of once per step (ocs_ntexp)
     int lamJ_one;           // reverse sweep: lam(end) == 1 for every trajectory (lamT null, or chained from a tail
                             // sweep that started from e_m), so the folded adjoint chain applies
     const double *basrec;   // [2N+1][BW]
@@ -725,6 +752,12 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
     double uL[T][nc], uM[T][nc], uR[T][nc];
     double uMn[T][nc], uRn[T][nc];      // UMODE_GRID: control of the next step, loaded one step ahead
     double *xsp[T];
+    // time exponentials by recurrence (see ocs_ntexp): the right-hand sides are then called in HM_TIME form on a
+    // per-trajectory table
+    constexpr int NE = ocs_ntexp<P>(PB);
+    constexpr int HMF = NE > 0 ? (int)HM_TIME : HM;
+    constexpr int NT1 = NE > 0 ? P::ntt(HM_TIME) : 1;
+    double Ecur[T][NE > 0 ? NE : 1], Eq[T][NE > 0 ? NE : 1], Erate[T][NE > 0 ? NE : 1];
 #pragma unroll
     for (int q = 0; q < T; ++q) {
         b[q] = ((long)blockIdx.x * T + q) * blockDim.x + threadIdx.x;
@@ -738,6 +771,7 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
         y[q][n] = 0.0;                                                // xK(:,1,1) = [x0; 0]   :33
         ctl[q].init(a, bb[q]);
         xsp[q] = a.xs + b[q];
+        if constexpr (NE > 0) ocs_dep<P, ocs_bool<(NE > 0)>>::type::texp_rates(p[q], Erate[q]);
     }
 
     if constexpr (OCS_ASYNC_STAGE) {
@@ -760,6 +794,16 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
             }
         } else {
             stage_tile<RB>(a, i0, ns, NEEDB ? BW : 0, gp, st, bs, fo, FW);
+        }
+        if constexpr (NE > 0) {     // anchor: exp() at the tile's first node, and the half-step factor of its first step
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    Ecur[q][e] = exp(Erate[q][e] * gp[0]);
+                    Eq[q][e] = exp(Erate[q][e] * st[1]);
+                }
+            }
         }
         if (i0 == 0) {
 #pragma unroll
@@ -868,22 +912,41 @@ __device__ __forceinline__ void forward_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                     for (int c = 0; c < n; ++c) y[q][c] = y[q][c] + h6 * (acc[c] + F[c]);        // :50-51
                 } else {
-                P::template F<HM>(rL + 1 + nc, rL[0], y[q], uL[q], p[q], F);         // F1   :39
+                // tables of the three grid points: the staged record, or (per-trajectory parameters, time
+                // exponentials by recurrence) this trajectory's own, one multiplication per grid point
+                double tqL[NT1], tqM[NT1], tqR[NT1];
+                if constexpr (NE > 0) {
+                    typedef typename ocs_dep<P, ocs_bool<(NE > 0)>>::type PE;
+                    double EM[NE], ER[NE];
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (!a.texp_uniform) Eq[q][e] = exp(Erate[q][e] * h2);
+                        EM[e] = Ecur[q][e] * Eq[q][e];
+                        ER[e] = EM[e] * Eq[q][e];
+                    }
+                    PE::table_from_texp(Ecur[q], rL[0], p[q], tqL);
+                    PE::table_from_texp(EM, rM[0], p[q], tqM);
+                    PE::table_from_texp(ER, rR[0], p[q], tqR);
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) Ecur[q][e] = ER[e];
+                }
+                const double *ttL = NE > 0 ? tqL : rL + 1 + nc, *ttM = NE > 0 ? tqM : rM + 1 + nc, *ttR = NE > 0 ? tqR : rR + 1 + nc;
+                P::template F<HMF>(ttL, rL[0], y[q], uL[q], p[q], F);                // F1   :39
 #pragma unroll
                 for (int c = 0; c < m; ++c) acc[c] = F[c];
 #pragma unroll
                 for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h2 * F[c];             // xK2  :40
-                P::template F<HM>(rM + 1 + nc, rM[0], ys, uM[q], p[q], F);           // F2   :42
+                P::template F<HMF>(ttM, rM[0], ys, uM[q], p[q], F);                  // F2   :42
 #pragma unroll
                 for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
 #pragma unroll
                 for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h2 * F[c];             // xK3  :43
-                P::template F<HM>(rM + 1 + nc, rM[0], ys, uM[q], p[q], F);           // F3   :45
+                P::template F<HMF>(ttM, rM[0], ys, uM[q], p[q], F);                  // F3   :45
 #pragma unroll
                 for (int c = 0; c < m; ++c) acc[c] = acc[c] + 2.0 * F[c];
 #pragma unroll
                 for (int c = 0; c < n; ++c) ys[c] = y[q][c] + h * F[c];              // xK4  :46
-                P::template F<HM>(rR + 1 + nc, rR[0], ys, uR[q], p[q], F);           // F4   :48
+                P::template F<HMF>(ttR, rR[0], ys, uR[q], p[q], F);                  // F4   :48
 #pragma unroll
                 for (int c = 0; c < m; ++c) y[q][c] = y[q][c] + h6 * (acc[c] + F[c]);   // :50-51
                 }
@@ -1301,6 +1364,11 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     GradAcc<nc, BMODE, KD> gacc[T];
     double uL[T][nc], uM[T][nc], uR[T][nc], dcar[T][nc], dR[T][nc], dM[T][nc];
     double uMn[T][nc], uLn[T][nc];      // UMODE_GRID: control of the next step, loaded one step ahead
+    // time exponentials by recurrence (see ocs_ntexp), walking the grid downwards
+    constexpr int NE = ocs_ntexp<P>(PB);
+    constexpr int HMF = NE > 0 ? (int)HM_TIME : HM;
+    constexpr int NT1 = NE > 0 ? P::ntt(HM_TIME) : 1;
+    double Ecur[T][NE > 0 ? NE : 1], Eq[T][NE > 0 ? NE : 1], Erate[T][NE > 0 ? NE : 1];
     constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
     constexpr int UNR = OCS_REV_UNROLL;
     constexpr int DP = OCS_RING;             // > 0: cp.async ring in shared memory [DP][T][n (+ 2 nc)][threads] instead of yn
@@ -1345,6 +1413,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             lam[q][c] = a.lamT ? (a.ldl ? a.lamT[soa(c, a.ldl, bb[q])] : a.lamT[c]) : (c == n ? 1.0 : 0.0);
         ctl[q].init(a, bb[q]);
         gacc[q].init();
+        if constexpr (NE > 0) P::texp_rates(p[q], Erate[q]);
 #pragma unroll
         for (int c = 0; c < nc; ++c) dcar[q][c] = 0.0;
         xsp[q] = a.xs + (size_t)(N - 1) * a.ldb + bb[q];     // node N-1; nodes below 0 fall into the slack
@@ -1397,6 +1466,16 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 }
             }
         }
+        if constexpr (NE > 0) {     // anchor: exp() at the tile's last node, and the (inverse) half-step factor of its last step
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    Ecur[q][e] = exp(Erate[q][e] * gp[(2 * ns) * RB]);
+                    Eq[q][e] = exp(-(Erate[q][e] * st[4 * (ns - 1) + 1]));
+                }
+            }
+        }
         // one RK4 step (all T trajectories) as a lambda, so that the step loop below can be unrolled by hand:
         // `#pragma unroll 2` on this loop miscompiled the peeled remainder iteration for odd step counts
         // (nvcc 12.9, caught by tests/test_gpu_edges.py); pairs + one explicit odd step are equivalent and safe.
@@ -1407,7 +1486,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
             const double *rL = gp + (2 * s) * RB, *rM = rL + RB, *rR = rM + RB;
             const double *bL = bs + (2 * s) * BW, *bM = bL + BW, *bR = bM + BW;
             const double h = st[4 * s], h2 = st[4 * s + 1], h3 = st[4 * s + 2], h6 = st[4 * s + 3];
-            const double *ttR = rR + 1 + nc, *ttM = rM + 1 + nc, *ttL = rL + 1 + nc;
+            const double *ttR0 = rR + 1 + nc, *ttM0 = rM + 1 + nc, *ttL0 = rL + 1 + nc;
             const double tR = rR[0], tM = rM[0], tL = rL[0];
             const bool moves = BMODE == BMODE_SPARSE ? (rec_flags(bM) & 4) != 0 : true;
             if constexpr (DP > 0) {
@@ -1494,14 +1573,33 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                     ctl[q].eval(a, rL, bL, 2 * i, bb[q], uL[q]);
                 }
 
+                // tables of the step's three grid points: the staged records, or this trajectory's own (time
+                // exponentials by recurrence: one multiplication per grid point, downwards)
+                double tqL[NT1], tqM[NT1], tqR[NT1];
+                if constexpr (NE > 0) {
+                    typedef typename ocs_dep<P, decltype(fold_tag)>::type PE;
+                    double EM[NE], EL[NE];
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (!a.texp_uniform) Eq[q][e] = exp(-(Erate[q][e] * h2));
+                        EM[e] = Ecur[q][e] * Eq[q][e];
+                        EL[e] = EM[e] * Eq[q][e];
+                    }
+                    PE::table_from_texp(Ecur[q], tR, p[q], tqR);
+                    PE::table_from_texp(EM, tM, p[q], tqM);
+                    PE::table_from_texp(EL, tL, p[q], tqL);
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) Ecur[q][e] = EL[e];
+                }
+                const double *ttR = NE > 0 ? tqR : ttR0, *ttM = NE > 0 ? tqM : ttM0, *ttL = NE > 0 ? tqL : ttL0;
                 double F[m], y2[n], y3[n], y4[n];
-                P::template F<HM>(ttL, tL, y1[q], uL[q], p[q], F);
+                P::template F<HMF>(ttL, tL, y1[q], uL[q], p[q], F);
 #pragma unroll
                 for (int c = 0; c < n; ++c) y2[c] = y1[q][c] + h2 * F[c];
-                P::template F<HM>(ttM, tM, y2, uM[q], p[q], F);
+                P::template F<HMF>(ttM, tM, y2, uM[q], p[q], F);
 #pragma unroll
                 for (int c = 0; c < n; ++c) y3[c] = y1[q][c] + h2 * F[c];
-                P::template F<HM>(ttM, tM, y3, uM[q], p[q], F);
+                P::template F<HMF>(ttM, tM, y3, uM[q], p[q], F);
 #pragma unroll
                 for (int c = 0; c < n; ++c) y4[c] = y1[q][c] + h * F[c];
 
@@ -1554,8 +1652,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                 } else {
 #pragma unroll
                 for (int c = 0; c < m; ++c) k4[c] = h6 * lam[q][c];                          // :73
-                if (du) P::template U<HM>(ttR, tR, y4, uR[q], p[q], k4, dRq);               // :119-120 / :116
-                P::template X<HM>(ttR, tR, y4, uR[q], p[q], k4, g3);                        // :74-75
+                if (du) P::template U<HMF>(ttR, tR, y4, uR[q], p[q], k4, dRq);               // :119-120 / :116
+                P::template X<HMF>(ttR, tR, y4, uR[q], p[q], k4, g3);                        // :74-75
 #pragma unroll
                 for (int c = 0; c < n; ++c) k3[c] = h3 * lam[q][c] + h * g3[c];              // :77
                 k3[n] = h3 * lam[q][n];
@@ -1563,8 +1661,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                     for (int c = 0; c < n; ++c) ls[c] = lam[q][c] + g3[c];
                 }
-                if (du) P::template U<HM>(ttM, tM, y3, uM[q], p[q], k3, dM3);               // :108-109
-                P::template X<HM>(ttM, tM, y3, uM[q], p[q], k3, g2);                        // :78-79
+                if (du) P::template U<HMF>(ttM, tM, y3, uM[q], p[q], k3, dM3);               // :108-109
+                P::template X<HMF>(ttM, tM, y3, uM[q], p[q], k3, g2);                        // :78-79
 #pragma unroll
                 for (int c = 0; c < n; ++c) k2[c] = h3 * lam[q][c] + h2 * g2[c];             // :81
                 k2[n] = h3 * lam[q][n];
@@ -1572,8 +1670,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                     for (int c = 0; c < n; ++c) ls[c] = ls[c] + g2[c];
                 }
-                if (du) P::template U<HM>(ttM, tM, y2, uM[q], p[q], k2, dM2);               // :106-107
-                P::template X<HM>(ttM, tM, y2, uM[q], p[q], k2, g1);                        // :82-83
+                if (du) P::template U<HMF>(ttM, tM, y2, uM[q], p[q], k2, dM2);               // :106-107
+                P::template X<HMF>(ttM, tM, y2, uM[q], p[q], k2, g1);                        // :82-83
 #pragma unroll
                 for (int c = 0; c < n; ++c) k1[c] = h6 * lam[q][c] + h2 * g1[c];             // :85
                 k1[n] = h6 * lam[q][n];
@@ -1581,7 +1679,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
 #pragma unroll
                     for (int c = 0; c < n; ++c) ls[c] = ls[c] + g1[c];
                 }
-                P::template X<HM>(ttL, tL, y1[q], uL[q], p[q], k1, g0);                     // :86-88
+                P::template X<HMF>(ttL, tL, y1[q], uL[q], p[q], k1, g0);                     // :86-88
                 }
 
                 if constexpr (GA) {
@@ -1591,7 +1689,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                         dM[q][c] = dM2[c] + dM3[c];            // stages 2 + 3
                     }
                     if constexpr (FO) PF::template Uf<HM>(ttL, fL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
-                    else P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);       // :101-102 / :112-116
+                    else P::template U<HMF>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);      // :101-102 / :112-116
                 } else {
                     if (dugout) {            // dJdu itself, SoA [nc][G][batch], coalesced (dense bases project it later)
 #pragma unroll
@@ -1602,7 +1700,7 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
                             }
                         }
                         if constexpr (FO) PF::template Uf<HM>(ttL, fL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
-                        else P::template U<HM>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
+                        else P::template U<HMF>(ttL, tL, y1[q], uL[q], p[q], k1, dcar[q]);
                     }
                 }
 #pragma unroll

@@ -242,3 +242,29 @@ def test_matlab_emitted_problem_matches_the_python_backend(ocs, cg):
     for key in ("J", "xT", "dJdv", "lam0"):
         assert relerr(res[1][0][key], res[0][0][key]) < 1e-12, key
     assert relerr(res[1][1]["J"], res[0][1]["J"]) < 1e-12 and relerr(res[1][1]["maxChange"], res[0][1]["maxChange"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_generated_problem_parameter_sweep_matches_builtin(ocs, oracle, cg):
+    """Per-trajectory (c, m, r) through a generated problem: the codegen's texp_rates / table_from_texp (exp(-r t) and
+    exp(r t) advanced along the grid by recurrence in the NVRTC-compiled sweeps) against the built-in problem and the
+    C oracle, which call exp() at every grid point."""
+    Bt, N, K = 700, 150, 9
+    rng = np.random.default_rng(17)
+    c, m, r = rng.uniform(1.0, 2.0, Bt), rng.uniform(2.5, 3.5, Bt), rng.uniform(0.0, 0.4, Bt)
+    gen = cg.test_problem_symbolic(c=c, m=m, r=r)
+    assert "static constexpr int ntexp = 2;" in gen.source
+    builtin = ocs.TestOCProblem(dict(c=c, m=m, r=r), [[0, 1]])
+    tspan = ocs.matlab_linspace(0.0, 6.0, N + 1)
+    x0, v = rng.uniform(.5, 2.5, (1, Bt)), rng.random((K, Bt))
+    res = {}
+    for name, prob in (("gen", gen), ("builtin", builtin)):
+        integ = ocs.CudaRK4Integrator(tspan)
+        ctl = ocs.PWLinearControl(integ.t, K, 1)
+        integ.attach_control(ctl)
+        res[name] = integ.evaluate(prob, x0, v)
+        integ.close()
+    ref = oracle.C.evaluate(np.stack([c, m, r]), tspan, ctl.B, x0, v)
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(res["gen"][key], ref[key]) < TOL, key
+        assert relerr(res["gen"][key], res["builtin"][key]) < TOL, key

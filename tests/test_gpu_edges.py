@@ -206,3 +206,36 @@ def test_grid_fetch_and_fb_sweep_for_odd_step_counts(ocs, oracle, N):
             assert relerr(un, ref["u"]) < TOL, (mode, N)
             assert relerr(one["maxChange"][b], ref["maxChange"]) < 1e-9
     integ.close()
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+@pytest.mark.parametrize("per_traj_v", [False, True])
+@pytest.mark.parametrize("N", [1, 5, 64, 65, 200])
+def test_parameter_sweep_time_exponentials_by_recurrence(ocs, oracle, uniform, per_traj_v, N):
+    """Per-trajectory (c, m, r): the fast build advances exp(-r t) along the grid by one multiplication per grid
+    point, re-anchored with exp() at every tile (rk4_kernels.cuh, ocs_ntexp); on a grid with unequal steps the factor
+    is recomputed per step.  Tile boundaries (64 / 65 steps), a single step, shared and per-trajectory coefficients,
+    against the C oracle (which calls exp() at every grid point)."""
+    rng = np.random.default_rng(100 + N)
+    T = 0.2 + 0.04 * N                   # steps of ~0.04-0.24: RK4 stays stable for every parameter set drawn below
+    if uniform:
+        tspan = ocs.matlab_linspace(0.0, T, N + 1)
+    else:
+        tspan = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, N))]) * (T / N)
+    Bt, K = 333, min(7, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ctl = ocs.PWLinearControl(integ.t, K, 1)
+    integ.attach_control(ctl)
+    c, m, r = rng.uniform(1.0, 2.0, Bt), rng.uniform(2.5, 3.5, Bt), rng.uniform(0.0, 0.5, Bt)
+    prob = ocs.TestOCProblem(dict(c=c, m=m, r=r), [[0, 1]])
+    x0 = rng.uniform(.5, 2.5, (1, Bt))
+    v = rng.random((K, Bt)) if per_traj_v else rng.random(K)
+    out = integ.evaluate(prob, x0, v)
+    ref = oracle.C.evaluate(np.stack([c, m, r]), tspan, ctl.B, x0, v)
+    assert not out["status"].any() and np.all(np.isfinite(ref["J"]))
+    for key in ("J", "xT", "dJdv", "lam0"):
+        assert relerr(out[key], ref[key]) < TOL, (key, N, uniform)
+    # the grids (single-trajectory fetch kernels keep exp()) agree with the batched sweep's results
+    x = integ.fetch_states(0, Bt)
+    assert relerr(x[1, -1, :], out["J"]) < 1e-12
+    integ.close()
