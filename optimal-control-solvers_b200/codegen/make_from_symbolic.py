@@ -30,6 +30,7 @@ from sympy.printing.c import C99CodePrinter
 
 from ..host.problems import OCProblem
 from .. import _lib
+from .fma_forms import fma_forms, inline_fused_products, order_terms
 
 __all__ = ["make_from_symbolic", "CodegenProblem"]
 
@@ -54,6 +55,13 @@ class _CudaPrinter(C99CodePrinter):
 
     def _print_Integer(self, expr):
         return f"{int(expr)}.0" if abs(int(expr)) < 2 ** 53 else super()._print_Integer(expr)
+
+
+class _FmaPrinter(_CudaPrinter):
+    """Sums with their non-product terms first: every later product contracts into an FMA (fma_forms.order_terms)."""
+
+    def _as_ordered_terms(self, expr, order=None):
+        return order_terms(super()._as_ordered_terms(expr, order=order))
 
 
 def _count_ops(exprs):
@@ -121,7 +129,7 @@ def _hoist(exprs, uniform_syms, grid_syms, table, prefix="tt"):
 
 
 def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, ControlBounds, MinMax="Min",
-                       solve_control=True):
+                       solve_control=True, fma=True):
     """CUDA-backend twin of functions/make_from_symbolic.m:1.
 
     symObjective : SymPy expression (or string) of the running cost f(t, x, u)
@@ -129,6 +137,8 @@ def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, Co
     params       : dict name -> value (scalar, or an array of per-trajectory values); the order of the
                    keys is the order of the generated parameter vector p (make_from_symbolic.m:3-4)
     ControlBounds: nControls x 2
+    fma          : also emit the FMA-shaped forms of fma_forms.py for the FMA-contracted build (the strict build
+                   always evaluates the expressions as derived)
     """
     n, nc = int(nStates), int(nControls)
     t = sp.Symbol("t")
@@ -164,6 +174,7 @@ def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, Co
             CC = None
 
     pr = _CudaPrinter()
+    prf = _FmaPrinter()
     subs_common = {}
     for i in range(n):
         subs_common[x[i]] = sp.Symbol(f"y[{i}]")
@@ -187,21 +198,58 @@ def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, Co
             lines.append(f"            {out}[{k}] = {pr.doprint(e.xreplace(sub))};")
         return "\n".join(lines)
 
-    uniform = {1: {t, *psyms}, 2: {t, *psyms, *u}}
-    grid = {1: {t}, 2: {t, *u}}
+    def emit_body_fast(defs, forms, out, table_syms):
+        """The FMA-shaped forms (fma_forms.py): stage constants first, then the rows."""
+        sub = dict(subs_common)
+        for k, s in enumerate(table_syms):
+            sub[s] = sp.Symbol(f"tt[{k}]")
+        lines = []
+        if defs:
+            repl, red = sp.cse([d for _, d in defs], symbols=sp.numbered_symbols("zc"), optimizations="basic")
+            for s, e in repl:
+                lines.append(f"            const double {s} = {prf.doprint(e.xreplace(sub))};")
+            for (s, _), e in zip(defs, red):
+                lines.append(f"            const double {s} = {prf.doprint(e.xreplace(sub))};")
+        repl, red = sp.cse(list(forms), symbols=sp.numbered_symbols("z"), optimizations="basic")
+        repl, red = inline_fused_products(repl, red)
+        for s, e in repl:
+            lines.append(f"            const double {s} = {prf.doprint(e.xreplace(sub))};")
+        for k, e in enumerate(red):
+            lines.append(f"            {out}[{k}] = {prf.doprint(e.xreplace(sub))};")
+        return "\n".join(lines)
+
+    uniform = {0: set(), 1: {t, *psyms}, 2: {t, *psyms, *u}}
+    grid = {0: set(), 1: {t}, 2: {t, *u}}
+    dynamic = dict(F=(set(x), [*x]), X=({*x, *vx, vJ}, [*vx, vJ, *x]), U=({*x, *vx, vJ}, [*vx, vJ, *x]),
+                   CC=({*x, *lam}, [*lam, *x]))
     variants = {}
+    fast = {}            # fast[hm][fn] = (stage constants, forms) or None: the FMA-contracted build's bodies
     tables = {}
     for hm in (0, 1, 2):
+        table = []
         if hm == 0:
             variants[hm] = dict(F=F, X=X, U=U, CC=CC)
-            tables[hm] = []
-            continue
-        table = []
-        Fh = _hoist(F, uniform[hm], grid[hm], table)
-        Xh = _hoist(X, uniform[hm], grid[hm], table)
-        Uh = _hoist(U, uniform[hm], grid[hm], table)
-        CCh = _hoist(CC, uniform[hm], grid[hm], table) if CC is not None else None
-        variants[hm] = dict(F=Fh, X=Xh, U=Uh, CC=CCh)
+        else:
+            Fh = _hoist(F, uniform[hm], grid[hm], table)
+            Xh = _hoist(X, uniform[hm], grid[hm], table)
+            Uh = _hoist(U, uniform[hm], grid[hm], table)
+            CCh = _hoist(CC, uniform[hm], grid[hm], table) if CC is not None else None
+            variants[hm] = dict(F=Fh, X=Xh, U=Uh, CC=CCh)
+        fast[hm] = {}
+        for fn, exprs in (("F", F), ("X", X), ("U", U), ("CC", CC)):
+            fast[hm][fn] = None
+            if exprs is None or not fma:
+                continue
+            prep = (lambda e, hm=hm: _hoist([e], uniform[hm], grid[hm], [])[0]) if hm else None
+            dyn, order = dynamic[fn]
+            defs, forms = fma_forms(exprs, dyn, order, prefix="c", prep=prep)
+            if all(a == b for a, b in zip(forms, exprs)):
+                continue                                      # nothing cheaper than the derived expressions
+            if hm:
+                hoisted = _hoist([d for _, d in defs] + forms, uniform[hm], grid[hm], table)
+                defs = [(s_, e) for (s_, _), e in zip(defs, hoisted[:len(defs)])]
+                forms = hoisted[len(defs):]
+            fast[hm][fn] = (defs, forms)
         tables[hm] = table
 
     def per_hm(fn, out):
@@ -209,7 +257,13 @@ def make_from_symbolic(symObjective, symStateRHS, nStates, nControls, params, Co
         for hm in (0, 1, 2):
             exprs = variants[hm][fn]
             kw = "if" if hm == 0 else "else if"
-            parts.append(f"        {kw} constexpr (HM == {hm}) {{\n{emit_body(exprs, out, [s for s, _ in tables[hm]])}\n        }}")
+            tsyms = [s for s, _ in tables[hm]]
+            body = emit_body(exprs, out, tsyms)
+            if fast[hm][fn] is not None:
+                # re-associated forms for the FMA-contracted build; the strict build keeps the derived expressions
+                body = ("#if defined(OCS_STRICT) && OCS_STRICT\n" + body + "\n#else\n" +
+                        emit_body_fast(*fast[hm][fn], out, tsyms) + "\n#endif")
+            parts.append(f"        {kw} constexpr (HM == {hm}) {{\n{body}\n        }}")
         return "\n".join(parts)
 
     def table_code():

@@ -2016,10 +2016,20 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
 #define OCS_COMMA ,
 // trajectories per thread / min blocks per SM of a sweep variant (the host mirrors these in kernel_tpt())
 #define OCS_FWD_T(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? OCS_TPT_FWD_PB : ((UM) == 1 ? OCS_TPT_FWD_COEF : OCS_TPT_FWD)))
-#define OCS_FWD_LB(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? OCS_MINBLOCKS_FWD_PB : ((UM) == 2 ? 4 : ((UM) == 1 ? OCS_MINBLOCKS_FWD_COEF : OCS_MINBLOCKS_FWD))))
+// explicit register caps (blocks per SM) of the variants the tuned defaults derive from the macros above
+#ifndef OCS_LB_FWD_DENSE
+#define OCS_LB_FWD_DENSE 1      // forward sweep evaluating a dense (Chebyshev) basis per trajectory
+#endif
+#ifndef OCS_LB_FWD_GRID
+#define OCS_LB_FWD_GRID 4       // forward sweep reading its control from the per-trajectory grid
+#endif
+#define OCS_FWD_LB(UM, BM, PB) ((BM) == 2 ? OCS_LB_FWD_DENSE : ((PB) != 0 ? OCS_MINBLOCKS_FWD_PB : ((UM) == 2 ? OCS_LB_FWD_GRID : ((UM) == 1 ? OCS_MINBLOCKS_FWD_COEF : OCS_MINBLOCKS_FWD))))
 #define OCS_REV_T(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? OCS_TPT_REV_PB : ((UM) == 1 ? OCS_TPT_REV_COEF : OCS_TPT_REV)))
 // (the variants without a sparse basis carry the generic dJdu-grid path and need a few registers more: one block less)
-#define OCS_REV_LB(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? ((UM) == 2 && OCS_MINBLOCKS_REV_PB > 1 ? OCS_MINBLOCKS_REV_PB - 1 : OCS_MINBLOCKS_REV_PB) : ((UM) == 1 ? OCS_MINBLOCKS_REV_COEF : ((BM) == 0 && OCS_MINBLOCKS_REV > 2 ? OCS_MINBLOCKS_REV - ((UM) == 2 ? 2 : 1) : OCS_MINBLOCKS_REV))))
+#ifndef OCS_LB_REV_GRID
+#define OCS_LB_REV_GRID (OCS_MINBLOCKS_REV > 2 ? OCS_MINBLOCKS_REV - 2 : OCS_MINBLOCKS_REV)   // gradient sweep over the per-trajectory control grid
+#endif
+#define OCS_REV_LB(UM, BM, PB) ((BM) == 2 ? 1 : ((PB) != 0 ? ((UM) == 2 && OCS_MINBLOCKS_REV_PB > 1 ? OCS_MINBLOCKS_REV_PB - 1 : OCS_MINBLOCKS_REV_PB) : ((UM) == 1 ? OCS_MINBLOCKS_REV_COEF : ((BM) == 0 && (UM) == 2 ? OCS_LB_REV_GRID : ((BM) == 0 && OCS_MINBLOCKS_REV > 2 ? OCS_MINBLOCKS_REV - 1 : OCS_MINBLOCKS_REV)))))
 #define OCS_FWD_KERNEL(P, tag, UM, BM, PB, KD) \
     OCS_KERNEL_(ocs_fwd_, forward_multi_body<P OCS_COMMA UM OCS_COMMA BM OCS_COMMA(PB != 0) OCS_COMMA KD OCS_COMMA OCS_FWD_T(UM, BM, PB)>, tag, UM, BM, PB, OCS_FWD_LB(UM, BM, PB))
 #define OCS_FWDG_KERNEL(P, tag, UM, BM, PB, KD) \

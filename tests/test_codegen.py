@@ -85,7 +85,8 @@ def test_every_kernel_unit_of_a_generated_problem_compiles_under_nvrtc(cg, stric
     inc = "-I" + os.path.join(ROOT, "optimal-control-solvers_b200", "csrc")
     opts = [o.encode() for o in NVRTC_OPTS + [inc, "--fmad=false" if strict else "--fmad=true"]]
     for unit in units:
-        src = '#define OCS_NS ocs_gen\n#include "rk4_kernels.cuh"\n' + p.source + "\n" + unit + "\n"
+        src = ('#define OCS_NS ocs_gen\n#define OCS_STRICT %d\n#include "rk4_kernels.cuh"\n' % int(strict) + p.source + "\n" +
+               unit + "\n")
         err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"ocs_generated_problem.cu", 0, [], [])
         assert int(err) == 0
         (rc,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
@@ -95,6 +96,60 @@ def test_every_kernel_unit_of_a_generated_problem_compiles_under_nvrtc(cg, stric
             nvrtc.nvrtcGetProgramLog(prog, log)
             pytest.fail("%s did not compile under NVRTC:\n%s" % (unit, log.decode(errors="replace")[:3000]))
         nvrtc.nvrtcDestroyProgram(prog)
+
+
+def test_fma_forms_are_cheaper_and_equal(cg):
+    """codegen/fma_forms.py: the forms printed for the FMA-contracted build are re-associations of the derived
+    expressions (equal as polynomials, and to rounding at random points) with fewer FP64 instructions; the strict
+    build's branch of every function still prints the derived expressions."""
+    ff = importlib.import_module("optimal-control-solvers_b200.codegen.fma_forms")
+    p = cg.harvest_chain_problem()
+    s = p.sym
+    x, vx, vJ, u, t = s["x"], s["vx"], s["vJ"], s["u"], s["t"]
+    rng = np.random.default_rng(5)
+    allsyms = [t, *x, *vx, vJ, *u, *s["params"]]
+    point = {a: float(rng.uniform(0.3, 1.7)) for a in allsyms}
+    before = after = 0
+    for fn, dyn, order in (("F", set(x), [*x]), ("X", {*x, *vx, vJ}, [*vx, vJ, *x]), ("U", {*x, *vx, vJ}, [*vx, vJ, *x])):
+        defs, forms = ff.fma_forms(s[fn], dyn, order)
+        sub = dict(defs)
+        for e, f in zip(s[fn], forms):
+            full = f.xreplace(sub)
+            assert sp.expand(full - e) == 0
+            assert abs(float(full.xreplace(point)) - float(e.xreplace(point))) <= 1e-13 * max(1.0, abs(float(e.xreplace(point))))
+        uni, grid = {t, *s["params"]}, {t}
+        mfs = importlib.import_module("optimal-control-solvers_b200.codegen.make_from_symbolic")
+        prep = lambda e: mfs._hoist([e], uni, grid, [])[0]
+        before += ff.dag_cost(s[fn], prep)
+        after += ff.dag_cost([d for _, d in defs] + forms, prep)
+    assert after <= 0.85 * before, (before, after)
+    assert "#if defined(OCS_STRICT) && OCS_STRICT" in p.source
+    # a sum prints with its non-product terms first: c - a*b contracts into one FMA, -a*b + c need not
+    a, b, c = sp.symbols("a b c")
+    assert [str(q) for q in ff.order_terms([-a * b, c])] == ["c", "-a*b"]
+    assert ff.fma_cost(a * b + c) == 1 and ff.fma_cost(a * b + c * a) == 2 and ff.fma_cost((a + b) * c) == 2
+    assert cg.make_from_symbolic("x1**2 + u1**2", ["-x1 + u1"], 1, 1, dict(k=1.0), [[0, 1]], fma=False).source.count("#if") == 0
+
+
+def test_fma_forms_leave_non_polynomial_problems_alone(cg):
+    """Exponentials, divisions and powers of sums of the states are never expanded: such rows keep the derived form
+    or use it as an atom, and the generated source still compiles."""
+    p = cg.make_from_symbolic("exp(-r*t)*(x1 - a)**2/(1 + x2**2) + u1**2",
+                              ["x1*exp(-x2) - k*u1*x1/(1 + x1)", "sqrt(1 + x1**2) - x2*u1"], 2, 1,
+                              dict(r=0.1, a=1.0, k=0.5), [[0, 1]], solve_control=False)
+    assert "exp(-y[1])" in p.source and "sqrt(" in p.source
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "gen.cu")
+        with open(src, "w") as f:
+            f.write('#define OCS_NS ocs_gen\n#define OCS_STRICT 0\n#include "rk4_kernels.cuh"\n' + p.source +
+                    "\nOCS_TT_KERNEL(ocs_gen::Problem, gen)\nOCS_REV_KERNEL(ocs_gen::Problem, gen, 0, 1, 0, 0)\n")
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1",
+                            "-I", os.path.join(ROOT, "optimal-control-solvers_b200", "csrc"), "-cubin", "-o",
+                            os.path.join(d, "gen.cubin"), src], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
 
 
 def test_oracle_twin_of_generated_problem(cg, oracle):
