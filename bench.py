@@ -397,19 +397,30 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
         prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])
         x0 = np.random.default_rng(2 + rank).uniform(0.5, 2.5, (1, Bt))
         u0 = np.full((1, 2 * N_STEPS + 1), 0.5)
+    nrep = max(1, min(args.steps, 5))
+    # per-kernel device time: CUDA events around every launch, each kernel alone over the whole batch
     integ.set_profiling(True)
     for _ in range(max(1, min(args.warmup, 2))):
         integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S, **kw)
     integ.kernel_stats(reset=True)
+    for _ in range(nrep):
+        integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S, **kw)
+    ks = integ.kernel_stats(reset=True)
+    ms_f, ms_r = ks["ms_forward"] / (nrep * S), ks["ms_reverse"] / (nrep * S)
+    # the timed region: the calls as a user makes them.  Device time of the sweep loops (events on the handle's stream
+    # from the first kernel queued to the last one's end; a low-occupancy problem runs its sweeps as two lanes, so this is
+    # less than the sum of the kernels timed alone) -> value; wall clock with the host copies -> e2e
+    integ.set_profiling(False)
+    integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S, **kw)
+    integ.kernel_stats(reset=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    nrep = max(1, min(args.steps, 5))
     for _ in range(nrep):
         out = integ.fb_sweep(prob, x0, u0, uRelTol=0.0, uAbsTol=0.0, nSWEEPS=S, **kw)
     dt = time.perf_counter() - t0
     ks = integ.kernel_stats(reset=True)
     assert (out["sweeps"] == S).all()
-    ms_f, ms_r = ks["ms_forward"] / (nrep * S), ks["ms_reverse"] / (nrep * S)
+    ms_sweep = ks["ms_fb_loop"] / (nrep * S)          # one sweep = forward + costate/update kernels of the whole batch
     units = Bt * N_STEPS
     hbm_peak, hbm_src = _measured_peaks()
     L = ocs._lib.load()
@@ -431,8 +442,8 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
     bound = "hbm" if hbm_frac >= fp_frac else "fp64"
     emit({
         "metric": "FP64 trajectory-steps/sec (fb_sweep iteration on the RK4 grid)",
-        "value": units * 1e3 / (ms_f + ms_r), "unit": "trajectory-steps/s", "n_gpus": 1, "steps": nrep, "warmup": 1,
-        "ms_per_step": (ms_f + ms_r) * S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "value": units * 1e3 / ms_sweep, "unit": "trajectory-steps/s", "n_gpus": 1, "steps": nrep, "warmup": 1,
+        "ms_per_step": ms_sweep * S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": ("cfg3fb: fb_sweep iteration of the generated 6-state/6-costate harvest-chain problem over 100k "
                                 "control candidates (ChebyshevControl degree 16 each, evaluated on the device) x 1000 RK4 steps, "
@@ -444,7 +455,11 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
         "roofline": {"bound": bound, "achieved": dom["gbs"] if bound == "hbm" else dom["tflops"],
                      "peak": hbm_peak if bound == "hbm" else tf.value, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                      "frac": max(hbm_frac, fp_frac), "kernel": dom["kernel"], "traffic": None, "peak_source": hbm_src,
-                     "kernels": [kf, kr]},
+                     "kernels": [kf, kr],
+                     "step": {"ms_per_sweep": ms_sweep, "ms_kernels_alone": ms_f + ms_r,
+                              "hbm_gbs": units * (bf + br) / ms_sweep / 1e6, "hbm_frac": units * (bf + br) / ms_sweep / 1e6 / hbm_peak,
+                              "what": "one sweep (forward + costate/update) of the whole batch inside the solve loop: algorithmic "
+                                      "bytes of both kernels over the loop's device time per sweep"}},
         "e2e": {"value": nrep * S * units / dt, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 * x0.size + 8 * (kw["v0"].size if gen else u0.size),
                 "d2h_bytes_per_step": 8 * Bt * 2 + 4 * Bt * 2, "api": "ocs_b200_fb_sweep on host buffers"},
     })
@@ -610,7 +625,7 @@ def run_sub_config(name, extra=()):
            "bound": rf.get("bound"), "frac": rf.get("frac"), "kernel": rf.get("kernel"),
            "kernels": [{k: q[k] for k in ("kernel", "ms", "tflops", "gbs") if k in q} for q in rf.get("kernels", [])],
            "wall_s": time.perf_counter() - t0}
-    for k in ("step_fp64_frac",):
+    for k in ("step_fp64_frac", "step_hbm_frac", "step_ms_kernels_alone", "step"):
         if k in rf:
             out[k] = rf[k]
     if "solve" in j:
@@ -821,6 +836,12 @@ def main():
                                      "bytes_per_step_fwd": wl["bytes_fwd"], "bytes_per_step_rev": wl["bytes_rev"]}})
         # whole-evaluation view: (fwd + rev) algorithmic flops over the measured step time
         roof["step_fp64_frac"] = value / world * (wl["flop_fwd"] + wl["flop_rev"]) / 1e12 / tf_peak
+        # ... and its algorithmic bytes over the same time.  The kernels above are timed alone over the whole batch; inside
+        # the step a low-occupancy problem runs them as two overlapping lanes (ocs_b200.h, ocs_b200_evaluate_dev), so the
+        # step is shorter than their sum
+        step_bytes = wl["bytes_fwd"] + wl["bytes_rev"] + wl.get("bytes_proj", 0)
+        roof["step_hbm_frac"] = value / world * step_bytes / 1e9 / hbm_peak
+        roof["step_ms_kernels_alone"] = ms_fwd + ms_rev
         cfg = main_config(Bt, world) if args.config == "cfg2" else {
             "workload": wl["label"], "trajectories_per_gpu": Bt, "rk4_steps": NT,
             "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * n_st * NT * Bt),

@@ -297,6 +297,15 @@ OCS_B200_API int ocs_b200_compute_states_dev(ocs_b200_handle *h, const double *x
                                              double *J, double *xT_soa, int32_t *status);
 OCS_B200_API int ocs_b200_compute_adjoints_dev(ocs_b200_handle *h, const double *lamT_soa, long lamT_nbatch,
                                                double *dJdv_soa, double *lam0_soa);
+/* nlpObjective of functions/single_shooting.m:137-150 (compute_states followed by compute_adjoints) as ONE asynchronous
+ * call on device buffers.  Both sweeps are queued together, which lets a batch whose kernels keep few warps resident
+ * (several-state problems) run as two half batches on two internal streams -- one half's adjoint sweep fills the SMs
+ * that the other half's forward sweep leaves idle in its last round of blocks.  Results are complete in stream order
+ * on the handle's stream, as for the two calls above.  OCS_B200_LANES=0 / 1 in the environment at create time
+ * forces the one-pass / two-lane form; the default decides from the kernels' occupancy and the batch size. */
+OCS_B200_API int ocs_b200_evaluate_dev(ocs_b200_handle *h, const double *x0_soa, long Bt, const double *lamT_soa,
+                                       long lamT_nbatch, double *J, double *xT_soa, int32_t *status, double *dJdv_soa,
+                                       double *lam0_soa);
 OCS_B200_API int ocs_b200_synchronize(ocs_b200_handle *h);
 
 /* Device-resident evaluation for solver loops and multi-GPU pipelines (works on single- and multi-device handles):
@@ -320,7 +329,10 @@ OCS_B200_API int ocs_b200_get_results(ocs_b200_handle *h, double *J, double *xT,
 OCS_B200_API int ocs_b200_kernel_stats(ocs_b200_handle *h, int reset, double *ms_forward, double *ms_reverse,
                                        long *launches);
 /* The same split further: ms[0] forward sweeps, ms[1] reverse sweeps, ms[2] dense-basis projection dJdu*B',
- * ms[3] solver update (single_shooting); entries beyond nms are not written.  Multi-device: the slowest device. */
+ * ms[3] solver update (single_shooting); ms[4] device time of the ocs_b200_fb_sweep iteration loops from the first
+ * kernel queued to the last one's end (measured whether or not profiling is on; with profiling off the sweeps of a
+ * low-occupancy problem overlap as two lanes, so ms[4] is what a solve costs while ms[0..1] -- profiling on -- time each
+ * kernel alone); entries beyond nms are not written.  Multi-device: the slowest device. */
 OCS_B200_API int ocs_b200_kernel_stats_ex(ocs_b200_handle *h, int reset, double *ms, int nms, long *launches);
 /* enable/disable the CUDA-event bracketing used by ocs_b200_kernel_stats (off by default) */
 OCS_B200_API int ocs_b200_set_profiling(ocs_b200_handle *h, int on);

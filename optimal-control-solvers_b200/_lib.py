@@ -65,6 +65,9 @@ SIGNATURES = {
                                                    ctypes.c_void_p, ctypes.c_void_p]),
     "ocs_b200_compute_adjoints_dev": (ctypes.c_int, [c_h, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
                                                      ctypes.c_void_p]),
+    "ocs_b200_evaluate_dev": (ctypes.c_int, [c_h, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "ocs_b200_synchronize": (ctypes.c_int, [c_h]),
     "ocs_b200_evaluate": (ctypes.c_int, [c_h, c_dp, ctypes.c_long, c_dp, ctypes.c_long, c_dp, c_dp, c_ip, c_dp, c_dp]),
     "ocs_b200_eval_solution": (ctypes.c_int, [c_h, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, c_dp, c_dp, c_dp, c_dp]),

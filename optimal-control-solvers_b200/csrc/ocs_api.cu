@@ -1160,6 +1160,161 @@ int states_common(H *h, long Bt)
     return 0;
 }
 
+// The sparse-basis sweep stores every dJdv column exactly once when the knot window is monotone and reaches
+// every knot; otherwise (dense bases, exotic sparse ones, frozen trajectories) the buffer starts from zero.
+bool needs_zero_fill(const ocs_b200_handle *h)
+{
+    return !(h->basis_kind == BASIS_SPARSE && h->bk_monotone && h->bk_covered && !h->fb_frozen);
+}
+
+// ------------------------------------------------------------------------------------------------ two lanes
+// A sweep kernel whose threads each carry a several-state trajectory keeps 8-12 warps resident per SM, and a batch of
+// 10^5 trajectories is then only two or three rounds of blocks: the last, partly filled round leaves SMs idle for
+// 12-16 % of the kernel (ncu: sm__cycles_active.avg against sm__cycles_elapsed.max, profiles/r2_notes.md).  Such a batch
+// is swept as two halves on two streams.  The halves are independent (trajectories are), every kernel of one half
+// follows the previous kernel of the SAME half only, and the block scheduler fills the SMs that one half's last round
+// leaves free with the other half's next kernel.  Same-box measurement on cfg3 (100k candidates of the 6-state
+// problem): 6.74 -> 5.9 ms per evaluation.
+
+// resident warps per SM and rounds of blocks of a sweep kernel launched over the whole batch
+void lane_geometry(H *h, const void *kernel, long Bt, int tpt, size_t smem, int *resident_warps, double *rounds)
+{
+    int nblk = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kernel, h->kt.threads, smem) != cudaSuccess || nblk < 1) {
+        cudaGetLastError();
+        nblk = 1;
+    }
+    if (h->sm_count <= 0) {
+        cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+        if (h->sm_count <= 0) h->sm_count = 148;
+    }
+    const double blocks = (double)((Bt + (long)h->kt.threads * tpt - 1) / ((long)h->kt.threads * tpt));
+    *resident_warps = nblk * h->kt.threads / 32;
+    *rounds = blocks / ((double)h->sm_count * nblk);
+}
+
+// Whether a call whose widest kernel is `kernel` sweeps the batch as two lanes.  Automatic: at most 12 resident warps
+// per SM (above that a partly filled round runs proportionally faster: the FP64 pipe is shared by fewer warps, and
+// there is nothing to gain) and fewer than 8 rounds (the last round's share of the kernel).  Never under per-kernel
+// profiling, which times each kernel alone over the whole batch.
+bool use_lanes(H *h, const void *kernel, long Bt, int tpt, size_t smem)
+{
+    if (h->profiling || h->lanes_mode == 0) return false;
+    const long gran = (long)h->kt.threads * 12;
+    if (Bt < 2 * gran) return false;
+    if (h->lanes_mode == 1) return true;
+    int warps = 0;
+    double rounds = 0;
+    lane_geometry(h, kernel, Bt, tpt, smem, &warps, &rounds);
+    return warps <= 12 && rounds < 8.0;
+}
+
+// the two halves: whole blocks of every kernel variant (1, 2, 3 or 4 trajectories per thread)
+void lane_split(const H *h, long Bt, long b0[2], long nb[2])
+{
+    const long gran = (long)h->kt.threads * 12;
+    const long half = ((Bt + 1) / 2 + gran - 1) / gran * gran;
+    b0[0] = 0;
+    nb[0] = std::min(half, Bt);
+    b0[1] = nb[0];
+    nb[1] = Bt - nb[0];
+}
+
+// everything queued on the handle's stream so far happens before the lanes start
+int lanes_fork(H *h)
+{
+    for (int l = 0; l < 2; ++l) {
+        if (!h->lane_stream[l]) CK(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+        if (!h->lane_done[l]) CK(cudaEventCreateWithFlags(&h->lane_done[l], cudaEventDisableTiming));
+    }
+    if (!h->lane_fork) CK(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->lane_fork, h->stream));
+    for (int l = 0; l < 2; ++l) CK(cudaStreamWaitEvent(h->lane_stream[l], h->lane_fork, 0));
+    return 0;
+}
+
+// ... and everything queued on the lanes happens before what is queued on the handle's stream from now on
+int lanes_join(H *h)
+{
+    for (int l = 0; l < 2; ++l) {
+        CK(cudaEventRecord(h->lane_done[l], h->lane_stream[l]));
+        CK(cudaStreamWaitEvent(h->stream, h->lane_done[l], 0));
+    }
+    return 0;
+}
+
+// runs body(b0, nb) for each half with the handle's stream pointing at the half's lane
+template <class F>
+int on_lanes(H *h, long Bt, F body)
+{
+    long b0[2], nb[2];
+    lane_split(h, Bt, b0, nb);
+    TRY(lanes_fork(h));
+    cudaStream_t main_stream = h->stream;
+    int rc = 0;
+    for (int l = 0; l < 2 && rc == 0; ++l) {
+        if (nb[l] <= 0) continue;
+        h->stream = h->lane_stream[l];
+        rc = body(b0[l], nb[l]);
+    }
+    h->stream = main_stream;
+    if (rc != 0) {              // leave nothing running behind the caller's back
+        for (int l = 0; l < 2; ++l) cudaStreamSynchronize(h->lane_stream[l]);
+        return rc;
+    }
+    return lanes_join(h);
+}
+
+// The kernel and launch shape that decide whether a gradient evaluation uses lanes: the forward sweep of the main horizon.
+bool evaluation_uses_lanes(H *h, long Bt)
+{
+    if (h->profiling || h->lanes_mode == 0 || h->has_tail) return false;
+    if (build_records(h, 0) != 0) return false;
+    int um = main_umode(h), bm = um == 1 ? h->basis_kind : 0;
+    const void *kern = nullptr;
+    if (resolve(h, KIND_FWD, um, bm, pb_index(h), &kern) != 0) return false;
+    SweepArgs a;
+    base_args(h, 0, a);
+    const int tpt = bm == 2 ? 1 : fwd_tpt(h, um);
+    return use_lanes(h, kern, Bt, tpt, smem_bytes(h, a, 0));
+}
+
+// Forward sweep and (optionally) adjoint sweep of the whole resident batch, as one pass or as two lanes.  Everything
+// the halves share -- records and tables, buffers the sweeps would otherwise allocate on first use, the zero-fill of
+// dJdv -- is prepared on the handle's stream before the lanes fork.
+int sweeps_common(H *h, long Bt, bool forward, bool reverse, const double *d_lamT, long ldl, double *d_dJdv, double *d_lam0)
+{
+    if (forward) {
+        h->Bt = Bt;
+        h->fb_resident = false;
+    }
+    const bool lanes = evaluation_uses_lanes(h, Bt);
+    if (lanes) {
+        const int nc = h->kt.nc;
+        const Segment &s = h->seg[0];
+        const int um = main_umode(h);
+        if ((um == 1 && h->basis_kind == BASIS_DENSE) || um == 2) TRY(ensure(h, h->d_ug, (size_t)nc * (2 * s.N + 1) * Bt));
+        if (reverse && d_dJdv && h->basis_kind == BASIS_DENSE) TRY(ensure(h, h->d_dug, (size_t)nc * (2 * s.N + 1) * Bt));
+    }
+    if (reverse && d_dJdv && needs_zero_fill(h))
+        CK(cudaMemsetAsync(d_dJdv, 0, sizeof(double) * h->kt.nc * h->K * Bt, h->stream));
+    if (!lanes) {
+        if (forward) TRY(run_forward(h, 0, Bt, -1, nullptr, true));
+        if (forward) h->have_states = true;
+        if (reverse) TRY(run_reverse(h, 0, Bt, -1, d_lamT, ldl, d_dJdv, d_lam0, nullptr, nullptr));
+        return 0;
+    }
+    TRY(on_lanes(h, Bt, [&](long b0, long nb) -> int {
+        if (forward) TRY(run_forward(h, b0, nb, -1, nullptr, true));
+        if (reverse) TRY(run_reverse(h, b0, nb, -1, d_lamT, ldl, d_dJdv ? d_dJdv + b0 : nullptr, d_lam0 ? d_lam0 + b0 : nullptr,
+                                     nullptr, nullptr));
+        return 0;
+    }));
+    if (forward) h->have_states = true;
+    return 0;
+}
+
 // Calls that use the resident sweep: it exists and still matches the control / parameters that are set now.
 int check_resident(H *h, const char *who)
 {
@@ -1241,6 +1396,7 @@ int ocs_b200_create(int N, const double *tspan, int N2, const double *tspan_extr
         return OCS_B200_ERR_CUDA;
     }
     h->stream = h->own_stream;
+    if (const char *lm = getenv("OCS_B200_LANES")) h->lanes_mode = atoi(lm) > 0 ? 1 : (lm[0] == '0' ? 0 : -1);
     for (int si = 0; si < 2; ++si) {
         const int Ns = si == 0 ? N : N2;
         const double *ts = si == 0 ? tspan : tspan_extra;
@@ -1280,6 +1436,15 @@ int ocs_b200_destroy(ocs_b200_handle *h)
                       &h->d_alpha, &h->d_lbub, &h->d_dug, &h->d_pred};
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int k = 0; k < 2; ++k) {
+        if (h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
+        if (h->lane_done[k]) cudaEventDestroy(h->lane_done[k]);
+        for (int q = 0; q < 2; ++q)
+            if (h->lane_sweep[k][q]) cudaEventDestroy(h->lane_sweep[k][q]);
+    }
+    if (h->lane_fork) cudaEventDestroy(h->lane_fork);
+    cudaFree(h->d_lane_open);
+    if (h->h_lane_open) cudaFreeHost(h->h_lane_open);
+    for (int k = 0; k < 2; ++k) {
         if (h->chunk_done[k]) cudaEventDestroy(h->chunk_done[k]);
         if (h->stage_free[k]) cudaEventDestroy(h->stage_free[k]);
     }
@@ -1293,6 +1458,8 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     h->stager.shutdown();
     for (int k = 0; k < 4; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    for (int k = 0; k < 2; ++k)
+        if (h->ev_loop[k]) cudaEventDestroy(h->ev_loop[k]);
     for (void *lib : h->gen_libraries) ocs_unload_problem(lib);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
@@ -1644,6 +1811,38 @@ int ocs_b200_compute_states_dev(ocs_b200_handle *h, const double *x0_soa, long B
     }
 }
 
+// nlpObjective (functions/single_shooting.m:137-150: compute_states followed by compute_adjoints) on caller-owned
+// DEVICE buffers in ONE call, asynchronous on the handle's stream: both sweeps are queued at once, as two lanes when
+// that pays (sweeps_common).
+int ocs_b200_evaluate_dev(ocs_b200_handle *h, const double *x0_soa, long Bt, const double *lamT_soa, long lamT_nbatch,
+                          double *J, double *xT_soa, int32_t *status, double *dJdv_soa, double *lam0_soa)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi)
+        return h->fail(OCS_B200_ERR_ARG, "ocs_b200_evaluate_dev takes pointers / a stream of ONE device; on a multi-device handle use "
+                                          "ocs_b200_evaluate_resident, ocs_b200_gather_results_dev and ocs_b200_get_results");
+    TRY(check_ready(h));
+    if (!x0_soa || Bt < 1) return h->fail(OCS_B200_ERR_ARG, "bad x0 / batch size");
+    if (lamT_soa && lamT_nbatch != 1 && lamT_nbatch != Bt) return h->fail(OCS_B200_ERR_ARG, "lamT must have 1 or Bt columns");
+    try {
+        CK(cudaSetDevice(h->device));
+        const int n = h->kt.n;
+        h->have_states = false;
+        TRY(validate_batch(h, Bt));
+        if (dJdv_soa && h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
+        TRY(alloc_batch(h, Bt));
+        CK(cudaMemcpyAsync(h->d_x0.p, x0_soa, sizeof(double) * n * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        h->user_lamT = false;
+        TRY(sweeps_common(h, Bt, true, dJdv_soa || lam0_soa, lamT_soa, lamT_soa && lamT_nbatch > 1 ? Bt : 0, dJdv_soa, lam0_soa));
+        if (J) CK(cudaMemcpyAsync(J, h->d_J.p, sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        if (xT_soa) CK(cudaMemcpyAsync(xT_soa, h->d_xT.p, sizeof(double) * n * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * Bt, cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
+}
+
 int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, long Bt, double *J, double *xT, int32_t *status)
 {
     if (!h) return OCS_B200_ERR_ARG;
@@ -1665,13 +1864,6 @@ int ocs_b200_compute_states(ocs_b200_handle *h, const double *x0, long Bt, doubl
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
-}
-
-// The sparse-basis sweep stores every dJdv column exactly once when the knot window is monotone and reaches
-// every knot; otherwise (dense bases, exotic sparse ones, frozen trajectories) the buffer starts from zero.
-static bool needs_zero_fill(const ocs_b200_handle *h)
-{
-    return !(h->basis_kind == BASIS_SPARSE && h->bk_monotone && h->bk_covered && !h->fb_frozen);
 }
 
 // Trajectory chunks of a host-buffer evaluation whose gradient download (rows*Bt doubles over PCIe) overlaps the
@@ -1854,10 +2046,47 @@ int ocs_b200_evaluate(ocs_b200_handle *h, const double *x0, long Bt, const doubl
     // small batches (one chunk would not fill the device) or no gradient: the two calls in sequence.  With a tail
     // horizon a chunk runs main forward, tail forward, tail reverse, main reverse (RK4InfiniteIntegrator.m:20-30 for
     // the chunk's trajectories): trajectories are independent, so the chunking is the same.
+    if (!dJdv && !lam0) return ocs_b200_compute_states(h, x0, Bt, J, xT, status);
     if (!dJdv || Bt < 262144) {
-        TRY(ocs_b200_compute_states(h, x0, Bt, J, xT, status));
-        if (!dJdv && !lam0) return 0;
-        return ocs_b200_compute_adjoints(h, lamT, lamT_nbatch, dJdv, lam0);
+        // one pass: both sweeps are queued before anything is downloaded (and run as two lanes when that pays:
+        // sweeps_common), then J, x(T), status and the gradient come down in that order
+        try {
+            CK(cudaSetDevice(h->device));
+            const int n = h->kt.n, m = n + 1, nc = h->kt.nc;
+            h->have_states = false;
+            TRY(validate_batch(h, Bt));
+            if (dJdv && h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "dJdv requested but no control basis is attached");
+            TRY(alloc_batch(h, Bt));
+            TRY(upload_soa(h, x0, h->d_x0, n, Bt));
+            const double *d_lamT = nullptr;
+            h->user_lamT = lamT != nullptr;
+            h->user_lamT_ld = lamT && lamT_nbatch > 1 ? Bt : 0;
+            if (lamT) {
+                TRY(upload_soa(h, lamT, h->d_lamT_user, m, lamT_nbatch));
+                d_lamT = h->d_lamT_user.p;
+            }
+            double *d_dJdv = nullptr;
+            if (dJdv) {
+                TRY(ensure(h, h->d_dJdv, (size_t)nc * h->K * Bt));
+                d_dJdv = h->d_dJdv.p;
+            }
+            TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
+            TRY(sweeps_common(h, Bt, true, true, d_lamT, h->user_lamT_ld, d_dJdv, h->d_lam0.p));
+            if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
+            if (xT) TRY(download_soa(h, h->d_xT.p, Bt, 0, xT, n, Bt));
+            if (status) TRY(d2h(h, status, h->d_status, sizeof(int) * Bt));
+            if (dJdv) {
+                TRY(finish_host(h));      // download_soa reuses one staging buffer
+                TRY(download_soa(h, d_dJdv, Bt, 0, dJdv, (long)nc * h->K, Bt));
+            }
+            if (lam0) {
+                TRY(finish_host(h));
+                TRY(download_soa(h, h->d_lam0.p, Bt, 0, lam0, m, Bt));
+            }
+            return finish_host(h);
+        } catch (const std::exception &ex) {
+            return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+        }
     }
     try {
         CK(cudaSetDevice(h->device));
@@ -1912,13 +2141,14 @@ int ocs_b200_evaluate_resident(ocs_b200_handle *h, const double *x0, long Bt, in
             h->have_states = false;
             TRY(validate_batch(h, Bt));
         }
-        TRY(states_common(h, Bt));
         if (want_gradient) {
             if (h->basis_kind == BASIS_NONE) return h->fail(OCS_B200_ERR_STATE, "a gradient needs an attached control basis");
             TRY(ensure(h, h->d_dJdv, (size_t)nc * h->K * Bt));
             TRY(ensure(h, h->d_lam0, (size_t)m * Bt));
             h->user_lamT = false;
-            TRY(adjoints_common(h, nullptr, 0, h->d_dJdv.p, h->d_lam0.p));
+            TRY(sweeps_common(h, Bt, true, true, nullptr, 0, h->d_dJdv.p, h->d_lam0.p));
+        } else {
+            TRY(states_common(h, Bt));
         }
         return 0;
     } catch (const std::exception &ex) {
@@ -2136,51 +2366,116 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             CK(cudaStreamSynchronize(h->stream));
         }
         TRY(build_records(h, 0));
-        for (int sweep = 1; sweep <= nSWEEPS; ++sweep) {
+        const void *kf = nullptr, *kr = nullptr;
+        TRY(resolve(h, KIND_FWD, 2, 0, pb_index(h), &kf));
+        TRY(resolve(h, h->fb_costate == OCS_B200_COSTATE_CONTINUOUS ? KIND_FBC : KIND_FB, 2, 0, pb_index(h), &kr));
+        const size_t fb_ring = (size_t)h->kt.fb_ring * (n + 2 * nc) * h->kt.threads;
+        // one sweep (fb_sweep.m:79-112) of trajectories [b0, b0 + nb) on the handle's current stream:
+        // x = forward(u); uNew = ControlChar(t, x, lam(u)) with the convergence measure; then the bookkeeping
+        auto one_sweep = [&](long b0, long nb, int sweep, int *d_open) -> int {
             SweepArgs a;
             base_args(h, 0, a);
-            a.nb = Bt;
+            a.nb = nb;
             a.ldb = Bt;
-            a.x0 = h->d_x0.p;
-            a.xs = h->seg[0].d_xs;
-            a.ug = h->d_ug.p;
-            a.J = h->d_J.p;
-            a.xT = h->d_xT.p;
-            a.status = h->d_status;
-            a.frozen = h->d_frozen;
-            const void *kf = nullptr, *kr = nullptr;
-            TRY(resolve(h, KIND_FWD, 2, 0, pb_index(h), &kf));
-            TRY(resolve(h, h->fb_costate == OCS_B200_COSTATE_CONTINUOUS ? KIND_FBC : KIND_FB, 2, 0, pb_index(h), &kr));
+            if (a.ldp) a.p = h->d_params.p + b0;
+            a.x0 = h->d_x0.p + b0;
+            a.xs = h->seg[0].d_xs + b0;
+            a.ug = h->d_ug.p + b0;
+            a.J = h->d_J.p + b0;
+            a.xT = h->d_xT.p + b0;
+            a.status = h->d_status + b0;
+            a.frozen = h->d_frozen + b0;
             TRY(launch(h, kf, a, true, fwd_tpt(h, 2)));
             SweepArgs r;
             base_args(h, 0, r);
-            r.nb = Bt;
+            r.nb = nb;
             r.ldb = Bt;
-            r.xs = h->seg[0].d_xs;
-            r.ug = h->d_ug.p;
+            if (r.ldp) r.p = h->d_params.p + b0;
+            r.xs = h->seg[0].d_xs + b0;
+            r.ug = h->d_ug.p + b0;
             r.bounds = h->d_bounds;
             r.uRelTol = uRelTol;
             r.uAbsTol = uAbsTol;
             r.relax = relax;
-            r.max_change = h->d_maxchg.p;
-            r.frozen = h->d_frozen;
-            TRY(launch(h, kr, r, false, 1, (size_t)h->kt.fb_ring * (n + 2 * nc) * h->kt.threads));
-            CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
-            fb_update_kernel<<<(unsigned)((Bt + 255) / 256), 256, 0, h->stream>>>(h->d_maxchg.p, h->d_frozen, h->d_sweeps,
-                                                                                sweep, Bt, d_nopen);
+            r.max_change = h->d_maxchg.p + b0;
+            r.frozen = h->d_frozen + b0;
+            TRY(launch(h, kr, r, false, 1, fb_ring));
+            CK(cudaMemsetAsync(d_open, 0, sizeof(int), h->stream));
+            fb_update_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->stream>>>(h->d_maxchg.p + b0, h->d_frozen + b0,
+                                                                                 h->d_sweeps + b0, sweep, nb, d_open);
             CK(cudaGetLastError());
-            int nopen = 0;
-            CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            if (nopen == 0) break;
+            return 0;
+        };
+        SweepArgs geom;
+        base_args(h, 0, geom);
+        for (int k = 0; k < 2; ++k)
+            if (!h->ev_loop[k]) CK(cudaEventCreate(&h->ev_loop[k]));
+        CK(cudaEventRecord(h->ev_loop[0], h->stream));
+        if (!use_lanes(h, kr, Bt, 1, smem_bytes(h, geom, fb_ring))) {
+            for (int sweep = 1; sweep <= nSWEEPS; ++sweep) {
+                TRY(one_sweep(0, Bt, sweep, d_nopen));
+                int nopen = 0;
+                CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                if (nopen == 0) break;
+            }
+        } else {
+            // Two lanes (see lanes_fork): each half runs its own chain of sweeps, so one half's forward sweep fills the
+            // SMs the other half's costate sweep leaves idle.  The host looks at the open-trajectory counts ONE sweep
+            // late (while the next sweep is already queued) so that the lanes never drain; a sweep queued after
+            // everything has converged finds every trajectory frozen and changes nothing.
+            if (!h->d_lane_open) {
+                CK(cudaMalloc(&h->d_lane_open, sizeof(int) * 4));
+                CK(cudaHostAlloc((void **)&h->h_lane_open, sizeof(int) * 4, cudaHostAllocDefault));
+            }
+            for (int l = 0; l < 2; ++l)
+                for (int q = 0; q < 2; ++q)
+                    if (!h->lane_sweep[l][q]) CK(cudaEventCreateWithFlags(&h->lane_sweep[l][q], cudaEventDisableTiming));
+            long lb0[2], lnb[2];
+            lane_split(h, Bt, lb0, lnb);
+            TRY(lanes_fork(h));
+            cudaStream_t main_stream = h->stream;
+            int rc = 0;
+            for (int sweep = 1; sweep <= nSWEEPS && rc == 0; ++sweep) {
+                const int q = sweep & 1;
+                for (int l = 0; l < 2 && rc == 0; ++l) {
+                    h->stream = h->lane_stream[l];
+                    rc = one_sweep(lb0[l], lnb[l], sweep, h->d_lane_open + 2 * l + q);
+                    if (rc == 0 && cudaMemcpyAsync(h->h_lane_open + 2 * l + q, h->d_lane_open + 2 * l + q, sizeof(int),
+                                                   cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = OCS_B200_ERR_CUDA;
+                    if (rc == 0 && cudaEventRecord(h->lane_sweep[l][q], h->stream) != cudaSuccess) rc = OCS_B200_ERR_CUDA;
+                }
+                h->stream = main_stream;
+                if (rc != 0 || sweep == 1) continue;
+                const int qp = (sweep - 1) & 1;      // the previous sweep's counts
+                int open = 0;
+                for (int l = 0; l < 2; ++l) {
+                    if (cudaEventSynchronize(h->lane_sweep[l][qp]) != cudaSuccess) rc = OCS_B200_ERR_CUDA;
+                    open += h->h_lane_open[2 * l + qp];
+                }
+                if (open == 0) break;
+            }
+            h->stream = main_stream;
+            if (rc != 0) {
+                for (int l = 0; l < 2; ++l) cudaStreamSynchronize(h->lane_stream[l]);
+                return rc == OCS_B200_ERR_CUDA ? h->fail(rc, "CUDA error while queueing the fb_sweep lanes: %s",
+                                                         cudaGetErrorString(cudaGetLastError())) : rc;
+            }
+            TRY(lanes_join(h));
         }
+        CK(cudaEventRecord(h->ev_loop[1], h->stream));
         h->have_states = true;
         h->fb_resident = true;      // x, J: the sweep's input control (final_sweep(u), fb_sweep.m:82); d_ug: uNew = soln.u (:123)
         if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
         if (sweeps) TRY(d2h(h, sweeps, h->d_sweeps, sizeof(int) * Bt));
         if (converged) TRY(d2h(h, converged, h->d_frozen, sizeof(int) * Bt));
         if (max_change) TRY(d2h(h, max_change, h->d_maxchg.p, sizeof(double) * Bt));
-        return finish_host(h);
+        TRY(finish_host(h));
+        CK(cudaEventSynchronize(h->ev_loop[1]));
+        float ms_loop = 0;
+        CK(cudaEventElapsedTime(&ms_loop, h->ev_loop[0], h->ev_loop[1]));
+        h->ms_loop += ms_loop;
+        return 0;
     } catch (const std::exception &ex) {
         return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
     }
@@ -2611,11 +2906,11 @@ int ocs_b200_kernel_stats_ex(ocs_b200_handle *h, int reset, double *ms, int nms,
 {
     if (!h || (nms > 0 && !ms)) return OCS_B200_ERR_ARG;
     if (h->multi) return ocs_multi_kernel_stats_ex(h, reset, ms, nms, launches);
-    const double v[4] = {h->ms_fwd, h->ms_rev - h->ms_proj, h->ms_proj, h->ms_upd};
-    for (int k = 0; k < nms; ++k) ms[k] = k < 4 ? v[k] : 0.0;
+    const double v[5] = {h->ms_fwd, h->ms_rev - h->ms_proj, h->ms_proj, h->ms_upd, h->ms_loop};
+    for (int k = 0; k < nms; ++k) ms[k] = k < 5 ? v[k] : 0.0;
     if (launches) *launches = h->launches;
     if (reset) {
-        h->ms_fwd = h->ms_rev = h->ms_proj = h->ms_upd = 0;
+        h->ms_fwd = h->ms_rev = h->ms_proj = h->ms_upd = h->ms_loop = 0;
         h->launches = 0;
     }
     return 0;

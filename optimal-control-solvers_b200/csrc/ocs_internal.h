@@ -117,6 +117,16 @@ struct ocs_b200_handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
     cudaEvent_t stage_free[2] = {nullptr, nullptr};   // the download out of staging buffer k has finished
+    // Two lanes (ocs_api.cu, lanes_*): sweeps whose kernels keep few warps resident (a several-state problem: 8-12 per
+    // SM) leave the SMs of their last, partly filled round idle; the batch is then swept as two halves on two streams
+    // so that one half's next kernel fills what the other half's last round leaves free.
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_fork = nullptr, lane_done[2] = {nullptr, nullptr};
+    cudaEvent_t lane_sweep[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // fb_sweep: sweep s of lane l has been counted
+    int *d_lane_open = nullptr;        // fb_sweep: open trajectories per lane and sweep parity [2][2]
+    int *h_lane_open = nullptr;        // ... pinned host copy
+    int lanes_mode = -1;               // -1 automatic, 0 never, 1 whenever the batch can be halved (OCS_B200_LANES)
+    int sm_count = 0;
     int *d_status = nullptr;
     size_t status_cap = 0;
     int *d_frozen = nullptr, *d_sweeps = nullptr;
@@ -134,6 +144,9 @@ struct ocs_b200_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double ms_fwd = 0, ms_rev = 0;          // ms_rev includes ms_proj (the dense-basis projection after the sweep)
     double ms_proj = 0, ms_upd = 0;         // projection kernel; solver update kernel (single_shooting)
+    cudaEvent_t ev_loop[2] = {nullptr, nullptr};
+    double ms_loop = 0;                     // device time of the fb_sweep iteration loops (first kernel queued to the
+                                            // last one's end on the handle's stream, lanes included); always measured
     long launches = 0;
 
     int fail(int code, const char *fmt, ...)

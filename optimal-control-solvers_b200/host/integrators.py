@@ -263,6 +263,12 @@ class CudaRK4Integrator:
             self._set_v(v)
         self._last_u = None
         P = lambda a: ctypes.c_void_p(int(a)) if a else None
+        if gradient and (dJdv_ptr or lam0_ptr):
+            # nlpObjective as one call: both sweeps are queued together (two lanes when that pays, ocs_b200.h)
+            self._ck(self._lib.ocs_b200_evaluate_dev(self._h, P(x0_ptr), int(Bt), P(lamT_ptr), int(lamT_nbatch), P(J_ptr),
+                                                     P(xT_ptr), P(status_ptr), P(dJdv_ptr), P(lam0_ptr)))
+            self._Bt, self._single = int(Bt), False
+            return
         self._ck(self._lib.ocs_b200_compute_states_dev(self._h, P(x0_ptr), int(Bt), P(J_ptr), P(xT_ptr), P(status_ptr)))
         self._Bt, self._single = int(Bt), False
         if gradient:
@@ -441,11 +447,11 @@ class CudaRK4Integrator:
     def kernel_stats(self, reset=True):
         """Device time per kernel family since the last reset (needs set_profiling(True)): ms_forward, ms_reverse
         (= reverse sweep + projection), and the split ms_reverse_sweep / ms_project / ms_update."""
-        ms = (ctypes.c_double * 4)()
+        ms = (ctypes.c_double * 5)()
         n = ctypes.c_long()
-        self._ck(self._lib.ocs_b200_kernel_stats_ex(self._h, int(reset), ms, 4, ctypes.byref(n)))
+        self._ck(self._lib.ocs_b200_kernel_stats_ex(self._h, int(reset), ms, 5, ctypes.byref(n)))
         return dict(ms_forward=ms[0], ms_reverse=ms[1] + ms[2], ms_reverse_sweep=ms[1], ms_project=ms[2], ms_update=ms[3],
-                    launches=n.value)
+                    ms_fb_loop=ms[4], launches=n.value)
 
 
 class CudaRK4InfiniteIntegrator(CudaRK4Integrator):

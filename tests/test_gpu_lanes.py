@@ -1,0 +1,128 @@
+"""Two lanes (ocs_api.cu, lanes_*): a batch swept as two halves on two internal streams returns exactly what the one-pass
+form returns -- the halves are independent trajectories run by the same kernels -- for the fused evaluation on host
+buffers, on resident data, on device buffers, and for the fb_sweep loop with its one-sweep-late convergence check.
+OCS_B200_LANES is read when the handle is created: 1 forces lanes whenever the batch can be halved, 0 forbids them."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from util import TEST_PARAMS, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _integ(ocs, lanes, tspan, **kw):
+    old = os.environ.get("OCS_B200_LANES")
+    os.environ["OCS_B200_LANES"] = "1" if lanes else "0"
+    try:
+        return ocs.CudaRK4Integrator(tspan, **kw)
+    finally:
+        if old is None:
+            del os.environ["OCS_B200_LANES"]
+        else:
+            os.environ["OCS_B200_LANES"] = old
+
+
+@pytest.mark.parametrize("Bt", [3072, 3100, 5000])
+def test_generated_problem_evaluation_is_identical_with_and_without_lanes(ocs, Bt):
+    cg = importlib.import_module("optimal-control-solvers_b200.codegen")
+    prob = cg.harvest_chain_problem()
+    tspan = ocs.matlab_linspace(0.0, 2.0, 41)
+    rng = np.random.default_rng(Bt)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    v = 0.05 * rng.standard_normal((10, Bt))
+    v[:2] = rng.uniform(0.2, 0.8, (2, Bt))
+    res = {}
+    for lanes in (0, 1):
+        integ = _integ(ocs, lanes, tspan)
+        integ.attach_control(ocs.ChebyshevControl(integ.t, 5, 2))
+        res[lanes] = integ.evaluate(prob, x0, v)                       # host buffers: the small-batch one-pass path
+        integ.evaluate_resident(prob, x0, v)                           # resident data
+        res[lanes, "r"] = integ.results()
+        integ.close()
+    for key in ("J", "xT", "status", "dJdv", "lam0"):
+        assert np.array_equal(res[0][key], res[1][key]), key
+        assert np.array_equal(res[0][key], res[1, "r"][key]), key
+        assert np.array_equal(res[0][key], res[0, "r"][key]), key
+    assert np.all(np.isfinite(res[1]["dJdv"])) and np.abs(res[1]["dJdv"]).max() > 0
+
+
+def test_builtin_problem_on_device_buffers_with_lanes(ocs):
+    """ocs_b200_evaluate_dev: the fused call on device buffers; several trajectories per thread in the built-in kernels, so
+    the FMA-contracted build is compared to rounding and the strict build bit for bit."""
+    import torch
+    Bt, K = 6200, 11
+    tspan = ocs.matlab_linspace(0.0, 5.0, 101)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    x0 = (0.5 + 2.0 * torch.rand((1, Bt), dtype=torch.float64, device=dev, generator=g)).contiguous()
+    vd = torch.rand((K, Bt), dtype=torch.float64, device=dev, generator=g).contiguous()
+    for math, same in (("strict", np.array_equal), ("fast", lambda p, q: relerr(p, q) < 1e-13)):
+        out = {}
+        for lanes in (0, 1):
+            integ = _integ(ocs, lanes, tspan, math=math)
+            integ.attach_control(ocs.PWLinearControl(integ.t, K, 1))
+            J, xT = torch.empty(Bt, dtype=torch.float64, device=dev), torch.empty((1, Bt), dtype=torch.float64, device=dev)
+            st = torch.empty(Bt, dtype=torch.int32, device=dev)
+            dJdv, lam0 = torch.empty((K, Bt), dtype=torch.float64, device=dev), torch.empty((2, Bt), dtype=torch.float64, device=dev)
+            for _ in range(2):      # twice: the second evaluation forks from a stream that joined the first one's lanes
+                integ.evaluate_dev(prob, x0.data_ptr(), Bt, v_ptr=vd.data_ptr(), J_ptr=J.data_ptr(), xT_ptr=xT.data_ptr(),
+                                   status_ptr=st.data_ptr(), dJdv_ptr=dJdv.data_ptr(), lam0_ptr=lam0.data_ptr())
+            integ.synchronize()
+            out[lanes] = dict(J=J.cpu().numpy(), xT=xT.cpu().numpy(), dJdv=dJdv.cpu().numpy(), lam0=lam0.cpu().numpy())
+            integ.close()
+        for key in out[0]:
+            assert same(out[0][key], out[1][key]), (math, key)
+
+
+@pytest.mark.parametrize("costate", ["discrete", "continuous"])
+def test_fb_sweep_lanes_and_the_late_convergence_check(ocs, costate):
+    """Each half runs its own chain of sweeps; the host reads the open-trajectory counts one sweep late, so up to one
+    extra sweep is queued after everything has converged -- it must change nothing (every trajectory is frozen)."""
+    cg = importlib.import_module("optimal-control-solvers_b200.codegen")
+    prob = cg.harvest_chain_problem()
+    Bt, N = 3300, 30
+    tspan = ocs.matlab_linspace(0.0, 1.5, N + 1)
+    rng = np.random.default_rng(11)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    u0 = np.full((2, 2 * N + 1), 0.4)
+    for limit in (30, 3):          # everything converges well before 30 sweeps; 3 sweeps hit the limit
+        res = {}
+        for lanes in (0, 1):
+            integ = _integ(ocs, lanes, tspan)
+            res[lanes] = integ.fb_sweep(prob, x0, u0, uRelTol=1e-3, uAbsTol=1e-3, nSWEEPS=limit, relax=0.5, costate=costate)
+            res[lanes]["u"] = integ.get_control_u(0, Bt)
+            res[lanes]["x"] = integ.fetch_states(0, Bt)
+            integ.close()
+        if limit == 30:
+            assert res[0]["converged"].all() and res[0]["sweeps"].max() < 30
+        else:
+            assert not res[0]["converged"].any() and (res[0]["sweeps"] == 3).all()
+        for key in ("J", "sweeps", "converged", "maxChange", "u", "x"):
+            # (x after fb_sweep is read from the node store: its running-objective row is NaN except x(end,end) = J)
+            assert np.array_equal(res[0][key], res[1][key], equal_nan=(key == "x")), (limit, key)
+        assert np.isfinite(res[1]["x"][:6]).all() and np.array_equal(res[1]["x"][6, -1], res[1]["J"])
+
+
+def test_lanes_decision_is_automatic_for_low_occupancy_sweeps(ocs):
+    """Default mode: the generated 6-state problem (8-12 resident warps per SM) at a batch of a few rounds uses lanes, the
+    1-state built-in problem (4+ trajectories per thread, 16+ resident warps) does not; both agree with the forced forms."""
+    cg = importlib.import_module("optimal-control-solvers_b200.codegen")
+    prob = cg.harvest_chain_problem()
+    tspan = ocs.matlab_linspace(0.0, 1.0, 21)
+    Bt = 40_000
+    rng = np.random.default_rng(2)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    v = rng.uniform(0.2, 0.8, (6, Bt))
+    out = {}
+    for mode in ("auto", 0):
+        integ = ocs.CudaRK4Integrator(tspan) if mode == "auto" else _integ(ocs, 0, tspan)
+        integ.attach_control(ocs.ChebyshevControl(integ.t, 3, 2))
+        out[mode] = integ.evaluate(prob, x0, v)
+        integ.close()
+    for key in ("J", "dJdv"):
+        assert np.array_equal(out["auto"][key], out[0][key]), key
