@@ -109,10 +109,14 @@ int ocs_compile_unit(const char *source, const char *unit, int strict, const cha
     // Sweep-kernel tuning by problem size (B200, profiles/r2_notes.md).  A problem with several states carries
     // 150+ live registers per trajectory, so only 8-12 warps are resident per SM: nothing hides a global-load
     // latency.  Its per-step loads therefore go through a cp.async ring 4 steps ahead, the reverse step loop is not
-    // unrolled (fewer live values) and the kernels are capped at 168 registers (3 blocks of 128 threads per SM).
+    // unrolled (fewer live values) and the kernels are capped at 168 registers (12 resident warps) except the two
+    // gradient/costate sweeps over a per-trajectory control grid, which spill below ~220 (8 warps).  Blocks are 64
+    // threads with 16-step record tiles: with so few rounds of blocks per kernel (10^5 trajectories are 2-3) the last
+    // round is filled in finer units (alone-kernel times -3 %; same-box A/B r2j/r2p).
     if (n_states >= 4) {
-        src += "#define OCS_REV_UNROLL 1\n#define OCS_RING 4\n#define OCS_FB_RING 4\n"
-               "#define OCS_MINBLOCKS_REV 3\n#define OCS_MINBLOCKS_FWD 3\n#define OCS_MINBLOCKS_FB 3\n";
+        src += "#define OCS_THREADS 64\n#define OCS_TILE 16\n#define OCS_REV_UNROLL 1\n#define OCS_RING 4\n#define OCS_FB_RING 4\n"
+               "#define OCS_MINBLOCKS_REV 6\n#define OCS_MINBLOCKS_FWD 6\n#define OCS_MINBLOCKS_FB 4\n"
+               "#define OCS_LB_FWD_DENSE 6\n#define OCS_LB_REV_GRID 4\n#define OCS_LB_FWD_GRID 8\n";
     }
     // kernel tuning experiments: OCS_B200_NVRTC_DEFS="OCS_MINBLOCKS_REV=3;OCS_TPT_FWD=2" -> #define lines
     if (const char *defs = getenv("OCS_B200_NVRTC_DEFS")) {

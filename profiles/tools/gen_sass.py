@@ -9,9 +9,10 @@ unit = sys.argv[1]
 extra = sys.argv[2:]
 prob = getattr(ocs, os.environ.get("PROB", "harvest_chain_problem"))()
 pre = "#define OCS_NS ocs_gen\n"
-if prob.nStates >= 4:
-    pre += ("#define OCS_REV_UNROLL 1\n#define OCS_RING 4\n#define OCS_FB_RING 4\n"
-            "#define OCS_MINBLOCKS_REV 3\n#define OCS_MINBLOCKS_FWD 3\n#define OCS_MINBLOCKS_FB 3\n")
+if prob.nStates >= 4:       # csrc/nvrtc_problem.cu, ocs_compile_unit
+    pre += ("#define OCS_THREADS 64\n#define OCS_TILE 16\n#define OCS_REV_UNROLL 1\n#define OCS_RING 4\n#define OCS_FB_RING 4\n"
+            "#define OCS_MINBLOCKS_REV 6\n#define OCS_MINBLOCKS_FWD 6\n#define OCS_MINBLOCKS_FB 4\n"
+            "#define OCS_LB_FWD_DENSE 6\n#define OCS_LB_REV_GRID 4\n#define OCS_LB_FWD_GRID 8\n")
 for d in extra:
     if d.startswith("-D"):
         k, _, v = d[2:].partition("=")

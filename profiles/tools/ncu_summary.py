@@ -12,7 +12,12 @@ KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed.sum', 'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum',
         'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
-        'sm__cycles_active.avg', 'sm__cycles_elapsed.avg']
+        'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum',
+        'sm__cycles_active.avg', 'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.max']
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 for r in rows[2:]:
