@@ -243,6 +243,26 @@ OCS_B200_API int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, 
                                           const double *free_ub, int max_iter, double tol,
                                           double *v_opt, double *J, int32_t *iters, int32_t *converged);
 
+/* Linear constraints of the batched solve (functions/single_shooting.m:106-111: [A, b] = control.compute_lincon(
+ * prob.ControlBounds), fmincon(..., A, b, ...)).  The reference's PW controls need none (their coefficient box bounds
+ * u(t), compute_nlp_bounds) and its ChebyshevControl left compute_lincon empty (Control/ChebyshevControl.m:51-53) although
+ * a box on Chebyshev coefficients does not bound u(t).  The finished constraint is ControlBounds at every grid point,
+ *     lb_c <= (reshape(v, nc, []) * B)(c, j) <= ub_c      i.e.  A = [kron(B', I); -kron(B', I)],  b = [ub; -lb],
+ * and that is what this switches on for the solves of a handle with a dense (Chebyshev) basis: an augmented-Lagrangian
+ * outer iteration (Powell-Hestenes-Rockafellar multipliers per grid value and trajectory, penalty parameter rho0, raised fourfold
+ * whenever a round does not cut the largest violation to a quarter, at most max_outer rounds) around the projected-gradient solve; the penalty and its gradient are applied on
+ * the control and dJdu grids the dense-basis gradient path holds anyway, before dJdu is projected onto B.  Trajectories
+ * are finished when their projected gradient meets tol AND their largest bound violation is <= feas_tol.
+ *   bounds [nc x 2] column-major ControlBounds (nc must equal the problem's control count when the solve runs), or
+ *   NULL to switch the constraints off
+ *   rho0, feas_tol, max_outer: <= 0 selects 100, 1e-4, 12.  The inner problems of an augmented Lagrangian are
+ *   ill-conditioned for a first-order method: expect 10^4 evaluations per solve where the unconstrained solve takes 10^1-10^2.
+ * ocs_b200_get_solve_violation: the largest violation per trajectory [Bt] after such a solve.  The reported J is the
+ * objective alone (no penalty term). */
+OCS_B200_API int ocs_b200_set_solve_control_bounds(ocs_b200_handle *h, const double *bounds, int nc, double rho0,
+                                                   double feas_tol, int max_outer);
+OCS_B200_API int ocs_b200_get_solve_violation(ocs_b200_handle *h, double *viol);
+
 /* The `soln` struct of the reference, evaluated on the device for trajectories [b0, b0+nb) at the query
  * times tq[nq]:
  *   x   [n  x nq x nb] = vectorInterpolant(tspan, xOpt(1:end-1,:), 'pchip')(tq)     functions/single_shooting.m:129

@@ -58,6 +58,8 @@ SIGNATURES = {
                                          ctypes.c_double, ctypes.c_int, ctypes.c_double, c_dp, c_ip, c_ip, c_dp]),
     "ocs_b200_single_shooting": (ctypes.c_int, [c_h, c_dp, ctypes.c_long, c_dp, ctypes.c_long, c_dp, c_dp, ctypes.c_int,
                                                 c_ip, c_dp, c_dp, ctypes.c_int, ctypes.c_double, c_dp, c_dp, c_ip, c_ip]),
+    "ocs_b200_set_solve_control_bounds": (ctypes.c_int, [c_h, c_dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    "ocs_b200_get_solve_violation": (ctypes.c_int, [c_h, c_dp]),
     "ocs_b200_reduce_J": (ctypes.c_int, [c_h, ctypes.c_int, c_dp, c_lp]),
     "ocs_b200_set_stream": (ctypes.c_int, [c_h, ctypes.c_void_p]),
     "ocs_b200_set_control_v_dev": (ctypes.c_int, [c_h, ctypes.c_void_p, ctypes.c_long]),

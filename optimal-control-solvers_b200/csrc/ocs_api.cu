@@ -444,6 +444,74 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
     }
 }
 
+// ControlBounds on the grid as constraints of the batched solve (functions/single_shooting.m:106-111: A v <= b from
+// control.compute_lincon(prob.ControlBounds); for a dense basis A = [kron(B', I); -kron(B', I)], b = [ub; -lb], i.e.
+// lb_c <= u_c(t_j) <= ub_c at every grid point).  Augmented Lagrangian (Powell-Hestenes-Rockafellar): the evaluation
+// adds  psi = ( max(0, mu+ + rho (u - ub))^2 - mu+^2 + max(0, mu- + rho (lb - u))^2 - mu-^2 ) / (2 rho)  per grid
+// value to J and  max(0, mu+ + rho (u - ub)) - max(0, mu- + rho (lb - u))  to dJdu, on the two SoA grids the
+// dense-basis gradient path materialises anyway (u from the forward sweep, dJdu before its projection onto B).
+// One thread per trajectory: every access is coalesced across the warp.
+__global__ void __launch_bounds__(128) cgb_penalty_kernel(const double *__restrict__ ug, double *__restrict__ dug,
+                                                          const double *__restrict__ mu, const double *__restrict__ lohi,
+                                                          double rho, int nc, int G, long nb, long ldb, double *J,
+                                                          const int *frozen)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb || (frozen && frozen[b])) return;
+    const double half_inv = 0.5 / rho;
+    double P = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        const double lo = lohi[2 * c], hi = lohi[2 * c + 1];
+        const double *up = ug + (size_t)c * G * ldb + b, *mp = mu + (size_t)c * G * ldb + b,
+                     *mm = mu + (size_t)(nc + c) * G * ldb + b;
+        double *dp = dug + (size_t)c * G * ldb + b;
+        for (int j = 0; j < G; ++j) {
+            const size_t o = (size_t)j * ldb;
+            const double u = up[o], a = mp[o], d = mm[o];
+            const double tp = fmax(0.0, a + rho * (u - hi)), tm = fmax(0.0, d + rho * (lo - u));
+            P += half_inv * ((tp * tp - a * a) + (tm * tm - d * d));
+            if (tp != 0.0 || tm != 0.0) dp[o] += tp - tm;
+        }
+    }
+    J[b] += P;
+}
+
+// End of an outer iteration: multipliers mu <- max(0, mu + rho (u - ub)) (and the lower twin) at the accepted points,
+// the largest bound violation per trajectory, and trajectories that still violate the bounds are reopened.
+__global__ void __launch_bounds__(128) cgb_update_kernel(const double *__restrict__ ug, double *__restrict__ mu,
+                                                         const double *__restrict__ lohi, double rho, int nc, int G, long nb,
+                                                         long ldb, double *viol, int *frozen, double feas_tol, int *n_reopened,
+                                                         unsigned long long *worst_bits)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int reopened = 0;
+    if (b < nb) {
+        double worst = 0.0;
+        for (int c = 0; c < nc; ++c) {
+            const double lo = lohi[2 * c], hi = lohi[2 * c + 1];
+            const double *up = ug + (size_t)c * G * ldb + b;
+            double *mp = mu + (size_t)c * G * ldb + b, *mm = mu + (size_t)(nc + c) * G * ldb + b;
+            for (int j = 0; j < G; ++j) {
+                const size_t o = (size_t)j * ldb;
+                const double u = up[o];
+                worst = fmax(worst, fmax(u - hi, lo - u));
+                mp[o] = fmax(0.0, mp[o] + rho * (u - hi));
+                mm[o] = fmax(0.0, mm[o] + rho * (lo - u));
+            }
+        }
+        viol[b] = worst;
+        if (isfinite(worst)) atomicMax(worst_bits, (unsigned long long)__double_as_longlong(worst));   // worst >= 0: the bit pattern is monotone
+        if (worst > feas_tol && frozen[b] != 0) {      // (not finite J etc. never freeze as converged: left alone)
+            frozen[b] = 0;
+            reopened = 1;
+        } else if (worst > feas_tol) {
+            reopened = 1;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, reopened);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_reopened, __popc(bal));
+}
+
 // dJdv = dJdu * B' for a dense basis (ChebyshevControl.m:34-37):
 // dug [nc][G][ldb] (SoA, written by the reverse sweep), basrec [G][BW] = B(:,j), dJdv [(k*nc+c)][ldb].
 // HBM-bound (every dJdu value is read once, K FMAs each), so what matters is bytes in flight and shared-memory
@@ -1065,6 +1133,13 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         }
         if (project) {
             const int G = 2 * s.N + 1;
+            if (h->cgb_active) {       // grid control bounds of the solve: dJdu += d(penalty)/du, J += penalty
+                cgb_penalty_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, h->stream>>>(
+                    a.ug, a.dug, h->d_cgb_mu.p + b0, h->d_cgb_b.p, h->cgb_rho, h->kt.nc, G, nb, Bt, h->d_J.p + b0,
+                    h->fb_frozen ? h->fb_frozen + b0 : nullptr);
+                CK(cudaGetLastError());
+                h->launches++;
+            }
             if (h->profiling) CK(cudaEventRecord(h->ev[2], h->stream));
             // K <= 18: one pass with 18 accumulators per stream; larger K in chunks of 16.  Two controls per thread when
             // the problem has them (the B row read from shared memory then feeds twice the FMAs)
@@ -1433,7 +1508,7 @@ int ocs_b200_destroy(ocs_b200_handle *h)
     DevBuf *bufs[] = {&h->d_params, &h->d_v,    &h->d_ug,    &h->d_x0,     &h->d_J,     &h->d_xT,   &h->d_lamT_tail,
                       &h->d_lamT_user, &h->d_dJdv, &h->d_lam0, &h->d_stage, &h->d_stage2, &h->d_maxchg,
                       &h->d_pipe[0], &h->d_pipe[1], &h->d_z, &h->d_g, &h->d_zt, &h->d_gt, &h->d_Jacc, &h->d_Jhist,
-                      &h->d_alpha, &h->d_lbub, &h->d_dug, &h->d_pred};
+                      &h->d_alpha, &h->d_lbub, &h->d_dug, &h->d_pred, &h->d_cgb_mu, &h->d_cgb_b, &h->d_cgb_viol};
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int k = 0; k < 2; ++k) {
         if (h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
@@ -2770,7 +2845,29 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         h->ctrl_nbatch = Bt;
         h->seg[0].records_dirty = true;
         const bool spg_serial = nz > 512 || getenv("OCS_B200_SPG_SERIAL") != nullptr;   // (the env switch is for the A/B test)
-        for (int iter = 0; iter < max_iter; ++iter) {
+        // ControlBounds on the grid (ocs_b200_set_solve_control_bounds): an outer augmented-Lagrangian iteration around
+        // the projected-gradient solve.  Only the dense-basis gradient path has the two grids the penalty works on;
+        // a sparse basis bounds u(t) through the coefficient box already (compute_nlp_bounds).
+        const bool cgb = h->cgb_on && h->basis_kind == BASIS_DENSE && !h->has_tail;
+        const int G0 = 2 * h->seg[0].N + 1;
+        if (cgb) {
+            if ((int)h->cgb_bounds.size() != 2 * nc) return h->fail(OCS_B200_ERR_ARG, "solve control bounds do not match the problem's controls");
+            TRY(ensure(h, h->d_cgb_mu, 2 * (size_t)nc * G0 * Bt));
+            TRY(ensure(h, h->d_cgb_b, 2 * (size_t)nc + 1));      // [nc][lo, hi] and the batch's largest violation
+            TRY(ensure(h, h->d_cgb_viol, (size_t)Bt));
+            CK(cudaMemsetAsync(h->d_cgb_mu.p, 0, sizeof(double) * 2 * nc * G0 * Bt, h->stream));
+            CK(cudaMemcpyAsync(h->d_cgb_b.p, h->cgb_bounds.data(), sizeof(double) * 2 * nc, cudaMemcpyHostToDevice, h->stream));
+            h->cgb_rho = h->cgb_rho0;
+        }
+        struct ActiveGuard {       // the penalty is part of this call's evaluations only
+            ocs_b200_handle *h;
+            ~ActiveGuard() { h->cgb_active = false; h->fb_frozen = nullptr; }
+        } guard{h};
+        h->cgb_active = cgb;
+        double cgb_worst_prev = INFINITY;
+        int iter = 0;
+        for (int outer = 0; outer < (cgb ? h->cgb_outer : 1) && iter < max_iter; ++outer) {
+        for (int inner = 0; iter < max_iter; ++iter, ++inner) {
             for (int f = 0; f < nfree; ++f)      // x0(FreeInitStates) = v(end-nFREE_STATES+1:end)   single_shooting.m:145
                 CK(cudaMemcpyAsync(h->d_x0.p + (size_t)free_states[f] * Bt, h->d_zt.p + (size_t)(nv + f) * Bt,
                                    sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
@@ -2806,15 +2903,15 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                 if (spg_serial) {
                     spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
-                        h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+                        h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);
                 } else if (Gk <= 16) {
                     spg_update_split_kernel<16, 512><<<grd, blk, sm, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
-                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);
                 } else {
                     spg_update_split_kernel<16, 1024><<<grd, blk, sm, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
-                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, iter == 0, d_nopen);
+                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);
                 }
             }
             h->launches++;
@@ -2829,15 +2926,40 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
             int nopen = 0;
             CK(cudaMemcpyAsync(&nopen, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
-            if (nopen == 0) break;
+            if (nopen == 0) {
+                ++iter;
+                break;
+            }
         }
         // leave the device state at the minimisers: one last evaluation of the accepted points (zt == z for
-        // frozen trajectories; the others get their best accepted point)
+        // frozen trajectories; the others get their best accepted point) -- J without any penalty term
         CK(cudaMemcpyAsync(h->d_zt.p, h->d_z.p, sizeof(double) * nz * Bt, cudaMemcpyDeviceToDevice, h->stream));
         for (int f = 0; f < nfree; ++f)
             CK(cudaMemcpyAsync(h->d_x0.p + (size_t)free_states[f] * Bt, h->d_zt.p + (size_t)(nv + f) * Bt,
                                sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
         TRY(run_forward(h, 0, Bt, -1, nullptr, true));
+        if (!cgb) break;
+        // multipliers, violations, and the trajectories that go round again (u of the accepted points is on the grid now)
+        CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));
+        unsigned long long *d_worst = reinterpret_cast<unsigned long long *>(h->d_cgb_b.p + 2 * nc);
+        CK(cudaMemsetAsync(d_worst, 0, sizeof(unsigned long long), h->stream));
+        cgb_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(h->d_ug.p, h->d_cgb_mu.p, h->d_cgb_b.p, h->cgb_rho, nc,
+                                                                              G0, Bt, Bt, h->d_cgb_viol.p, h->d_frozen, h->cgb_tol,
+                                                                              d_nopen, d_worst);
+        CK(cudaGetLastError());
+        h->launches++;
+        int reopened = 0;
+        double worst = 0.0;
+        CK(cudaMemcpyAsync(&reopened, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&worst, d_worst, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (reopened == 0) break;
+        // the usual safeguard: the penalty parameter grows only when the multiplier update alone did not cut the
+        // largest violation of the batch to a quarter (a large rho makes the inner problem ill-conditioned)
+        if (worst > 0.25 * cgb_worst_prev) h->cgb_rho = std::min(h->cgb_rho * 4.0, 1e8);
+        cgb_worst_prev = worst;
+        }
+        h->cgb_active = false;
         h->have_states = true;
         if (v_opt) TRY(download_soa(h, h->d_z.p, Bt, 0, v_opt, nz, Bt));
         if (J) TRY(d2h(h, J, h->d_J.p, sizeof(double) * Bt));
@@ -2886,6 +3008,44 @@ int ocs_b200_set_profiling(ocs_b200_handle *h, int on)
     if (h->multi) return ocs_multi_set_profiling(h, on);
     h->profiling = on != 0;
     return 0;
+}
+
+// ControlBounds at every grid point as linear constraints of ocs_b200_single_shooting (see cgb_penalty_kernel).
+int ocs_b200_set_solve_control_bounds(ocs_b200_handle *h, const double *bounds, int nc, double rho0, double feas_tol, int max_outer)
+{
+    if (!h) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_set_solve_control_bounds(h, bounds, nc, rho0, feas_tol, max_outer);
+    if (!bounds) {
+        h->cgb_on = false;
+        return 0;
+    }
+    if (nc < 1 || nc > 64) return h->fail(OCS_B200_ERR_ARG, "bad control count");
+    h->cgb_bounds.resize(2 * (size_t)nc);
+    for (int c = 0; c < nc; ++c) {          // nc x 2 column-major -> [c][lo, hi]
+        h->cgb_bounds[2 * c] = bounds[c];
+        h->cgb_bounds[2 * c + 1] = bounds[c + nc];
+        if (!(h->cgb_bounds[2 * c] <= h->cgb_bounds[2 * c + 1])) return h->fail(OCS_B200_ERR_ARG, "control bounds must satisfy lb <= ub");
+    }
+    h->cgb_rho0 = rho0 > 0 ? rho0 : 100.0;
+    h->cgb_tol = feas_tol > 0 ? feas_tol : 1e-4;
+    h->cgb_outer = max_outer > 0 ? max_outer : 12;
+    h->cgb_on = true;
+    return 0;
+}
+
+// Largest violation of the grid control bounds per trajectory after the last constrained solve: [Bt].
+int ocs_b200_get_solve_violation(ocs_b200_handle *h, double *viol)
+{
+    if (!h || !viol) return OCS_B200_ERR_ARG;
+    if (h->multi) return ocs_multi_get_solve_violation(h, viol);
+    if (!h->have_states || h->d_cgb_viol.cap < (size_t)h->Bt) return h->fail(OCS_B200_ERR_STATE, "no constrained solve on this handle");
+    try {
+        CK(cudaSetDevice(h->device));
+        TRY(d2h(h, viol, h->d_cgb_viol.p, sizeof(double) * h->Bt));
+        return finish_host(h);
+    } catch (const std::exception &ex) {
+        return h->fail(OCS_B200_ERR_NOMEM, "exception: %s", ex.what());
+    }
 }
 
 int ocs_b200_kernel_stats(ocs_b200_handle *h, int reset, double *ms_forward, double *ms_reverse, long *launches)

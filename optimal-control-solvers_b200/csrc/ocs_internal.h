@@ -127,6 +127,14 @@ struct ocs_b200_handle {
     int *h_lane_open = nullptr;        // ... pinned host copy
     int lanes_mode = -1;               // -1 automatic, 0 never, 1 whenever the batch can be halved (OCS_B200_LANES)
     int sm_count = 0;
+    // ControlBounds at every grid point as constraints of the batched solve (ocs_b200_set_solve_control_bounds):
+    // augmented-Lagrangian multipliers mu [2][nc][G][Bt] (upper, lower), the bounds [nc][2], the largest violation
+    // per trajectory, and the penalty parameter of the evaluation in flight (cgb_active: run_reverse adds the term)
+    bool cgb_on = false, cgb_active = false;
+    std::vector<double> cgb_bounds;
+    double cgb_rho0 = 100.0, cgb_tol = 1e-4, cgb_rho = 0.0;
+    int cgb_outer = 12;
+    DevBuf d_cgb_mu, d_cgb_b, d_cgb_viol;
     int *d_status = nullptr;
     size_t status_cap = 0;
     int *d_frozen = nullptr, *d_sweeps = nullptr;
@@ -204,6 +212,8 @@ int ocs_multi_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doub
                        double uRelTol, double uAbsTol, int nSWEEPS, double relax, double *J, int32_t *sweeps,
                        int32_t *converged, double *max_change);
 int ocs_multi_set_fb_costate(ocs_b200_handle *h, int mode);
+int ocs_multi_set_solve_control_bounds(ocs_b200_handle *h, const double *bounds, int nc, double rho0, double feas_tol, int max_outer);
+int ocs_multi_get_solve_violation(ocs_b200_handle *h, double *viol);
 int ocs_multi_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, const double *v0, long v0_nbatch, const double *Lb,
                               const double *Ub, int nfree, const int32_t *free_states, const double *free_lb,
                               const double *free_ub, int max_iter, double tol, double *v_opt, double *J, int32_t *iters,

@@ -318,6 +318,16 @@ int ocs_multi_set_fb_costate(ocs_b200_handle *h, int mode)
 {
     return fan(h, [=](int, ocs_b200_handle *c) { return ocs_b200_set_fb_costate(c, mode); });
 }
+int ocs_multi_set_solve_control_bounds(ocs_b200_handle *h, const double *bounds, int nc, double rho0, double feas_tol, int max_outer)
+{
+    return fan(h, [=](int, ocs_b200_handle *c) { return ocs_b200_set_solve_control_bounds(c, bounds, nc, rho0, feas_tol, max_outer); });
+}
+int ocs_multi_get_solve_violation(ocs_b200_handle *h, double *viol)
+{
+    M *m = h->multi;
+    if (m->Bt < 1 || m->off.empty()) return h->fail(OCS_B200_ERR_STATE, "no constrained solve on this handle");
+    return fan(h, [&](int k, ocs_b200_handle *c) { return ocs_b200_get_solve_violation(c, viol + m->off[k]); }, &m->off);
+}
 int ocs_multi_set_profiling(ocs_b200_handle *h, int on)
 {
     return fan(h, [=](int, ocs_b200_handle *c) { return ocs_b200_set_profiling(c, on); });

@@ -176,6 +176,26 @@ class ChebyshevControl(Control):
         u0 = np.atleast_1d(np.asarray(u0, dtype=np.float64))
         return np.concatenate([u0, np.zeros((self.nControlBasis - 1) * self.nControls)])
 
+    def compute_nlp_bounds(self, ControlBounds):
+        """A box on Chebyshev coefficients does not bound u(t): the coefficient vector is free and the control
+        bounds enter as linear constraints (compute_lincon)."""
+        nz = self.nControlBasis * self.nControls
+        return np.full(nz, -np.inf), np.full(nz, np.inf)
+
+    def compute_lincon(self, ControlBounds):
+        """[A, b] of Control/ChebyshevControl.m:51-53, which the reference left empty: ControlBounds at every grid
+        point, lb <= reshape(v, nc, []) * B <= ub, as A v <= b with v = vec of the (nc x K) coefficient matrix
+        (functions/single_shooting.m:106-111).  The device solve applies exactly this set through
+        CudaRK4Integrator.set_solve_control_bounds without forming A."""
+        cb = np.asarray(ControlBounds, dtype=np.float64).reshape(-1, 2)
+        Bk = np.kron(self.B.T, np.eye(self.nControls))           # u(c, j) = sum_k v(c + nc k) B(k, j)
+        A = np.vstack([Bk, -Bk])
+        G = self.B.shape[1]
+        b = np.concatenate([np.tile(cb[:, 1], G), -np.tile(cb[:, 0], G)])
+        return A, b
+
+    grid_bounds_as_constraints = True
+
     def ufunc_spec(self):
         return "chebyshev", np.array([self._t0, self._t1])
 

@@ -152,6 +152,9 @@ def single_shooting(prob, x0, tspan, nCONTROL_PTS, Control=None, Integrator=None
     v0 = control.compute_initial_v(u0 if nc > 1 else u0[0])
     Lb, Ub = control.compute_nlp_bounds(cb)
     integ.attach_control(control)
+    # [A, b] = control.compute_lincon(prob.ControlBounds) (:106-111): the reference's PW controls have none; a control
+    # whose coefficient box does not bound u(t) (ChebyshevControl) constrains the control on the grid instead
+    integ.set_solve_control_bounds(cb if getattr(control, "grid_bounds_as_constraints", False) else None)
     out = integ.single_shooting(prob, x0, v0, Lb, Ub, FreeInitStates=FreeInitStates, FreeStateBounds=FreeStateBounds,
                                 max_iter=MaxIter, tol=TolX)
     J = out["J"]

@@ -400,6 +400,22 @@ class CudaRK4Integrator:
         self._last_u = None
         return out
 
+    def set_solve_control_bounds(self, ControlBounds, rho0=0.0, feas_tol=0.0, max_outer=0):
+        """ControlBounds (nc x 2) at every grid point as linear constraints of single_shooting -- what a finished
+        ChebyshevControl.compute_lincon would hand to fmincon (single_shooting.m:106-111); None switches them off
+        (ocs_b200_set_solve_control_bounds)."""
+        if ControlBounds is None:
+            self._ck(self._lib.ocs_b200_set_solve_control_bounds(self._h, None, 0, 0.0, 0.0, 0))
+            return
+        cb = _lib.f64(np.asarray(ControlBounds, dtype=np.float64).reshape(-1, 2))
+        self._ck(self._lib.ocs_b200_set_solve_control_bounds(self._h, _lib.dp(cb), cb.shape[0], float(rho0), float(feas_tol), int(max_outer)))
+
+    def solve_violation(self):
+        """Largest violation of the grid control bounds per trajectory after the last constrained solve."""
+        out = np.empty(self._Bt)
+        self._ck(self._lib.ocs_b200_get_solve_violation(self._h, _lib.dp(out)))
+        return out
+
     # ------------------------------------------------------------------ batched single shooting on the device
     def single_shooting(self, prob, x0, v0, Lb, Ub, FreeInitStates=(), FreeStateBounds=None, max_iter=200, tol=1e-6,
                         out=None):
