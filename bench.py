@@ -454,7 +454,8 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
         "gpu_launches": int(ks["launches"]),
         "roofline": {"bound": bound, "achieved": dom["gbs"] if bound == "hbm" else dom["tflops"],
                      "peak": hbm_peak if bound == "hbm" else tf.value, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                     "frac": max(hbm_frac, fp_frac), "kernel": dom["kernel"], "traffic": None, "peak_source": hbm_src,
+                     "frac": max(hbm_frac, fp_frac), "kernel": dom["kernel"], "traffic": _committed_traffic("cfg3fb" if gen else "fbsweep", dom["kernel"]),
+                     "peak_source": hbm_src,
                      "kernels": [kf, kr],
                      "step": {"ms_per_sweep": ms_sweep, "ms_kernels_alone": ms_f + ms_r,
                               "hbm_gbs": units * (bf + br) / ms_sweep / 1e6, "hbm_frac": units * (bf + br) / ms_sweep / 1e6 / hbm_peak,
@@ -605,6 +606,15 @@ def pcie_ceiling(nbytes, dev, world):
             best = max(best, nbytes / dt / 1e9)
     del src, dst
     return best
+
+
+def _committed_traffic(config, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(config, {}).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def run_sub_config(name, extra=()):

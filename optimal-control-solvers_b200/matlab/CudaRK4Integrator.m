@@ -132,8 +132,12 @@ classdef CudaRK4Integrator < Integrator
          p.addParameter('FreeStateBounds', []);
          p.addParameter('MaxIter', 300);
          p.addParameter('TolX', 1e-6);
+         % [A, b] = control.compute_lincon(prob.ControlBounds) of single_shooting.m:106-111 for a control whose
+         % coefficient box does not bound u(t) (ChebyshevControl): ControlBounds (nc x 2) at every grid point
+         p.addParameter('GridControlBounds', []);
          parse(p, varargin{:});
          obj.bind(prob);
+         ocs_b200_mex('set_solve_control_bounds', obj.handle, p.Results.GridControlBounds);
          free = int32(p.Results.FreeInitStates(:)') - 1;
          fb = p.Results.FreeStateBounds;
          if isempty(free), flb = []; fub = []; else, flb = fb(:,1); fub = fb(:,2); end

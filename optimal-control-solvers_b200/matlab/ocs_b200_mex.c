@@ -489,6 +489,25 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         check(rc, h);
         return;
     }
+    /* ---- mex('set_solve_control_bounds', h, ControlBounds | [] [, rho0, feasTol, maxOuter])
+     *      [A, b] = control.compute_lincon(prob.ControlBounds) of functions/single_shooting.m:106-111 for a dense
+     *      (Chebyshev) basis: ControlBounds (nc x 2) at every grid point; [] switches the constraints off */
+    if (!strcmp(cmd, "set_solve_control_bounds")) {
+        FAIL_IF(nrhs < 3, "ocs_b200:nargin", "set_solve_control_bounds(h, ControlBounds [, rho0, feasTol, maxOuter])");
+        const double *cb = dbl(prhs[2], "ControlBounds");
+        FAIL_IF(cb && mxGetN(prhs[2]) != 2, "ocs_b200:size", "ControlBounds must be nc x 2");
+        check(ocs_b200_set_solve_control_bounds(h, cb, cb ? (int)mxGetM(prhs[2]) : 0, nrhs > 3 ? scalar(prhs[3]) : 0.0,
+                                                nrhs > 4 ? scalar(prhs[4]) : 0.0, nrhs > 5 ? (int)scalar(prhs[5]) : 0), h);
+        return;
+    }
+    /* ---- viol = mex('get_solve_violation', h)   largest bound violation per trajectory of the last constrained solve */
+    if (!strcmp(cmd, "get_solve_violation")) {
+        const ocs_dims dd = dims_of(h);
+        need_batch(&dd);
+        plhs[0] = mxCreateDoubleMatrix(1, (mwSize)dd.Bt, mxREAL);
+        check(ocs_b200_get_solve_violation(h, mxGetPr(plhs[0])), h);
+        return;
+    }
     /* ---- [value, index] = mex('reduce_J', h, op)   op: 0 sum, 1 min, 2 max (index 1-based) */
     if (!strcmp(cmd, "reduce_J")) {
         FAIL_IF(nrhs < 3, "ocs_b200:nargin", "reduce_J(h, op)");

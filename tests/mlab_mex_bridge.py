@@ -179,6 +179,20 @@ def make_mex(ocs):
                                                L.ip(free) if free.size else None, L.dp(flb), L.dp(fub), int(sc(a[8])),
                                                sc(a[9]), L.dp(v), L.dp(J), L.ip(it), L.ip(cv)), h)
             return (v, J, it.astype(float).reshape(1, -1), cv.astype(float).reshape(1, -1))[:max(nargout, 1)]
+        if cmd == "set_solve_control_bounds":
+            cb = np.asarray(a[1], dtype=float)
+            if cb.size == 0:
+                check(lib.ocs_b200_set_solve_control_bounds(h, None, 0, 0.0, 0.0, 0), h)
+            else:
+                cb = arr(cb.reshape(-1, 2))
+                check(lib.ocs_b200_set_solve_control_bounds(h, L.dp(cb), cb.shape[0], sc(a[2]) if len(a) > 2 else 0.0,
+                                                            sc(a[3]) if len(a) > 3 else 0.0, int(sc(a[4])) if len(a) > 4 else 0), h)
+            return ()
+        if cmd == "get_solve_violation":
+            Bt = int(lib.ocs_b200_get_batch(h))
+            out = np.empty((1, Bt))
+            check(lib.ocs_b200_get_solve_violation(h, L.dp(out)), h)
+            return (out,)
         if cmd == "reduce_J":
             val, idx = ctypes.c_double(), ctypes.c_long()
             check(lib.ocs_b200_reduce_J(h, int(sc(a[1])), ctypes.byref(val), ctypes.byref(idx)), h)
