@@ -146,6 +146,18 @@ classdef CudaRK4Integrator < Integrator
          obj.Bt = size(x0, 2);
       end
 
+      function [value, index] = reduce_J(obj, op)
+         % Reduction of the last sweep's J over the batch on the device(s): op 'sum', 'min' or 'max';
+         % index (1-based) is the arg min / arg max -- the best of a sweep over control candidates or parameter sets.
+         codes = struct('sum', 0, 'min', 1, 'max', 2);
+         [value, index] = ocs_b200_mex('reduce_J', obj.handle, codes.(op));
+      end
+
+      function viol = solve_violation(obj)
+         % Largest violation of 'GridControlBounds' per trajectory after the last constrained single_shooting.
+         viol = ocs_b200_mex('get_solve_violation', obj.handle);
+      end
+
       function [xStar, lamStar, uStar, resnorm, residual, exitflag] = compute_equilibrium(obj, prob, xGuess, lamGuess, uGuess, lb, ub, r, params)
          % functions/compute_equilibrium.m for every parameter set at once (one GPU thread per set).
          % params (np x nsets) overrides prob's parameters for a sweep; guesses may be columns or (. x nsets).
