@@ -622,7 +622,9 @@ def run_sub_config(name, extra=()):
     memory); returns a compact record for the `configs` block of the main line."""
     import subprocess
     cmd = [sys.executable, os.path.abspath(__file__), "--config", name, "--steps", "5", "--warmup", "3", "--no-cpu",
-           "--no-e2e", "--no-configs", *extra]
+           "--no-configs", *extra]
+    if name not in ("cfg3", "cfg3fb", "fbsweep", "cfg2solve"):      # (those carry a cheap end-to-end figure of their own)
+        cmd.append("--no-e2e")
     t0 = time.perf_counter()
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
@@ -874,31 +876,38 @@ def main():
 
     # ---- end to end through the host-buffer C ABI (rank-local; copies inside the timed region)
     e2e = None
-    if not args.no_e2e and args.config in ("cfg2", "cfg4"):
+    if not args.no_e2e and args.config in ("cfg2", "cfg4", "cfg3", "cfg2v", "cfg2p", "cfg2pv"):
         # pinned host buffers on the NUMA node of this rank's GPU (first touch under the GPU's CPU affinity):
         # with several ranks per box the downloads otherwise cross the socket interconnect
         restore = _bind_to_gpu_numa_node(local_rank)
-        x0_h = torch.empty((1, Bt), dtype=torch.float64).pin_memory()
-        x0_h.copy_(x0.cpu())
+        # host arrays in MATLAB layout (column-major, trajectory index last): a C-ordered (Bt, rows) array
+        x0_h = torch.empty((Bt, n_st), dtype=torch.float64).pin_memory()
+        x0_h.copy_(x0.cpu().T)
         J_h = torch.empty(Bt, dtype=torch.float64).pin_memory()
-        xT_h = torch.empty((1, Bt), dtype=torch.float64).pin_memory()
+        xT_h = torch.empty((Bt, n_st), dtype=torch.float64).pin_memory()
         st_h = torch.empty(Bt, dtype=torch.int32).pin_memory()
-        dJdv_h = torch.empty((Bt, K_PWL), dtype=torch.float64).pin_memory()   # MATLAB (nc*K) x Bt, column-major
-        lam0_h = torch.empty((Bt, 2), dtype=torch.float64).pin_memory()
+        dJdv_h = torch.empty((Bt, rows), dtype=torch.float64).pin_memory()   # MATLAB (nc*K) x Bt, column-major
+        lam0_h = torch.empty((Bt, n_st + 1), dtype=torch.float64).pin_memory()
         for buf in (x0_h, J_h, xT_h, dJdv_h, lam0_h):
             buf.view(-1)[::512].add_(0)          # touch every page while the affinity is in place
         # the same arrays as a MATLAB caller holds them: ordinary pageable memory (every mxArray is)
-        pg_bufs = dict(x0=np.array(x0_h.numpy()), J=np.empty(Bt), xT=np.empty((1, Bt)), st=np.empty(Bt, dtype=np.int32),
-                       dJdv=np.zeros((Bt, K_PWL)), lam0=np.zeros((Bt, 2)))
+        pg_bufs = dict(x0=np.array(x0_h.numpy()), J=np.empty(Bt), xT=np.empty((Bt, n_st)), st=np.empty(Bt, dtype=np.int32),
+                       dJdv=np.zeros((Bt, rows)), lam0=np.zeros((Bt, n_st + 1)))
         restore()
         lib = ocs._lib
-        vf = lib.f64(v)
+        # coefficients: shared (one column) or one column per trajectory, uploaded with every evaluation
+        if v_dev is not None:
+            v_h = torch.empty((Bt, rows), dtype=torch.float64).pin_memory()
+            v_h.copy_(v_dev.cpu().T)
+            vf, v_cols = v_h.numpy(), Bt
+        else:
+            vf, v_cols = lib.f64(v), 1
         hnd = integ._h
         L = lib.load()
         pin_bufs = dict(x0=x0_h.numpy(), J=J_h.numpy(), xT=xT_h.numpy(), st=st_h.numpy(), dJdv=dJdv_h.numpy(), lam0=lam0_h.numpy())
 
         def e2e_step(b):
-            lib.check(L.ocs_b200_set_control_v(hnd, lib.dp(vf), 1), hnd)
+            lib.check(L.ocs_b200_set_control_v(hnd, lib.dp(vf), v_cols), hnd)
             lib.check(L.ocs_b200_evaluate(hnd, lib.dp(b["x0"]), Bt, None, 0, lib.dp(b["J"]), lib.dp(b["xT"]),
                                           lib.ip(b["st"]), lib.dp(b["dJdv"]), lib.dp(b["lam0"])), hnd)
 
@@ -919,7 +928,7 @@ def main():
         ne, dt = timed_e2e(pin_bufs)
         nep, dtp = timed_e2e(pg_bufs)
         same = bool(np.array_equal(pg_bufs["J"], pin_bufs["J"]) and np.array_equal(pg_bufs["dJdv"], pin_bufs["dJdv"]))
-        d2h_bytes = 8 * Bt * (1 + 1 + K_PWL + 2) + 4 * Bt
+        d2h_bytes = 8 * Bt * (1 + n_st + rows + n_st + 1) + 4 * Bt
         ceiling = pcie_ceiling(d2h_bytes, dev, world)           # GB/s per rank with every rank copying at once
         if world > 1:
             t = torch.tensor([ceiling], dtype=torch.float64, device=dev)
@@ -927,7 +936,7 @@ def main():
             ceiling = float(t.item())
         per_rank_gbs = d2h_bytes * ne / dt / 1e9
         e2e = {"value": world * Bt * NT * ne / dt, "unit": "trajectory-steps/s",
-               "h2d_bytes_per_step": 8 * Bt + 8 * K_PWL,
+               "h2d_bytes_per_step": 8 * Bt * n_st + 8 * rows * v_cols,
                "d2h_bytes_per_step": d2h_bytes,
                "steps": ne, "ms_per_step": 1e3 * dt / ne,
                "api": "ocs_b200_evaluate (nlpObjective: compute_states + compute_adjoints) on pinned host buffers; J, xT, status, dJdv, lam0 returned",

@@ -126,3 +126,46 @@ def test_lanes_decision_is_automatic_for_low_occupancy_sweeps(ocs):
         integ.close()
     for key in ("J", "dJdv"):
         assert np.array_equal(out["auto"][key], out[0][key]), key
+
+
+@pytest.mark.parametrize("which", ["builtin", "generated"])
+@pytest.mark.parametrize("lanes", [0, 1])
+def test_device_outputs_stay_inside_their_buffers(ocs, which, lanes):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are looked for directly: every output of the
+    fused device-buffer evaluation lives inside a larger NaN-filled allocation (one guard row before and after, and a
+    ragged batch that ends in the middle of a block, a warp and a 16-byte pair); the guards must come back untouched and
+    every element inside must have been written."""
+    import torch
+    dev = torch.device("cuda", 0)
+    if which == "builtin":
+        prob, n, K, nc = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]]), 1, 11, 1
+        ctl_of = lambda integ: ocs.PWLinearControl(integ.t, K, nc)
+    else:
+        cg = importlib.import_module("optimal-control-solvers_b200.codegen")
+        prob, n, K, nc = cg.harvest_chain_problem(), 6, 5, 2
+        ctl_of = lambda integ: ocs.ChebyshevControl(integ.t, K, nc)
+    Bt = 3 * 1536 + 77                       # two lanes of whole blocks plus a ragged tail
+    tspan = ocs.matlab_linspace(0.0, 2.0, 34)      # 33 steps: not a multiple of any tile size
+    integ = _integ(ocs, lanes, tspan)
+    integ.attach_control(ctl_of(integ))
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    x0 = (1.0 + 1.4 * torch.rand((n, Bt), dtype=torch.float64, device=dev, generator=g)).contiguous()
+    v = (0.2 + 0.5 * torch.rand((nc * K, Bt), dtype=torch.float64, device=dev, generator=g)).contiguous()
+    if which == "generated":
+        v[2 * nc:] *= 0.05
+
+    def guarded(rows, dtype=torch.float64):
+        fill = float("nan") if dtype == torch.float64 else -7
+        return torch.full((rows + 2, Bt), fill, dtype=dtype, device=dev)
+    J, xT, st, dJdv, lam0 = guarded(1), guarded(n), guarded(1, torch.int32), guarded(nc * K), guarded(n + 1)
+    row = lambda t: t[1:].data_ptr()
+    for _ in range(2):
+        integ.evaluate_dev(prob, x0.data_ptr(), Bt, v_ptr=v.data_ptr(), J_ptr=row(J), xT_ptr=row(xT), status_ptr=row(st),
+                           dJdv_ptr=row(dJdv), lam0_ptr=row(lam0))
+    integ.synchronize()
+    for name, t in (("J", J), ("xT", xT), ("dJdv", dJdv), ("lam0", lam0)):
+        assert torch.isnan(t[0]).all() and torch.isnan(t[-1]).all(), name + ": a guard row was written"
+        assert torch.isfinite(t[1:-1]).all(), name + ": an element inside was not written"
+    assert (st[0] == -7).all() and (st[-1] == -7).all() and (st[1] == 0).all()
+    integ.close()
