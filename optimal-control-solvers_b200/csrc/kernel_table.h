@@ -16,6 +16,7 @@ struct ocs_kernel_table {
     int tpt_fwd_pb, tpt_rev_pb;   // ... with per-trajectory parameters
     int fb_ring;   // ... and of the fb_sweep costate kernels (ring*(n + 2 nc)*threads doubles)
     int rev_ring;  // depth of the gradient kernels' cp.async node-state ring (shared memory: ring*tpt*(n [+ 2 nc])*threads doubles)
+    int rev_ring_pb;   // ... of the variants with per-trajectory parameters
     int async_stage;   // multi-trajectory bodies keep two record tiles in shared memory (the next one is fetched with cp.async)
     const void *fwd[3][3][2];   // [UMODE][BMODE][params batched]
     const void *rev[3][3][2];

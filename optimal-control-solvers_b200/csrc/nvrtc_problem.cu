@@ -227,6 +227,7 @@ int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, c
     table->np = inf[2];
     for (int hm = 0; hm < 3; ++hm) table->ntt[hm] = inf[3 + hm] & 0xffff;
     table->tpt_fwd_coef = (inf[5] >> 16) & 0xff;
+    table->rev_ring_pb = (inf[5] >> 24) & 0xff;
     table->tpt_fwd_pb = (inf[4] >> 16) & 0xf;
     table->tpt_rev_pb = (inf[4] >> 20) & 0xf;
     table->tile = inf[6] & 0xffff;

@@ -1128,7 +1128,8 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             const int tpt = (grids || bm == 2) ? 1 : rev_tpt(h, um);
             // the gradient kernels (not the fetch variants) keep a cp.async ring of node states in shared memory
             // (with a per-trajectory control grid a ring slot also carries the step's two controls)
-            const size_t ring = grids ? 0 : (size_t)h->kt.rev_ring * tpt * (h->kt.n + (um == 2 ? 2 * h->kt.nc : 0)) * h->kt.threads;
+            const int depth = pb_index(h) ? h->kt.rev_ring_pb : h->kt.rev_ring;
+            const size_t ring = grids ? 0 : (size_t)depth * tpt * (h->kt.n + (um == 2 ? 2 * h->kt.nc : 0)) * h->kt.threads;
             TRY(launch(h, kern, a, false, tpt, ring));
         }
         if (project) {

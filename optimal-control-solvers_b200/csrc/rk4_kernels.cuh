@@ -101,6 +101,12 @@
                             // Measured on B200 (profiles/r1_notes.md): 0: 3.71 ms, 2: 3.90, 4: 3.75, 8: 3.76 -- the
                             // FP64-bound gradient kernel does not gain from it, the HBM-bound fb_sweep kernel does.
 #endif
+#ifndef OCS_RING_PB
+#define OCS_RING_PB OCS_RING  // ... the same for the variants with per-trajectory parameters: their reverse step is long
+                              // (nothing is tabulated) and their top stall was the node-state load (long_scoreboard
+                              // 2.8 warps per issue); ring of 4: 5.32 -> 4.96 ms on cfg2p, while the uniform-parameter
+                              // kernels lose 5 % with it (profiles/r2_notes.md)
+#endif
 // How the sweeps with per-trajectory coefficients move the sparse-basis control window, per sweep direction:
 //   0  compare the knot index at every grid point, reload under a branch
 //   1  ... reload by predicated loads (ld_global_if)
@@ -1371,8 +1377,8 @@ __device__ __forceinline__ void reverse_multi_body(const SweepArgs &a, double *s
     double Ecur[T][NE > 0 ? NE : 1], Eq[T][NE > 0 ? NE : 1], Erate[T][NE > 0 ? NE : 1];
     constexpr int D = OCS_PREFETCH;          // ring of node states in flight: yn[0] is the next one consumed
     constexpr int UNR = OCS_REV_UNROLL;
-    constexpr int DP = OCS_RING;             // > 0: cp.async ring in shared memory [DP][T][n (+ 2 nc)][threads] instead of yn
-    static_assert(DP == 0 || ((DP & (DP - 1)) == 0 && DP <= OCS_XS_SLACK), "OCS_RING must be a power of two <= OCS_XS_SLACK");
+    constexpr int DP = PB ? OCS_RING_PB : OCS_RING;   // > 0: cp.async ring in shared memory [DP][T][n (+ 2 nc)][threads] instead of yn
+    static_assert(DP == 0 || ((DP & (DP - 1)) == 0 && DP <= OCS_XS_SLACK), "OCS_RING / OCS_RING_PB must be a power of two <= OCS_XS_SLACK");
     // with a per-trajectory control grid the ring also carries the step's two controls (midpoint, left node): every
     // per-step global load of the sweep then completes through cp.async groups, DP steps ahead, instead of the
     // scoreboard -- with 8 resident warps per SM a quarter of the generated 6-state reverse sweep was ONE instruction
@@ -2059,7 +2065,7 @@ __device__ __forceinline__ void equilibrium_body(const EqArgs &a)
     {                                                                                                  \
         o[0] = P::n; o[1] = P::nc; o[2] = P::np;                                                       \
         o[3] = P::ntt(0); o[4] = P::ntt(1) | (OCS_TPT_FWD_PB << 16) | (OCS_TPT_REV_PB << 20);          \
-        o[5] = P::ntt(2) | (OCS_TPT_FWD_COEF << 16);                                                   \
+        o[5] = P::ntt(2) | (OCS_TPT_FWD_COEF << 16) | (OCS_RING_PB << 24);                              \
         o[6] = OCS_TILE | (OCS_RING << 16) | (OCS_FB_RING << 24) | (OCS_ASYNC_STAGE << 28); o[7] = OCS_THREADS | (OCS_TPT_REV << 16) | (OCS_TPT_FWD << 24) | (OCS_TPT_REV_COEF << 28); \
     }
 
