@@ -516,6 +516,18 @@ def run_solve(args, ocs, local_rank, rank, world):
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = integ.kernel_stats(reset=True)["launches"]
+    # where a solve spends its device time: one more solve with CUDA events around every launch
+    integ.set_profiling(True)
+    ssp = solve()
+    ksp = integ.kernel_stats(reset=True)
+    integ.set_profiling(False)
+    n_it = int(ssp["iters"].max())
+    breakdown = {"iterations": n_it, "ms_forward": ksp["ms_forward"], "ms_reverse": ksp["ms_reverse"], "ms_update": ksp["ms_update"],
+                 "ms_per_iteration": {"forward": ksp["ms_forward"] / (n_it + 1), "reverse": ksp["ms_reverse"] / n_it,
+                                      "update": ksp["ms_update"] / n_it},
+                 "update_gbs": 5 * 8.0 * K_PWL * Bt * n_it / (ksp["ms_update"] * 1e-3) / 1e9 if ksp["ms_update"] > 0 else None,
+                 "what": "sums over one solve (the last forward sweep re-evaluates the minimisers); update = the projected-gradient "
+                         "step, 5 passes over the (nc K) x Bt coefficient arrays"}
     evals = float(ss["iters"].astype(np.int64).sum())        # objective/gradient evaluations actually carried out
     t = torch.tensor([dt, evals, float(ss["converged"].sum()), float(ss["iters"].max())], dtype=torch.float64, device=dev)
     if world > 1:
@@ -542,7 +554,7 @@ def run_solve(args, ocs, local_rank, rank, world):
                          "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * N_STEPS * Bt)},
               "clocks": clocks, "gpu_launches": int(launches),
               "solve": {"solves_per_s": world * Bt / per, "converged": int(nconv), "trajectories": world * Bt,
-                        "mean_evaluations": evals / (world * Bt), "max_evaluations": int(itmax)},
+                        "mean_evaluations": evals / (world * Bt), "max_evaluations": int(itmax), "device_time": breakdown},
               "e2e": {"value": val, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 * Bt + 8 * 3 * nv,
                       "d2h_bytes_per_step": 8 * Bt * (nv + 1) + 8 * Bt,
                       "api": "ocs_b200_single_shooting on host buffers: x0 up; vOpt, J, iters, converged down"}})

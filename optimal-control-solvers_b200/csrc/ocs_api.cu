@@ -266,7 +266,7 @@ __global__ void fb_update_kernel(const double *__restrict__ maxchg, int *frozen,
 //   Jhist     : the last SPG_M accepted objectives (non-monotone reference value)
 // first != 0: the trial IS the starting point (accepted unconditionally).
 #define SPG_M 5
-__global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double *zt, const double *gt, double *J,
+__global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double *zt, double *gt, double *J,
                                   const double *Jt, double *Jhist, double *alpha, const double *lb, const double *ub,
                                   int *frozen, int *iters, int iter, double tol, int first, int *n_open)
 {
@@ -290,8 +290,7 @@ __global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double
                 const double sk = zn - z[i], yk = gn - g[i];
                 sts += sk * sk;
                 sty += sk * yk;
-                z[i] = zn;
-                g[i] = gn;
+                // (the accepted point stays where it is: the host swaps the roles of (z, g) and (zt, gt) after this kernel)
                 const double proj = fmin(ub[k], fmax(lb[k], zn - gn));
                 pg = fmax(pg, fabs(zn - proj));
                 gmax = fmax(gmax, fabs(gn));
@@ -311,14 +310,24 @@ __global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double
         }
         alpha[b] = a;
         iters[b] = iter;
-        if (!frozen[b]) {
-            open = 1;
-            for (long k = 0; k < nz; ++k) {
-                const size_t i = (size_t)k * nb + b;
-                zt[i] = fmin(ub[k], fmax(lb[k], z[i] - a * g[i]));
+        // Roles after this kernel (the host swaps the pointers): (zt, gt) hold the accepted point, z receives the new
+        // trial point and g the gradient the next sweep writes.  An accepted trial is therefore not copied at all; a
+        // rejected one is replaced by the old accepted point.
+        const bool fz = frozen[b] != 0;
+        if (!fz) open = 1;
+        for (long k = 0; k < nz; ++k) {
+            const size_t i = (size_t)k * nb + b;
+            double zc, gc;                                       // the accepted point
+            if (accept) {
+                zc = zt[i];
+                gc = gt[i];
+            } else {
+                zc = z[i];
+                gc = g[i];
+                zt[i] = zc;
+                gt[i] = gc;
             }
-        } else {
-            for (long k = 0; k < nz; ++k) zt[(size_t)k * nb + b] = z[(size_t)k * nb + b];   // leave the minimiser in place
+            z[i] = fz ? zc : fmin(ub[k], fmax(lb[k], zc - a * gc));   // frozen: the minimiser in both buffers
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, open);
@@ -326,14 +335,14 @@ __global__ void spg_update_kernel(long nz, long nb, double *z, double *g, double
 }
 
 // The same update with the rows of a trajectory split over G thread groups (block = 32 trajectories x G groups,
-// group kg owns rows kg, kg + G, ...): every row of zt, gt, z, g is read once and z, g, zt are written once
-// (7 passes over the (nc K) x Bt arrays instead of the 12 of the kernel above) -- the trial rows wait in
+// group kg owns rows kg, kg + G, ...): every row of zt, gt, z, g is read once and only the new trial point is written
+// (5 passes over the (nc K) x Bt arrays; the accepted point changes buffers by a pointer swap on the host) -- the trial rows wait in
 // registers while the Barzilai-Borwein sums are reduced across the groups through shared memory.  The Armijo
 // term g.(z - zt) of the NEXT acceptance test is formed while zt is written and kept in pred[b].  Sums run in a
 // different (fixed) order than in spg_update_kernel, so the two differ by rounding only.
 template <int VPT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
-    long nz, long nb, double *__restrict__ z, double *__restrict__ g, double *__restrict__ zt, const double *__restrict__ gt,
+    long nz, long nb, double *__restrict__ z, double *__restrict__ g, double *__restrict__ zt, double *__restrict__ gt,
     double *J, const double *Jt, double *Jhist, double *alpha, double *pred, const double *__restrict__ lb,
     const double *__restrict__ ub, int *frozen, int *iters, int iter, double tol, int first, int *n_open)
 {
@@ -411,11 +420,14 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
             if (k < nz) {
                 const size_t i = (size_t)k * nb + b;
                 const double zn_new = fz ? zn[j] : fmin(ub[k], fmax(lb[k], zn[j] - a * gn[j]));   // frozen: the minimiser stays
-                if (accept) {
-                    z[i] = zn[j];
-                    g[i] = gn[j];
+                // Roles after this kernel (the host swaps the pointers): (zt, gt) hold the accepted point and z receives
+                // the new trial point.  An accepted trial is not copied at all (5 passes over the coefficient arrays
+                // instead of 7); a rejected one is replaced by the old accepted point.
+                if (!accept) {
+                    zt[i] = zn[j];
+                    gt[i] = gn[j];
                 }
-                zt[i] = zn_new;
+                z[i] = zn_new;
                 pr += gn[j] * (zn[j] - zn_new);
             }
         }
@@ -2917,6 +2929,10 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
             }
             h->launches++;
             CK(cudaGetLastError());
+            // the update left the accepted point in (zt, gt) and wrote the new trial point into z: swap the roles
+            std::swap(h->d_z, h->d_zt);
+            std::swap(h->d_g, h->d_gt);
+            h->v_ext = h->d_zt.p;
             if (h->profiling) {
                 CK(cudaEventRecord(h->ev[3], h->stream));
                 CK(cudaEventSynchronize(h->ev[3]));
