@@ -323,3 +323,37 @@ def test_generated_problem_parameter_sweep_matches_builtin(ocs, oracle, cg):
     for key in ("J", "xT", "dJdv", "lam0"):
         assert relerr(res["gen"][key], ref[key]) < TOL, key
         assert relerr(res["gen"][key], res["builtin"][key]) < TOL, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math", ["fast", "strict"])
+def test_six_state_adjoint_equals_central_differences(ocs, cg, math):
+    """The property of the reference's tests/backprop_test.m for the generated 6-state problem: the gradient from the
+    adjoint sweep (dFdx_times_vec / dFdu_times_vec derived by SymPy, in the fast build in their FMA-shaped forms) equals
+    central differences of J, which only uses F.  A wrong derivation of X or U -- which the comparison with the
+    lambdified twin of the same expressions could not see -- fails here.  Coefficients of both controls and every
+    initial state (lam(:,1), the free-initial-state gradient of single_shooting.m:147-148)."""
+    prob = cg.harvest_chain_problem()
+    Bt, N, K = 48, 200, 5
+    tspan = ocs.matlab_linspace(0.0, 3.0, N + 1)
+    integ = ocs.CudaRK4Integrator(tspan, math=math)
+    integ.attach_control(ocs.ChebyshevControl(integ.t, K, 2))
+    rng = np.random.default_rng(17)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    v = 0.05 * rng.standard_normal((2 * K, Bt))
+    v[:2] = rng.uniform(0.2, 0.8, (2, Bt))
+    base = integ.evaluate(prob, x0, v)
+    d = 1e-5
+    for k in (0, 1, 2, 5, 2 * K - 1):                      # rows of v: (basis k, control c) at k*nc + c
+        vp, vm = v.copy(), v.copy()
+        vp[k] += d
+        vm[k] -= d
+        fd = (integ.evaluate(prob, x0, vp)["J"] - integ.evaluate(prob, x0, vm)["J"]) / (2 * d)
+        assert np.abs(fd - base["dJdv"][k]).max() <= 2e-7 * max(1.0, np.abs(base["dJdv"][k]).max()), (k, math)
+    for c in range(6):
+        xp, xm = x0.copy(), x0.copy()
+        xp[c] += d
+        xm[c] -= d
+        fd = (integ.evaluate(prob, xp, v)["J"] - integ.evaluate(prob, xm, v)["J"]) / (2 * d)
+        assert np.abs(fd - base["lam0"][c]).max() <= 2e-7 * max(1.0, np.abs(base["lam0"][c]).max()), (c, math)
+    integ.close()
