@@ -1007,6 +1007,7 @@ int run_forward(H *h, long b0, long nb, int only_segment, double *d_xgrid, bool 
         a.nb = nb;
         a.ldb = Bt;
         if (a.ldp) a.p = h->d_params.p + b0;
+        if (a.frozen) a.frozen += b0;
         a.x0 = (si == 0 ? h->d_x0.p : h->d_xT.p) + b0;
         a.xs = s.d_xs + b0;
         a.xgrid = d_xgrid;
@@ -1052,6 +1053,7 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
         a.nb = nb;
         a.ldb = Bt;
         if (a.ldp) a.p = h->d_params.p + b0;
+        if (a.frozen) a.frozen += b0;
         a.xs = s.d_xs + b0;
         int um = 0, bm = 0;
         bool project = false;
