@@ -392,6 +392,8 @@ def run_fbsweep(args, ocs, local_rank, rank, world):
         x0 = rng.uniform(1.0, 2.5, (6, Bt))
         v0 = 0.05 * rng.standard_normal((34, Bt))
         v0[:2] = rng.uniform(0.2, 0.8, (2, Bt))
+        # host arrays as a MATLAB caller holds them: column-major (otherwise the Python mirror re-orders 27 MB per call)
+        x0, v0 = np.asfortranarray(x0), np.asfortranarray(v0)
         u0, kw = None, dict(v0=v0)
     else:
         prob = ocs.TestOCProblem(PARAMS, [[0.0, 1.0]])

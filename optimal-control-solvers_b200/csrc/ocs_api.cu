@@ -675,6 +675,43 @@ __global__ void __launch_bounds__(128) basis_eval_kernel(const double *__restric
     }
 }
 
+// The dense-basis case of basis_eval_kernel at full speed (a Chebyshev solve that starts from coefficients evaluates
+// u0 = v*B for every candidate: 2 nc K G FMAs and nc G stores per trajectory; the generic kernel above re-reads every
+// coefficient from L1 for every grid value and took longer than a whole fb_sweep iteration at 10^5 candidates).  A block
+// is 128 trajectories x one segment of the grid (blockIdx.y); a control's K <= BE_KC coefficients sit in registers, the
+// rows B(:, j) of a 32-point tile in shared memory (every lane reads the same entries: a broadcast), and the sum runs in
+// the order of ControlEval / basis_eval_kernel, so the results are bit-identical to theirs.
+#define BE_KC 32
+#define BE_JT 32
+__global__ void __launch_bounds__(128) basis_eval_dense_kernel(const double *__restrict__ v, const double *__restrict__ basrec, int BW,
+                                                               int K, int nc, int G, int seg, long nb, long ldb,
+                                                               double *__restrict__ ug)
+{
+    extern __shared__ double be_sm[];                    // [BE_JT][BW]
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long bb = b < nb ? b : nb - 1;
+    const int ja = blockIdx.y * seg, jb = ja + seg < G ? ja + seg : G;
+    for (int c = 0; c < nc; ++c) {
+        double vc[BE_KC];
+#pragma unroll
+        for (int k = 0; k < BE_KC; ++k) vc[k] = k < K ? v[(size_t)(k * nc + c) * ldb + bb] : 0.0;
+        for (int j0 = ja; j0 < jb; j0 += BE_JT) {
+            const int nj = jb - j0 < BE_JT ? jb - j0 : BE_JT;
+            __syncthreads();
+            for (int q = threadIdx.x; q < nj * BW; q += blockDim.x) be_sm[q] = basrec[(size_t)j0 * BW + q];
+            __syncthreads();
+            for (int jj = 0; jj < nj; ++jj) {
+                const double *rec = be_sm + jj * BW;
+                double u = vc[0] * rec[0];
+#pragma unroll
+                for (int k = 1; k < BE_KC; ++k)
+                    if (k < K) u = u + vc[k] * rec[k];
+                if (b < nb) ug[((size_t)c * G + j0 + jj) * ldb + b] = u;
+            }
+        }
+    }
+}
+
 // x grid (MATLAB layout m x NP x nb) read back from the resident node store [n][NP][ld]; the running-objective row is
 // not kept there: NaN, except its last entry = J
 __global__ void store_to_grid_kernel(const double *__restrict__ xs, long ld, int n, int NP, long nb, const double *__restrict__ J,
@@ -2410,8 +2447,20 @@ int ocs_b200_fb_sweep(ocs_b200_handle *h, const double *x0, long Bt, const doubl
             TRY(build_records(h, 0));      // basis records of the attached control
             TRY(ensure(h, h->d_ug, (size_t)nc * G * Bt));
             const double *vp = h->v_ext ? h->v_ext : h->d_v.p;
-            basis_eval_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
-                vp, h->seg[0].d_basrec, h->seg[0].BW, h->basis_kind == BASIS_SPARSE, h->K, nc, G, Bt, Bt, h->d_ug.p);
+            if (h->basis_kind == BASIS_DENSE && h->K <= BE_KC && getenv("OCS_B200_BASIS_EVAL_GENERIC") == nullptr) {
+                // enough blocks for the device whatever the batch: the grid is cut into segments (blockIdx.y)
+                const unsigned bx = (unsigned)((Bt + 127) / 128);
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+                int ny = (int)std::max<long>(1, std::min<long>(32, (8L * sms + bx - 1) / bx));
+                const int segl = ((G + ny - 1) / ny + BE_JT - 1) / BE_JT * BE_JT;
+                ny = (G + segl - 1) / segl;
+                basis_eval_dense_kernel<<<dim3(bx, (unsigned)ny), 128, sizeof(double) * BE_JT * h->seg[0].BW, h->stream>>>(
+                    vp, h->seg[0].d_basrec, h->seg[0].BW, h->K, nc, G, segl, Bt, Bt, h->d_ug.p);
+            } else {
+                basis_eval_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
+                    vp, h->seg[0].d_basrec, h->seg[0].BW, h->basis_kind == BASIS_SPARSE, h->K, nc, G, Bt, Bt, h->d_ug.p);
+            }
             CK(cudaGetLastError());
             h->launches++;
         } else if (u0_nbatch == Bt) {

@@ -169,3 +169,34 @@ def test_device_outputs_stay_inside_their_buffers(ocs, which, lanes):
         assert torch.isfinite(t[1:-1]).all(), name + ": an element inside was not written"
     assert (st[0] == -7).all() and (st[-1] == -7).all() and (st[1] == 0).all()
     integ.close()
+
+
+@pytest.mark.parametrize("K,N,Bt", [(17, 70, 777), (5, 33, 4000), (32, 16, 130)])
+def test_dense_basis_evaluation_kernel_matches_the_generic_one(ocs, K, N, Bt):
+    """fb_sweep started from coefficients evaluates u0 = v*B on the device.  The dense-basis kernel (coefficients in
+    registers, B tiles in shared memory, the grid cut into segments) must reproduce the generic kernel bit for bit -- same
+    summation order -- for ragged batches, grids that are no multiple of the tile and K up to its register limit; with
+    relax = 0 the sweep leaves the control alone, so the grid control that comes back IS u0."""
+    cg = importlib.import_module("optimal-control-solvers_b200.codegen")
+    prob = cg.harvest_chain_problem()
+    tspan = ocs.matlab_linspace(0.0, 1.0, N + 1)
+    rng = np.random.default_rng(K)
+    x0 = rng.uniform(1.0, 2.5, (6, Bt))
+    v0 = 0.02 * rng.standard_normal((2 * K, Bt))
+    v0[:2] = rng.uniform(0.2, 0.8, (2, Bt))
+    got = {}
+    for generic in (False, True):
+        if generic:
+            os.environ["OCS_B200_BASIS_EVAL_GENERIC"] = "1"
+        try:
+            integ = ocs.CudaRK4Integrator(tspan)
+            ctl = ocs.ChebyshevControl(integ.t, K, 2)
+            integ.attach_control(ctl)
+            out = integ.fb_sweep(prob, x0, None, v0=v0, nSWEEPS=1, relax=0.0)
+            got[generic] = (integ.get_control_u(0, Bt), out["J"])
+            integ.close()
+        finally:
+            os.environ.pop("OCS_B200_BASIS_EVAL_GENERIC", None)
+    assert np.array_equal(got[False][0], got[True][0]) and np.array_equal(got[False][1], got[True][1])
+    ref = np.einsum("ckb,kj->cjb", v0.reshape(K, 2, Bt).transpose(1, 0, 2), ctl.B)      # rows of v: k*nc + c
+    assert relerr(got[False][0], ref) < 1e-14
