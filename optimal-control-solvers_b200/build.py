@@ -26,7 +26,8 @@ COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibi
 
 # (object name, source, extra flags)
 UNITS = [
-    ("kernels_fast.o", "kernels_builtin.cu", ["-DOCS_STRICT=0", "-fmad=true"]),
+    ("kernels_fast.o", "kernels_builtin.cu", ["-DOCS_STRICT=0", "-DOCS_UNIFORM_H=1", "-fmad=true"]),
+    ("kernels_fastv.o", "kernels_builtin.cu", ["-DOCS_STRICT=0", "-DOCS_UNIFORM_H=0", "-fmad=true"]),
     ("kernels_strict.o", "kernels_builtin.cu", ["-DOCS_STRICT=1", "-fmad=false"]),
     ("ocs_api.o", "ocs_api.cu", []),
     ("ocs_multi.o", "ocs_multi.cu", []),
@@ -82,7 +83,7 @@ def build_variant(name: str, flags: list[str]) -> str:
     vdir = os.path.join(OBJ, "variants")
     os.makedirs(vdir, exist_ok=True)
     obj = os.path.join(vdir, f"kernels_fast_{name}.o")
-    cmd = [NVCC] + COMMON + ["-DOCS_STRICT=0", "-fmad=true"] + flags + ["-c", os.path.join(CSRC, "kernels_builtin.cu"), "-o", obj]
+    cmd = [NVCC] + COMMON + ["-DOCS_STRICT=0", "-DOCS_UNIFORM_H=1", "-fmad=true"] + flags + ["-c", os.path.join(CSRC, "kernels_builtin.cu"), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + ".ptxas.log", "w") as f:
         f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)

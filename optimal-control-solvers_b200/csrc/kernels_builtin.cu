@@ -1,15 +1,20 @@
 // kernels_builtin.cu -- instantiates the sweep kernels for the built-in problems.
-// Compiled twice: -DOCS_STRICT=0 (FMA contraction on, namespace ocs_fast, kernel
-// tag test_fast) and -DOCS_STRICT=1 -fmad=false (namespace ocs_strict, tag
-// test_strict), so one library carries both arithmetic modes.
+// Compiled three times, so one library carries both arithmetic modes:
+//   -DOCS_STRICT=1 -fmad=false                   namespace ocs_strict, kernel tag test_strict
+//   -DOCS_STRICT=0 -DOCS_UNIFORM_H=1 -fmad=true  namespace ocs_fast,   tag test_fast   (grids whose steps agree to
+//                                                rounding -- every linspace grid: step sizes as constant operands)
+//   -DOCS_STRICT=0 -DOCS_UNIFORM_H=0 -fmad=true  namespace ocs_fastv,  tag test_fastv  (any other grid: per-step sizes)
 #include <cuda_runtime.h>
 
 #if OCS_STRICT
 #define OCS_NS ocs_strict
 #define OCS_TAGNAME test_strict
-#else
+#elif defined(OCS_UNIFORM_H) && OCS_UNIFORM_H
 #define OCS_NS ocs_fast
 #define OCS_TAGNAME test_fast
+#else
+#define OCS_NS ocs_fastv
+#define OCS_TAGNAME test_fastv
 #endif
 
 // Two trajectories per thread at 5 resident blocks/SM (92 registers) measured fastest for the test problem's
@@ -79,8 +84,10 @@
 
 #if OCS_STRICT
 OCS_DEFINE_KERNELS(ocs_strict::TestOCProblem, test_strict, 0)
-#else
+#elif defined(OCS_UNIFORM_H) && OCS_UNIFORM_H
 OCS_DEFINE_KERNELS(ocs_fast::TestOCProblem, test_fast, 0)
+#else
+OCS_DEFINE_KERNELS(ocs_fastv::TestOCProblem, test_fastv, 0)
 #endif
 
 #define OCS_CAT5_(a, b, c, d, e) a##b##c##d##e

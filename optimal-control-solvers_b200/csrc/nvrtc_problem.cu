@@ -105,7 +105,12 @@ int ocs_compile_unit(const char *source, const char *unit, int strict, const cha
     src += "#define OCS_NS ocs_gen\n";
     // the strict build keeps the reference's operation order everywhere it matters: the sweep bodies (rk4_kernels.cuh)
     // and the generated right-hand sides (codegen/fma_forms.py prints re-associated forms for the other build only)
+    // `strict` carries two flags: bit 0 = the strict arithmetic mode, bit 1 = the grid's steps agree to rounding, so the
+    // FMA-contracted build may take the step sizes as constant-bank operands (OCS_UNIFORM_H, rk4_kernels.cuh)
+    const bool uniform_h = (strict & 2) != 0;
+    strict &= 1;
     src += strict ? "#define OCS_STRICT 1\n" : "#define OCS_STRICT 0\n";
+    src += (uniform_h && !strict) ? "#define OCS_UNIFORM_H 1\n" : "#define OCS_UNIFORM_H 0\n";
     // Sweep-kernel tuning by problem size (B200, profiles/r2_notes.md).  A problem with several states carries
     // 150+ live registers per trajectory, so only 8-12 warps are resident per SM: nothing hides a global-load
     // latency.  Its per-step loads therefore go through a cp.async ring 4 steps ahead, the reverse step loop is not

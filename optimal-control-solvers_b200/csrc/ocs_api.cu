@@ -16,6 +16,7 @@ using ocs_host::SweepArgs;
 using ocs_host::EqArgs;
 
 extern "C" void ocs_builtin_table_test_fast(ocs_kernel_table *t);
+extern "C" void ocs_builtin_table_test_fastv(ocs_kernel_table *t);
 extern "C" void ocs_builtin_table_test_strict(ocs_kernel_table *t);
 // nvrtc_problem.cu
 int ocs_compile_problem(const char *source, int n, int nc, int np, int strict, const char *include_dir,
@@ -453,6 +454,113 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
         }
         const unsigned bal = __ballot_sync(0xffffffffu, open);
         if (lane == 0 && bal) atomicAdd(n_open, __popc(bal));
+    }
+}
+
+// The split update without the register-held rows.  spg_update_split_kernel keeps a trajectory's trial rows in registers
+// between its two phases (2 x 16 doubles per thread: 124 registers, two 224-thread blocks per SM at K = 101), and a warp
+// load touches 256 contiguous bytes of a row whose neighbours belong to other blocks.  Here a block covers 32 TW
+// consecutive trajectories (TW adjacent warps read TW x 256 contiguous bytes of every row), phase 1 only accumulates, and
+// phase 2 reads the accepted rows a second time -- a block's rows (TW x 52 KB at K = 101) are still in the 126 MB L2,
+// so DRAM sees the same 5 passes while the SM holds 2-3x the warps.  Same row groups and summation order as the split
+// kernel: bit-identical results.
+template <int TW>
+__global__ void __launch_bounds__(1024, 1) spg_update_l2_kernel(
+    long nz, long nb, double *z, const double *g, double *zt, double *gt,
+    double *J, const double *Jt, double *Jhist, double *alpha, double *pred, const double *__restrict__ lb,
+    const double *__restrict__ ub, int *frozen, int *iters, int iter, double tol, int first, int *n_open)
+{
+    extern __shared__ double spg_sm[];                   // [5][G][32 TW]
+    constexpr int W = 32 * TW;
+    const int lane = threadIdx.x, kg = threadIdx.y, G = blockDim.y;
+    const long b = (long)blockIdx.x * W + lane;
+    const bool live = b < nb && !frozen[b];
+    bool accept = first != 0;
+    double a = 0.0, Jtb = 0.0;
+    if (live) {
+        a = alpha[b];
+        Jtb = Jt[b];
+        if (!first) {
+            double Jref = -INFINITY;
+            for (int j = 0; j < SPG_M; ++j) Jref = fmax(Jref, Jhist[(size_t)j * nb + b]);
+            accept = isfinite(Jtb) && Jtb <= Jref - 1e-4 * pred[b];
+        }
+    }
+    double sts = 0.0, sty = 0.0, pg = 0.0, gmax = 0.0;
+    if (live && accept) {
+#pragma unroll 4
+        for (long k = kg; k < nz; k += G) {
+            const size_t i = (size_t)k * nb + b;
+            const double zn = zt[i], gn = gt[i];
+            const double sk = zn - z[i], yk = gn - g[i];
+            sts += sk * sk;
+            sty += sk * yk;
+            const double proj = fmin(ub[k], fmax(lb[k], zn - gn));
+            pg = fmax(pg, fabs(zn - proj));
+            gmax = fmax(gmax, fabs(gn));
+        }
+    }
+    double *r0 = spg_sm, *r1 = r0 + G * W, *r2 = r1 + G * W, *r3 = r2 + G * W, *r4 = r3 + G * W;
+    r0[kg * W + lane] = sts;
+    r1[kg * W + lane] = sty;
+    r2[kg * W + lane] = pg;
+    r3[kg * W + lane] = gmax;
+    __syncthreads();
+    sts = sty = pg = gmax = 0.0;
+    for (int q = 0; q < G; ++q) {
+        sts += r0[q * W + lane];
+        sty += r1[q * W + lane];
+        pg = fmax(pg, r2[q * W + lane]);
+        gmax = fmax(gmax, r3[q * W + lane]);
+    }
+    int fz = 0;
+    if (live) {
+        if (accept) {
+            if (first) a = 1.0 / fmax(gmax, 1e-8);
+            else a = sty > 0.0 ? fmin(1e10, fmax(1e-10, sts / sty)) : fmin(1e10, 10.0 * a);
+            if (pg <= tol) fz = 1;
+        } else {
+            a *= 0.25;
+            if (a < 1e-14) fz = 2;                               // stalled
+        }
+    }
+    double pr = 0.0;
+    if (live) {
+        const double *zs = accept ? zt : z, *gs = accept ? gt : g;   // the accepted point
+#pragma unroll 4
+        for (long k = kg; k < nz; k += G) {
+            const size_t i = (size_t)k * nb + b;
+            const double zn = zs[i], gn = gs[i];
+            const double zn_new = fz ? zn : fmin(ub[k], fmax(lb[k], zn - a * gn));
+            if (!accept) {
+                zt[i] = zn;
+                gt[i] = gn;
+            }
+            z[i] = zn_new;
+            pr += gn * (zn - zn_new);
+        }
+    }
+    r4[kg * W + lane] = pr;
+    __syncthreads();
+    if (kg == 0) {
+        int open = 0;
+        if (live) {
+            pr = 0.0;
+            for (int q = 0; q < G; ++q) pr += r4[q * W + lane];
+            pred[b] = pr;
+            alpha[b] = a;
+            iters[b] = iter;
+            if (accept) {
+                J[b] = Jtb;
+                Jhist[(size_t)(iter % SPG_M) * nb + b] = Jtb;
+                if (first)
+                    for (int j = 0; j < SPG_M; ++j) Jhist[(size_t)j * nb + b] = Jtb;
+            }
+            if (fz) frozen[b] = fz;
+            else open = 1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, open);
+        if ((lane & 31) == 0 && bal) atomicAdd(n_open, __popc(bal));
     }
 }
 
@@ -928,6 +1036,13 @@ void base_args(H *h, int si, SweepArgs &a)
         double dmax = 0.0;
         for (double hi : s.h) dmax = std::max(dmax, std::fabs(hi - s.h[0]));
         a.texp_uniform = dmax <= 1e-12 * std::fabs(s.h[0]) ? 1 : 0;
+        // the mean step (the horizon's length is kept exactly); only the OCS_UNIFORM_H kernels read it, and those are
+        // only selected for grids whose steps agree to rounding (steps_uniform)
+        const double hm = (s.tspan[s.N] - s.tspan[0]) / s.N;
+        a.hc[0] = hm;
+        a.hc[1] = hm / 2;
+        a.hc[2] = hm / 3;
+        a.hc[3] = hm / 6;
     }
     a.basrec = s.d_basrec;
     a.p = h->d_params.p;
@@ -988,6 +1103,27 @@ int rev_tpt(const H *h, int um)
     return std::max(h->params_nbatch > 1 ? h->kt.tpt_rev_pb : (um == 1 ? h->kt.tpt_rev_coef : h->kt.tpt_rev), 1);
 }
 
+// Every segment's steps agree to rounding (any linspace grid does: 1e-12 relative, the bound of the time-exponential
+// recurrence): the FMA-contracted kernels may then read ONE step size per segment as a constant-bank operand.
+bool steps_uniform(const H *h)
+{
+    for (int si = 0; si < (h->has_tail ? 2 : 1); ++si) {
+        const Segment &s = h->seg[si];
+        if (s.N < 1) continue;
+        const double hm = (s.tspan[s.N] - s.tspan[0]) / s.N;
+        for (double hi : s.h)
+            if (!(std::fabs(hi - hm) <= 1e-12 * std::fabs(hm))) return false;
+    }
+    return true;
+}
+
+// flags of ocs_compile_unit / ocs_compile_problem: bit 0 strict arithmetic, bit 1 uniform steps
+int nvrtc_flags(const H *h)
+{
+    const bool strict = h->math_mode == OCS_B200_MATH_STRICT;
+    return (strict ? 1 : 0) | ((!strict && steps_uniform(h)) ? 2 : 0);
+}
+
 enum { KIND_FWD = 0, KIND_FWDG, KIND_REV, KIND_REVG, KIND_FB, KIND_FBC, KIND_FBCG };
 
 // The kernel of one sweep variant.  Built-in problems have every variant compiled in; generated
@@ -1016,7 +1152,7 @@ int resolve(H *h, int kind, int um, int bm, int pb, const void **out)
         const void *kern[1] = {nullptr};
         void *lib = nullptr;
         std::string log;
-        int rc = ocs_compile_unit(h->gen_source.c_str(), unit, h->math_mode == OCS_B200_MATH_STRICT,
+        int rc = ocs_compile_unit(h->gen_source.c_str(), unit, nvrtc_flags(h),
                                   h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log,
                                   h->gen_n);
         if (rc != 0) return h->fail(rc, "kernel %s of the generated problem did not compile:\n%s", name, log.c_str());
@@ -1611,8 +1747,10 @@ int ocs_b200_set_problem_builtin(ocs_b200_handle *h, int problem_id)
     if (problem_id != OCS_B200_PROBLEM_TEST) return h->fail(OCS_B200_ERR_ARG, "unknown built-in problem %d", problem_id);
     if (h->math_mode == OCS_B200_MATH_STRICT)
         ocs_builtin_table_test_strict(&h->kt);
+    else if (steps_uniform(h))
+        ocs_builtin_table_test_fast(&h->kt);       // step sizes as constant-bank operands
     else
-        ocs_builtin_table_test_fast(&h->kt);
+        ocs_builtin_table_test_fastv(&h->kt);      // per-step sizes from the step records
     h->have_problem = true;
     h->is_generated = false;
     h->have_states = false;
@@ -1631,7 +1769,7 @@ int ocs_b200_set_problem_source(ocs_b200_handle *h, const char *cuda_source, int
         std::string log;
         ocs_kernel_table kt{};
         void *lib = nullptr;
-        int rc = ocs_compile_problem(cuda_source, n, nc, np, h->math_mode == OCS_B200_MATH_STRICT,
+        int rc = ocs_compile_problem(cuda_source, n, nc, np, nvrtc_flags(h),
                                      (kernel_include_dir && kernel_include_dir[0]) ? kernel_include_dir : nullptr, &kt, &lib, &log);
         // a failed compilation leaves the handle as it was (problem, lazily compiled variants and their source)
         if (rc != 0) return h->fail(rc, "generated problem did not compile:\n%s", log.c_str());
@@ -2770,7 +2908,7 @@ int ocs_b200_compute_equilibrium(ocs_b200_handle *h, const double *params, int n
             void *lib = nullptr;
             std::string log;
             int rc = ocs_compile_unit(h->gen_source.c_str(), "OCS_EQ_KERNEL(ocs_gen::Problem, gen)",
-                                      h->math_mode == OCS_B200_MATH_STRICT,
+                                      nvrtc_flags(h),
                                       h->gen_include.empty() ? nullptr : h->gen_include.c_str(), names, 1, kern, &lib, &log,
                                       h->gen_n);
             if (rc != 0) return h->fail(rc, "equilibrium kernel of the generated problem did not compile:\n%s", log.c_str());
@@ -2909,6 +3047,11 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         h->ctrl_nbatch = Bt;
         h->seg[0].records_dirty = true;
         const bool spg_serial = nz > 512 || getenv("OCS_B200_SPG_SERIAL") != nullptr;   // (the env switch is for the A/B test)
+        // OCS_B200_SPG_L2 = 1 | 2 | 4: the L2 re-read update kernel over 32 / 64 / 128 trajectories per block; 0: the
+        // register-held split kernel
+        int spg_l2 = 0;
+        if (const char *e = getenv("OCS_B200_SPG_L2")) spg_l2 = atoi(e);
+        if (spg_l2 != 1 && spg_l2 != 2 && spg_l2 != 4) spg_l2 = 0;
         // ControlBounds on the grid (ocs_b200_set_solve_control_bounds): an outer augmented-Lagrangian iteration around
         // the projected-gradient solve.  Only the dense-basis gradient path has the two grids the penalty works on;
         // a sparse basis bounds u(t) through the coefficient box already (compute_nlp_bounds).
@@ -2968,6 +3111,12 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                     spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
                         h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);
+                } else if (spg_l2 && Gk * 32 * spg_l2 <= 1024) {
+                    const dim3 blk2(32 * spg_l2, Gk), grd2((unsigned)((Bt + 32 * spg_l2 - 1) / (32 * spg_l2)));
+                    auto kern = spg_l2 == 4 ? spg_update_l2_kernel<4> : spg_l2 == 2 ? spg_update_l2_kernel<2> : spg_update_l2_kernel<1>;
+                    kern<<<grd2, blk2, sm * spg_l2, h->stream>>>(
+                        nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
+                        h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);
                 } else if (Gk <= 16) {
                     spg_update_split_kernel<16, 512><<<grd, blk, sm, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,

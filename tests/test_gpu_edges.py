@@ -239,3 +239,73 @@ def test_parameter_sweep_time_exponentials_by_recurrence(ocs, oracle, uniform, p
     x = integ.fetch_states(0, Bt)
     assert relerr(x[1, -1, :], out["J"]) < 1e-12
     integ.close()
+
+
+def _unequal(rng, t0, t1, N):
+    s = rng.uniform(0.5, 1.5, N)
+    return t0 + np.concatenate([[0.0], np.cumsum(s)]) * ((t1 - t0) / s.sum())
+
+
+@pytest.mark.parametrize("N", [1, 5, 33, 130])
+def test_unequal_steps_take_the_per_step_kernels(ocs, oracle, N):
+    """The fast build has two kernel sets: grids whose steps agree to rounding read ONE step size as a constant
+    operand (OCS_UNIFORM_H), every other grid reads per-step sizes from the step records (kernels_builtin.cu).  A
+    grid with steps between 0.5 and 1.5 of the mean must take the second set in every sweep -- grid controls,
+    coefficients, fetch kernels, both fb_sweep costates -- and match the oracle like the uniform ones do."""
+    rng = np.random.default_rng(300 + N)
+    tspan = _unequal(rng, 0.0, 0.5 + 0.05 * N, N)
+    integ = ocs.CudaRK4Integrator(tspan)
+    ointeg = oracle.RK4Integrator(tspan)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    oprob = oracle.TestOCProblem(**TEST_PARAMS)
+    Bt, G = 37, 2 * N + 1
+    x0 = rng.uniform(.5, 2.5, (1, Bt))
+    u = rng.uniform(0, 1, (1, G, Bt))
+    x, J = integ.compute_states(prob, x0, u, return_x=True)
+    lam, dJdu = integ.compute_adjoints(prob, u, grids=True)
+    for b in (0, 36):
+        ox, oJ = ointeg.compute_states(oprob, x0[:, b], u[:, :, b])
+        olam, odu = ointeg.compute_adjoints(oprob, u[:, :, b])
+        assert relerr(x[:, :, b], ox) < TOL and relerr(J[b], oJ) < TOL
+        assert relerr(lam[:, :, b], olam) < TOL and relerr(dJdu[:, :, b], odu) < TOL
+    cc = lambda t, xx, ll: oracle.control_char_test_problem(oprob, t, xx, ll)
+    for mode in ("discrete", "continuous"):
+        integ.fb_sweep(prob, x0, u, nSWEEPS=1, costate=mode)
+        ref = oracle.fb_sweep_rk4(oprob, ointeg, x0[:, 36], u[:, :, 36].copy(), cc, nSWEEPS=1, costate=mode)
+        assert relerr(integ.get_control_u(36, 1)[:, :, 0], ref["u"]) < TOL, (mode, N)
+    K = min(6, N + 1)
+    ctl = ocs.PWLinearControl(integ.t, K, 1)
+    integ.attach_control(ctl)
+    for v in (rng.random(K), rng.random((K, Bt))):
+        out = integ.evaluate(prob, x0, v)
+        ref = oracle.C.evaluate(P, tspan, ctl.B, x0, v)
+        for key in ("J", "xT", "dJdv", "lam0"):
+            assert relerr(out[key], ref[key]) < TOL, (key, N)
+    integ.close()
+
+
+@pytest.mark.parametrize("which", ["main", "tail"])
+def test_infinite_horizon_with_one_unequal_segment(ocs, oracle, which):
+    """One segment of an RK4InfiniteIntegrator with unequal steps switches BOTH segments to the per-step kernels
+    (the kernel set is chosen per handle)."""
+    rng = np.random.default_rng(7)
+    tspan = _unequal(rng, 0.0, 6.0, 150) if which == "main" else ocs.matlab_linspace(0.0, 6.0, 151)
+    tspanE = _unequal(rng, 6.0, 14.0, 90) if which == "tail" else ocs.matlab_linspace(6.0, 14.0, 91)
+    uStar = 0.723368780097983
+    x0 = rng.uniform(.5, 2.5, (1, 40))
+    v = rng.random(11)
+    prob = ocs.TestOCProblem(TEST_PARAMS, [[0, 1]])
+    with ocs.CudaRK4InfiniteIntegrator(tspan, tspanE, uStar) as integ:
+        ctl = ocs.PWLinearControl(integ.t, 11, 1)
+        integ.attach_control(ctl)
+        out = integ.evaluate(prob, x0, v)
+    ointeg = oracle.RK4InfiniteIntegrator(tspan, tspanE, [uStar])
+    oprob = oracle.TestOCProblem(**TEST_PARAMS)
+    octl = oracle.PWLinearControl(ointeg.t, 11, 1)
+    u = octl.compute_u(v)
+    for b in (0, 39):
+        _, J = ointeg.compute_states(oprob, x0[:, b], u)
+        lam, dJdu = ointeg.compute_adjoints(oprob, u)
+        assert relerr(out["J"][b], J) < TOL
+        assert relerr(out["lam0"][:, b], lam[:, 0]) < TOL
+        assert relerr(out["dJdv"][:, b], octl.compute_dJdv(dJdu)) < TOL
