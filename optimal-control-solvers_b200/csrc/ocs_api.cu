@@ -457,15 +457,16 @@ __global__ void __launch_bounds__(MAXT, 1) spg_update_split_kernel(
     }
 }
 
-// The split update without the register-held rows.  spg_update_split_kernel keeps a trajectory's trial rows in registers
-// between its two phases (2 x 16 doubles per thread: 124 registers, two 224-thread blocks per SM at K = 101), and a warp
-// load touches 256 contiguous bytes of a row whose neighbours belong to other blocks.  Here a block covers 32 TW
-// consecutive trajectories (TW adjacent warps read TW x 256 contiguous bytes of every row), phase 1 only accumulates, and
-// phase 2 reads the accepted rows a second time -- a block's rows (TW x 52 KB at K = 101) are still in the 126 MB L2,
-// so DRAM sees the same 5 passes while the SM holds 2-3x the warps.  Same row groups and summation order as the split
-// kernel: bit-identical results.
-template <int TW>
-__global__ void __launch_bounds__(1024, 1) spg_update_l2_kernel(
+// The split update without the register-held rows (the default).  spg_update_split_kernel keeps a trajectory's trial
+// rows in registers between its two phases (2 x 16 doubles per thread: 124 registers, two 224-thread blocks per SM at
+// K = 101) and reaches 2.4 TB/s.  Here phase 1 only accumulates and phase 2 reads the accepted rows a second time: a
+// block's rows (52 KB at K = 101) are still in the 126 MB L2, so DRAM sees the same 5 passes, no thread holds more than
+// the UNR rows in flight, and twice the warps are resident: 4.3 TB/s (profiles/r2_ab_spg_update.txt; wider blocks of
+// 64 / 128 adjacent trajectories and 1344-1792 resident threads at 36-40 registers measured 3-30 % slower than
+// this shape, 4 / 8 rows in flight per thread 7 / 65 % slower than 2).  Same row groups and summation order as the
+// split kernel: bit-identical results.
+template <int TW, int UNR>
+__global__ void __launch_bounds__(TW * 512, 2 / TW) spg_update_l2_kernel(
     long nz, long nb, double *z, const double *g, double *zt, double *gt,
     double *J, const double *Jt, double *Jhist, double *alpha, double *pred, const double *__restrict__ lb,
     const double *__restrict__ ub, int *frozen, int *iters, int iter, double tol, int first, int *n_open)
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(1024, 1) spg_update_l2_kernel(
     }
     double sts = 0.0, sty = 0.0, pg = 0.0, gmax = 0.0;
     if (live && accept) {
-#pragma unroll 4
+#pragma unroll UNR
         for (long k = kg; k < nz; k += G) {
             const size_t i = (size_t)k * nb + b;
             const double zn = zt[i], gn = gt[i];
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(1024, 1) spg_update_l2_kernel(
     double pr = 0.0;
     if (live) {
         const double *zs = accept ? zt : z, *gs = accept ? gt : g;   // the accepted point
-#pragma unroll 4
+#pragma unroll UNR
         for (long k = kg; k < nz; k += G) {
             const size_t i = (size_t)k * nb + b;
             const double zn = zs[i], gn = gs[i];
@@ -3047,11 +3048,12 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         h->ctrl_nbatch = Bt;
         h->seg[0].records_dirty = true;
         const bool spg_serial = nz > 512 || getenv("OCS_B200_SPG_SERIAL") != nullptr;   // (the env switch is for the A/B test)
-        // OCS_B200_SPG_L2 = 1 | 2 | 4: the L2 re-read update kernel over 32 / 64 / 128 trajectories per block; 0: the
-        // register-held split kernel
-        int spg_l2 = 0;
+        // A/B switches: OCS_B200_SPG_L2 = 0 selects the register-held split kernel, 2 the L2 re-read kernel over 64 adjacent
+        // trajectories per block (default 1: 32); OCS_B200_SPG_UNROLL = 1 | 4 its rows in flight per thread (default 2)
+        int spg_l2 = 1, spg_unr = 2;
         if (const char *e = getenv("OCS_B200_SPG_L2")) spg_l2 = atoi(e);
-        if (spg_l2 != 1 && spg_l2 != 2 && spg_l2 != 4) spg_l2 = 0;
+        if (const char *e = getenv("OCS_B200_SPG_UNROLL")) spg_unr = atoi(e);
+        if (spg_l2 != 1 && spg_l2 != 2) spg_l2 = 0;
         // ControlBounds on the grid (ocs_b200_set_solve_control_bounds): an outer augmented-Lagrangian iteration around
         // the projected-gradient solve.  Only the dense-basis gradient path has the two grids the penalty works on;
         // a sparse basis bounds u(t) through the coefficient box already (compute_nlp_bounds).
@@ -3111,9 +3113,10 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
                     spg_update_kernel<<<(unsigned)((Bt + 127) / 128), 128, 0, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
                         h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);
-                } else if (spg_l2 && Gk * 32 * spg_l2 <= 1024) {
+                } else if (spg_l2 && Gk * 32 * spg_l2 <= 512 * spg_l2) {
                     const dim3 blk2(32 * spg_l2, Gk), grd2((unsigned)((Bt + 32 * spg_l2 - 1) / (32 * spg_l2)));
-                    auto kern = spg_l2 == 4 ? spg_update_l2_kernel<4> : spg_l2 == 2 ? spg_update_l2_kernel<2> : spg_update_l2_kernel<1>;
+                    auto kern = spg_l2 == 2 ? spg_update_l2_kernel<2, 2> : spg_unr == 1 ? spg_update_l2_kernel<1, 1>
+                              : spg_unr == 4 ? spg_update_l2_kernel<1, 4> : spg_update_l2_kernel<1, 2>;
                     kern<<<grd2, blk2, sm * spg_l2, h->stream>>>(
                         nz, Bt, h->d_z.p, h->d_g.p, h->d_zt.p, h->d_gt.p, h->d_Jacc.p, h->d_J.p, h->d_Jhist.p, h->d_alpha.p,
                         h->d_pred.p, h->d_lbub.p, h->d_lbub.p + nz, h->d_frozen, h->d_sweeps, iter + 1, tol, inner == 0, d_nopen);

@@ -121,6 +121,24 @@ def test_split_spg_update_matches_the_serial_kernel(ocs, K, free):
         assert np.all(a["v"][K] >= 0.5) and np.all(a["v"][K] <= 2.0)
 
 
+@pytest.mark.parametrize("variant", [("OCS_B200_SPG_L2", "0"), ("OCS_B200_SPG_L2", "2"), ("OCS_B200_SPG_UNROLL", "1"),
+                                     ("OCS_B200_SPG_UNROLL", "4")])
+@pytest.mark.parametrize("K,free,Bt", [(5, True, 77), (17, False, 130), (101, False, 300), (128, False, 65), (300, False, 40)])
+def test_l2_spg_update_is_bit_identical_to_the_split_kernel(ocs, variant, K, free, Bt):
+    """spg_update_l2_kernel (the default) re-reads the accepted rows from L2 instead of holding them in registers; same
+    row groups and summation order as the register-held split kernel (OCS_B200_SPG_L2=0), so every bit agrees -- its
+    64-trajectory and unroll variants too, ragged last blocks and a batch smaller than one block included (K = 300 is
+    beyond the L2 kernel's 16 row groups: both runs take the split kernel)."""
+    a = _solve(ocs, K, Bt, free=free)
+    os.environ[variant[0]] = variant[1]
+    try:
+        b = _solve(ocs, K, Bt, free=free)
+    finally:
+        os.environ.pop(variant[0], None)
+    for key in ("v", "J", "iters", "converged"):
+        assert np.array_equal(a[key], b[key]), key
+
+
 def test_single_shooting_writes_into_caller_buffers(ocs):
     K, Bt = 9, 50
     bufs = dict(v=np.full((K, Bt), np.nan, order="F"), J=np.full(Bt, np.nan), iters=np.zeros(Bt, dtype=np.int32),
