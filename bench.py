@@ -529,7 +529,9 @@ def run_solve(args, ocs, local_rank, rank, world):
                                       "update": ksp["ms_update"] / n_it},
                  "update_gbs": 5 * 8.0 * K_PWL * Bt * n_it / (ksp["ms_update"] * 1e-3) / 1e9 if ksp["ms_update"] > 0 else None,
                  "what": "sums over one solve (the last forward sweep re-evaluates the minimisers); update = the projected-gradient "
-                         "step, 5 passes over the (nc K) x Bt coefficient arrays"}
+                         "step, 5 passes over the (nc K) x Bt coefficient arrays",
+                 # how many trajectories stopped after exactly k evaluations (rank 0's shard)
+                 "evaluations_histogram": {str(k): int(c) for k, c in enumerate(np.bincount(ss["iters"].astype(np.int64))) if c}}
     evals = float(ss["iters"].astype(np.int64).sum())        # objective/gradient evaluations actually carried out
     t = torch.tensor([dt, evals, float(ss["converged"].sum()), float(ss["iters"].max())], dtype=torch.float64, device=dev)
     if world > 1:

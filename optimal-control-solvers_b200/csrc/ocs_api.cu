@@ -3153,11 +3153,29 @@ int ocs_b200_single_shooting(ocs_b200_handle *h, const double *x0, long Bt, cons
         }
         // leave the device state at the minimisers: one last evaluation of the accepted points (zt == z for
         // frozen trajectories; the others get their best accepted point) -- J without any penalty term
+        // Without the outer (constraint) iteration the minimisers in z are final here: their download -- the transposition
+        // and the 8 nz Bt bytes over PCIe, 17 ms of a 2^20 x 101 solve -- starts on the copy stream now and runs under the
+        // last evaluation instead of after it.
+        const bool early_v = !cgb && v_opt && nz > 1;
+        if (early_v) {
+            if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            if (!h->chunk_done[0]) CK(cudaEventCreateWithFlags(&h->chunk_done[0], cudaEventDisableTiming));
+            TRY(ensure(h, h->d_stage, (size_t)nz * Bt));
+            CK(cudaEventRecord(h->chunk_done[0], h->stream));
+        }
         CK(cudaMemcpyAsync(h->d_zt.p, h->d_z.p, sizeof(double) * nz * Bt, cudaMemcpyDeviceToDevice, h->stream));
         for (int f = 0; f < nfree; ++f)
             CK(cudaMemcpyAsync(h->d_x0.p + (size_t)free_states[f] * Bt, h->d_zt.p + (size_t)(nv + f) * Bt,
                                sizeof(double) * Bt, cudaMemcpyDeviceToDevice, h->stream));
         TRY(run_forward(h, 0, Bt, -1, nullptr, true));
+        if (early_v) {
+            // issued after the sweep's launches: a pageable destination blocks this thread while it drains through the
+            // pinned ring, and the device has its work queued meanwhile
+            CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[0], 0));
+            TRY(from_soa(h, h->d_z.p, h->d_stage.p, nz, Bt, Bt, 1, h->copy_stream));
+            TRY(d2h(h, v_opt, h->d_stage.p, sizeof(double) * nz * Bt, h->copy_stream));
+            v_opt = nullptr;      // delivered by finish_host
+        }
         if (!cgb) break;
         // multipliers, violations, and the trajectories that go round again (u of the accepted points is on the grid now)
         CK(cudaMemsetAsync(d_nopen, 0, sizeof(int), h->stream));

@@ -87,7 +87,7 @@ def test_infinite_horizon_folds_behind_the_tail(ocs, oracle):
         assert relerr(out["dJdv"][:, b], octl.compute_dJdv(dJdu)) < TOL
 
 
-def _solve(ocs, K, Bt, free=False, serial=False, out=None):
+def _solve(ocs, K, Bt, free=False, serial=False, out=None, max_iter=400):
     if serial:
         os.environ["OCS_B200_SPG_SERIAL"] = "1"
     try:
@@ -99,7 +99,7 @@ def _solve(ocs, K, Bt, free=False, serial=False, out=None):
             x0 = np.random.default_rng(K).uniform(.5, 2.5, (1, Bt))
             Lb, Ub = ctl.compute_nlp_bounds(prob.ControlBounds)
             kw = dict(FreeInitStates=(0,), FreeStateBounds=[[0.5, 2.0]]) if free else {}
-            return integ.single_shooting(prob, x0, ctl.compute_initial_v(0.5), Lb, Ub, max_iter=400, tol=1e-7, out=out, **kw)
+            return integ.single_shooting(prob, x0, ctl.compute_initial_v(0.5), Lb, Ub, max_iter=max_iter, tol=1e-7, out=out, **kw)
     finally:
         os.environ.pop("OCS_B200_SPG_SERIAL", None)
 
@@ -137,6 +137,26 @@ def test_l2_spg_update_is_bit_identical_to_the_split_kernel(ocs, variant, K, fre
         os.environ.pop(variant[0], None)
     for key in ("v", "J", "iters", "converged"):
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("K,free,Bt,max_iter", [(5, True, 77, 400), (101, False, 1500, 400), (33, False, 300, 6), (17, True, 40, 1)])
+def test_vopt_download_under_the_last_evaluation(ocs, K, free, Bt, max_iter):
+    """The minimisers are final before the last forward sweep (which only leaves the device state at them), so their
+    transposition and download run on the copy stream under it -- into pinned and pageable arrays alike, also when the
+    iteration limit stops the solve with trajectories still open."""
+    import torch
+    nz = K + (1 if free else 0)
+    ref = _solve(ocs, K, Bt, free=free, max_iter=max_iter)
+    assert ref["converged"].all() == (max_iter == 400)
+    again = _solve(ocs, K, Bt, free=free, max_iter=max_iter)
+    vp = torch.full((Bt, nz), float("nan"), dtype=torch.float64).pin_memory()
+    bufs = dict(v=vp.numpy().T, J=np.empty(Bt), iters=np.zeros(Bt, dtype=np.int32), converged=np.zeros(Bt, dtype=np.int32))
+    res = _solve(ocs, K, Bt, free=free, out=bufs, max_iter=max_iter)
+    assert res["v"] is bufs["v"]
+    for key in ("v", "J", "iters", "converged"):
+        assert np.array_equal(ref[key], bufs[key]) and np.array_equal(ref[key], again[key]), key
+    # the coefficients on the device are the ones returned
+    assert np.all(np.isfinite(bufs["v"]))
 
 
 def test_single_shooting_writes_into_caller_buffers(ocs):
