@@ -48,8 +48,14 @@
 #ifndef OCS_TPT_REV_COEF
 #define OCS_TPT_REV_COEF 2
 #endif
+// (with the step sizes as constant operands, r3j: reverse (2,4: 128 regs) 4.125 ms / (2,5: 96 regs, 16 B spilled) 3.993;
+//  forward (2,6: 76 regs) and the shared-control reverse at (2,6: 80 regs) unchanged within 0.4 %)
 #ifndef OCS_MINBLOCKS_REV_COEF
-#define OCS_MINBLOCKS_REV_COEF 4
+#if !OCS_STRICT && defined(OCS_UNIFORM_H) && OCS_UNIFORM_H
+#define OCS_MINBLOCKS_REV_COEF 5
+#else
+#define OCS_MINBLOCKS_REV_COEF 4      // per-step sizes need the registers: 40-52 B spilled at 5
+#endif
 #endif
 // Per-trajectory parameters (a parameter sweep, bench.py --config cfg2p / cfg2pv): exp(-r t) runs in the thread and
 // (c, m, r) live in registers, so the uniform-parameter settings above spilled (808 B in the grid-control forward
