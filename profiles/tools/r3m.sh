@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, call 3m: projection dJdu * B' with B as a kernel-parameter (constant-bank) operand -- dense-basis tests, A/B on cfg3
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_codegen.py tests/test_gpu_golden.py tests/test_gpu_parity.py tests/test_gpu_lanes.py tests/test_gpu_solve_constraints.py tests/test_gpu_fullsize.py tests/test_gpu_edges.py -m gpu -x -q > gpurun_out/r3m_pytest.log 2>&1; echo "pytest rc=$?" > gpurun_out/r3m_sum.txt
+tail -5 gpurun_out/r3m_pytest.log >> gpurun_out/r3m_sum.txt
+for v in "OCS_B200_PROJECT=lds" "X=0" "OCS_B200_PROJECT=lds" "X=0"; do
+  env $v timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import sys,json
+j=json.loads(sys.stdin.read()); ks=j['roofline']['kernels']; print('cfg3 $v','%.3e'%j['value'], 'ms/step %.3f'%j['ms_per_step'], ' '.join('%s=%.3f'%(k['kernel'][-22:],k['ms']) for k in ks))
+" >> gpurun_out/r3m_sum.txt 2>&1
+done
+for v in "OCS_B200_PROJECT=lds" "X=0"; do
+  env $v OCS_B200_LANES=0 timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import sys,json
+j=json.loads(sys.stdin.read()); ks=j['roofline']['kernels']; print('cfg3 no lanes $v','%.3e'%j['value'], 'ms/step %.3f'%j['ms_per_step'], ' '.join('%s=%.3f'%(k['kernel'][-22:],k['ms']) for k in ks))
+" >> gpurun_out/r3m_sum.txt 2>&1
+done
+cat gpurun_out/r3m_sum.txt
