@@ -756,6 +756,106 @@ static cudaError_t launch_project(cudaStream_t st, const double *dug, const doub
     return cudaGetLastError();
 }
 
+// The same projection with B as an OPERAND instead of a shared-memory read.  The kernel above issues one LDS.128 per four
+// FMAs, and a broadcast LDS.128 still delivers 512 bytes to the register file (4 cycles of the SM's shared-memory path):
+// 9 of them per grid point and warp against 18 SM-cycles of FP64 issue -- it is bound by shared-memory bandwidth
+// (short_scoreboard / wait stalls, FP64 pipe 36 % active, 0.45 of HBM).  Here up to 220 columns of B travel in the
+// kernel's PARAMETER space (constant bank 0, 32 764 bytes per launch since CUDA 12.1): the compiler reads them with
+// LDCU.64 into uniform registers -- once per warp, not once per lane -- and every FMA takes the form
+// DFMA acc, d.reuse, UR, acc, which also occupies the FP64 pipe for 2 cycles instead of 3 (profiles/r2_notes.md section 1).
+// One thread per trajectory and NS controls, KC accumulators each (128 registers), two batches of 8 / NS grid points in
+// flight per stream; G / 220 launches, each adding its columns' contribution to dJdv in ascending grid order (the first
+// one stores).  K <= KC only; wider bases keep the kernel above.  Measured (cfg3, same box, profiles/r2_ab_project.txt):
+// 1.14 -> 1.08 ms -- the accumulators of 100k trajectories are three quarters of the GPU's registers, so every launch
+// runs 1.3 rounds of blocks at 16 warps per SM and the loads' latency is what remains; without the double-buffered
+// loads 1.41-1.46 ms, one control per thread at 6 blocks per SM 1.20 ms.
+constexpr int PROJC_DOUBLES = 3960;
+struct ProjChunk {
+    double b[PROJC_DOUBLES];      // [nj][KC]: B(0..K-1, j0 + jj), zero-padded to KC
+};
+template <int KC, int NS>
+__global__ void __launch_bounds__(128, 4) dense_project_const_kernel(const __grid_constant__ ProjChunk B, const double *__restrict__ dug,
+                                                                    int K, int nc, int G, int j0, int nj, long nb, long ldb,
+                                                                    double *dJdv, int first)
+{
+    const long b = (long)blockIdx.x * 128 + threadIdx.x;
+    const int c0 = blockIdx.y * NS;
+    const long bb = b < nb ? b : nb - 1;
+    const double *dp[NS];
+    int cs[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        cs[s] = c0 + s < nc ? c0 + s : nc - 1;
+        dp[s] = dug + ((size_t)cs[s] * G + j0) * ldb + bb;
+    }
+    double acc[NS][KC];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[s][k] = (first || k >= K) ? 0.0 : dJdv[(size_t)(k * nc + cs[s]) * ldb + bb];
+    // two batches of R grid points: the loads of one are in flight while the other is multiplied
+    constexpr int R = 8 / NS;
+    auto load_batch = [&](double (&d)[NS][R], int jj) {      // clamped: entries past nj are loaded but never multiplied
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int jc = jj + r < nj ? jj + r : nj - 1;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) d[s][r] = dp[s][(size_t)jc * ldb];
+        }
+    };
+    auto fma_batch = [&](const double (&d)[NS][R], int jj) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (jj + r < nj) {                               // uniform
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const double bk = B.b[(jj + r) * KC + k];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) acc[s][k] = fma(d[s][r], bk, acc[s][k]);
+                }
+            }
+        }
+    };
+    double dA[NS][R], dB[NS][R];
+    load_batch(dA, 0);
+#pragma unroll 1
+    for (int jj = 0; jj < nj; jj += 2 * R) {
+        load_batch(dB, jj + R);
+        fma_batch(dA, jj);
+        load_batch(dA, jj + 2 * R);
+        fma_batch(dB, jj + R);
+    }
+    if (b < nb) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (c0 + s < nc)
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k < K) dJdv[(size_t)(k * nc + c0 + s) * ldb + b] = acc[s][k];
+    }
+}
+
+// bdense: the host's B, K x G column-major (B(k, j) at bdense[k + K j])
+template <int KC, int NS>
+static cudaError_t launch_project_const(cudaStream_t st, const double *dug, const double *bdense, int K, int nc, int G, long nb, long ldb,
+                                        double *dJdv, long *launches)
+{
+    static_assert((size_t)PROJC_DOUBLES * sizeof(double) + 128 <= 32764, "B chunk must fit the kernel parameter space");
+    const int JT = PROJC_DOUBLES / KC;
+    const dim3 grid((unsigned)((nb + 127) / 128), (unsigned)((nc + NS - 1) / NS));
+    ProjChunk chunk;
+    for (int j0 = 0; j0 < G; j0 += JT) {
+        const int nj = G - j0 < JT ? G - j0 : JT;
+        for (int jj = 0; jj < nj; ++jj)
+            for (int k = 0; k < KC; ++k) chunk.b[jj * KC + k] = k < K ? bdense[k + (size_t)K * (j0 + jj)] : 0.0;
+        dense_project_const_kernel<KC, NS><<<grid, 128, 0, st>>>(chunk, dug, K, nc, G, j0, nj, nb, ldb, dJdv, j0 == 0);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+    }
+    return cudaSuccess;
+}
+
 // ug[c][j][b] = sum_k v[(k*nc+c)][b] B(k,j): control.compute_u for every trajectory (Control/*Control.m compute_u),
 // from the basis records of build_records (sparse: the two weights by knot parity; dense: the column B(:,j)), in
 // the summation order of ControlEval.  Used once per fb_sweep solve that starts from coefficients.
@@ -1335,7 +1435,15 @@ int run_reverse(H *h, long b0, long nb, int only_segment, const double *d_lamT, 
             {
                 const int ncv = h->kt.nc;
                 cudaError_t pe;
-                if (h->K <= 18) pe = ncv >= 2 ? launch_project<18, 2>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv)
+                // K <= 18: B travels as a kernel parameter (dense_project_const_kernel); OCS_B200_PROJECT=lds keeps the
+                // shared-memory kernel (A/B)
+                static const bool proj_lds = getenv("OCS_B200_PROJECT") && !strcmp(getenv("OCS_B200_PROJECT"), "lds");
+                if (h->K <= 18 && !proj_lds) {
+                    long nl = 0;
+                    pe = ncv >= 2 ? launch_project_const<18, 2>(h->stream, a.dug, h->bdense.data(), h->K, ncv, G, nb, Bt, d_dJdv, &nl)
+                                  : launch_project_const<18, 1>(h->stream, a.dug, h->bdense.data(), h->K, ncv, G, nb, Bt, d_dJdv, &nl);
+                    h->launches += nl - 1;      // (one launch is counted below)
+                } else if (h->K <= 18) pe = ncv >= 2 ? launch_project<18, 2>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv)
                                               : launch_project<18, 1>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv);
                 else pe = ncv >= 2 ? launch_project<16, 2>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv)
                                    : launch_project<16, 1>(h->stream, a.dug, s.d_basrec, s.BW, h->K, ncv, G, nb, Bt, d_dJdv);
