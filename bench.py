@@ -246,11 +246,15 @@ class CpuOracle:
         return self.oc.num_threads()
 
 
+COLLECTIVE = ("gather of J and x(T) to rank 0 every step: peer copies over NVLink into the root's buffers (CUDA IPC) ordered by a "
+              "4-byte NCCL all-reduce; NCCL send/recv when IPC is unavailable (gather_check.mode says which ran)")
+
+
 def main_config(Bt, world):
     """The `config` object of the bench line; the reference arm prints the same keys (plus `sample`)."""
     return {"workload": WORKLOAD, "trajectories_per_gpu": Bt, "rk4_steps": N_STEPS,
             "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * N_STEPS * Bt),
-            "collective": "gather of J and x(T) to rank 0 (NCCL send/recv)" if world > 1 else "none"}
+            "collective": COLLECTIVE if world > 1 else "none"}
 
 
 def run_reference(args, rank, world):
@@ -673,7 +677,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the bounded runs of the other BASELINE configs")
-    ap.add_argument("--gather", default="root", choices=["root", "all"], help="N > 1: gather J, x(T) to rank 0 (default) or all-gather")
+    ap.add_argument("--gather", default="peer", choices=["peer", "root", "all"],
+                    help="N > 1: gather J, x(T) to rank 0 by peer copies over CUDA IPC + a 4-byte NCCL completion all-reduce "
+                         "(default; falls back to root), by NCCL send/recv (root), or all-gather")
     ap.add_argument("--config", default="cfg2",
                     choices=["cfg2", "cfg2v", "cfg2p", "cfg2pv", "cfg2solve", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")
@@ -809,7 +815,7 @@ def main():
                 got = torch.stack([out_root[r, 0].sum(), out_root[r, 1:].sum(), out_root[r, 0][Bt // 2], out_root[r, 0].max()])
                 ok = ok and bool(torch.equal(got, alls[r]))
             gather_check = {"gathered_equals_local": ok, "ranks": world, "bytes_per_rank_per_step": 8 * (1 + n_st) * Bt,
-                            "mode": args.gather}
+                            "mode": pg.mode}
             assert ok, "the J / x(T) gathered on rank 0 differ from what the ranks computed"
     value = world * Bt * NT * args.steps / (ms * 1e-3)
 
@@ -873,7 +879,7 @@ def main():
         cfg = main_config(Bt, world) if args.config == "cfg2" else {
             "workload": wl["label"], "trajectories_per_gpu": Bt, "rk4_steps": NT,
             "l2": "inputs larger than L2 (%.1f GB node-state store per GPU)" % (8e-9 * n_st * NT * Bt),
-            "collective": "gather of J and x(T) to rank 0 (NCCL send/recv)" if world > 1 else "none"}
+            "collective": COLLECTIVE if world > 1 else "none"}
         out = {
             "metric": METRIC, "value": value,
             "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -61,8 +61,14 @@ class PipelinedGather:
     """Gather of the packed per-trajectory results [J; x(T)] ((1+n) x Bt_local per rank) that overlaps with the
     next evaluation: results are double-buffered, the collective runs on its own CUDA stream behind an event of
     the compute stream, and a buffer is only handed out again once its gather has completed.
-    mode "root" (default): gather to rank 0 (the north star's "gather the small per-trajectory J and final-state
-    results"); mode "all": all-gather (every rank gets everything; 8x the bytes at 8 ranks).
+    mode "root": gather to rank 0 with NCCL send/recv (the north star's "gather the small per-trajectory J and
+    final-state results"); mode "all": all-gather (every rank gets everything; 8x the bytes at 8 ranks);
+    mode "peer": gather to rank 0 by PEER COPIES -- the root's two result buffers are opened by the other ranks
+    over CUDA IPC and every rank pushes its slice with one cudaMemcpyAsync on its own copy engine over NVLink; NCCL
+    only carries the 4-byte completion all-reduce that orders the pushes on the root's stream.  The NCCL receive
+    kernels of mode "root" run on the root's SMs next to its sweeps (root 5.00 ms per step against 4.85 on the other
+    ranks at 8 GPUs); a peer copy uses no SM on either side.  Falls back to "root" (on every rank) when the IPC
+    export / open fails anywhere.
 
         pg = PipelinedGather(n, Bt, world, device, rank=rank)
         for step in ...:
@@ -82,6 +88,60 @@ class PipelinedGather:
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.done = [None, None]
         self.k = 1
+        self.peer = None            # mode "peer", ranks > 0: device pointers of this rank's slice in the root's two buffers
+        if mode == "peer":
+            if world > 1 and self.cuda:
+                self._peer_setup(n, Bt, device)
+            else:
+                self.mode = "root"
+
+    def _peer_setup(self, n, Bt, device):
+        """Exports the root's buffers over CUDA IPC and opens them everywhere else; agrees on the mode."""
+        import torch
+        import torch.distributed as dist
+        ok, exports = 1, None
+        try:
+            try:
+                from cuda.bindings import driver as cu, runtime as rt
+            except ImportError:         # older cuda-python layouts
+                from cuda import cuda as cu, cudart as rt
+            self._rt = rt
+            torch.cuda.set_device(device)
+            if self.rank == 0:
+                exports = []
+                for t in self.out:
+                    err, base, _size = cu.cuMemGetAddressRange(t.data_ptr())
+                    if int(err) != 0:
+                        raise RuntimeError(f"cuMemGetAddressRange: {err}")
+                    err, h = rt.cudaIpcGetMemHandle(int(base))
+                    if int(err) != 0:
+                        raise RuntimeError(f"cudaIpcGetMemHandle: {err}")
+                    exports.append((bytes(h.reserved), t.data_ptr() - int(base)))
+        except Exception:
+            ok, exports = 0, None
+        box = [exports]
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        if self.rank != 0 and ok:
+            try:
+                if box[0] is None:
+                    raise RuntimeError("the root exported nothing")
+                self.peer = []
+                slice_bytes = 8 * (1 + n) * Bt
+                for hb, off in box[0]:
+                    h = self._rt.cudaIpcMemHandle_t()
+                    h.reserved = hb
+                    err, ptr = self._rt.cudaIpcOpenMemHandle(h, self._rt.cudaIpcMemLazyEnablePeerAccess)
+                    if int(err) != 0:
+                        raise RuntimeError(f"cudaIpcOpenMemHandle: {err}")
+                    self.peer.append(int(ptr) + off + self.rank * slice_bytes)
+            except Exception:
+                ok, self.peer = 0, None
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.mode, self.peer = "root", None
+        else:
+            self.flag = torch.zeros(1, dtype=torch.int32, device=device)
 
     def next_buffer(self):
         import torch
@@ -101,6 +161,18 @@ class PipelinedGather:
         def collective():
             if self.mode == "all":
                 dist.all_gather_into_tensor(self.out[k].view(-1), res.view(-1), group=self.group)
+            elif self.mode == "peer":
+                if self.rank == 0:
+                    self.out[k][0].copy_(res)
+                else:
+                    rt = self._rt
+                    (err,) = rt.cudaMemcpyAsync(self.peer[k], res.data_ptr(), res.numel() * 8,
+                                                rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice, self.stream.cuda_stream)
+                    if int(err) != 0:
+                        raise RuntimeError(f"peer copy to the root failed: {err}")
+                # completion: the root's stream passes this point once every rank's push (stream-ordered before its
+                # contribution) has been issued and finished
+                dist.all_reduce(self.flag, group=self.group)
             else:
                 gather_to_root(res, self.out[k], self.world, self.rank, group=self.group)
         if not self.cuda:

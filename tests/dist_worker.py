@@ -29,8 +29,10 @@ def main():
     for r in range(world):
         assert torch.all(J_all[r * Bt:(r + 1) * Bt] == r) and torch.all(xT_all[r] == r + 0.25)
     # packed, double-buffered gather used by bench.py (synchronous on CPU): to rank 0 (default) and to everybody
-    for mode in ("root", "all"):
+    # ("peer" needs CUDA IPC: on CPU tensors it falls back to the NCCL/gloo gather to the root on every rank)
+    for mode in ("root", "all", "peer"):
         pg = d.PipelinedGather(2, Bt, world, "cpu", rank=rank, mode=mode)
+        assert pg.mode == ("root" if mode == "peer" else mode)
         for step in range(3):
             res = pg.next_buffer()
             res[0] = rank + 10 * step
