@@ -246,8 +246,7 @@ class CpuOracle:
         return self.oc.num_threads()
 
 
-COLLECTIVE = ("gather of J and x(T) to rank 0 every step: peer copies over NVLink into the root's buffers (CUDA IPC) ordered by a "
-              "4-byte NCCL all-reduce; NCCL send/recv when IPC is unavailable (gather_check.mode says which ran)")
+COLLECTIVE = "gather of J and x(T) to rank 0 (NCCL send/recv)"
 
 
 def main_config(Bt, world):
@@ -677,9 +676,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the bounded runs of the other BASELINE configs")
-    ap.add_argument("--gather", default="peer", choices=["peer", "root", "all"],
-                    help="N > 1: gather J, x(T) to rank 0 by peer copies over CUDA IPC + a 4-byte NCCL completion all-reduce "
-                         "(default; falls back to root), by NCCL send/recv (root), or all-gather")
+    ap.add_argument("--gather", default="root", choices=["root", "peer", "all"],
+                    help="N > 1: gather J, x(T) to rank 0 by NCCL send/recv (default), by peer copies over CUDA IPC + a 4-byte NCCL "
+                         "completion all-reduce (measured slower at 8 GPUs: the all-reduce couples the ranks every step), or all-gather")
     ap.add_argument("--config", default="cfg2",
                     choices=["cfg2", "cfg2v", "cfg2p", "cfg2pv", "cfg2solve", "cfg3", "cfg3fb", "cfg4", "fbsweep", "rows"],
                     help="cfg2 (default) is BASELINE.json's bench configuration; cfg3/cfg4 are its other GPU configs")

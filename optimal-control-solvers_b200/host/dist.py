@@ -66,9 +66,11 @@ class PipelinedGather:
     mode "peer": gather to rank 0 by PEER COPIES -- the root's two result buffers are opened by the other ranks
     over CUDA IPC and every rank pushes its slice with one cudaMemcpyAsync on its own copy engine over NVLink; NCCL
     only carries the 4-byte completion all-reduce that orders the pushes on the root's stream.  The NCCL receive
-    kernels of mode "root" run on the root's SMs next to its sweeps (root 5.00 ms per step against 4.85 on the other
-    ranks at 8 GPUs); a peer copy uses no SM on either side.  Falls back to "root" (on every rank) when the IPC
-    export / open fails anywhere.
+    kernels of mode "root" run on the root's SMs next to its sweeps (root 5.00 ms per step against 4.82-4.88 on the
+    other ranks at 8 GPUs) and a peer copy uses no SM on either side -- but the completion all-reduce makes EVERY
+    rank wait for the slowest one each step, and at 8 GPUs that cost more than it saved: 5.22 ms per step against
+    5.00 (profiles/r2_scale_cfg2_n8_peer_gather.json; at 2 GPUs the two modes measure the same).  Kept as an option,
+    not the default.  Falls back to "root" (on every rank) when the IPC export / open fails anywhere.
 
         pg = PipelinedGather(n, Bt, world, device, rank=rank)
         for step in ...:
