@@ -65,7 +65,7 @@ class PipelinedGather:
     final-state results"); mode "all": all-gather (every rank gets everything; 8x the bytes at 8 ranks);
     mode "peer": gather to rank 0 by PEER COPIES -- the root's two result buffers are opened by the other ranks
     over CUDA IPC and every rank pushes its slice with one cudaMemcpyAsync on its own copy engine over NVLink; NCCL
-    only carries the 4-byte completion all-reduce that orders the pushes on the root's stream.  The NCCL receive
+    only carries a 4-byte completion token per rank (gathered to the root) that orders the pushes on the root's stream.  The NCCL receive
     kernels of mode "root" run on the root's SMs next to its sweeps (root 5.00 ms per step against 4.82-4.88 on the
     other ranks at 8 GPUs) and a peer copy uses no SM on either side -- but the completion all-reduce makes EVERY
     rank wait for the slowest one each step, and at 8 GPUs that cost more than it saved: 5.22 ms per step against
@@ -144,6 +144,7 @@ class PipelinedGather:
             self.mode, self.peer = "root", None
         else:
             self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+            self.flag_out = torch.zeros((self.world if self.rank == 0 else 1, 1), dtype=torch.int32, device=device)
 
     def next_buffer(self):
         import torch
@@ -172,9 +173,9 @@ class PipelinedGather:
                                                 rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice, self.stream.cuda_stream)
                     if int(err) != 0:
                         raise RuntimeError(f"peer copy to the root failed: {err}")
-                # completion: the root's stream passes this point once every rank's push (stream-ordered before its
-                # contribution) has been issued and finished
-                dist.all_reduce(self.flag, group=self.group)
+                # completion: a 4-byte token gathered to the root -- its stream passes this point once every rank's push
+                # (stream-ordered before that rank's send) has finished; no rank waits for any rank but the root
+                gather_to_root(self.flag, self.flag_out, self.world, self.rank, group=self.group)
             else:
                 gather_to_root(res, self.out[k], self.world, self.rank, group=self.group)
         if not self.cuda:
