@@ -65,11 +65,11 @@ class PipelinedGather:
     final-state results"); mode "all": all-gather (every rank gets everything; 8x the bytes at 8 ranks);
     mode "peer": gather to rank 0 by PEER COPIES -- the root's two result buffers are opened by the other ranks
     over CUDA IPC and every rank pushes its slice with one cudaMemcpyAsync on its own copy engine over NVLink; NCCL
-    only carries a 4-byte completion token per rank (gathered to the root) that orders the pushes on the root's stream.  The NCCL receive
-    kernels of mode "root" run on the root's SMs next to its sweeps (root 5.00 ms per step against 4.82-4.88 on the
-    other ranks at 8 GPUs) and a peer copy uses no SM on either side -- but the completion all-reduce makes EVERY
-    rank wait for the slowest one each step, and at 8 GPUs that cost more than it saved: 5.22 ms per step against
-    5.00 (profiles/r2_scale_cfg2_n8_peer_gather.json; at 2 GPUs the two modes measure the same).  Kept as an option,
+    only carries a 4-byte completion token per rank (gathered to the root) that orders the pushes on the root's stream.
+    Measured at 8 GPUs on one box: 4.987 ms per step against 4.961 for mode "root" -- rank 0 is the slow rank in both
+    (4.96-4.99 against 4.82-4.92 ms), so it is not the 112 MiB the root receives that costs; with an all-reduce as the
+    completion every rank waits for the slowest and the step grows to 5.22 ms (profiles/r2_ab_gather_n8.txt).  Kept as
+    an option,
     not the default.  Falls back to "root" (on every rank) when the IPC export / open fails anywhere.
 
         pg = PipelinedGather(n, Bt, world, device, rank=rank)

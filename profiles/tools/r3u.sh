@@ -1,9 +1,7 @@
 #!/bin/bash
-# round 2, call 3u: last check of the final tree -- whole GPU suite, smoke, default bench line
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r3u_pytest.log 2>&1; echo "pytest rc=$?" > gpurun_out/r3u_sum.txt
 tail -3 gpurun_out/r3u_pytest.log >> gpurun_out/r3u_sum.txt
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> gpurun_out/r3u_sum.txt 2>&1
 timeout 600 python bench.py > gpurun_out/r3u_bench_n1.json 2> gpurun_out/r3u_bench_n1.err; echo "bench rc=$?" >> gpurun_out/r3u_sum.txt
 python - <<'PY' >> gpurun_out/r3u_sum.txt
 import json
