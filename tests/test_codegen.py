@@ -65,10 +65,12 @@ def test_six_state_problem_source_compiles_for_sm100a(cg):
 NVRTC_OPTS = ["--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"]
 
 
-@pytest.mark.parametrize("strict", [False, True])
-def test_every_kernel_unit_of_a_generated_problem_compiles_under_nvrtc(cg, strict):
+@pytest.mark.parametrize("strict,uniform_h", [(False, False), (False, True), (True, False)])
+def test_every_kernel_unit_of_a_generated_problem_compiles_under_nvrtc(cg, strict, uniform_h):
     """What the GPU box does on demand (NVRTC, one unit per kernel variant), done here without a device: the
-    table/info kernels and every sweep variant a generated problem can be asked for."""
+    table/info kernels and every sweep variant a generated problem can be asked for -- in the strict build and in the
+    FMA-contracted build with per-step sizes and with the step sizes as constant operands (OCS_UNIFORM_H, what a
+    linspace grid selects)."""
     nvrtc = pytest.importorskip("cuda.bindings.nvrtc")
     src_api = open(os.path.join(ROOT, "optimal-control-solvers_b200", "csrc", "nvrtc_problem.cu")).read()
     for opt in NVRTC_OPTS:
@@ -85,8 +87,8 @@ def test_every_kernel_unit_of_a_generated_problem_compiles_under_nvrtc(cg, stric
     inc = "-I" + os.path.join(ROOT, "optimal-control-solvers_b200", "csrc")
     opts = [o.encode() for o in NVRTC_OPTS + [inc, "--fmad=false" if strict else "--fmad=true"]]
     for unit in units:
-        src = ('#define OCS_NS ocs_gen\n#define OCS_STRICT %d\n#include "rk4_kernels.cuh"\n' % int(strict) + p.source + "\n" +
-               unit + "\n")
+        src = ('#define OCS_NS ocs_gen\n#define OCS_STRICT %d\n#define OCS_UNIFORM_H %d\n#include "rk4_kernels.cuh"\n'
+               % (int(strict), int(uniform_h)) + p.source + "\n" + unit + "\n")
         err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"ocs_generated_problem.cu", 0, [], [])
         assert int(err) == 0
         (rc,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
